@@ -1,0 +1,212 @@
+"""Host side of tracking: marshals ``settings``/``channel`` into the C ABI and assembles the
+``trackResults`` struct array exactly as the reference lays it out:
+field creation order, initial values (0 / Inf / '-') and 1xN double row vectors of
+BDS-3_B1C/WB_tracking.m:53-112, NB_tracking.m:53-100 and BDS-3_B2a/tracking.m:48-96."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+from . import loopcoef
+from .settings import Struct, matlab_round
+
+_MODE = {"WB": L.TRK_B1C_WB, "NB": L.TRK_B1C_NB, "B2a": L.TRK_B2A}
+
+
+def num_to_process(mode, settings) -> int:
+    if mode == "B2a":
+        return int(settings.msToProcess)                                   # B2a/tracking.m:100
+    return matlab_round(settings.msToProcess / 1000 / settings.intTime)    # WB_tracking.m:56
+
+
+def has_pilot(mode, settings) -> bool:
+    f = settings.pilotTRKflag
+    return (mode == "WB" and f == 2) or (mode in ("NB", "B2a") and f == 1)
+
+
+def make_cfg(mode, settings, kernel=L.KERNEL_AUTO) -> L.bds_trk_cfg:
+    tau1, tau2 = loopcoef.calcLoopCoef(settings.dllNoiseBandwidth, settings.dllDampingRatio, 1.0)
+    pf3, pf2, pf1 = loopcoef.calcLoopCoefCarr(settings)
+    factor = loopcoef.CalcWeighingFactor(settings) if mode == "WB" else 0.0   # WB_tracking.m:138
+    return L.bds_trk_cfg(samplingFreq=settings.samplingFreq, codeFreqBasis=settings.codeFreqBasis,
+                         codeLength=int(settings.codeLength), dllCorrelatorSpacing=settings.dllCorrelatorSpacing,
+                         intTime=settings.intTime, pilotTRKflag=int(settings.pilotTRKflag),
+                         CNoInterval=int(settings.CNoInterval), tau1code=tau1, tau2code=tau2, pf3=pf3, pf2=pf2,
+                         pf1=pf1, wbFactor=factor, kernel=int(kernel), reserved=0)
+
+
+def make_channels(channel):
+    arr = (L.bds_channel * len(channel))()
+    for i, ch in enumerate(channel):
+        arr[i].PRN = int(ch.PRN)
+        arr[i].status = ord(ch.status[0]) if isinstance(ch.status, str) else int(ch.status)
+        arr[i].acquiredFreq = float(ch.acquiredFreq)
+        arr[i].codePhase = float(ch.codePhase)
+        arr[i].codeFreq = float(ch.codeFreq)
+    return arr
+
+
+def template(mode, settings, N) -> Struct:
+    tr = Struct()
+    tr.status = "-"
+    tr.absoluteSample = np.zeros(N)
+    tr.codeFreq = np.full(N, np.inf)
+    tr.carrFreq = np.full(N, np.inf)
+    for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L"):
+        tr[f] = np.zeros(N)
+    if has_pilot(mode, settings):
+        names = (("Pilot_I_P", "Pilot_I_E", "Pilot_I_L", "Pilot_Q_E", "Pilot_Q_P", "Pilot_Q_L") if mode == "WB"
+                 else ("Pilot_I_P", "Pilot_Q_P"))
+        for f in names:
+            tr[f] = np.zeros(N)
+    for f in ("dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt", "remCodePhase", "remCarrPhase"):
+        tr[f] = np.full(N, np.inf)
+    nc = N // int(settings.CNoInterval)
+    tr.DataCNo = np.zeros(nc)
+    tr.DataPLD = np.zeros(nc)
+    if has_pilot(mode, settings):
+        tr.PilotCNo = np.zeros(nc)
+        tr.PilotPLD = np.zeros(nc)
+        tr["B2a_CNo" if mode == "B2a" else "B1C_CNo"] = np.zeros(nc)
+    return tr
+
+
+class TrackSession:
+    """Thin RAII wrapper over bds_trk* (bds_track_open / run / fetch / close)."""
+
+    def __init__(self, mode, settings, channel, source=None, kernel=L.KERNEL_AUTO, device_ptr=None, n_samples=None):
+        self.mode, self.settings = mode, settings
+        self.nch = len(channel)
+        self.cfg = make_cfg(mode, settings, kernel)
+        self.chs = make_channels(channel)
+        self.h = C.c_void_p()
+        lib = L.lib()
+        skip = int(settings.get("skipNumberOfBytes", 0))
+        self._keep = None
+        if device_ptr is not None:
+            L.check(lib.bds_track_open(_MODE[mode], C.byref(self.cfg), C.c_void_p(device_ptr), int(n_samples),
+                                       L.LOC_DEVICE, skip, self.chs, self.nch, C.byref(self.h)))
+        elif isinstance(source, (str, os.PathLike)) or (hasattr(source, "name") and not isinstance(source, np.ndarray)):
+            path = os.fspath(source if isinstance(source, (str, os.PathLike)) else source.name)
+            L.check(lib.bds_track_open_file(_MODE[mode], C.byref(self.cfg), path.encode(), skip, 0, self.chs, self.nch,
+                                            C.byref(self.h)))
+        else:
+            x = L.as_int8(source)
+            self._keep = x
+            L.check(lib.bds_track_open(_MODE[mode], C.byref(self.cfg), L.ptr(x), x.size, L.LOC_HOST, skip, self.chs,
+                                       self.nch, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            L.lib().bds_track_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def feed(self, x=None, first_sample=0, device_ptr=None, n=None):
+        if device_ptr is not None:
+            L.check(L.lib().bds_track_feed(self.h, C.c_void_p(device_ptr), int(n), L.LOC_DEVICE, int(first_sample)))
+        else:
+            x = L.as_int8(x)
+            self._keep = x
+            L.check(L.lib().bds_track_feed(self.h, L.ptr(x), x.size, L.LOC_HOST, int(first_sample)))
+
+    def run_async(self, n_epochs):
+        L.check(L.lib().bds_track_run_async(self.h, int(n_epochs)))
+
+    def sync(self):
+        L.check(L.lib().bds_track_sync(self.h))
+
+    def reset(self):
+        L.check(L.lib().bds_track_reset(self.h))
+
+    def stats(self):
+        cs, ep, ms = C.c_longlong(), C.c_int(), C.c_float()
+        L.check(L.lib().bds_track_stats(self.h, C.byref(cs), C.byref(ep), C.byref(ms)))
+        return cs.value, ep.value, ms.value
+
+    def device_block(self):
+        p, b, nf, cap = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
+        L.check(L.lib().bds_track_device_block(self.h, C.byref(p), C.byref(b), C.byref(nf), C.byref(cap)))
+        return p.value, b.value, nf.value, cap.value
+
+    def fetch(self, N, raw=False):
+        """-> dict of [nch, N] planes (+ CNo planes [nch, N//CNoInterval], raw [nch,N,18], epochsDone [nch])."""
+        out = L.bds_trk_out()
+        planes = {}
+        for name in L.TRK_PLANES:
+            a = np.empty((self.nch, N))
+            planes[name] = a
+            setattr(out, name, a.ctypes.data_as(L._PD))
+        nc = N // int(self.settings.CNoInterval)
+        for name in L.CNO_PLANES:
+            a = np.zeros((self.nch, nc))
+            planes[name] = a
+            if nc > 0:
+                setattr(out, name, a.ctypes.data_as(L._PD))
+        if raw:
+            r = np.zeros((self.nch, N, 18))
+            planes["raw"] = r
+            out.raw = r.ctypes.data_as(L._PD)
+        done = np.zeros(self.nch, dtype=np.int32)
+        out.epochsDone = done.ctypes.data_as(C.POINTER(C.c_int32))
+        planes["epochsDone"] = done
+        L.check(L.lib().bds_track_fetch(self.h, C.byref(out), N))
+        return planes
+
+
+def assemble(mode, settings, channel, planes, N):
+    """trackResults struct array from the fetched planes, mirroring the reference's control flow:
+    channels are processed in order; a short read leaves that channel partially filled with
+    status '-' and *returns*, so later channels keep the template (WB_tracking.m:279-283,485-488)."""
+    results = []
+    stopped = False
+    pilot = has_pilot(mode, settings)
+    cno_name = "B2a_CNo" if mode == "B2a" else "B1C_CNo"
+    for c, ch in enumerate(channel):
+        tr = template(mode, settings, N)
+        if ch.PRN != 0 and not stopped:
+            done = int(planes["epochsDone"][c])
+            for f in list(tr.keys()):
+                if f in L.TRK_PLANES:
+                    tr[f] = planes[f][c].copy()
+            ncd = min(tr.DataCNo.size, done // int(settings.CNoInterval))
+            tr.DataCNo[:ncd] = planes["DataCNo"][c, :ncd]
+            tr.DataPLD[:ncd] = planes["DataPLD"][c, :ncd]
+            if pilot:
+                tr.PilotCNo[:ncd] = planes["PilotCNo"][c, :ncd]
+                tr.PilotPLD[:ncd] = planes["PilotPLD"][c, :ncd]
+                tr[cno_name][:ncd] = planes["TotalCNo"][c, :ncd]
+            tr.PRN = int(ch.PRN)                                        # WB_tracking.m:167
+            if done >= N:
+                tr.status = ch.status                                    # WB_tracking.m:485-488
+            else:
+                stopped = True
+            if "raw" in planes:
+                tr.raw = planes["raw"][c].copy()
+            tr.epochsDone = done
+        results.append(tr)
+    return results
+
+
+def run_tracking(mode, source, channel, settings, n_epochs=None, kernel=L.KERNEL_AUTO, raw=False):
+    N = num_to_process(mode, settings) if n_epochs is None else int(n_epochs)
+    if not any(ch.PRN != 0 for ch in channel):
+        return [template(mode, settings, N) for _ in channel], channel
+    with TrackSession(mode, settings, channel, source, kernel=kernel) as s:
+        s.run_async(N)
+        planes = s.fetch(N, raw=raw)
+    return assemble(mode, settings, channel, planes, N), channel

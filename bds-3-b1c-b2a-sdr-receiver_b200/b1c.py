@@ -1,0 +1,66 @@
+"""BDS-3_B1C call surface: initSettings / acquisition / GPU_acquisition / preRun / WB_tracking /
+NB_tracking / postProcessing with the reference's names and argument order."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _acq, _lib as L, _track
+from .codes import generateDataBOC11, generatePilotBOC11, generatePilotBOC61, makeDataTable, makePilotTable  # noqa: F401
+from .settings import Settings, samples_per_code
+
+
+def initSettings(**over) -> Settings:
+    """BDS-3_B1C/initSettings.m:48-151 (shipped values)."""
+    s = Settings(
+        fileName="Set_Jan17_2018_13_53_for_Jimi_ch0.bin", dataType="schar", fileType=1,
+        IF=1590e6 - 1575.42e6, samplingFreq=53e6, FEBW=27e6, msToProcess=37000,
+        acqSatelliteList=[19, 20], pilotACQflag=1, gpuACQflag=1, pilotTRKflag=2, numberOfChannels=10,
+        skipNumberOfBytes=0, codeLength=10230, codeFreqBasis=1.023e6, carrFreqBasis=1575.42e6,
+        skipAcquisition=0, acqSearchBand=5000, acqCohT=10, acqStep=1000 / 10 / 2, acqThreshold=7.5,
+        resamplingThreshold=15e6, resamplingflag=0, dllDampingRatio=0.7, dllNoiseBandwidth=1,
+        dllCorrelatorSpacing=0.06, pllDampingRatio=0.7, pllNoiseBandwidth=12, intTime=0.01,
+        navSolPeriod=200, elevationMask=5, useTropCorr=1, plotTracking=1, c=299792458, startOffset=68.802,
+        CNoInterval=50)
+    s.update(over)
+    return s
+
+
+def acquisition(longSignal, settings, **kw):
+    """acqResults = acquisition(longSignal, settings)   (BDS-3_B1C/acquisition.m:1)"""
+    return _acq.acquire(L.SIG_B1C, longSignal, settings, **kw)
+
+
+GPU_acquisition = acquisition   # BDS-3_B1C/GPU_acquisition.m:1 — same contract
+
+
+def preRun(acqResults, settings):
+    return _acq.preRun(acqResults, settings, b1c=True)
+
+
+def WB_tracking(fid, channel, settings, **kw):
+    """[trackResults, channel] = WB_tracking(fid, channel, settings)   (BDS-3_B1C/WB_tracking.m:1)"""
+    return _track.run_tracking("WB", fid, channel, settings, **kw)
+
+
+def NB_tracking(fid, channel, settings, **kw):
+    """[trackResults, channel] = NB_tracking(fid, channel, settings)   (BDS-3_B1C/NB_tracking.m:1)"""
+    return _track.run_tracking("NB", fid, channel, settings, **kw)
+
+
+def postProcessing(settings, acqResults=None):
+    """Acquisition -> preRun -> tracking part of BDS-3_B1C/postProcessing.m:61-149 (navigation and
+    plots stay in MATLAB).  Returns (acqResults, channel, trackResults)."""
+    with open(settings.fileName, "rb") as fid:
+        if settings.skipAcquisition == 0 or acqResults is None:
+            spc = samples_per_code(settings)
+            fid.seek(int(settings.skipNumberOfBytes))
+            data = np.frombuffer(fid.read(20 * spc), dtype=np.int8)        # postProcessing.m:94
+            acqResults = acquisition(data, settings)
+        if not np.any(acqResults.carrFreq):
+            return acqResults, None, []
+        channel = preRun(acqResults, settings)
+        if settings.pilotTRKflag == 2:
+            trackResults, channel = WB_tracking(fid, channel, settings)
+        else:
+            trackResults, channel = NB_tracking(fid, channel, settings)
+    return acqResults, channel, trackResults

@@ -1,0 +1,1151 @@
+// Tracking correlator + closed-loop persistent kernel (sm_100a).
+//
+// Replaces the per-channel, per-epoch loop of the reference
+//   BDS-3_B1C/WB_tracking.m:223-483, BDS-3_B1C/NB_tracking.m:205-448, BDS-3_B2a/tracking.m:195-441
+// Design: one persistent cooperative grid; work items are
+// (channel, epoch, slice).  A slice correlates a contiguous part of the epoch's
+// sample block; the last slice to arrive (atomic counter) reduces the partials in a
+// fixed order, closes the PLL/DLL in fp64 exactly as the reference does and
+// publishes the next epoch's NCO parameters with a release store, which makes
+// that channel's next-epoch slices runnable.  CTAs interleave the channels of their
+// group so the loop-closure latency of one channel is hidden behind the others.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include "bds_codes.h"
+#include "bds_track.cuh"
+#include "bds_track_fast.cuh"
+
+namespace bds {
+
+// ======================================================================================
+// General (exact, any configuration) slice correlator
+// ======================================================================================
+// Follows the reference sample by sample, including MATLAB's two-ended colon
+// construction of the code-phase vectors (SURVEY §8 quirk ii) so that chip lookups
+// are decided by the same IEEE expressions as the float64 oracle.
+struct SliceCtx {
+    const int8_t* x;        // window base
+    long long winFirst, winLen;
+    EpochParams p;
+    int mode, hasPilot, hasP61;
+    double L, d, fs;
+};
+
+template <typename T>
+__device__ __forceinline__ T load_cg(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+    T v;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = __ldcg(s + i);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ void store_cg(T* p, const T& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) __stcg(d + i, s[i]);
+}
+
+__device__ __forceinline__ int code_bit(const uint32_t* w, int chip) { return (w[chip >> 5] >> (chip & 31)) & 1; }
+
+// two-ended colon element k of a:dd:stop with n steps (numel = n+1)
+__device__ __forceinline__ double colon_elem(double a, double dd, double stop, int n, int k) {
+    int h = n >> 1;
+    if (!(n & 1) && k == h) return __dmul_rn(__dadd_rn(a, stop), 0.5);
+    if (k <= h) return __dadd_rn(a, __dmul_rn((double)k, dd));
+    return __dadd_rn(stop, -__dmul_rn((double)(n - k), dd));
+}
+
+// sign (+1/-1 as float) of the BOC(1,1)-expanded code at padded index idx (0-based
+// into [code(end) code code(1)]): WB_tracking.m:181,292-294
+__device__ __forceinline__ float boc11_sign(const uint32_t* w, int idx, int L2) {
+    int h = idx - 1;
+    if (h < 0) h = L2 - 1;
+    if (h >= L2) h = 0;
+    int neg = code_bit(w, h >> 1) ^ ((h & 1) == 0);
+    return neg ? -1.f : 1.f;
+}
+__device__ __forceinline__ float boc61_sign(const uint32_t* w, int idx, int L12) {
+    int s = idx - 1;
+    if (s < 0) s = L12 - 1;
+    if (s >= L12) s = 0;
+    int chip = s / 12;
+    int i = s - chip * 12;
+    int neg = code_bit(w, chip) ^ ((i & 1) == 0);
+    return neg ? -1.f : 1.f;
+}
+__device__ __forceinline__ float plain_sign(const uint32_t* w, int idx, int L) {
+    int c = idx - 1;
+    if (c < 0) c = L - 1;
+    if (c >= L) c = 0;
+    return code_bit(w, c) ? -1.f : 1.f;
+}
+
+// Accumulates this thread's share of block-relative samples in the 16-byte chunk
+// range [q0, q1) of the window into acc[18].
+__device__ void correlate_general(const SliceCtx& c, const uint32_t* bitsData, const uint32_t* bitsPilot,
+                                  long long q0, long long q1, float* acc) {
+    const EpochParams& p = c.p;
+    const long long B0 = p.pos - c.winFirst;  // byte offset of the block in the window
+    const int n = p.blksize - 1;              // colon steps
+    const bool b1c = c.mode != BDS_TRK_B2A;
+    const double mul = b1c ? 2.0 : 1.0;
+    const double dd = b1c ? __dmul_rn(p.step, 2.0) : p.step;
+    const double base = __dadd_rn(__dmul_rn((double)n, p.step), p.rem);  // (blksize-1)*step + rem
+    double a[3], stop[3];
+    // order E, P, L: offsets -d, 0, +d   (WB_tracking.m:289-317)
+    a[0] = __dmul_rn(__dadd_rn(p.rem, -c.d), mul);
+    a[1] = __dmul_rn(p.rem, mul);
+    a[2] = __dmul_rn(__dadd_rn(p.rem, c.d), mul);
+    stop[0] = __dmul_rn(__dadd_rn(base, -c.d), mul);
+    stop[1] = __dmul_rn(base, mul);
+    stop[2] = __dmul_rn(__dadd_rn(base, c.d), mul);
+    // carrier NCO in 2^-64 turns
+    double r = p.carrFreq / c.fs;
+    r -= floor(r);
+    const unsigned long long dphi = __double2ull_rn(r * 18446744073709551616.0);
+    double r0 = p.remCarr / 6.283185307179586476925286766559;
+    r0 -= floor(r0);
+    const unsigned long long phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
+    const int Li = (int)c.L;
+
+    for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const int8_t* src = c.x + q * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((q + 1) * 16 <= c.winLen) {
+            v = ldg_nc_v4(src);
+        } else {  // last, partial chunk of a caller-owned buffer: byte loads only
+            int8_t* vb = reinterpret_cast<int8_t*>(&v);
+            for (int j = 0; j < 16 && q * 16 + j < c.winLen; ++j) vb[j] = src[j];
+        }
+        const int8_t* b = reinterpret_cast<const int8_t*>(&v);
+#pragma unroll 1
+        for (int j = 0; j < 16; ++j) {
+            long long k = q * 16 + j - B0;
+            if (k < 0 || k > n) continue;
+            float xs = (float)b[j];
+            unsigned long long ph = phi0 + (unsigned long long)k * dphi;
+            float sn, cs;
+            sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);  // 2^-31 -> angle/pi
+            float iB, qB;
+            if (b1c) {  // carrsig = exp(-i*theta): WB_tracking.m:341-346
+                iB = xs * cs;
+                qB = -xs * sn;
+            } else {    // exp(+i*theta), I = imag, Q = real: B2a tracking.m:309-314
+                qB = xs * cs;
+                iB = xs * sn;
+            }
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                double t = colon_elem(a[o], dd, stop[o], n, (int)k);
+                int idx = (int)ceil(t);
+                float sd, sp = 0.f, s6 = 0.f;
+                if (b1c) {
+                    sd = boc11_sign(bitsData, idx, 2 * Li);
+                    if (c.hasPilot) sp = boc11_sign(bitsPilot, idx, 2 * Li);
+                    if (c.hasP61) s6 = boc61_sign(bitsPilot, (int)ceil(__dmul_rn(t, 6.0)), 12 * Li);
+                } else {
+                    sd = plain_sign(bitsData, idx, Li);
+                    if (c.hasPilot) sp = plain_sign(bitsPilot, idx, Li);
+                }
+                acc[sum_idx(0, o, 0)] += sd * iB;
+                acc[sum_idx(0, o, 1)] += sd * qB;
+                acc[sum_idx(1, o, 0)] += sp * iB;
+                acc[sum_idx(1, o, 1)] += sp * qB;
+                acc[sum_idx(2, o, 0)] += s6 * iB;
+                acc[sum_idx(2, o, 1)] += s6 * qB;
+            }
+        }
+    }
+}
+
+// chunk range of slice sl of S for the epoch block
+__device__ __forceinline__ void slice_chunks(const EpochParams& p, long long winFirst, int sl, int S, long long& q0,
+                                             long long& q1) {
+    long long B0 = p.pos - winFirst;
+    long long B1 = B0 + p.blksize;
+    long long qa = B0 >> 4, qb = (B1 + 15) >> 4;
+    long long nq = qb - qa;
+    q0 = qa + nq * sl / S;
+    q1 = qa + nq * (sl + 1) / S;
+}
+
+// block-wide reduction of acc[18] (fp32 per thread) -> double, result valid in
+// threads 0..17 of warp 0 ... returned through smem red[18]
+__device__ void block_reduce18(float* acc, double* red /*[8][18] smem*/, double* out18 /*smem [18]*/) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) {
+        double v = warp_sum((double)acc[i]);
+        if (lane == 0) red[wid * kNSum + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNSum) {
+        double s = 0;
+        int nw = blockDim.x >> 5;
+        for (int w = 0; w < nw; ++w) s += red[w * kNSum + threadIdx.x];
+        out18[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// ======================================================================================
+// Loop closure (fp64, one thread)  — WB_tracking.m:375-481, NB_tracking.m:349-445,
+// B2a/tracking.m:337-434, Calc_CNo_PLD.m
+// ======================================================================================
+__device__ __forceinline__ double dll_disc(double ie, double qe, double il, double ql) {
+    double e = sqrt(ie * ie + qe * qe), l = sqrt(il * il + ql * ql);
+    return (e - l) / (e + l);
+}
+
+__device__ void cno_pld(const double* ip, const double* qp, int n, double T, double& cno, double& pld) {
+    // Calc_CNo_PLD.m:52-73 ; var() normalises by N-1
+    double zm = 0;
+    for (int i = 0; i < n; ++i) {
+        double a = __ldcg(ip + i), b = __ldcg(qp + i);
+        zm += a * a + b * b;
+    }
+    zm /= n;
+    double zv = 0, pos = 0, neg = 0, sq = 0;
+    for (int i = 0; i < n; ++i) {
+        double a = __ldcg(ip + i), b = __ldcg(qp + i);
+        double z = a * a + b * b - zm;
+        zv += z * z;
+        if (a > 0) pos += a;
+        if (a < 0) neg += a;
+        sq += b;
+    }
+    zv /= (n - 1);
+    double pav = sqrt(zm * zm - zv);
+    double nv = 0.5 * (zm - pav);
+    cno = fabs((1.0 / T) * pav / (2.0 * nv));
+    double aa = (pos - neg) * (pos - neg), qq = sq * sq;
+    pld = (aa - qq) / (aa + qq);
+}
+
+// Computes the params of the epoch that follows state `st`; returns false if the
+// block is not fully inside the resident window (short read, WB_tracking.m:279-283).
+__device__ bool next_params(const TrkDev& g, const ChanState& st, EpochParams& np) {
+    np.pos = st.pos;
+    np.rem = st.remCodePhase;
+    np.step = st.codeFreq / g.fs;                                 // WB:258
+    np.blksize = (int)ceil((g.L - st.remCodePhase) / np.step);    // WB:261
+    np.carrFreq = st.carrFreq;
+    np.remCarr = st.remCarrPhase;
+    np.pad = 0;
+    long long off = np.pos - g.winFirst;
+    return off >= 0 && off + np.blksize <= g.winLen && np.blksize > 0;
+}
+
+__device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 sums*/) {
+    ChanState st = load_cg(g.st + c);
+    const EpochParams p = load_cg(g.params + c * 2 + (e & 1));
+    double* out = g.out + (size_t)c * kNFields * g.capacity;
+    const int cap = g.capacity;
+    const double twopi = 6.283185307179586476925286766559;
+    const bool b1c = g.mode != BDS_TRK_B2A;
+
+    out[F_ABS * cap + e] = (double)p.pos;           // WB:254
+    out[F_REMCODE * cap + e] = p.rem;               // WB:287
+    out[F_REMCARR * cap + e] = p.remCarr;           // WB:332
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) out[(F_RAW0 + i) * cap + e] = s[i];
+
+    // remCodePhase / remCarrPhase updates (WB:327,335-337; B2a:295,303-305)
+    double base = (double)(p.blksize - 1) * p.step + p.rem;
+    st.remCodePhase = base + p.step - g.L;
+    double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
+    st.remCarrPhase = fmod(trig, twopi);
+    st.pos = p.pos + p.blksize;
+    st.samples += p.blksize;
+
+    double I_E = s[sum_idx(0, EPL_E, 0)], Q_E = s[sum_idx(0, EPL_E, 1)];
+    double I_P = s[sum_idx(0, EPL_P, 0)], Q_P = s[sum_idx(0, EPL_P, 1)];
+    double I_L = s[sum_idx(0, EPL_L, 0)], Q_L = s[sum_idx(0, EPL_L, 1)];
+    double carrError = atan(Q_P / I_P) / twopi;
+    double codeError = dll_disc(I_E, Q_E, I_L, Q_L);
+    if (b1c) codeError = codeError * (1.0 - g.d);
+    if (g.mode == BDS_TRK_B1C_WB && g.hasPilot) {
+        const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
+        double pI[3], pQ[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {  // WB:375-380
+            pI[o] = -ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)];
+            pQ[o] = -ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)];
+        }
+        double pe = atan(pQ[EPL_P] / pI[EPL_P]) / twopi;
+        carrError = (carrError * 1 + pe * 3) / 4;
+        double pc = dll_disc(pI[EPL_E], pQ[EPL_E], pI[EPL_L], pQ[EPL_L]) * (1.0 - g.d);
+        codeError = codeError * g.factor + pc * (1.0 - g.factor);
+        out[F_PI_P * cap + e] = pI[EPL_P];
+        out[F_PI_E * cap + e] = pI[EPL_E];
+        out[F_PI_L * cap + e] = pI[EPL_L];
+        out[F_PQ_P * cap + e] = pQ[EPL_P];
+        out[F_PQ_E * cap + e] = pQ[EPL_E];
+        out[F_PQ_L * cap + e] = pQ[EPL_L];
+    } else if (g.hasPilot) {
+        double pIP = s[sum_idx(1, EPL_P, 0)], pQP = s[sum_idx(1, EPL_P, 1)];
+        double pc = dll_disc(s[sum_idx(1, EPL_E, 0)], s[sum_idx(1, EPL_E, 1)], s[sum_idx(1, EPL_L, 0)],
+                             s[sum_idx(1, EPL_L, 1)]);
+        if (g.mode == BDS_TRK_B1C_NB) {
+            double pe = atan(-pIP / pQP) / twopi;   // NB:357
+            carrError = (carrError * 11 + pe * 29) / 40;
+            codeError = (codeError * 11 + pc * (1.0 - g.d) * 29) / 40;
+        } else {
+            const double cr = 6.123233995736766e-17;  // cos(pi/2) in double, B2a:345
+            double re = pIP * cr + pQP, im = pQP * cr - pIP;
+            double pe = atan(im / re) / twopi;
+            carrError = (carrError + pe) / 2;
+            codeError = (codeError + pc) / 2;
+        }
+        out[F_PI_P * cap + e] = pIP;
+        out[F_PQ_P * cap + e] = pQP;
+    }
+    // PLL filter WB:399-406
+    st.d2CarrError = st.d2CarrError + carrError * g.pf3;
+    st.dCarrError = st.d2CarrError + carrError * g.pf2 + st.dCarrError;
+    double carrNco = st.dCarrError + carrError * g.pf1;
+    out[F_CARRFREQ * cap + e] = st.carrFreq;
+    st.carrFreq = st.carrFreqBasis + carrNco;
+    // DLL filter WB:422-430
+    double codeNco = st.oldCodeNco + (g.tau2 / g.tau1) * (codeError - st.oldCodeError) + codeError * (g.PDI / g.tau1);
+    st.oldCodeNco = codeNco;
+    st.oldCodeError = codeError;
+    out[F_CODEFREQ * cap + e] = st.codeFreq;
+    st.codeFreq = g.cc[c].chCodeFreq - codeNco;
+    out[F_DLL * cap + e] = codeError;
+    out[F_DLLF * cap + e] = codeNco;
+    out[F_PLL * cap + e] = carrError;
+    out[F_PLLF * cap + e] = carrNco;
+    out[F_I_E * cap + e] = I_E;
+    out[F_I_P * cap + e] = I_P;
+    out[F_I_L * cap + e] = I_L;
+    out[F_Q_E * cap + e] = Q_E;
+    out[F_Q_P * cap + e] = Q_P;
+    out[F_Q_L * cap + e] = Q_L;
+
+    // C/N0 + lock detector every CNoInterval epochs (WB:459-481)
+    if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
+        int ci = (e + 1) / g.cnoInterval - 1;
+        if (ci < g.cnoCap) {
+            __threadfence();
+            int n = g.cnoInterval, e0 = e + 1 - n;
+            double* cn = g.cno + (size_t)c * kNCno * g.cnoCap;
+            double d, dp, pv = 0, pp = 0;
+            cno_pld(out + F_I_P * cap + e0, out + F_Q_P * cap + e0, n, g.PDI, d, dp);
+            double c0 = 10.0 * log10(d), c1 = 0;
+            if (g.hasPilot) {
+                if (g.mode == BDS_TRK_B1C_WB)
+                    cno_pld(out + F_PI_P * cap + e0, out + F_PQ_P * cap + e0, n, g.PDI, pv, pp);
+                else  // NB / B2a swap pilot I and Q (Calc_CNo_PLD.m:80-88)
+                    cno_pld(out + F_PQ_P * cap + e0, out + F_PI_P * cap + e0, n, g.PDI, pv, pp);
+                c1 = 10.0 * log10(pv);
+            }
+            double c2 = 10.0 * log10(d + pv);
+            cn[0 * g.cnoCap + ci] = c0 * 0.5 + st.cnoPrev[0] * 0.5;
+            cn[1 * g.cnoCap + ci] = dp;
+            if (g.hasPilot) {
+                cn[2 * g.cnoCap + ci] = c1 * 0.5 + st.cnoPrev[1] * 0.5;
+                cn[3 * g.cnoCap + ci] = pp;
+                cn[4 * g.cnoCap + ci] = c2 * 0.5 + st.cnoPrev[2] * 0.5;
+            }
+            st.cnoPrev[0] = c0;
+            st.cnoPrev[1] = c1;
+            st.cnoPrev[2] = c2;
+        }
+    }
+    st.epoch = e + 1;
+    store_cg(g.st + c, st);
+
+    // publish the next epoch or stop the channel
+    EpochParams np;
+    bool ok = next_params(g, st, np);
+    if (ok && e + 1 < g.capacity) {
+        store_cg(g.params + c * 2 + ((e + 1) & 1), np);
+        __threadfence();
+        st_release(g.ready + c, e + 1);
+    } else {
+        // WB_tracking.m:254 records absoluteSample of the epoch whose read then fails
+        if (e + 1 < g.capacity) out[F_ABS * cap + e + 1] = (double)st.pos;
+        __threadfence();
+        st_release(g.stop + c, e + 1);
+    }
+}
+
+// ======================================================================================
+// Persistent closed-loop kernel
+// ======================================================================================
+struct __align__(16) TrkSmem {
+    uint32_t bits[2][kPackedWordsDev];
+    double red[8 * kNSum];
+    double sums[kNSum];
+    double part[kNSum * 14];
+    EpochParams p;
+    int go;
+    int last;
+    int curChan;
+};
+
+__device__ void load_code_bits(const TrkDev& g, TrkSmem& sm, int c) {
+    if (sm.curChan == c) return;
+    __syncthreads();
+    const uint32_t* src = g.codeBits + (size_t)c * 2 * kPackedWordsDev;
+    for (int i = threadIdx.x; i < 2 * kPackedWordsDev; i += blockDim.x) (&sm.bits[0][0])[i] = __ldg(src + i);
+    __syncthreads();
+    if (threadIdx.x == 0) sm.curChan = c;
+    __syncthreads();
+}
+
+// Sum the S slice partials of channel c in a fixed order (deterministic).
+__device__ void reduce_partials(const TrkDev& g, TrkSmem& sm, int c) {
+    const double* part = g.partial + (size_t)c * g.S * kNSum;
+    int t = threadIdx.x;
+    if (t < kNSum * 14) {
+        int l = t / 14, j = t % 14;
+        double a = 0;
+        for (int s = j; s < g.S; s += 14) a += __ldcg(part + (size_t)s * kNSum + l);
+        sm.part[l * 14 + j] = a;
+    }
+    __syncthreads();
+    if (t < kNSum) {
+        double a = 0;
+#pragma unroll
+        for (int j = 0; j < 14; ++j) a += sm.part[t * 14 + j];
+        sm.sums[t] = a;
+    }
+    __syncthreads();
+}
+
+template <bool kFast>
+__device__ __forceinline__ void correlate_slice(const TrkDev& g, TrkSmem& sm, const EpochParams& p, int sl, int S,
+                                                float* acc, FastSmem* fsm) {
+    if constexpr (kFast) {
+        correlate_fast_wb(g, p, sm.bits[0], sm.bits[1], sl, S, acc, fsm);
+    } else {
+        SliceCtx ctx{g.x, g.winFirst, g.winLen, p, g.mode, g.hasPilot, g.hasP61, g.L, g.d, g.fs};
+        long long q0, q1;
+        slice_chunks(p, g.winFirst, sl, S, q0, q1);
+        correlate_general(ctx, sm.bits[0], sm.bits[1], q0, q1, acc);
+    }
+}
+
+template <bool kFast>
+__global__ void __launch_bounds__(kTrkThreads) trk_persistent_kernel(TrkDev g, int epochBase /*unused*/) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
+    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + sizeof(TrkSmem));
+    const int grp = blockIdx.x / g.S, sl = blockIdx.x % g.S;
+    if (grp >= g.nGroups) return;
+    if (threadIdx.x == 0) sm.curChan = -1;
+    __syncthreads();
+
+    for (int i = 0; i < g.maxEpochs; ++i) {
+        bool any = false;
+        for (int c = grp; c < g.nCh; c += g.nGroups) {
+            if (!g.cc[c].active) continue;
+            // epoch index of this channel for round i: every channel advances from its
+            // own completed-epoch count at launch, kept in `pad` of ChanConst by the host
+            const int e = g.cc[c].pad + i;
+            if (threadIdx.x == 0) {
+                int go = 0;
+                while (true) {
+                    if (ld_acquire(g.stop + c) <= e) break;
+                    if (ld_acquire(g.ready + c) >= e) {
+                        go = 1;
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+                sm.go = go;
+                if (go) sm.p = load_cg(g.params + c * 2 + (e & 1));
+            }
+            __syncthreads();
+            if (!sm.go) {
+                __syncthreads();
+                continue;
+            }
+            any = true;
+            load_code_bits(g, sm, c);
+            const EpochParams p = sm.p;
+            float acc[kNSum];
+#pragma unroll
+            for (int k = 0; k < kNSum; ++k) acc[k] = 0.f;
+            correlate_slice<kFast>(g, sm, p, sl, g.S, acc, fsm);
+            block_reduce18(acc, sm.red, sm.sums);
+            if (threadIdx.x < kNSum) {
+                g.partial[((size_t)c * g.S + sl) * kNSum + threadIdx.x] = sm.sums[threadIdx.x];
+                __threadfence();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int old = atomicAdd(g.count + c, 1);
+                sm.last = (old == g.S - 1);
+                if (sm.last) g.count[c] = 0;
+            }
+            __syncthreads();
+            if (sm.last) {
+                __threadfence();
+                reduce_partials(g, sm, c);
+                if (threadIdx.x == 0) close_epoch(g, c, e, sm.sums);
+            }
+            __syncthreads();
+        }
+        if (!any) break;
+    }
+}
+
+// Computes the first params of every channel for the current window (run start).
+__global__ void trk_prepare_kernel(TrkDev g) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.nCh) return;
+    g.count[c] = 0;
+    if (!g.cc[c].active) {
+        g.stop[c] = 0;
+        g.ready[c] = -1;
+        return;
+    }
+    ChanState st = g.st[c];
+    g.cc[c].pad = st.epoch;
+    EpochParams np;
+    if (next_params(g, st, np) && st.epoch < g.capacity) {
+        g.params[c * 2 + (st.epoch & 1)] = np;
+        g.ready[c] = st.epoch;
+        g.stop[c] = INT_MAX;
+    } else {
+        if (st.epoch < g.capacity) g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
+        g.ready[c] = st.epoch - 1;
+        g.stop[c] = st.epoch;
+    }
+}
+
+// ======================================================================================
+// Open-loop ("teacher forced") correlator: grid = (S, n_ch * n_epochs)
+// ======================================================================================
+template <bool kFast>
+__global__ void __launch_bounds__(kTrkThreads) trk_open_loop_kernel(TrkDev g, const EpochParams* params, int nEpochs,
+                                                                   double* partial /*[ce][S][18]*/) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
+    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + sizeof(TrkSmem));
+    const int ce = blockIdx.y, sl = blockIdx.x, S = gridDim.x;
+    const int c = ce / nEpochs;
+    if (threadIdx.x == 0) sm.curChan = -1;
+    __syncthreads();
+    load_code_bits(g, sm, c);
+    const EpochParams p = params[ce];
+    float acc[kNSum];
+#pragma unroll
+    for (int k = 0; k < kNSum; ++k) acc[k] = 0.f;
+    correlate_slice<kFast>(g, sm, p, sl, S, acc, fsm);
+    block_reduce18(acc, sm.red, sm.sums);
+    if (threadIdx.x < kNSum) partial[((size_t)ce * S + sl) * kNSum + threadIdx.x] = sm.sums[threadIdx.x];
+}
+
+__global__ void trk_open_loop_reduce_kernel(const double* partial, int S, int nce, double* sums) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nce * kNSum) return;
+    int ce = i / kNSum, l = i % kNSum;
+    double a = 0;
+    for (int s = 0; s < S; ++s) a += partial[((size_t)ce * S + s) * kNSum + l];
+    sums[i] = a;
+}
+
+}  // namespace bds
+
+// ======================================================================================
+// Host side: session object + C ABI
+// ======================================================================================
+using namespace bds;
+
+struct bds_trk {
+    int mode = 0;
+    bds_trk_cfg cfg{};
+    int nCh = 0;
+    std::vector<bds_channel> ch;
+    long long skip = 0;
+    // IF window
+    int8_t* dX = nullptr;
+    bool ownX = false;
+    size_t xCap = 0;
+    long long winFirst = 0, winLen = 0;
+    // device tables
+    uint32_t* dBits = nullptr;
+    ChanConst* dCC = nullptr;
+    ChanState* dSt = nullptr;
+    EpochParams* dParams = nullptr;
+    int *dReady = nullptr, *dStop = nullptr, *dCount = nullptr;
+    double* dPartial = nullptr;
+    double* dOut = nullptr;
+    double* dCno = nullptr;
+    int capacity = 0, cnoCap = 0;
+    int S = 0, nGroups = 0, gridBlocks = 0;
+    bool fast = false;
+    size_t smemBytes = 0;
+    int epochsRun = 0;  // max over channels, as seen by the host
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float lastMs = 0.f;
+    bool pending = false;
+    std::vector<ChanState> hSt;
+    // mmap'd file
+    void* map = nullptr;
+    size_t mapLen = 0;
+};
+
+namespace {
+
+bool mode_flags(int mode, int flag, int& hasPilot, int& hasP61) {
+    hasPilot = (mode == BDS_TRK_B1C_WB && flag == 2) || (mode != BDS_TRK_B1C_WB && flag == 1);
+    hasP61 = (mode == BDS_TRK_B1C_WB && flag == 2);
+    return mode == BDS_TRK_B1C_WB || mode == BDS_TRK_B1C_NB || mode == BDS_TRK_B2A;
+}
+
+int build_code_bits(int mode, const int32_t* prn, int nCh, std::vector<uint32_t>& bits) {
+    bits.assign((size_t)nCh * 2 * kPackedWords, 0);
+    std::vector<uint8_t> chips;
+    for (int c = 0; c < nCh; ++c) {
+        if (prn[c] == 0) continue;
+        if (prn[c] < 1 || prn[c] > 63) return set_error(BDS_ERR_ARG, "channel %d: PRN %d out of range", c, prn[c]);
+        int cd = mode == BDS_TRK_B2A ? BDS_CODE_B2A_DATA : BDS_CODE_B1C_DATA_PRIMARY;
+        int cp = mode == BDS_TRK_B2A ? BDS_CODE_B2A_PILOT : BDS_CODE_B1C_PILOT_PRIMARY;
+        primary_bits(cd, prn[c], chips);
+        pack_bits(chips, &bits[((size_t)c * 2 + 0) * kPackedWords]);
+        primary_bits(cp, prn[c], chips);
+        pack_bits(chips, &bits[((size_t)c * 2 + 1) * kPackedWords]);
+    }
+    return BDS_OK;
+}
+
+void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
+    std::memset(&g, 0, sizeof(g));
+    g.x = h->dX;
+    g.winFirst = h->winFirst;
+    g.winLen = h->winLen;
+    g.mode = h->mode;
+    mode_flags(h->mode, h->cfg.pilotTRKflag, g.hasPilot, g.hasP61);
+    g.nCh = h->nCh;
+    g.S = h->S;
+    g.nGroups = h->nGroups;
+    g.maxEpochs = maxEpochs;
+    g.capacity = h->capacity;
+    g.cnoCap = h->cnoCap;
+    g.cnoInterval = h->cfg.CNoInterval;
+    g.kernelKind = h->fast ? BDS_KERNEL_FAST : BDS_KERNEL_GENERAL;
+    g.fs = h->cfg.samplingFreq;
+    g.L = (double)h->cfg.codeLength;
+    g.d = h->cfg.dllCorrelatorSpacing;
+    g.PDI = h->cfg.intTime;
+    g.tau1 = h->cfg.tau1code;
+    g.tau2 = h->cfg.tau2code;
+    g.pf1 = h->cfg.pf1;
+    g.pf2 = h->cfg.pf2;
+    g.pf3 = h->cfg.pf3;
+    g.factor = h->cfg.wbFactor;
+    g.codeBits = h->dBits;
+    g.cc = h->dCC;
+    g.st = h->dSt;
+    g.params = h->dParams;
+    g.ready = h->dReady;
+    g.stop = h->dStop;
+    g.count = h->dCount;
+    g.partial = h->dPartial;
+    g.out = h->dOut;
+    g.cno = h->dCno;
+}
+
+int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
+    int hasPilot, hasP61;
+    mode_flags(mode, cfg->pilotTRKflag, hasPilot, hasP61);
+    bool can = fast_wb_supported(mode, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
+                                 cfg->dllCorrelatorSpacing);
+    if (cfg->kernel == BDS_KERNEL_FAST && !can)
+        return set_error(BDS_ERR_UNSUPPORTED, "fast tracking kernel does not support this configuration");
+    fast = (cfg->kernel == BDS_KERNEL_FAST) || (cfg->kernel == BDS_KERNEL_AUTO && can);
+    return BDS_OK;
+}
+
+size_t smem_bytes(bool fast) { return sizeof(TrkSmem) + (fast ? sizeof(FastSmem) : 0); }
+
+int init_state(bds_trk* h) {
+    std::vector<ChanConst> cc(h->nCh);
+    h->hSt.assign(h->nCh, ChanState{});
+    for (int c = 0; c < h->nCh; ++c) {
+        const bds_channel& ch = h->ch[c];
+        cc[c].prn = ch.PRN;
+        cc[c].active = ch.PRN != 0;
+        cc[c].status = ch.status;
+        cc[c].pad = 0;
+        cc[c].chCodeFreq = ch.codeFreq;
+        cc[c].acquiredFreq = ch.acquiredFreq;
+        cc[c].startPos = h->skip + (long long)ch.codePhase - 1;  // WB_tracking.m:174-176
+        ChanState& s = h->hSt[c];
+        s.codeFreq = ch.codeFreq;           // WB:195-206
+        s.carrFreq = ch.acquiredFreq;
+        s.carrFreqBasis = ch.acquiredFreq;
+        s.pos = cc[c].startPos;
+    }
+    BDS_CUDA(cudaMemcpy(h->dCC, cc.data(), sizeof(ChanConst) * h->nCh, cudaMemcpyHostToDevice));
+    BDS_CUDA(cudaMemcpy(h->dSt, h->hSt.data(), sizeof(ChanState) * h->nCh, cudaMemcpyHostToDevice));
+    h->epochsRun = 0;
+    return BDS_OK;
+}
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// initial values exactly as the reference preallocates them (WB_tracking.m:53-112)
+int init_out_block(bds_trk* h, double* out, int cap, int e0) {
+    const double inf = INFINITY;
+    static const int infFields[] = {F_CODEFREQ, F_CARRFREQ, F_DLL, F_DLLF, F_PLL, F_PLLF, F_REMCODE, F_REMCARR};
+    if (cap <= e0) return BDS_OK;
+    for (int c = 0; c < h->nCh; ++c) {
+        double* base = out + (size_t)c * kNFields * cap;
+        for (int f = 0; f < kNFields; ++f)
+            BDS_CUDA(cudaMemsetAsync(base + (size_t)f * cap + e0, 0, sizeof(double) * (cap - e0), h->stream));
+        for (int f : infFields) {
+            size_t n = cap - e0;
+            fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(base + (size_t)f * cap + e0, n, inf);
+            count_launch();
+        }
+    }
+    return BDS_OK;
+}
+
+int ensure_capacity(bds_trk* h, int need) {
+    if (need <= h->capacity) return BDS_OK;
+    int ncap = std::max(need, h->capacity * 2);
+    ncap = (ncap + 7) & ~7;
+    double* nout = nullptr;
+    BDS_CUDA(cudaMalloc(&nout, sizeof(double) * (size_t)h->nCh * kNFields * ncap));
+    int ci = std::max(1, h->cfg.CNoInterval);
+    int ncno = std::max(1, ncap / ci);
+    double* ncn = nullptr;
+    BDS_CUDA(cudaMalloc(&ncn, sizeof(double) * (size_t)h->nCh * kNCno * ncno));
+    BDS_CUDA(cudaMemsetAsync(ncn, 0, sizeof(double) * (size_t)h->nCh * kNCno * ncno, h->stream));
+    int old = h->capacity;
+    if (old > 0) {
+        BDS_CUDA(cudaMemcpy2DAsync(nout, sizeof(double) * ncap, h->dOut, sizeof(double) * old, sizeof(double) * old,
+                                   (size_t)h->nCh * kNFields, cudaMemcpyDeviceToDevice, h->stream));
+        BDS_CUDA(cudaMemcpy2DAsync(ncn, sizeof(double) * ncno, h->dCno, sizeof(double) * h->cnoCap,
+                                   sizeof(double) * h->cnoCap, (size_t)h->nCh * kNCno, cudaMemcpyDeviceToDevice,
+                                   h->stream));
+    }
+    int rc = init_out_block(h, nout, ncap, old);
+    if (rc) return rc;
+    BDS_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->dOut) cudaFree(h->dOut);
+    if (h->dCno) cudaFree(h->dCno);
+    h->dOut = nout;
+    h->dCno = ncn;
+    h->capacity = ncap;
+    h->cnoCap = ncno;
+    return BDS_OK;
+}
+
+// grid geometry: nGroups groups of S slice-CTAs; all CTAs co-resident (cooperative launch)
+int plan_grid(bds_trk* h) {
+    int occ = 0;
+    h->smemBytes = smem_bytes(h->fast);
+    if (h->fast) {
+        BDS_CUDA(cudaFuncSetAttribute(trk_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)h->smemBytes));
+        BDS_CUDA(cudaFuncSetAttribute(trk_open_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)h->smemBytes));
+        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel<true>, kTrkThreads,
+                                                               h->smemBytes));
+    } else {
+        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel<false>, kTrkThreads,
+                                                               h->smemBytes));
+    }
+    if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
+    occ = std::min(occ, 4);
+    int total = g_num_sms * occ;
+    int nAct = 0;
+    for (auto& c : h->ch) nAct += c.PRN != 0;
+    nAct = std::max(nAct, 1);
+    // prefer >= 2 channels per group (hides loop-closure latency) and S >= 8
+    int best = 1;
+    for (int ng = 1; ng <= std::min(nAct, total); ++ng) {
+        int chPer = (nAct + ng - 1) / ng;
+        int S = total / ng;
+        if (S < 8) break;
+        if (chPer >= 2 || nAct < 2) best = ng;
+    }
+    h->nGroups = best;
+    h->S = std::min(total / best, 512);
+    h->gridBlocks = h->nGroups * h->S;
+    return BDS_OK;
+}
+
+int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_channel* ch, int n_ch, bds_trk** out) {
+    if (!cfg || !ch || !out || n_ch <= 0) return set_error(BDS_ERR_ARG, "bds_track_open: null/empty argument");
+    int hp, h6;
+    if (!mode_flags(mode, cfg->pilotTRKflag, hp, h6)) return set_error(BDS_ERR_ARG, "unknown tracking mode %d", mode);
+    if (cfg->codeLength != kCodeLen) return set_error(BDS_ERR_UNSUPPORTED, "codeLength must be 10230");
+    int rc = require_device();
+    if (rc) return rc;
+    bds_trk* h = new bds_trk();
+    h->mode = mode;
+    h->cfg = *cfg;
+    h->nCh = n_ch;
+    h->ch.assign(ch, ch + n_ch);
+    h->skip = skip;
+    rc = choose_fast(mode, cfg, h->fast);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    auto fail = [&](int code) {
+        bds_track_close(h);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
+        return fail(set_error(BDS_ERR_CUDA, "stream/event creation failed"));
+    std::vector<int32_t> prn(n_ch);
+    for (int c = 0; c < n_ch; ++c) prn[c] = ch[c].PRN;
+    std::vector<uint32_t> bits;
+    rc = build_code_bits(mode, prn.data(), n_ch, bits);
+    if (rc) return fail(rc);
+    rc = plan_grid(h);
+    if (rc) return fail(rc);
+#define TRY(x)                                                                                       \
+    if ((x) != cudaSuccess) return fail(set_error(BDS_ERR_NOMEM, "device allocation failed: %s", #x))
+    TRY(cudaMalloc(&h->dBits, bits.size() * 4));
+    TRY(cudaMemcpy(h->dBits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    TRY(cudaMalloc(&h->dCC, sizeof(ChanConst) * n_ch));
+    TRY(cudaMalloc(&h->dSt, sizeof(ChanState) * n_ch));
+    TRY(cudaMalloc(&h->dParams, sizeof(EpochParams) * n_ch * 2));
+    TRY(cudaMalloc(&h->dReady, sizeof(int) * n_ch));
+    TRY(cudaMalloc(&h->dStop, sizeof(int) * n_ch));
+    TRY(cudaMalloc(&h->dCount, sizeof(int) * n_ch));
+    TRY(cudaMalloc(&h->dPartial, sizeof(double) * (size_t)n_ch * h->S * kNSum));
+#undef TRY
+    rc = init_state(h);
+    if (rc) return fail(rc);
+    *out = h;
+    return BDS_OK;
+}
+
+int set_window(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long first) {
+    if (!x && n) return set_error(BDS_ERR_ARG, "null IF buffer");
+    if (x_loc == BDS_LOC_DEVICE) {
+        if (((uintptr_t)x & 15) != 0) return set_error(BDS_ERR_ARG, "device IF buffer must be 16-byte aligned");
+        if (h->ownX && h->dX) cudaFree(h->dX);
+        h->dX = const_cast<int8_t*>(x);
+        h->ownX = false;
+        h->xCap = n;
+    } else {
+        if (!h->ownX || h->xCap < n + 64) {
+            if (h->ownX && h->dX) cudaFree(h->dX);
+            h->dX = nullptr;
+            h->ownX = true;
+            h->xCap = n + 64;
+            BDS_CUDA(cudaMalloc(&h->dX, h->xCap));
+        }
+        BDS_CUDA(cudaMemcpyAsync(h->dX, x, n, cudaMemcpyHostToDevice, h->stream));
+        BDS_CUDA(cudaMemsetAsync(h->dX + n, 0, 64, h->stream));
+    }
+    h->winFirst = first;
+    h->winLen = (long long)n;
+    return BDS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bds_track_open(int mode, const bds_trk_cfg* cfg, const int8_t* x, size_t n, int x_loc, long long skip,
+                   const bds_channel* ch, int n_ch, bds_trk** out) {
+    bds_trk* h = nullptr;
+    int rc = open_common(mode, cfg, skip, ch, n_ch, &h);
+    if (rc) return rc;
+    rc = set_window(h, x, n, x_loc, 0);
+    if (rc) {
+        bds_track_close(h);
+        return rc;
+    }
+    *out = h;
+    return BDS_OK;
+}
+
+int bds_track_open_file(int mode, const bds_trk_cfg* cfg, const char* path, long long skip, long long max_samples,
+                        const bds_channel* ch, int n_ch, bds_trk** out) {
+    if (!path) return set_error(BDS_ERR_ARG, "null path");
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return set_error(BDS_ERR_IO, "cannot open %s", path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size <= 0) {
+        ::close(fd);
+        return set_error(BDS_ERR_IO, "cannot stat %s", path);
+    }
+    size_t len = (size_t)sb.st_size;
+    if (max_samples > 0 && (size_t)max_samples < len) len = (size_t)max_samples;
+    void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (m == MAP_FAILED) return set_error(BDS_ERR_IO, "mmap of %s failed", path);
+    bds_trk* h = nullptr;
+    int rc = open_common(mode, cfg, skip, ch, n_ch, &h);
+    if (rc == BDS_OK) rc = set_window(h, (const int8_t*)m, len, BDS_LOC_HOST, 0);
+    if (rc == BDS_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = set_error(BDS_ERR_CUDA, "H2D copy failed");
+    munmap(m, len);
+    if (rc) {
+        if (h) bds_track_close(h);
+        return rc;
+    }
+    *out = h;
+    return BDS_OK;
+}
+
+int bds_track_feed(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long first_sample) {
+    if (!h) return set_error(BDS_ERR_ARG, "null handle");
+    return set_window(h, x, n, x_loc, first_sample);
+}
+
+int bds_track_run_async(bds_trk* h, int n_epochs) {
+    if (!h || n_epochs <= 0) return set_error(BDS_ERR_ARG, "bds_track_run: bad arguments");
+    int rc = BDS_OK;
+    if (h->pending) {  // the output block may be re-allocated below: finish the previous run first
+        rc = bds_track_sync(h);
+        if (rc) return rc;
+    }
+    rc = ensure_capacity(h, h->epochsRun + n_epochs);
+    if (rc) return rc;
+    TrkDev g;
+    fill_dev(h, g, n_epochs);
+    trk_prepare_kernel<<<(h->nCh + 63) / 64, 64, 0, h->stream>>>(g);
+    count_launch();
+    BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    int zero = 0;
+    void* args[] = {&g, &zero};
+    const void* fn = h->fast ? (const void*)trk_persistent_kernel<true> : (const void*)trk_persistent_kernel<false>;
+    BDS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(h->gridBlocks), dim3(kTrkThreads), args, h->smemBytes, h->stream));
+    count_launch();
+    BDS_CUDA(cudaEventRecord(h->ev1, h->stream));
+    h->pending = true;
+    return BDS_OK;
+}
+
+int bds_track_sync(bds_trk* h) {
+    if (!h) return set_error(BDS_ERR_ARG, "null handle");
+    BDS_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->pending) {
+        cudaEventElapsedTime(&h->lastMs, h->ev0, h->ev1);
+        h->pending = false;
+    }
+    BDS_CUDA(cudaMemcpy(h->hSt.data(), h->dSt, sizeof(ChanState) * h->nCh, cudaMemcpyDeviceToHost));
+    int me = 0;
+    for (auto& s : h->hSt) me = std::max(me, s.epoch);
+    h->epochsRun = me;
+    return BDS_OK;
+}
+
+int bds_track_fetch(bds_trk* h, const bds_trk_out* o, int stride) {
+    if (!h || !o) return set_error(BDS_ERR_ARG, "null argument");
+    int rc = bds_track_sync(h);
+    if (rc) return rc;
+    if (stride < h->epochsRun) return set_error(BDS_ERR_ARG, "out_stride %d < epochs run %d", stride, h->epochsRun);
+    // entries past the last completed epoch carry the reference's preallocation values
+    int nE = std::min(stride, h->capacity);
+    if (nE == 0) return BDS_OK;
+    std::vector<double> host((size_t)h->nCh * kNFields * h->capacity);
+    BDS_CUDA(cudaMemcpy(host.data(), h->dOut, host.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    double* planes[kNFieldsLoop] = {o->absoluteSample, o->codeFreq, o->carrFreq, o->I_P, o->I_E, o->I_L, o->Q_E,
+                                    o->Q_P, o->Q_L, o->Pilot_I_P, o->Pilot_I_E, o->Pilot_I_L, o->Pilot_Q_E,
+                                    o->Pilot_Q_P, o->Pilot_Q_L, o->dllDiscr, o->dllDiscrFilt, o->pllDiscr,
+                                    o->pllDiscrFilt, o->remCodePhase, o->remCarrPhase};
+    for (int c = 0; c < h->nCh; ++c) {
+        const double* base = host.data() + (size_t)c * kNFields * h->capacity;
+        for (int f = 0; f < kNFieldsLoop; ++f)
+            if (planes[f]) std::memcpy(planes[f] + (size_t)c * stride, base + (size_t)f * h->capacity, sizeof(double) * nE);
+        if (o->raw)
+            for (int e = 0; e < nE; ++e)
+                for (int k = 0; k < kNSum; ++k)
+                    o->raw[((size_t)c * stride + e) * kNSum + k] = base[(size_t)(F_RAW0 + k) * h->capacity + e];
+        if (o->epochsDone) o->epochsDone[c] = h->hSt[c].epoch;
+    }
+    int ci = std::max(1, h->cfg.CNoInterval);
+    int nC = stride / ci;
+    if (nC > 0 && (o->DataCNo || o->DataPLD || o->PilotCNo || o->PilotPLD || o->TotalCNo)) {
+        std::vector<double> cn((size_t)h->nCh * kNCno * h->cnoCap);
+        BDS_CUDA(cudaMemcpy(cn.data(), h->dCno, cn.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        double* cp[kNCno] = {o->DataCNo, o->DataPLD, o->PilotCNo, o->PilotPLD, o->TotalCNo};
+        int n = std::min(nC, h->cnoCap);
+        for (int c = 0; c < h->nCh; ++c)
+            for (int f = 0; f < kNCno; ++f)
+                if (cp[f]) {
+                    std::memset(cp[f] + (size_t)c * nC, 0, sizeof(double) * nC);
+                    std::memcpy(cp[f] + (size_t)c * nC, cn.data() + ((size_t)c * kNCno + f) * h->cnoCap, sizeof(double) * n);
+                }
+    }
+    return BDS_OK;
+}
+
+int bds_track_run(bds_trk* h, int n_epochs, const bds_trk_out* out, int out_stride) {
+    int rc = bds_track_run_async(h, n_epochs);
+    if (rc) return rc;
+    return bds_track_fetch(h, out, out_stride);
+}
+
+int bds_track_device_block(bds_trk* h, void** dev_ptr, size_t* bytes, int* n_fields, int* capacity) {
+    if (!h) return set_error(BDS_ERR_ARG, "null handle");
+    if (dev_ptr) *dev_ptr = h->dOut;
+    if (bytes) *bytes = sizeof(double) * (size_t)h->nCh * kNFields * h->capacity;
+    if (n_fields) *n_fields = kNFields;
+    if (capacity) *capacity = h->capacity;
+    return BDS_OK;
+}
+
+int bds_track_stats(bds_trk* h, long long* channel_samples, int* epochs_run, float* last_kernel_ms) {
+    if (!h) return set_error(BDS_ERR_ARG, "null handle");
+    int rc = bds_track_sync(h);
+    if (rc) return rc;
+    long long tot = 0;
+    int me = 0;
+    for (auto& s : h->hSt) {
+        tot += s.samples;
+        me = std::max(me, s.epoch);
+    }
+    if (channel_samples) *channel_samples = tot;
+    if (epochs_run) *epochs_run = me;
+    if (last_kernel_ms) *last_kernel_ms = h->lastMs;
+    return BDS_OK;
+}
+
+int bds_track_reset(bds_trk* h) {
+    if (!h) return set_error(BDS_ERR_ARG, "null handle");
+    BDS_CUDA(cudaStreamSynchronize(h->stream));
+    int rc = init_state(h);
+    if (rc) return rc;
+    if (h->capacity > 0) {
+        rc = init_out_block(h, h->dOut, h->capacity, 0);
+        if (rc) return rc;
+        BDS_CUDA(cudaMemsetAsync(h->dCno, 0, sizeof(double) * (size_t)h->nCh * kNCno * h->cnoCap, h->stream));
+    }
+    return BDS_OK;
+}
+
+void bds_track_close(bds_trk* h) {
+    if (!h) return;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->ownX && h->dX) cudaFree(h->dX);
+    cudaFree(h->dBits);
+    cudaFree(h->dCC);
+    cudaFree(h->dSt);
+    cudaFree(h->dParams);
+    cudaFree(h->dReady);
+    cudaFree(h->dStop);
+    cudaFree(h->dCount);
+    cudaFree(h->dPartial);
+    cudaFree(h->dOut);
+    cudaFree(h->dCno);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t* x, size_t n, int x_loc,
+                                  const int32_t* prn, int n_ch, int n_epochs, const double* nco, double* sums) {
+    if (!cfg || !x || !prn || !nco || !sums || n_ch <= 0 || n_epochs <= 0)
+        return set_error(BDS_ERR_ARG, "bds_track_correlate_open_loop: bad arguments");
+    int hp, h6;
+    if (!mode_flags(mode, cfg->pilotTRKflag, hp, h6)) return set_error(BDS_ERR_ARG, "unknown tracking mode %d", mode);
+    int rc = require_device();
+    if (rc) return rc;
+    bool fast = false;
+    rc = choose_fast(mode, cfg, fast);
+    if (rc) return rc;
+    const int nce = n_ch * n_epochs;
+    std::vector<EpochParams> hp_(nce);
+    for (int i = 0; i < nce; ++i) {
+        const double* q = nco + (size_t)i * 6;
+        EpochParams& p = hp_[i];
+        p.pos = (long long)q[0];
+        p.blksize = (int)q[1];
+        p.pad = 0;
+        p.rem = q[2];
+        p.step = q[3];
+        p.carrFreq = q[4];
+        p.remCarr = q[5];
+        if (p.pos < 0 || p.blksize <= 0 || (size_t)(p.pos + p.blksize) > n)
+            return set_error(BDS_ERR_ARG, "open loop: block %d outside the record", i);
+    }
+    std::vector<uint32_t> bits;
+    rc = build_code_bits(mode, prn, n_ch, bits);
+    if (rc) return rc;
+    int8_t* dX = nullptr;
+    uint32_t* dBits = nullptr;
+    EpochParams* dP = nullptr;
+    double *dPart = nullptr, *dSums = nullptr;
+    const int S = 32;
+    auto cleanup = [&]() {
+        if (x_loc == BDS_LOC_HOST) cudaFree(dX);
+        cudaFree(dBits);
+        cudaFree(dP);
+        cudaFree(dPart);
+        cudaFree(dSums);
+    };
+#define TRYC(x_)                                                       \
+    if ((x_) != cudaSuccess) {                                         \
+        cleanup();                                                     \
+        return set_error(BDS_ERR_CUDA, "open loop: %s failed", #x_);   \
+    }
+    if (x_loc == BDS_LOC_HOST) {
+        TRYC(cudaMalloc(&dX, n + 64));
+        TRYC(cudaMemcpy(dX, x, n, cudaMemcpyHostToDevice));
+        TRYC(cudaMemset(dX + n, 0, 64));
+    } else {
+        dX = const_cast<int8_t*>(x);
+    }
+    TRYC(cudaMalloc(&dBits, bits.size() * 4));
+    TRYC(cudaMemcpy(dBits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    TRYC(cudaMalloc(&dP, sizeof(EpochParams) * nce));
+    TRYC(cudaMemcpy(dP, hp_.data(), sizeof(EpochParams) * nce, cudaMemcpyHostToDevice));
+    TRYC(cudaMalloc(&dPart, sizeof(double) * (size_t)nce * S * kNSum));
+    TRYC(cudaMalloc(&dSums, sizeof(double) * (size_t)nce * kNSum));
+    TrkDev g;
+    std::memset(&g, 0, sizeof(g));
+    g.x = dX;
+    g.winFirst = 0;
+    g.winLen = (long long)n;
+    g.mode = mode;
+    g.hasPilot = hp;
+    g.hasP61 = h6;
+    g.nCh = n_ch;
+    g.fs = cfg->samplingFreq;
+    g.L = (double)cfg->codeLength;
+    g.d = cfg->dllCorrelatorSpacing;
+    g.codeBits = dBits;
+    size_t smem = smem_bytes(fast);
+    if (fast) {
+        TRYC(cudaFuncSetAttribute(trk_open_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        trk_open_loop_kernel<true><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);
+    } else {
+        trk_open_loop_kernel<false><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);
+    }
+    count_launch();
+    trk_open_loop_reduce_kernel<<<(nce * kNSum + 127) / 128, 128>>>(dPart, S, nce, dSums);
+    count_launch();
+    TRYC(cudaGetLastError());
+    TRYC(cudaMemcpy(sums, dSums, sizeof(double) * (size_t)nce * kNSum, cudaMemcpyDeviceToHost));
+#undef TRYC
+    cleanup();
+    return BDS_OK;
+}
+
+}  // extern "C"

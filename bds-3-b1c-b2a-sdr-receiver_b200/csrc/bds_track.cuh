@@ -1,0 +1,77 @@
+// Device-side data layout of a tracking session (see DESIGN.md "HBM layout").
+#pragma once
+#include "bds_common.cuh"
+
+namespace bds {
+
+constexpr int kNSum = 18;       // {data,p11,p61} x {E,P,L} x {I,Q}
+constexpr int kNFieldsLoop = 21;  // trackResults planes written per epoch
+constexpr int kNFields = kNFieldsLoop + kNSum;
+constexpr int kNCno = 5;        // DataCNo, DataPLD, PilotCNo, PilotPLD, TotalCNo
+constexpr int kPackedWordsDev = 320;
+constexpr int kTrkThreads = 256;
+
+enum Field {
+    F_ABS = 0, F_CODEFREQ, F_CARRFREQ, F_I_P, F_I_E, F_I_L, F_Q_E, F_Q_P, F_Q_L,
+    F_PI_P, F_PI_E, F_PI_L, F_PQ_E, F_PQ_P, F_PQ_L, F_DLL, F_DLLF, F_PLL, F_PLLF,
+    F_REMCODE, F_REMCARR, F_RAW0
+};
+
+// index into the 18 raw sums
+__host__ __device__ constexpr int sum_idx(int fam, int epl, int iq) { return fam * 6 + epl * 2 + iq; }
+enum { EPL_E = 0, EPL_P = 1, EPL_L = 2 };
+
+struct ChanConst {
+    int prn;
+    int active;
+    int status;
+    int pad;
+    double chCodeFreq;    // channel.codeFreq
+    double acquiredFreq;  // channel.acquiredFreq
+    long long startPos;   // skipNumberOfBytes + codePhase - 1
+};
+
+struct ChanState {
+    double codeFreq, remCodePhase, carrFreq, carrFreqBasis, remCarrPhase;
+    double oldCodeNco, oldCodeError, d2CarrError, dCarrError;
+    double cnoPrev[3];
+    long long pos;        // absolute sample index of the next block
+    long long samples;    // samples consumed so far
+    int epoch;            // epochs completed
+    int pad;
+    long long pad2;       // keep sizeof a multiple of 16 (cache-global vector copies)
+};
+static_assert(sizeof(ChanState) % 16 == 0, "ChanState must be a 16-byte multiple");
+
+struct EpochParams {
+    long long pos;   // absolute 0-based sample index of the block start
+    int blksize;
+    int pad;
+    double rem;      // remCodePhase at block start [chips]
+    double step;     // codePhaseStep [chips/sample]
+    double carrFreq; // [Hz]
+    double remCarr;  // [rad]
+};
+static_assert(sizeof(EpochParams) % 16 == 0, "EpochParams must be a 16-byte multiple");
+
+struct TrkDev {
+    const int8_t* x;      // resident IF window
+    long long winFirst;   // absolute index of x[0]
+    long long winLen;
+    int mode, hasPilot, hasP61, nCh;
+    int S, nGroups, maxEpochs, capacity;
+    int cnoCap, cnoInterval, kernelKind, pad;
+    double fs, L, d, PDI, tau1, tau2, pf1, pf2, pf3, factor;
+    const uint32_t* codeBits;  // [nCh][3][320] packed primaries: data, pilot, (unused)
+    ChanConst* cc;
+    ChanState* st;
+    EpochParams* params;       // [nCh][2]
+    int* ready;                // [nCh] params valid up to this epoch index
+    int* stop;                 // [nCh] first epoch that cannot run (INT_MAX while running)
+    int* count;                // [nCh] slice arrival counter
+    double* partial;           // [nCh][S][18]
+    double* out;               // [nCh][kNFields][capacity]
+    double* cno;               // [nCh][kNCno][cnoCap]
+};
+
+}  // namespace bds

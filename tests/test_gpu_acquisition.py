@@ -1,0 +1,76 @@
+"""GPU parity of acquisition against the float64 oracle (run with -m gpu).
+Bar: identical codePhase and carrFreq grid point, peakMetric within 1e-4 relative."""
+import numpy as np
+import pytest
+
+import bds_oracle as O
+import util
+import bds3_b200 as B
+from bds3_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _b1c_record(n_sats, seconds, seed, **over):
+    s = O.initSettings_B1C(samplingFreq=util.FS, **over)
+    sats = synth.make_sats(n_sats, s, "B1C", seed=seed, max_doppler=min(4500.0, s.acqSearchBand - 60), cn0=47.0)
+    x = synth.synth_numpy("B1C", s, sats, int(seconds * s.samplingFreq), seed=seed)
+    return s, sats, x
+
+
+def test_b1c_acquisition_parity_reduced_band():
+    s, sats, x = _b1c_record(2, 0.0305, 5, acqSearchBand=200, acqSatelliteList=[1, 2, 3])
+    want, wd = O.acquisition_B1C(x, s, return_debug=True)
+    got, gd = B.b1c.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for prn in (1, 2, 3):
+        assert gd[prn - 1, 0] == wd[prn]["bin"]
+        assert gd[prn - 1, 1] == wd[prn]["codePhase"]
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+    assert want.carrFreq[0] != 0 and want.carrFreq[1] != 0 and want.carrFreq[2] == 0
+    # injected parameters are recovered
+    for st in sats:
+        assert abs(got.carrFreq[st.PRN - 1] - (s.IF + st.doppler)) <= 25
+        spc = O.samples_per_code(s)
+        d = (got.codePhase[st.PRN - 1] - 1 - st.codeDelay) % spc
+        assert min(d, spc - d) <= 1.5
+
+
+def test_b1c_acquisition_data_only():
+    s, sats, x = _b1c_record(1, 0.0305, 6, acqSearchBand=100, acqSatelliteList=[1], pilotACQflag=0)
+    want = O.acquisition_B1C(x, s)
+    got = B.b1c.acquisition(x, B.Settings(dict(s)))
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+
+
+def test_b2a_acquisition_parity_full_grid_config():
+    """BASELINE config 1: B2a single-PRN acquisition, 17 ms record, reference defaults."""
+    s = O.initSettings_B2a(acqSatelliteList=[4, 9])
+    sats = synth.make_sats(1, s, "B2a", seed=3, prns=[4], cn0=47.0)
+    x = synth.synth_numpy("B2a", s, sats, 17 * 99375, seed=3)
+    want, wd = O.acquisition_B2a(x, s, return_debug=True)
+    got, gd = B.b2a.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for prn in (4, 9):
+        assert gd[prn - 1, 0] == wd[prn]["bin"] and gd[prn - 1, 1] == wd[prn]["codePhase"]
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+    assert want.carrFreq[3] != 0 and want.carrFreq[8] == 0
+    assert abs(got.carrFreq[3] - (s.IF + sats[0].doppler)) <= 25
+
+
+def test_acquisition_then_tracking_pipeline():
+    """acquisition -> preRun -> WB_tracking through the reference-named call surface."""
+    s, sats, x = _b1c_record(2, 0.12, 8, acqSearchBand=200, acqSatelliteList=[1, 2], numberOfChannels=2)
+    ps = B.Settings(dict(s))
+    acq = B.b1c.acquisition(x, ps)
+    ch = B.b1c.preRun(acq, ps)
+    assert sorted(c.PRN for c in ch) == [1, 2]
+    tr, _ = B.b1c.WB_tracking(x, ch, ps, n_epochs=8)
+    for r in tr:
+        assert r.status == "T"
+        # locked: prompt power dominates, sign sequence is +-1 data
+        assert np.all(np.abs(r.I_P[3:]) > 5 * np.abs(r.Q_P[3:]))
