@@ -138,6 +138,9 @@ class TrackSession:
         L.check(L.lib().bds_track_stats(self.h, C.byref(cs), C.byref(ep), C.byref(ms)))
         return cs.value, ep.value, ms.value
 
+    def counters(self):
+        return counters(self.h)
+
     def device_block(self):
         p, b, nf, cap = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
         L.check(L.lib().bds_track_device_block(self.h, C.byref(p), C.byref(b), C.byref(nf), C.byref(cap)))
@@ -166,6 +169,13 @@ class TrackSession:
         planes["epochsDone"] = done
         L.check(L.lib().bds_track_fetch(self.h, C.byref(out), N))
         return planes
+
+
+def counters(handle=None):
+    """(fast-body chips, exact-path chips, general-kernel slices, 0); handle None = last open-loop call."""
+    out = (C.c_longlong * 4)()
+    L.check(L.lib().bds_track_counters(handle, out))
+    return tuple(int(v) for v in out)
 
 
 def assemble(mode, settings, channel, planes, N):
@@ -209,4 +219,5 @@ def run_tracking(mode, source, channel, settings, n_epochs=None, kernel=L.KERNEL
     with TrackSession(mode, settings, channel, source, kernel=kernel) as s:
         s.run_async(N)
         planes = s.fetch(N, raw=raw)
+        run_tracking.last_counters = s.counters()
     return assemble(mode, settings, channel, planes, N), channel

@@ -249,7 +249,7 @@ __device__ bool next_params(const TrkDev& g, const ChanState& st, EpochParams& n
     return off >= 0 && off + np.blksize <= g.winLen && np.blksize > 0;
 }
 
-__device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 sums*/) {
+__device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 sums*/, EpochParams& npOut, int& npOk) {
     ChanState st = load_cg(g.st + c);
     const EpochParams p = load_cg(g.params + c * 2 + (e & 1));
     double* out = g.out + (size_t)c * kNFields * g.capacity;
@@ -369,19 +369,12 @@ __device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 
     st.epoch = e + 1;
     store_cg(g.st + c, st);
 
-    // publish the next epoch or stop the channel
+    // stage the next epoch's params; the CTA publishes them (publish_next)
     EpochParams np;
-    bool ok = next_params(g, st, np);
-    if (ok && e + 1 < g.capacity) {
-        store_cg(g.params + c * 2 + ((e + 1) & 1), np);
-        __threadfence();
-        st_release(g.ready + c, e + 1);
-    } else {
-        // WB_tracking.m:254 records absoluteSample of the epoch whose read then fails
-        if (e + 1 < g.capacity) out[F_ABS * cap + e + 1] = (double)st.pos;
-        __threadfence();
-        st_release(g.stop + c, e + 1);
-    }
+    bool ok = next_params(g, st, np) && e + 1 < g.capacity;
+    if (!ok && e + 1 < g.capacity) out[F_ABS * cap + e + 1] = (double)st.pos;  // WB_tracking.m:254 precedes the failed read
+    npOut = np;
+    npOk = ok;
 }
 
 // ======================================================================================
@@ -393,9 +386,12 @@ struct __align__(16) TrkSmem {
     double sums[kNSum];
     double part[kNSum * 14];
     EpochParams p;
+    EpochParams np;      // next epoch's params, staged between loop closure and publication
+    unsigned scratch[128];
     int go;
     int last;
     int curChan;
+    int npOk;
 };
 
 __device__ void load_code_bits(const TrkDev& g, TrkSmem& sm, int c) {
@@ -430,10 +426,14 @@ __device__ void reduce_partials(const TrkDev& g, TrkSmem& sm, int c) {
 
 template <bool kFast>
 __device__ __forceinline__ void correlate_slice(const TrkDev& g, TrkSmem& sm, const EpochParams& p, int sl, int S,
-                                                float* acc, FastSmem* fsm) {
+                                                float* acc, FastSmem* fsm, const FastTab* gtab, unsigned& mbarPhase) {
+    bool general = true;
     if constexpr (kFast) {
-        correlate_fast_wb(g, p, sm.bits[0], sm.bits[1], sl, S, acc, fsm);
-    } else {
+        general = !fast_load_tab(fsm, gtab);   // pattern not valid for this epoch's code rate -> exact kernel
+        if (!general) correlate_fast_wb(g, p, sm.bits[0], sm.bits[1], sl, S, acc, fsm, mbarPhase);
+    }
+    if (general) {
+        if (g.counters && threadIdx.x == 0) atomicAdd(g.counters + 2, 1ull);
         SliceCtx ctx{g.x, g.winFirst, g.winLen, p, g.mode, g.hasPilot, g.hasP61, g.L, g.d, g.fs};
         long long q0, q1;
         slice_chunks(p, g.winFirst, sl, S, q0, q1);
@@ -441,93 +441,120 @@ __device__ __forceinline__ void correlate_slice(const TrkDev& g, TrkSmem& sm, co
     }
 }
 
+// Publishes the params staged in sm.np (after building the fast-path tables for them) or stops
+// the channel.  Whole CTA.
 template <bool kFast>
-__global__ void __launch_bounds__(kTrkThreads) trk_persistent_kernel(TrkDev g, int epochBase /*unused*/) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
-    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + sizeof(TrkSmem));
-    const int grp = blockIdx.x / g.S, sl = blockIdx.x % g.S;
-    if (grp >= g.nGroups) return;
-    if (threadIdx.x == 0) sm.curChan = -1;
+__device__ void publish_next(const TrkDev& g, TrkSmem& sm, int c, int eNext) {
     __syncthreads();
-
-    for (int i = 0; i < g.maxEpochs; ++i) {
-        bool any = false;
-        for (int c = grp; c < g.nCh; c += g.nGroups) {
-            if (!g.cc[c].active) continue;
-            // epoch index of this channel for round i: every channel advances from its
-            // own completed-epoch count at launch, kept in `pad` of ChanConst by the host
-            const int e = g.cc[c].pad + i;
-            if (threadIdx.x == 0) {
-                int go = 0;
-                while (true) {
-                    if (ld_acquire(g.stop + c) <= e) break;
-                    if (ld_acquire(g.ready + c) >= e) {
-                        go = 1;
-                        break;
-                    }
-                    __nanosleep(64);
-                }
-                sm.go = go;
-                if (go) sm.p = load_cg(g.params + c * 2 + (e & 1));
-            }
-            __syncthreads();
-            if (!sm.go) {
-                __syncthreads();
-                continue;
-            }
-            any = true;
-            load_code_bits(g, sm, c);
-            const EpochParams p = sm.p;
-            float acc[kNSum];
-#pragma unroll
-            for (int k = 0; k < kNSum; ++k) acc[k] = 0.f;
-            correlate_slice<kFast>(g, sm, p, sl, g.S, acc, fsm);
-            block_reduce18(acc, sm.red, sm.sums);
-            if (threadIdx.x < kNSum) {
-                g.partial[((size_t)c * g.S + sl) * kNSum + threadIdx.x] = sm.sums[threadIdx.x];
-                __threadfence();
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int old = atomicAdd(g.count + c, 1);
-                sm.last = (old == g.S - 1);
-                if (sm.last) g.count[c] = 0;
-            }
-            __syncthreads();
-            if (sm.last) {
-                __threadfence();
-                reduce_partials(g, sm, c);
-                if (threadIdx.x == 0) close_epoch(g, c, e, sm.sums);
-            }
-            __syncthreads();
-        }
-        if (!any) break;
+    const int ok = sm.npOk;
+    if (ok) {
+        if constexpr (kFast) fast_build_tab(g.fastTab + (size_t)c * 2 + (eNext & 1), sm.np, g.fs, sm.scratch);
+        if (threadIdx.x == 0) store_cg(g.params + c * 2 + (eNext & 1), sm.np);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (ok) st_release(g.ready + c, eNext);
+        else st_release(g.stop + c, eNext);
     }
 }
 
-// Computes the first params of every channel for the current window (run start).
-__global__ void trk_prepare_kernel(TrkDev g) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.nCh) return;
-    g.count[c] = 0;
+// Persistent closed-loop kernel.  Work items t = blockIdx.x, blockIdx.x + gridDim.x, ... in the
+// global order (round, channel, slice); the item's channel-epoch must have been published.
+template <bool kFast>
+__global__ void __launch_bounds__(kTrkThreads) trk_persistent_kernel(TrkDev g, int unused) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
+    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + ((sizeof(TrkSmem) + 127) & ~(size_t)127));
+    unsigned mbarPhase = 0;
+    if (threadIdx.x == 0) {
+        sm.curChan = -1;
+        if constexpr (kFast) mbar_init(&fsm->mbar, 1);
+    }
+    __syncthreads();
+    const long long perRound = (long long)g.nAct * g.S;
+    const long long total = perRound * g.maxEpochs;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        const int i = (int)(t / perRound);
+        const int idx = (int)(t - (long long)i * perRound);
+        const int c = g.act[idx / g.S], sl = idx % g.S;
+        const int e = g.cc[c].pad + i;   // channels advance from their own completed-epoch count
+        if (threadIdx.x == 0) {
+            int go = 0;
+            while (true) {
+                if (ld_acquire(g.stop + c) <= e) break;
+                if (ld_acquire(g.ready + c) >= e) {
+                    go = 1;
+                    break;
+                }
+                __nanosleep(32);
+            }
+            sm.go = go;
+            if (go) sm.p = load_cg(g.params + c * 2 + (e & 1));
+        }
+        __syncthreads();
+        if (!sm.go) {
+            __syncthreads();
+            continue;
+        }
+        load_code_bits(g, sm, c);
+        const EpochParams p = sm.p;
+        float acc[kNSum];
+#pragma unroll
+        for (int k = 0; k < kNSum; ++k) acc[k] = 0.f;
+        correlate_slice<kFast>(g, sm, p, sl, g.S, acc, fsm, g.fastTab + (size_t)c * 2 + (e & 1), mbarPhase);
+        block_reduce18(acc, sm.red, sm.sums);
+        if (threadIdx.x < kNSum) {
+            g.partial[((size_t)c * g.S + sl) * kNSum + threadIdx.x] = sm.sums[threadIdx.x];
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int old = atomicAdd(g.count + c, 1);
+            sm.last = (old == g.S - 1);
+            if (sm.last) g.count[c] = 0;
+        }
+        __syncthreads();
+        if (sm.last) {
+            __threadfence();
+            reduce_partials(g, sm, c);
+            if (threadIdx.x == 0) close_epoch(g, c, e, sm.sums, sm.np, sm.npOk);
+            publish_next<kFast>(g, sm, c, e + 1);
+        }
+        __syncthreads();
+    }
+}
+
+// Computes the first params of every channel for the current window (run start): one CTA per channel.
+template <bool kFast>
+__global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
+    const int c = blockIdx.x;
     if (!g.cc[c].active) {
-        g.stop[c] = 0;
-        g.ready[c] = -1;
+        if (threadIdx.x == 0) {
+            g.count[c] = 0;
+            g.stop[c] = 0;
+            g.ready[c] = -1;
+        }
         return;
     }
-    ChanState st = g.st[c];
-    g.cc[c].pad = st.epoch;
-    EpochParams np;
-    if (next_params(g, st, np) && st.epoch < g.capacity) {
-        g.params[c * 2 + (st.epoch & 1)] = np;
-        g.ready[c] = st.epoch;
-        g.stop[c] = INT_MAX;
-    } else {
-        if (st.epoch < g.capacity) g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
+    int e = 0;
+    if (threadIdx.x == 0) {
+        g.count[c] = 0;
+        ChanState st = g.st[c];
+        g.cc[c].pad = st.epoch;
+        sm.npOk = next_params(g, st, sm.np) && st.epoch < g.capacity;
+        if (!sm.npOk && st.epoch < g.capacity)
+            g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
         g.ready[c] = st.epoch - 1;
-        g.stop[c] = st.epoch;
+        g.stop[c] = INT_MAX;
+        sm.go = st.epoch;
     }
+    __syncthreads();
+    e = sm.go;
+    publish_next<kFast>(g, sm, c, e);
 }
 
 // ======================================================================================
@@ -535,10 +562,10 @@ __global__ void trk_prepare_kernel(TrkDev g) {
 // ======================================================================================
 template <bool kFast>
 __global__ void __launch_bounds__(kTrkThreads) trk_open_loop_kernel(TrkDev g, const EpochParams* params, int nEpochs,
-                                                                   double* partial /*[ce][S][18]*/) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+                                                                   double* partial /*[ce][S][18]*/, FastTab* tabs) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
-    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + sizeof(TrkSmem));
+    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + ((sizeof(TrkSmem) + 127) & ~(size_t)127));
     const int ce = blockIdx.y, sl = blockIdx.x, S = gridDim.x;
     const int c = ce / nEpochs;
     if (threadIdx.x == 0) sm.curChan = -1;
@@ -548,7 +575,15 @@ __global__ void __launch_bounds__(kTrkThreads) trk_open_loop_kernel(TrkDev g, co
     float acc[kNSum];
 #pragma unroll
     for (int k = 0; k < kNSum; ++k) acc[k] = 0.f;
-    correlate_slice<kFast>(g, sm, p, sl, S, acc, fsm);
+    unsigned mbarPhase = 0;
+    if constexpr (kFast) {
+        // open loop: this CTA builds the per-epoch table itself
+        if (threadIdx.x == 0) mbar_init(&fsm->mbar, 1);
+        fast_build_tab(tabs + ce, p, g.fs, sm.scratch);
+        __threadfence();
+        __syncthreads();
+    }
+    correlate_slice<kFast>(g, sm, p, sl, S, acc, fsm, tabs + ce, mbarPhase);
     block_reduce18(acc, sm.red, sm.sums);
     if (threadIdx.x < kNSum) partial[((size_t)ce * S + sl) * kNSum + threadIdx.x] = sm.sums[threadIdx.x];
 }
@@ -590,7 +625,10 @@ struct bds_trk {
     double* dOut = nullptr;
     double* dCno = nullptr;
     int capacity = 0, cnoCap = 0;
-    int S = 0, nGroups = 0, gridBlocks = 0;
+    int S = 0, nAct = 0, gridBlocks = 0;
+    int* dAct = nullptr;
+    unsigned long long* dCounters = nullptr;
+    FastTab* dFastTab = nullptr;
     bool fast = false;
     size_t smemBytes = 0;
     int epochsRun = 0;  // max over channels, as seen by the host
@@ -605,6 +643,8 @@ struct bds_trk {
 };
 
 namespace {
+
+unsigned long long g_open_loop_counters[4] = {0, 0, 0, 0};
 
 bool mode_flags(int mode, int flag, int& hasPilot, int& hasP61) {
     hasPilot = (mode == BDS_TRK_B1C_WB && flag == 2) || (mode != BDS_TRK_B1C_WB && flag == 1);
@@ -637,12 +677,16 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     mode_flags(h->mode, h->cfg.pilotTRKflag, g.hasPilot, g.hasP61);
     g.nCh = h->nCh;
     g.S = h->S;
-    g.nGroups = h->nGroups;
+    g.nAct = h->nAct;
+    g.act = h->dAct;
+    g.fastTab = h->dFastTab;
+    g.counters = h->dCounters;
     g.maxEpochs = maxEpochs;
     g.capacity = h->capacity;
     g.cnoCap = h->cnoCap;
     g.cnoInterval = h->cfg.CNoInterval;
     g.kernelKind = h->fast ? BDS_KERNEL_FAST : BDS_KERNEL_GENERAL;
+    g.pad = h->cfg.reserved & 1;  // test hook: wide guard band in the fast kernel
     g.fs = h->cfg.samplingFreq;
     g.L = (double)h->cfg.codeLength;
     g.d = h->cfg.dllCorrelatorSpacing;
@@ -676,7 +720,7 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
     return BDS_OK;
 }
 
-size_t smem_bytes(bool fast) { return sizeof(TrkSmem) + (fast ? sizeof(FastSmem) : 0); }
+size_t smem_bytes(bool fast) { return ((sizeof(TrkSmem) + 127) & ~(size_t)127) + (fast ? sizeof(FastSmem) : 0); }
 
 int init_state(bds_trk* h) {
     std::vector<ChanConst> cc(h->nCh);
@@ -756,14 +800,12 @@ int ensure_capacity(bds_trk* h, int need) {
     return BDS_OK;
 }
 
-// grid geometry: nGroups groups of S slice-CTAs; all CTAs co-resident (cooperative launch)
+// grid geometry: a cooperative grid of co-resident CTAs; S slices per channel-epoch.
 int plan_grid(bds_trk* h) {
     int occ = 0;
     h->smemBytes = smem_bytes(h->fast);
     if (h->fast) {
         BDS_CUDA(cudaFuncSetAttribute(trk_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)h->smemBytes));
-        BDS_CUDA(cudaFuncSetAttribute(trk_open_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)h->smemBytes));
         BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel<true>, kTrkThreads,
                                                                h->smemBytes));
@@ -773,21 +815,19 @@ int plan_grid(bds_trk* h) {
     }
     if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
     occ = std::min(occ, 4);
-    int total = g_num_sms * occ;
+    h->gridBlocks = g_num_sms * occ;
     int nAct = 0;
     for (auto& c : h->ch) nAct += c.PRN != 0;
-    nAct = std::max(nAct, 1);
-    // prefer >= 2 channels per group (hides loop-closure latency) and S >= 8
-    int best = 1;
-    for (int ng = 1; ng <= std::min(nAct, total); ++ng) {
-        int chPer = (nAct + ng - 1) / ng;
-        int S = total / ng;
-        if (S < 8) break;
-        if (chPer >= 2 || nAct < 2) best = ng;
+    h->nAct = std::max(nAct, 1);
+    if (h->fast) {
+        // slices of 256*k chips (one chip per thread and pass); at least ~2 work items per CTA and round
+        int k = 4;
+        while (k > 1 && (long long)h->nAct * ((10230 + 256 * k - 1) / (256 * k)) < 2LL * h->gridBlocks) --k;
+        h->S = (10230 + 256 * k - 1) / (256 * k);
+    } else {
+        int S = (3 * h->gridBlocks + h->nAct - 1) / h->nAct;
+        h->S = std::max(4, std::min(S, 512));
     }
-    h->nGroups = best;
-    h->S = std::min(total / best, 512);
-    h->gridBlocks = h->nGroups * h->S;
     return BDS_OK;
 }
 
@@ -834,6 +874,17 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
     TRY(cudaMalloc(&h->dStop, sizeof(int) * n_ch));
     TRY(cudaMalloc(&h->dCount, sizeof(int) * n_ch));
     TRY(cudaMalloc(&h->dPartial, sizeof(double) * (size_t)n_ch * h->S * kNSum));
+    TRY(cudaMalloc(&h->dAct, sizeof(int) * n_ch));
+    TRY(cudaMalloc(&h->dCounters, 32));
+    TRY(cudaMemset(h->dCounters, 0, 32));
+    {
+        std::vector<int> act;
+        for (int c = 0; c < n_ch; ++c)
+            if (ch[c].PRN != 0) act.push_back(c);
+        act.resize(n_ch, 0);
+        TRY(cudaMemcpy(h->dAct, act.data(), sizeof(int) * n_ch, cudaMemcpyHostToDevice));
+    }
+    if (h->fast) TRY(cudaMalloc(&h->dFastTab, sizeof(FastTab) * (size_t)n_ch * 2));
 #undef TRY
     rc = init_state(h);
     if (rc) return fail(rc);
@@ -927,7 +978,8 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
     if (rc) return rc;
     TrkDev g;
     fill_dev(h, g, n_epochs);
-    trk_prepare_kernel<<<(h->nCh + 63) / 64, 64, 0, h->stream>>>(g);
+    if (h->fast) trk_prepare_kernel<true><<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
+    else trk_prepare_kernel<false><<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
     count_launch();
     BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
     int zero = 0;
@@ -1026,6 +1078,19 @@ int bds_track_stats(bds_trk* h, long long* channel_samples, int* epochs_run, flo
     return BDS_OK;
 }
 
+int bds_track_counters(bds_trk* h, long long* out4) {
+    if (!out4) return set_error(BDS_ERR_ARG, "null argument");
+    if (!h) {  // counters of the last bds_track_correlate_open_loop call
+        for (int i = 0; i < 4; ++i) out4[i] = (long long)g_open_loop_counters[i];
+        return BDS_OK;
+    }
+    BDS_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned long long v[4];
+    BDS_CUDA(cudaMemcpy(v, h->dCounters, 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out4[i] = (long long)v[i];
+    return BDS_OK;
+}
+
 int bds_track_reset(bds_trk* h) {
     if (!h) return set_error(BDS_ERR_ARG, "null handle");
     BDS_CUDA(cudaStreamSynchronize(h->stream));
@@ -1053,6 +1118,9 @@ void bds_track_close(bds_trk* h) {
     cudaFree(h->dPartial);
     cudaFree(h->dOut);
     cudaFree(h->dCno);
+    cudaFree(h->dAct);
+    cudaFree(h->dCounters);
+    cudaFree(h->dFastTab);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1092,13 +1160,17 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     uint32_t* dBits = nullptr;
     EpochParams* dP = nullptr;
     double *dPart = nullptr, *dSums = nullptr;
-    const int S = 32;
+    FastTab* dTabs = nullptr;
+    unsigned long long* dCnt = nullptr;
+    const int S = fast ? 10 : 32;
     auto cleanup = [&]() {
         if (x_loc == BDS_LOC_HOST) cudaFree(dX);
         cudaFree(dBits);
         cudaFree(dP);
         cudaFree(dPart);
         cudaFree(dSums);
+        cudaFree(dTabs);
+        cudaFree(dCnt);
     };
 #define TRYC(x_)                                                       \
     if ((x_) != cudaSuccess) {                                         \
@@ -1131,18 +1203,25 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     g.L = (double)cfg->codeLength;
     g.d = cfg->dllCorrelatorSpacing;
     g.codeBits = dBits;
+    g.S = S;
+    g.pad = cfg->reserved & 1;
+    TRYC(cudaMalloc(&dCnt, 32));
+    TRYC(cudaMemset(dCnt, 0, 32));
+    g.counters = dCnt;
     size_t smem = smem_bytes(fast);
     if (fast) {
+        TRYC(cudaMalloc(&dTabs, sizeof(FastTab) * (size_t)nce));
         TRYC(cudaFuncSetAttribute(trk_open_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        trk_open_loop_kernel<true><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);
+        trk_open_loop_kernel<true><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart, dTabs);
     } else {
-        trk_open_loop_kernel<false><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);
+        trk_open_loop_kernel<false><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart, nullptr);
     }
     count_launch();
     trk_open_loop_reduce_kernel<<<(nce * kNSum + 127) / 128, 128>>>(dPart, S, nce, dSums);
     count_launch();
     TRYC(cudaGetLastError());
     TRYC(cudaMemcpy(sums, dSums, sizeof(double) * (size_t)nce * kNSum, cudaMemcpyDeviceToHost));
+    TRYC(cudaMemcpy(g_open_loop_counters, dCnt, 32, cudaMemcpyDeviceToHost));
 #undef TRYC
     cleanup();
     return BDS_OK;

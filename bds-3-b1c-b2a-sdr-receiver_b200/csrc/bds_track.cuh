@@ -59,7 +59,7 @@ struct TrkDev {
     long long winFirst;   // absolute index of x[0]
     long long winLen;
     int mode, hasPilot, hasP61, nCh;
-    int S, nGroups, maxEpochs, capacity;
+    int S, nAct, maxEpochs, capacity;
     int cnoCap, cnoInterval, kernelKind, pad;
     double fs, L, d, PDI, tau1, tau2, pf1, pf2, pf3, factor;
     const uint32_t* codeBits;  // [nCh][3][320] packed primaries: data, pilot, (unused)
@@ -72,6 +72,9 @@ struct TrkDev {
     double* partial;           // [nCh][S][18]
     double* out;               // [nCh][kNFields][capacity]
     double* cno;               // [nCh][kNCno][cnoCap]
+    const int* act;            // [nAct] indices of the active channels
+    struct FastTab* fastTab;   // [nCh][2] per-epoch tables of the chip-synchronous kernel (or null)
+    unsigned long long* counters;  // [4] diagnostics: fast chips, exact-path chips, general-kernel slices
 };
 
 }  // namespace bds

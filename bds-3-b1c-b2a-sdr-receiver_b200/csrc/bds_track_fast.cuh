@@ -1,9 +1,395 @@
-// Chip-synchronous fast path for B1C wide-band tracking (placeholder until bds_track_fast is filled in).
+// Chip-synchronous fast path of the B1C wide-band correlator (sm_100a).
+//
+// Same arithmetic as BDS-3_B1C/WB_tracking.m:289-372 (nine +-1 replicas x carrier-wiped
+// samples -> 18 sums), reorganised so that the per-sample work is ~3 instructions:
+//   * one thread integrates one primary-code chip (~97 samples at 99.375 MHz);
+//   * inside a chip all nine replicas are constant on 36 segments (gen_fast_wb.py); the
+//     per-sample work is a fused int8 x Q16-carrier multiply-accumulate into the running
+//     segment sum (2 IMAD + 1 PRMT); segment sums are folded into nine complex
+//     "basis" sums (SA,SB,SC,H1,H2,W1a,W1b,W2a,W2b) from which E/P/L of data, BOC(1,1)
+//     pilot and BOC(6,1) pilot follow by +-1 combinations with the chip signs;
+//   * the carrier is exp(-i theta(n_c)) * exp(-i 2 pi r dphi): a per-epoch table of the
+//     second factor (r = 0..97, Q16) is broadcast from shared memory, the first factor is
+//     applied once per chip in fp32;
+//   * the IF samples of a pass are staged into shared memory with one TMA bulk copy.
+// Which of two neighbouring segments the sample at a boundary belongs to depends only on
+// the sub-sample phase psi of the thread's first sample; it is looked up from a per-epoch
+// table of sorted thresholds.  When psi is within 4e-9 of a threshold the chip is
+// re-evaluated sample by sample with the exact float64 expressions of the general kernel,
+// so chip-edge decisions are identical to the oracle's.
 #pragma once
 #include "bds_track.cuh"
+
 namespace bds {
-struct FastSmem { int dummy; };
-inline bool fast_wb_supported(int, int, double, double, int, double) { return false; }
-__device__ inline void correlate_fast_wb(const TrkDev&, const EpochParams&, const uint32_t*, const uint32_t*, int, int,
-                                         float*, FastSmem*) {}
+
+#include "bds_track_fast_gen.inc"
+
+constexpr int kFastTile = 25600;  // bytes of IF staged per pass (256 chips x 97.2 + slack)
+constexpr int kFastBins = 128;
+constexpr unsigned kFastGuard = 16u;  // fixed-point guard band (2^-32 units of one sample)
+
+struct __align__(16) FastTab {
+    int4 w[(FAST_NSAMP + 2) / 2];       // {wr_r, wi_r, wr_{r+1}, wi_{r+1}}, Q16, exp(-i 2 pi r dphi)
+    unsigned thr[40];                   // sorted thresholds (2^32 fixed point), thr[36..] = 0xffffffff
+    uint2 mask[40];                     // decision masks by rank
+    unsigned char binStart[kFastBins + 16];
+    double u0, sigma, S;                // 12*rem, 12*step, 1/sigma
+    unsigned long long dphi, phi0;      // carrier NCO, 2^-64 turns
+    int valid;
+    int pad[3];
+};
+static_assert(sizeof(FastTab) % 16 == 0, "FastTab must be a 16-byte multiple");
+
+struct __align__(128) FastSmem {
+    FastTab tab;
+    unsigned long long mbar;
+    long long tileBase;                 // window byte offset of tile[0]
+    int pad[12];
+    __align__(128) unsigned char tile[kFastTile + 256];
+};
+
+inline bool fast_wb_supported(int mode, int hasP61, double fs, double fc, int codeLength, double d) {
+    return mode == BDS_TRK_B1C_WB && hasP61 && codeLength == 10230 && fs == FAST_FS_HZ && fc == FAST_FC_HZ &&
+           d == FAST_D;
+}
+
+// ---- per-epoch table construction (whole CTA) ----------------------------------------------
+// tab lives in global memory (one per channel and epoch parity); smem scratch: 40 floats/uints.
+__device__ void fast_build_tab(FastTab* tab, const EpochParams& np, double fs, unsigned* scratch /*>=128 words smem*/) {
+    const int t = threadIdx.x;
+    const double sigma = 12.0 * np.step, S = 1.0 / sigma;
+    double r = np.carrFreq / fs;
+    r -= floor(r);
+    const unsigned long long dphi = __double2ull_rn(r * 18446744073709551616.0);
+    if (t < FAST_NSAMP + 1) {
+        unsigned long long ph = (unsigned long long)t * dphi;
+        double sn, cs;
+        sincospi((double)(long long)ph * (1.0 / 9223372036854775808.0), &sn, &cs);
+        int* w = reinterpret_cast<int*>(tab->w);
+        w[2 * t + 0] = __double2int_rn(cs * 65536.0);
+        w[2 * t + 1] = __double2int_rn(-sn * 65536.0);
+    }
+    unsigned* thr = scratch;       // [36] unsorted thresholds
+    unsigned* okf = scratch + 40;  // validity flags
+    if (t < 36) {
+        const int k = t + 1;
+        double th = kFastBeta[k] * S - (double)kFastR[k];  // theta_k / sigma
+        okf[t] = (th > 1e-6 && th < 1.0 - 1e-6);
+        th = fmin(fmax(th, 0.0), 1.0);
+        thr[t] = (unsigned)fmin(th * 4294967296.0, 4294967295.0);
+    }
+    __syncthreads();
+    if (t < 36) {
+        // rank sort (ties broken by index)
+        const unsigned v = thr[t];
+        int rank = 0;
+        for (int j = 0; j < 36; ++j) rank += (thr[j] < v) || (thr[j] == v && j < t);
+        tab->thr[rank] = v;
+        scratch[80 + t] = rank;  // pos[k-1]
+    }
+    if (t >= 36 && t < 40) tab->thr[t] = 0xffffffffu;
+    __syncthreads();
+    if (t < 37) {
+        // mask[j]: bit (k-1) set  <=>  boundary sample R_k belongs to the OLD segment  <=>  Theta_k >= Psi
+        //          <=> sorted position of k >= j   (j = number of thresholds < Psi)
+        unsigned lo = 0, hi = 0;
+        for (int k = 1; k <= 36; ++k)
+            if ((int)scratch[80 + k - 1] >= t) {
+                if (k <= 32) lo |= 1u << (k - 1);
+                else hi |= 1u << (k - 33);
+            }
+        tab->mask[t] = make_uint2(lo, hi);
+    }
+    if (t < kFastBins + 1) {
+        int cnt = 0;
+        for (int j = 0; j < 36; ++j) cnt += (thr[j] >> 25) < (unsigned)t;
+        tab->binStart[t] = (unsigned char)cnt;
+    }
+    __syncthreads();
+    if (t == 0) {
+        int ok = 1;
+        for (int j = 0; j < 36; ++j) ok &= (int)okf[j];
+        for (int b = 0; b < kFastBins; ++b) {
+            int cnt = 0;
+            for (int j = 0; j < 36; ++j) cnt += (thr[j] >> 25) == (unsigned)b;
+            ok &= cnt <= 4;
+        }
+        double r0 = np.remCarr / 6.283185307179586476925286766559;
+        r0 -= floor(r0);
+        tab->u0 = 12.0 * np.rem;
+        tab->sigma = sigma;
+        tab->S = S;
+        tab->dphi = dphi;
+        tab->phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
+        tab->valid = ok;
+    }
+    __syncthreads();
+}
+
+// ---- exact per-sample evaluation (shared with the general kernel's arithmetic) --------------
+struct ExactCtx {
+    double a[3], stop[3], dd;
+    unsigned long long dphi, phi0;
+    int n;  // colon steps = blksize-1
+};
+__device__ inline void make_exact_ctx(const EpochParams& p, double d, double fs, ExactCtx& c) {
+    c.n = p.blksize - 1;
+    c.dd = __dmul_rn(p.step, 2.0);
+    const double base = __dadd_rn(__dmul_rn((double)c.n, p.step), p.rem);
+    c.a[0] = __dmul_rn(__dadd_rn(p.rem, -d), 2.0);
+    c.a[1] = __dmul_rn(p.rem, 2.0);
+    c.a[2] = __dmul_rn(__dadd_rn(p.rem, d), 2.0);
+    c.stop[0] = __dmul_rn(__dadd_rn(base, -d), 2.0);
+    c.stop[1] = __dmul_rn(base, 2.0);
+    c.stop[2] = __dmul_rn(__dadd_rn(base, d), 2.0);
+    double r = p.carrFreq / fs;
+    r -= floor(r);
+    c.dphi = __double2ull_rn(r * 18446744073709551616.0);
+    double r0 = p.remCarr / 6.283185307179586476925286766559;
+    r0 -= floor(r0);
+    c.phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
+}
+__device__ __forceinline__ double colon_elem_f(double a, double dd, double stop, int n, int k) {
+    int h = n >> 1;
+    if (!(n & 1) && k == h) return __dmul_rn(__dadd_rn(a, stop), 0.5);
+    if (k <= h) return __dadd_rn(a, __dmul_rn((double)k, dd));
+    return __dadd_rn(stop, -__dmul_rn((double)(n - k), dd));
+}
+__device__ __forceinline__ int bit_of(const uint32_t* w, int chip) { return (w[chip >> 5] >> (chip & 31)) & 1; }
+
+// Accumulates block-relative samples k in [k0, k1] whose exact prompt BOC(6,1) index lies in
+// [idxLo, idxHi] (chip membership exactly as the oracle decides it).
+__device__ __noinline__ void fast_exact_range(const ExactCtx& c, const int8_t* xblk, const uint32_t* bitsData,
+                                              const uint32_t* bitsPilot, int k0, int k1, int idxLo, int idxHi,
+                                              float* acc) {
+    for (int k = k0; k <= k1; ++k) {
+        double tP = colon_elem_f(c.a[1], c.dd, c.stop[1], c.n, k);
+        int i6 = (int)ceil(__dmul_rn(tP, 6.0));
+        if (i6 < idxLo || i6 > idxHi) continue;
+        float xs = (float)xblk[k];
+        unsigned long long ph = c.phi0 + (unsigned long long)k * c.dphi;
+        float sn, cs;
+        sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+        float iB = xs * cs, qB = -xs * sn;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            double t = colon_elem_f(c.a[o], c.dd, c.stop[o], c.n, k);
+            int h = (int)ceil(t) - 1;
+            if (h < 0) h = 20459;
+            if (h >= 20460) h = 0;
+            float e0 = (h & 1) ? 1.f : -1.f;
+            float sd = bit_of(bitsData, h >> 1) ? -e0 : e0;
+            float sp = bit_of(bitsPilot, h >> 1) ? -e0 : e0;
+            int s = (int)ceil(__dmul_rn(t, 6.0)) - 1;
+            if (s < 0) s = 122759;
+            if (s >= 122760) s = 0;
+            int chip = s / 12;
+            float e6 = ((s - chip * 12) & 1) ? 1.f : -1.f;
+            float s6 = bit_of(bitsPilot, chip) ? -e6 : e6;
+            acc[sum_idx(0, o, 0)] += sd * iB;
+            acc[sum_idx(0, o, 1)] += sd * qB;
+            acc[sum_idx(1, o, 0)] += sp * iB;
+            acc[sum_idx(1, o, 1)] += sp * qB;
+            acc[sum_idx(2, o, 0)] += s6 * iB;
+            acc[sum_idx(2, o, 1)] += s6 * qB;
+        }
+    }
+}
+
+// ---- TMA bulk copy helpers -------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// sign-extended byte b of a 32-bit word (PRMT with sign replication)
+// (__byte_perm masks the selector nibbles to 3 bits, so the PTX form is needed for the sign mode)
+template <int B>
+__device__ __forceinline__ int sext_byte(unsigned w) {
+    int r;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "n"(B | ((B | 8) << 4) | ((B | 8) << 8) | ((B | 8) << 12)));
+    return r;
+}
+// s if bit BIT of m is set, else 0 (LOP3 with predicate result + SEL)
+template <int BIT>
+__device__ __forceinline__ int sel_bit(int s, unsigned m) {
+    int r;
+    asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %2, %3;\n setp.ne.u32 p, t, 0;\n selp.s32 %0, %1, 0, p;\n}"
+        : "=r"(r)
+        : "r"(s), "r"(m), "n"(1u << BIT));
+    return r;
+}
+
+// number of chips per slice: multiple of the CTA size so that every pass is full
+__host__ __device__ inline int fast_chips_per_slice(int S, int threads) {
+    int cps = (10230 + S - 1) / S;
+    return ((cps + threads - 1) / threads) * threads;
+}
+
+// Copies the per-epoch tables into shared memory; returns tab.valid (CTA-uniform).
+__device__ bool fast_load_tab(FastSmem* fsm, const FastTab* gtab) {
+    const uint4* src = reinterpret_cast<const uint4*>(gtab);
+    uint4* dst = reinterpret_cast<uint4*>(&fsm->tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(FastTab) / 16); i += blockDim.x) dst[i] = __ldcg(src + i);
+    __syncthreads();
+    return fsm->tab.valid != 0;
+}
+
+// The slice correlator (tables already in fsm->tab).  mbarPhase is CTA-uniform state carried
+// across tasks by the caller.
+__device__ void correlate_fast_wb(const TrkDev& g, const EpochParams& p, const uint32_t* bitsData,
+                                  const uint32_t* bitsPilot, int sl, int S, float* acc, FastSmem* fsm,
+                                  unsigned& mbarPhase) {
+    const int t = threadIdx.x;
+    const FastTab& tab = fsm->tab;
+    const long long B0 = p.pos - g.winFirst;
+    const int cps = fast_chips_per_slice(S, blockDim.x);
+    const int cLo = sl * cps, cHi = min(10230, cLo + cps);
+    ExactCtx ex;
+    make_exact_ctx(p, g.d, g.fs, ex);
+    const int8_t* xblk = g.x + B0;
+    if (sl == 0 && t == 0 && p.rem == 0.0) {  // the t = 0 sample takes the previous period's last chip
+        float tmp[kNSum];
+#pragma unroll
+        for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
+        fast_exact_range(ex, xblk, bitsData, bitsPilot, 0, 0, -100, 0, tmp);
+#pragma unroll
+        for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
+    }
+
+    for (int c0 = cLo; c0 < cHi; c0 += blockDim.x) {
+        const int cEnd = min(c0 + (int)blockDim.x, cHi);
+        // ---- stage the pass's samples: [n(c0)-2, n(cEnd)+2) ----
+        if (t == 0) {
+            double qa = ((double)(12 * c0) - tab.u0) * tab.S, qb = ((double)(12 * cEnd) - tab.u0) * tab.S;
+            long long na = (long long)floor(qa) - 2, nb = (long long)floor(qb) + 4;
+            if (na < 0) na = 0;
+            if (nb > p.blksize) nb = p.blksize;
+            long long gA = (B0 + na) & ~15LL;
+            long long gE = (B0 + nb + 15) & ~15LL;
+            unsigned bytes = (unsigned)(gE - gA);
+            if (bytes > (unsigned)kFastTile) bytes = kFastTile;
+            fsm->tileBase = gA;
+            tma_load_1d(fsm->tile, g.x + gA, bytes, &fsm->mbar);
+        }
+        const int c = c0 + t;
+        const bool active = c < cEnd;
+        // ---- per-chip phase bookkeeping (fp64) ----
+        const double q = ((double)(12 * c) - tab.u0) * tab.S;  // sample position of the chip start
+        const double fq = floor(q);
+        const int nc = (int)fq + 1;                              // first sample of the chip
+        const double psi = (double)nc - q;                       // in (0,1] samples
+        const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
+        int j = tab.binStart[Psi >> 25];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) j += (tab.thr[j] < Psi);
+        const uint2 mk = tab.mask[j];
+        // near-miss of any decision (including the chip start/end) -> exact path
+        const unsigned below = j > 0 ? Psi - tab.thr[j - 1] : Psi;
+        const unsigned above = j < 36 ? tab.thr[j] - Psi : 0xffffffffu - Psi;
+        const unsigned guard = g.pad ? (1u << 24) : kFastGuard;  // g.pad: test hook, widens the guard band
+        bool exact = below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
+        const int len = FAST_RLAST + ((mk.y >> 3) & 1);         // bit 35 (k = 36): last sample still mine
+        if (nc < 0 || nc + len > p.blksize) exact = true;
+        __syncthreads();  // tileBase visible
+        mbar_wait(&fsm->mbar, mbarPhase);
+        if (active) {
+            if (!exact) {
+                const long long o = B0 + nc - fsm->tileBase;
+                const unsigned* raw = reinterpret_cast<const unsigned*>(fsm->tile) + (o >> 2);
+                const unsigned sh = (unsigned)(o & 3) * 8u;
+                const int4* wt = tab.w;
+                int Ur, Ui;
+                int SAr = 0, SAi = 0, SBr = 0, SBi = 0, SCr = 0, SCi = 0, H1r = 0, H1i = 0, H2r = 0, H2i = 0;
+                int W1ar = 0, W1ai = 0, W1br = 0, W1bi = 0, W2ar = 0, W2ai = 0, W2br = 0, W2bi = 0;
+#define FAST_RAW(i) raw[i]
+#define FAST_FSH(lo, hi) __funnelshift_r(lo, hi, sh)
+#define FAST_WTAB(pi) wt[pi]
+#define FAST_SB(w, b) sext_byte<b>(w)
+#define FAST_SEL(k, s) ((k) <= 32 ? sel_bit<((k)-1) & 31>(s, mk.x) : sel_bit<((k)-33) & 31>(s, mk.y))
+                FAST_CHIP_BODY
+#undef FAST_RAW
+#undef FAST_FSH
+#undef FAST_WTAB
+#undef FAST_SB
+#undef FAST_SEL
+                // ---- chip-level: rotate by exp(-i theta(nc)), combine with chip signs ----
+                const unsigned long long ph = tab.phi0 + (unsigned long long)(long long)nc * tab.dphi;
+                float sn, cs;
+                sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+                const float rr = cs * (1.0f / 65536.0f), ri = -sn * (1.0f / 65536.0f);
+#define ROT(N) const float N##x = (float)N##r * rr - (float)N##i * ri, N##y = (float)N##r * ri + (float)N##i * rr;
+                ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
+#undef ROT
+                const int cp_ = c == 0 ? 10229 : c - 1, cn_ = c == 10229 ? 0 : c + 1;
+                const float cd = bit_of(bitsData, c) ? -1.f : 1.f, cdp = bit_of(bitsData, cp_) ? -1.f : 1.f,
+                            cdn = bit_of(bitsData, cn_) ? -1.f : 1.f;
+                const float cp = bit_of(bitsPilot, c) ? -1.f : 1.f, cpp = bit_of(bitsPilot, cp_) ? -1.f : 1.f,
+                            cpn = bit_of(bitsPilot, cn_) ? -1.f : 1.f;
+                const float Xx = H2x - H1x, Xy = H2y - H1y;
+                const float XEx = Xx + W1ax - 2.f * W1bx, XEy = Xy + W1ay - 2.f * W1by;
+                const float XLx = Xx + 2.f * W2ax - W2bx, XLy = Xy + 2.f * W2ay - W2by;
+                acc[sum_idx(0, EPL_P, 0)] += cd * Xx;
+                acc[sum_idx(0, EPL_P, 1)] += cd * Xy;
+                acc[sum_idx(0, EPL_E, 0)] += cd * XEx + cdp * W1ax;
+                acc[sum_idx(0, EPL_E, 1)] += cd * XEy + cdp * W1ay;
+                acc[sum_idx(0, EPL_L, 0)] += cd * XLx - cdn * W2bx;
+                acc[sum_idx(0, EPL_L, 1)] += cd * XLy - cdn * W2by;
+                acc[sum_idx(1, EPL_P, 0)] += cp * Xx;
+                acc[sum_idx(1, EPL_P, 1)] += cp * Xy;
+                acc[sum_idx(1, EPL_E, 0)] += cp * XEx + cpp * W1ax;
+                acc[sum_idx(1, EPL_E, 1)] += cp * XEy + cpp * W1ay;
+                acc[sum_idx(1, EPL_L, 0)] += cp * XLx - cpn * W2bx;
+                acc[sum_idx(1, EPL_L, 1)] += cp * XLy - cpn * W2by;
+                const float SPx = SAx + SBx + SCx, SPy = SAy + SBy + SCy;
+                const float SEx = SCx - SAx - SBx, SEy = SCy - SAy - SBy;
+                const float SLx = SAx - SBx - SCx, SLy = SAy - SBy - SCy;
+                acc[sum_idx(2, EPL_P, 0)] += cp * SPx;
+                acc[sum_idx(2, EPL_P, 1)] += cp * SPy;
+                acc[sum_idx(2, EPL_E, 0)] += cp * SEx + (cpp - cp) * W1ax;
+                acc[sum_idx(2, EPL_E, 1)] += cp * SEy + (cpp - cp) * W1ay;
+                acc[sum_idx(2, EPL_L, 0)] += cp * SLx + (cp - cpn) * W2bx;
+                acc[sum_idx(2, EPL_L, 1)] += cp * SLy + (cp - cpn) * W2by;
+            } else {
+                // rare (~1e-5 of chips): keep the fast path's accumulators in registers
+                int k0 = max(0, nc - 2), k1 = min(p.blksize - 1, nc + FAST_RLAST + 2);
+                float tmp[kNSum];
+#pragma unroll
+                for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
+                fast_exact_range(ex, xblk, bitsData, bitsPilot, k0, k1, 12 * c + 1, 12 * c + 12, tmp);
+#pragma unroll
+                for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
+            }
+        }
+        if (g.counters) {  // diagnostics: chips through the fast body / the exact path
+            unsigned bf = __ballot_sync(0xffffffffu, active && !exact), be = __ballot_sync(0xffffffffu, active && exact);
+            if ((t & 31) == 0) {
+                if (bf) atomicAdd(g.counters + 0, (unsigned long long)__popc(bf));
+                if (be) atomicAdd(g.counters + 1, (unsigned long long)__popc(be));
+            }
+        }
+        mbarPhase ^= 1u;
+        __syncthreads();  // everyone done with the tile before the next pass overwrites it
+    }
+}
+
 }  // namespace bds

@@ -131,7 +131,7 @@ typedef struct bds_trk_cfg {
     double pf3, pf2, pf1;
     double wbFactor;             /* WB only */
     int32_t kernel;              /* BDS_KERNEL_* */
-    int32_t reserved;
+    int32_t reserved;            /* 0; bit 0 = test hook: widen the fast kernel's exact-path guard band */
 } bds_trk_cfg;
 
 typedef struct bds_channel {
@@ -189,6 +189,10 @@ int bds_track_fetch(bds_trk* h, const bds_trk_out* out, int out_stride);
 int bds_track_device_block(bds_trk* h, void** dev_ptr, size_t* bytes, int* n_fields, int* capacity);
 /* total IF samples consumed so far (sum over channels of blksize), epochs run */
 int bds_track_stats(bds_trk* h, long long* channel_samples, int* epochs_run, float* last_kernel_ms);
+/* diagnostics: out4 = {chips integrated by the chip-synchronous body, chips re-evaluated by its exact
+ * per-sample path, slices run by the general kernel, 0}.  h == NULL: counters of the last
+ * bds_track_correlate_open_loop call. */
+int bds_track_counters(bds_trk* h, long long* out4);
 /* reset loop state to the initial channel state (re-run the same record) */
 int bds_track_reset(bds_trk* h);
 void bds_track_close(bds_trk* h);

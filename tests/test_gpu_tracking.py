@@ -39,6 +39,55 @@ def test_open_loop_parity_general(mode, seconds, epochs):
     assert np.nanmax(err[np.isfinite(err)]) <= 1e-4, np.nanmax(err[np.isfinite(err)])
 
 
+@pytest.mark.parametrize("wide_guard", [0, 1])
+def test_open_loop_parity_fast(wide_guard):
+    """Chip-synchronous kernel vs oracle, strict tolerance; wide_guard=1 sends ~25 % of the chips through
+    the exact per-sample path (cfg.reserved test hook), exercising the seam between the two paths."""
+    s, sats, x, ch = util.record("WB", 2, 0.06)
+    tr, raw = util.oracle_track("WB", s, x, ch, 3)
+    nco = np.stack([t.nco for t in tr])
+    cfg_s = util.product_settings(s)
+    cfg = _track.make_cfg("WB", cfg_s, L.KERNEL_FAST)
+    cfg.reserved = wide_guard
+    sums = np.zeros((2, 3, 18))
+    prn = np.asarray([c.PRN for c in ch], dtype=np.int32)
+    nco = np.ascontiguousarray(nco)
+    L.check(L.lib().bds_track_correlate_open_loop(L.TRK_B1C_WB, C.byref(cfg), L.ptr(x), x.size, L.LOC_HOST, L.ptr(prn),
+                                                  2, 3, L.ptr(nco), L.ptr(sums)))
+    err = np.abs(sums - raw) / util.family_scale(raw)
+    assert np.max(err) <= 1e-4, np.max(err)
+    fast_chips, exact_chips, general_slices, _ = _track.counters(None)
+    assert general_slices == 0 and fast_chips + exact_chips == 2 * 3 * 10230
+    if wide_guard:
+        assert 0.1 < exact_chips / (2 * 3 * 10230) < 0.6
+    else:
+        assert exact_chips <= 2 * 3 + 2      # only chip 0 of a first epoch (rem = 0) and rare near-edge chips
+
+
+def test_fast_kernel_rejects_unsupported_config():
+    s, sats, x, ch = util.record("NB", 2, 0.06)
+    with pytest.raises(L.BdsError):
+        _track.run_tracking("NB", x, ch, util.product_settings(s), n_epochs=2, kernel=L.KERNEL_FAST)
+
+
+def test_closed_loop_fast_matches_general_and_oracle():
+    s, sats, x, ch = util.record("WB", 2, 0.13)
+    ps = util.product_settings(s)
+    tr, raw = util.oracle_track("WB", s, x, ch, 10)
+    gen, _ = _track.run_tracking("WB", x, ch, ps, n_epochs=10, kernel=L.KERNEL_GENERAL, raw=True)
+    fast, _ = _track.run_tracking("WB", x, ch, ps, n_epochs=10, kernel=L.KERNEL_FAST, raw=True)
+    for c in range(2):
+        sc = util.family_scale(raw[c])
+        for got in (gen[c], fast[c]):
+            err = np.abs(got.raw - raw[c]) / sc
+            assert np.max(err) <= 1e-3 and np.mean(err <= 1e-4) >= 0.99, np.max(err)
+        np.testing.assert_array_equal(fast[c].absoluteSample, tr[c].absoluteSample)
+        np.testing.assert_allclose(fast[c].carrFreq, tr[c].carrFreq, rtol=1e-9)
+        assert fast[c].status == "T"
+    fast_chips, exact_chips, general_slices, _ = _track.run_tracking.last_counters
+    assert general_slices == 0 and fast_chips >= 2 * 10 * 10230 - 64
+
+
 def test_open_loop_first_epoch_t0_sample():
     """remCodePhase = 0: the t = 0 sample takes the previous period's last chip (SURVEY quirk i)."""
     s, sats, x, ch = util.record("WB", 2, 0.06)

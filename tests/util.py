@@ -68,6 +68,7 @@ def family_scale(raw):
         ip = np.abs(raw[..., fam * 6 + 2])
         qp = np.abs(raw[..., fam * 6 + 3])
         m = np.maximum(ip, qp)
+        m = np.where(m > 0, m, np.inf)   # family absent in this mode: sums are exactly 0 on both sides
         for k in range(6):
             sc[..., fam * 6 + k] = m
     return sc
