@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -267,7 +268,7 @@ __device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 
     double base = (double)(p.blksize - 1) * p.step + p.rem;
     st.remCodePhase = base + p.step - g.L;
     double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
-    st.remCarrPhase = fmod(trig, twopi);
+    st.remCarrPhase = fmod(trig, twopi);  // rem(trigarg(blksize+1), 2*pi), WB:337
     st.pos = p.pos + p.blksize;
     st.samples += p.blksize;
 
@@ -424,33 +425,20 @@ __device__ void reduce_partials(const TrkDev& g, TrkSmem& sm, int c) {
     __syncthreads();
 }
 
-template <bool kFast>
 __device__ __forceinline__ void correlate_slice(const TrkDev& g, TrkSmem& sm, const EpochParams& p, int sl, int S,
-                                                float* acc, FastSmem* fsm, const FastTab* gtab, unsigned& mbarPhase) {
-    bool general = true;
-    if constexpr (kFast) {
-        general = !fast_load_tab(fsm, gtab);   // pattern not valid for this epoch's code rate -> exact kernel
-        if (!general) correlate_fast_wb(g, p, sm.bits[0], sm.bits[1], sl, S, acc, fsm, mbarPhase);
-    }
-    if (general) {
-        if (g.counters && threadIdx.x == 0) atomicAdd(g.counters + 2, 1ull);
-        SliceCtx ctx{g.x, g.winFirst, g.winLen, p, g.mode, g.hasPilot, g.hasP61, g.L, g.d, g.fs};
-        long long q0, q1;
-        slice_chunks(p, g.winFirst, sl, S, q0, q1);
-        correlate_general(ctx, sm.bits[0], sm.bits[1], q0, q1, acc);
-    }
+                                                float* acc) {
+    if (g.counters && threadIdx.x == 0) atomicAdd(g.counters + 2, 1ull);
+    SliceCtx ctx{g.x, g.winFirst, g.winLen, p, g.mode, g.hasPilot, g.hasP61, g.L, g.d, g.fs};
+    long long q0, q1;
+    slice_chunks(p, g.winFirst, sl, S, q0, q1);
+    correlate_general(ctx, sm.bits[0], sm.bits[1], q0, q1, acc);
 }
 
-// Publishes the params staged in sm.np (after building the fast-path tables for them) or stops
-// the channel.  Whole CTA.
-template <bool kFast>
+// Publishes the params staged in sm.np or stops the channel.  Whole CTA.
 __device__ void publish_next(const TrkDev& g, TrkSmem& sm, int c, int eNext) {
     __syncthreads();
     const int ok = sm.npOk;
-    if (ok) {
-        if constexpr (kFast) fast_build_tab(g.fastTab + (size_t)c * 2 + (eNext & 1), sm.np, g.fs, sm.scratch);
-        if (threadIdx.x == 0) store_cg(g.params + c * 2 + (eNext & 1), sm.np);
-    }
+    if (ok && threadIdx.x == 0) store_cg(g.params + c * 2 + (eNext & 1), sm.np);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -460,18 +448,13 @@ __device__ void publish_next(const TrkDev& g, TrkSmem& sm, int c, int eNext) {
     }
 }
 
-// Persistent closed-loop kernel.  Work items t = blockIdx.x, blockIdx.x + gridDim.x, ... in the
-// global order (round, channel, slice); the item's channel-epoch must have been published.
-template <bool kFast>
-__global__ void __launch_bounds__(kTrkThreads) trk_persistent_kernel(TrkDev g, int unused) {
+// Persistent closed-loop kernel (general correlator).  Work items t = blockIdx.x, blockIdx.x +
+// gridDim.x, ... in the global order (round, channel, slice); the item's channel-epoch must have
+// been published.
+__global__ void __launch_bounds__(kTrkThreads) trk_persistent_kernel(TrkDev g) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
-    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + ((sizeof(TrkSmem) + 127) & ~(size_t)127));
-    unsigned mbarPhase = 0;
-    if (threadIdx.x == 0) {
-        sm.curChan = -1;
-        if constexpr (kFast) mbar_init(&fsm->mbar, 1);
-    }
+    if (threadIdx.x == 0) sm.curChan = -1;
     __syncthreads();
     const long long perRound = (long long)g.nAct * g.S;
     const long long total = perRound * g.maxEpochs;
@@ -503,7 +486,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_persistent_kernel(TrkDev g, i
         float acc[kNSum];
 #pragma unroll
         for (int k = 0; k < kNSum; ++k) acc[k] = 0.f;
-        correlate_slice<kFast>(g, sm, p, sl, g.S, acc, fsm, g.fastTab + (size_t)c * 2 + (e & 1), mbarPhase);
+        correlate_slice(g, sm, p, sl, g.S, acc);
         block_reduce18(acc, sm.red, sm.sums);
         if (threadIdx.x < kNSum) {
             g.partial[((size_t)c * g.S + sl) * kNSum + threadIdx.x] = sm.sums[threadIdx.x];
@@ -520,14 +503,13 @@ __global__ void __launch_bounds__(kTrkThreads) trk_persistent_kernel(TrkDev g, i
             __threadfence();
             reduce_partials(g, sm, c);
             if (threadIdx.x == 0) close_epoch(g, c, e, sm.sums, sm.np, sm.npOk);
-            publish_next<kFast>(g, sm, c, e + 1);
+            publish_next(g, sm, c, e + 1);
         }
         __syncthreads();
     }
 }
 
 // Computes the first params of every channel for the current window (run start): one CTA per channel.
-template <bool kFast>
 __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
@@ -540,7 +522,6 @@ __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
         }
         return;
     }
-    int e = 0;
     if (threadIdx.x == 0) {
         g.count[c] = 0;
         ChanState st = g.st[c];
@@ -553,19 +534,20 @@ __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
         sm.go = st.epoch;
     }
     __syncthreads();
-    e = sm.go;
-    publish_next<kFast>(g, sm, c, e);
+    publish_next(g, sm, c, sm.go);
 }
+
+}  // namespace bds
+#include "bds_track_fw.cuh"
+namespace bds {
 
 // ======================================================================================
 // Open-loop ("teacher forced") correlator: grid = (S, n_ch * n_epochs)
 // ======================================================================================
-template <bool kFast>
 __global__ void __launch_bounds__(kTrkThreads) trk_open_loop_kernel(TrkDev g, const EpochParams* params, int nEpochs,
-                                                                   double* partial /*[ce][S][18]*/, FastTab* tabs) {
+                                                                   double* partial /*[ce][S][18]*/) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     TrkSmem& sm = *reinterpret_cast<TrkSmem*>(dyn_smem);
-    FastSmem* fsm = reinterpret_cast<FastSmem*>(dyn_smem + ((sizeof(TrkSmem) + 127) & ~(size_t)127));
     const int ce = blockIdx.y, sl = blockIdx.x, S = gridDim.x;
     const int c = ce / nEpochs;
     if (threadIdx.x == 0) sm.curChan = -1;
@@ -575,15 +557,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_open_loop_kernel(TrkDev g, co
     float acc[kNSum];
 #pragma unroll
     for (int k = 0; k < kNSum; ++k) acc[k] = 0.f;
-    unsigned mbarPhase = 0;
-    if constexpr (kFast) {
-        // open loop: this CTA builds the per-epoch table itself
-        if (threadIdx.x == 0) mbar_init(&fsm->mbar, 1);
-        fast_build_tab(tabs + ce, p, g.fs, sm.scratch);
-        __threadfence();
-        __syncthreads();
-    }
-    correlate_slice<kFast>(g, sm, p, sl, S, acc, fsm, tabs + ce, mbarPhase);
+    correlate_slice(g, sm, p, sl, S, acc);
     block_reduce18(acc, sm.red, sm.sums);
     if (threadIdx.x < kNSum) partial[((size_t)ce * S + sl) * kNSum + threadIdx.x] = sm.sums[threadIdx.x];
 }
@@ -720,7 +694,7 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
     return BDS_OK;
 }
 
-size_t smem_bytes(bool fast) { return ((sizeof(TrkSmem) + 127) & ~(size_t)127) + (fast ? sizeof(FastSmem) : 0); }
+size_t smem_bytes(bool fast) { return fast ? sizeof(FwSmem) : sizeof(TrkSmem); }
 
 int init_state(bds_trk* h) {
     std::vector<ChanConst> cc(h->nCh);
@@ -746,26 +720,25 @@ int init_state(bds_trk* h) {
     return BDS_OK;
 }
 
-__global__ void fill_kernel(double* p, size_t n, double v) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+// initial values exactly as the reference preallocates them (WB_tracking.m:53-112): Inf for the
+// frequency / discriminator / remainder planes, 0 elsewhere.  Epochs [e0, cap) of every channel.
+__global__ void init_out_kernel(double* out, int nCh, int cap, int e0) {
+    const size_t per = (size_t)(cap - e0);
+    const size_t total = (size_t)nCh * kNFields * per;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t row = i / per;
+        int f = (int)(row % kNFields);
+        bool isInf = f == F_CODEFREQ || f == F_CARRFREQ || f == F_DLL || f == F_DLLF || f == F_PLL || f == F_PLLF ||
+                     f == F_REMCODE || f == F_REMCARR;
+        out[row * cap + e0 + (i - row * per)] = isInf ? INFINITY : 0.0;
+    }
 }
 
-// initial values exactly as the reference preallocates them (WB_tracking.m:53-112)
 int init_out_block(bds_trk* h, double* out, int cap, int e0) {
-    const double inf = INFINITY;
-    static const int infFields[] = {F_CODEFREQ, F_CARRFREQ, F_DLL, F_DLLF, F_PLL, F_PLLF, F_REMCODE, F_REMCARR};
     if (cap <= e0) return BDS_OK;
-    for (int c = 0; c < h->nCh; ++c) {
-        double* base = out + (size_t)c * kNFields * cap;
-        for (int f = 0; f < kNFields; ++f)
-            BDS_CUDA(cudaMemsetAsync(base + (size_t)f * cap + e0, 0, sizeof(double) * (cap - e0), h->stream));
-        for (int f : infFields) {
-            size_t n = cap - e0;
-            fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(base + (size_t)f * cap + e0, n, inf);
-            count_launch();
-        }
-    }
+    init_out_kernel<<<g_num_sms * 4, 256, 0, h->stream>>>(out, h->nCh, cap, e0);
+    count_launch();
+    BDS_CUDA(cudaGetLastError());
     return BDS_OK;
 }
 
@@ -804,27 +777,24 @@ int ensure_capacity(bds_trk* h, int need) {
 int plan_grid(bds_trk* h) {
     int occ = 0;
     h->smemBytes = smem_bytes(h->fast);
-    if (h->fast) {
-        BDS_CUDA(cudaFuncSetAttribute(trk_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)h->smemBytes));
-        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel<true>, kTrkThreads,
-                                                               h->smemBytes));
-    } else {
-        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel<false>, kTrkThreads,
-                                                               h->smemBytes));
-    }
-    if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
-    occ = std::min(occ, 4);
-    h->gridBlocks = g_num_sms * occ;
     int nAct = 0;
     for (auto& c : h->ch) nAct += c.PRN != 0;
     h->nAct = std::max(nAct, 1);
     if (h->fast) {
-        // slices of 256*k chips (one chip per thread and pass); at least ~2 work items per CTA and round
+        BDS_CUDA(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_fw_kernel, kFwThreads, h->smemBytes));
+        if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
+        h->gridBlocks = g_num_sms;
+        // slices of 448*k chips (one chip per compute thread and pass); >= ~2.5 work items per CTA and round
         int k = 4;
-        while (k > 1 && (long long)h->nAct * ((10230 + 256 * k - 1) / (256 * k)) < 2LL * h->gridBlocks) --k;
-        h->S = (10230 + 256 * k - 1) / (256 * k);
+        while (k > 1 && (long long)h->nAct * ((10230 + kFwChips * k - 1) / (kFwChips * k)) * 2 < 5LL * h->gridBlocks) --k;
+        if (const char* e = getenv("BDS_TRK_PASSES")) k = std::max(1, std::min(8, atoi(e)));  // tuning knob
+        h->S = (10230 + kFwChips * k - 1) / (kFwChips * k);
     } else {
+        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel, kTrkThreads, h->smemBytes));
+        if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
+        occ = std::min(occ, 4);
+        h->gridBlocks = g_num_sms * occ;
         int S = (3 * h->gridBlocks + h->nAct - 1) / h->nAct;
         h->S = std::max(4, std::min(S, 512));
     }
@@ -900,6 +870,8 @@ int set_window(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long first
         h->dX = const_cast<int8_t*>(x);
         h->ownX = false;
         h->xCap = n;
+        // kernels read whole 16-byte chunks / TMA tiles: keep the last 32 bytes of a caller-owned buffer as slack
+        n = n > 32 ? n - 32 : 0;
     } else {
         if (!h->ownX || h->xCap < n + 64) {
             if (h->ownX && h->dX) cudaFree(h->dX);
@@ -978,14 +950,17 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
     if (rc) return rc;
     TrkDev g;
     fill_dev(h, g, n_epochs);
-    if (h->fast) trk_prepare_kernel<true><<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
-    else trk_prepare_kernel<false><<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
+    if (h->fast) fw_prepare_kernel<<<(h->nCh + 3) / 4, 128, 0, h->stream>>>(g);
+    else trk_prepare_kernel<<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
     count_launch();
     BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
-    int zero = 0;
-    void* args[] = {&g, &zero};
-    const void* fn = h->fast ? (const void*)trk_persistent_kernel<true> : (const void*)trk_persistent_kernel<false>;
-    BDS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(h->gridBlocks), dim3(kTrkThreads), args, h->smemBytes, h->stream));
+    void* args[] = {&g};
+    if (h->fast)
+        BDS_CUDA(cudaLaunchCooperativeKernel((const void*)trk_fw_kernel, dim3(h->gridBlocks), dim3(kFwThreads), args,
+                                             h->smemBytes, h->stream));
+    else
+        BDS_CUDA(cudaLaunchCooperativeKernel((const void*)trk_persistent_kernel, dim3(h->gridBlocks), dim3(kTrkThreads),
+                                             args, h->smemBytes, h->stream));
     count_launch();
     BDS_CUDA(cudaEventRecord(h->ev1, h->stream));
     h->pending = true;
@@ -1162,7 +1137,7 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     double *dPart = nullptr, *dSums = nullptr;
     FastTab* dTabs = nullptr;
     unsigned long long* dCnt = nullptr;
-    const int S = fast ? 10 : 32;
+    const int S = fast ? (10230 + kFwChips * 3 - 1) / (kFwChips * 3) : 32;
     auto cleanup = [&]() {
         if (x_loc == BDS_LOC_HOST) cudaFree(dX);
         cudaFree(dBits);
@@ -1211,10 +1186,17 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     size_t smem = smem_bytes(fast);
     if (fast) {
         TRYC(cudaMalloc(&dTabs, sizeof(FastTab) * (size_t)nce));
-        TRYC(cudaFuncSetAttribute(trk_open_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        trk_open_loop_kernel<true><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart, dTabs);
+        TRYC(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fw_tab_kernel<<<(nce + 3) / 4, 128>>>(dP, nce, g.fs, dTabs);
+        count_launch();
+        g.fastTab = dTabs;
+        g.partial = dPart;
+        g.olParams = dP;
+        g.olEpochs = n_epochs;
+        g.olCount = nce;
+        trk_fw_kernel<<<g_num_sms, kFwThreads, smem>>>(g);
     } else {
-        trk_open_loop_kernel<false><<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart, nullptr);
+        trk_open_loop_kernel<<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);
     }
     count_launch();
     trk_open_loop_reduce_kernel<<<(nce * kNSum + 127) / 128, 128>>>(dPart, S, nce, dSums);

@@ -75,6 +75,8 @@ struct TrkDev {
     const int* act;            // [nAct] indices of the active channels
     struct FastTab* fastTab;   // [nCh][2] per-epoch tables of the chip-synchronous kernel (or null)
     unsigned long long* counters;  // [4] diagnostics: fast chips, exact-path chips, general-kernel slices
+    const EpochParams* olParams;   // open loop (teacher forced): params per channel-epoch, else null
+    int olEpochs, olCount;         // open loop: epochs per channel, number of channel-epochs
 };
 
 }  // namespace bds

@@ -24,7 +24,6 @@ namespace bds {
 
 #include "bds_track_fast_gen.inc"
 
-constexpr int kFastTile = 25600;  // bytes of IF staged per pass (256 chips x 97.2 + slack)
 constexpr int kFastBins = 128;
 constexpr unsigned kFastGuard = 16u;  // fixed-point guard band (2^-32 units of one sample)
 
@@ -40,80 +39,73 @@ struct __align__(16) FastTab {
 };
 static_assert(sizeof(FastTab) % 16 == 0, "FastTab must be a 16-byte multiple");
 
-struct __align__(128) FastSmem {
-    FastTab tab;
-    unsigned long long mbar;
-    long long tileBase;                 // window byte offset of tile[0]
-    int pad[12];
-    __align__(128) unsigned char tile[kFastTile + 256];
-};
-
 inline bool fast_wb_supported(int mode, int hasP61, double fs, double fc, int codeLength, double d) {
     return mode == BDS_TRK_B1C_WB && hasP61 && codeLength == 10230 && fs == FAST_FS_HZ && fc == FAST_FC_HZ &&
            d == FAST_D;
 }
 
-// ---- per-epoch table construction (whole CTA) ----------------------------------------------
-// tab lives in global memory (one per channel and epoch parity); smem scratch: 40 floats/uints.
-__device__ void fast_build_tab(FastTab* tab, const EpochParams& np, double fs, unsigned* scratch /*>=128 words smem*/) {
-    const int t = threadIdx.x;
+// ---- per-epoch table construction (one warp) -------------------------------------------------
+// tab lives in global memory (one per channel and epoch parity); scratch: >= 128 words of shared
+// memory private to the calling warp.
+__device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double fs, unsigned* scratch) {
+    const int lane = threadIdx.x & 31;
     const double sigma = 12.0 * np.step, S = 1.0 / sigma;
     double r = np.carrFreq / fs;
     r -= floor(r);
     const unsigned long long dphi = __double2ull_rn(r * 18446744073709551616.0);
-    if (t < FAST_NSAMP + 1) {
+    int* w = reinterpret_cast<int*>(tab->w);
+    for (int t = lane; t < FAST_NSAMP + 1; t += 32) {
         unsigned long long ph = (unsigned long long)t * dphi;
         double sn, cs;
         sincospi((double)(long long)ph * (1.0 / 9223372036854775808.0), &sn, &cs);
-        int* w = reinterpret_cast<int*>(tab->w);
         w[2 * t + 0] = __double2int_rn(cs * 65536.0);
         w[2 * t + 1] = __double2int_rn(-sn * 65536.0);
     }
-    unsigned* thr = scratch;       // [36] unsorted thresholds
-    unsigned* okf = scratch + 40;  // validity flags
-    if (t < 36) {
+    unsigned* thr = scratch;        // [36] unsorted thresholds
+    unsigned* pos = scratch + 40;   // [36] sorted position of threshold k-1
+    int ok = 1;
+    for (int t = lane; t < 36; t += 32) {
         const int k = t + 1;
         double th = kFastBeta[k] * S - (double)kFastR[k];  // theta_k / sigma
-        okf[t] = (th > 1e-6 && th < 1.0 - 1e-6);
+        ok &= (th > 1e-6 && th < 1.0 - 1e-6);
         th = fmin(fmax(th, 0.0), 1.0);
         thr[t] = (unsigned)fmin(th * 4294967296.0, 4294967295.0);
     }
-    __syncthreads();
-    if (t < 36) {
-        // rank sort (ties broken by index)
-        const unsigned v = thr[t];
-        int rank = 0;
-        for (int j = 0; j < 36; ++j) rank += (thr[j] < v) || (thr[j] == v && j < t);
-        tab->thr[rank] = v;
-        scratch[80 + t] = rank;  // pos[k-1]
+    __syncwarp();
+    for (int t = lane; t < 40; t += 32) {
+        if (t < 36) {  // rank sort (ties broken by index)
+            const unsigned v = thr[t];
+            int rank = 0;
+            for (int j = 0; j < 36; ++j) rank += (thr[j] < v) || (thr[j] == v && j < t);
+            tab->thr[rank] = v;
+            pos[t] = rank;
+        } else {
+            tab->thr[t] = 0xffffffffu;
+        }
     }
-    if (t >= 36 && t < 40) tab->thr[t] = 0xffffffffu;
-    __syncthreads();
-    if (t < 37) {
+    __syncwarp();
+    for (int t = lane; t < 37; t += 32) {
         // mask[j]: bit (k-1) set  <=>  boundary sample R_k belongs to the OLD segment  <=>  Theta_k >= Psi
         //          <=> sorted position of k >= j   (j = number of thresholds < Psi)
         unsigned lo = 0, hi = 0;
         for (int k = 1; k <= 36; ++k)
-            if ((int)scratch[80 + k - 1] >= t) {
+            if ((int)pos[k - 1] >= t) {
                 if (k <= 32) lo |= 1u << (k - 1);
                 else hi |= 1u << (k - 33);
             }
         tab->mask[t] = make_uint2(lo, hi);
     }
-    if (t < kFastBins + 1) {
-        int cnt = 0;
-        for (int j = 0; j < 36; ++j) cnt += (thr[j] >> 25) < (unsigned)t;
-        tab->binStart[t] = (unsigned char)cnt;
-    }
-    __syncthreads();
-    if (t == 0) {
-        int ok = 1;
-        for (int j = 0; j < 36; ++j) ok &= (int)okf[j];
-        for (int b = 0; b < kFastBins; ++b) {
-            int cnt = 0;
-            for (int j = 0; j < 36; ++j) cnt += (thr[j] >> 25) == (unsigned)b;
-            ok &= cnt <= 4;
+    for (int t = lane; t < kFastBins + 1; t += 32) {
+        int cnt = 0, here = 0;
+        for (int j = 0; j < 36; ++j) {
+            cnt += (thr[j] >> 25) < (unsigned)t;
+            here += (thr[j] >> 25) == (unsigned)t;
         }
+        tab->binStart[t] = (unsigned char)cnt;
+        ok &= here <= 4;  // the rank refinement in the correlator does 4 steps
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
         double r0 = np.remCarr / 6.283185307179586476925286766559;
         r0 -= floor(r0);
         tab->u0 = 12.0 * np.rem;
@@ -123,7 +115,7 @@ __device__ void fast_build_tab(FastTab* tab, const EpochParams& np, double fs, u
         tab->phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
         tab->valid = ok;
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 // ---- exact per-sample evaluation (shared with the general kernel's arithmetic) --------------
@@ -239,157 +231,99 @@ __device__ __forceinline__ int sel_bit(int s, unsigned m) {
     return r;
 }
 
-// number of chips per slice: multiple of the CTA size so that every pass is full
-__host__ __device__ inline int fast_chips_per_slice(int S, int threads) {
-    int cps = (10230 + S - 1) / S;
-    return ((cps + threads - 1) / threads) * threads;
-}
-
-// Copies the per-epoch tables into shared memory; returns tab.valid (CTA-uniform).
-__device__ bool fast_load_tab(FastSmem* fsm, const FastTab* gtab) {
-    const uint4* src = reinterpret_cast<const uint4*>(gtab);
-    uint4* dst = reinterpret_cast<uint4*>(&fsm->tab);
-    for (int i = threadIdx.x; i < (int)(sizeof(FastTab) / 16); i += blockDim.x) dst[i] = __ldcg(src + i);
-    __syncthreads();
-    return fsm->tab.valid != 0;
-}
-
-// The slice correlator (tables already in fsm->tab).  mbarPhase is CTA-uniform state carried
-// across tasks by the caller.
-__device__ void correlate_fast_wb(const TrkDev& g, const EpochParams& p, const uint32_t* bitsData,
-                                  const uint32_t* bitsPilot, int sl, int S, float* acc, FastSmem* fsm,
-                                  unsigned& mbarPhase) {
-    const int t = threadIdx.x;
-    const FastTab& tab = fsm->tab;
-    const long long B0 = p.pos - g.winFirst;
-    const int cps = fast_chips_per_slice(S, blockDim.x);
-    const int cLo = sl * cps, cHi = min(10230, cLo + cps);
-    ExactCtx ex;
-    make_exact_ctx(p, g.d, g.fs, ex);
-    const int8_t* xblk = g.x + B0;
-    if (sl == 0 && t == 0 && p.rem == 0.0) {  // the t = 0 sample takes the previous period's last chip
-        float tmp[kNSum];
+// ---- one chip (one thread) ---------------------------------------------------------------------
+// Integrates chip c of the epoch described by (tab, p) into acc[18].  tile/tileBase: staged IF
+// bytes (window byte offset of tile[0]); xblk = g.x + B0 for the exact path.  Returns true if the
+// chip went through the exact per-sample path.
+__device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams& p, const uint32_t* bitsData,
+                                          const uint32_t* bitsPilot, const unsigned char* tile, long long tileBase,
+                                          long long B0, const int8_t* xblk, double dSpacing, double fs, int c,
+                                          unsigned guard, float* acc) {
+    // ---- per-chip phase bookkeeping (fp64) ----
+    const double q = ((double)(12 * c) - tab.u0) * tab.S;  // sample position of the chip start
+    const int nc = (int)floor(q) + 1;                        // first sample of the chip
+    const double psi = (double)nc - q;                       // in (0,1] samples
+    const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
+    int j = tab.binStart[Psi >> 25];
 #pragma unroll
-        for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
-        fast_exact_range(ex, xblk, bitsData, bitsPilot, 0, 0, -100, 0, tmp);
-#pragma unroll
-        for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
-    }
-
-    for (int c0 = cLo; c0 < cHi; c0 += blockDim.x) {
-        const int cEnd = min(c0 + (int)blockDim.x, cHi);
-        // ---- stage the pass's samples: [n(c0)-2, n(cEnd)+2) ----
-        if (t == 0) {
-            double qa = ((double)(12 * c0) - tab.u0) * tab.S, qb = ((double)(12 * cEnd) - tab.u0) * tab.S;
-            long long na = (long long)floor(qa) - 2, nb = (long long)floor(qb) + 4;
-            if (na < 0) na = 0;
-            if (nb > p.blksize) nb = p.blksize;
-            long long gA = (B0 + na) & ~15LL;
-            long long gE = (B0 + nb + 15) & ~15LL;
-            unsigned bytes = (unsigned)(gE - gA);
-            if (bytes > (unsigned)kFastTile) bytes = kFastTile;
-            fsm->tileBase = gA;
-            tma_load_1d(fsm->tile, g.x + gA, bytes, &fsm->mbar);
-        }
-        const int c = c0 + t;
-        const bool active = c < cEnd;
-        // ---- per-chip phase bookkeeping (fp64) ----
-        const double q = ((double)(12 * c) - tab.u0) * tab.S;  // sample position of the chip start
-        const double fq = floor(q);
-        const int nc = (int)fq + 1;                              // first sample of the chip
-        const double psi = (double)nc - q;                       // in (0,1] samples
-        const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
-        int j = tab.binStart[Psi >> 25];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) j += (tab.thr[j] < Psi);
-        const uint2 mk = tab.mask[j];
-        // near-miss of any decision (including the chip start/end) -> exact path
-        const unsigned below = j > 0 ? Psi - tab.thr[j - 1] : Psi;
-        const unsigned above = j < 36 ? tab.thr[j] - Psi : 0xffffffffu - Psi;
-        const unsigned guard = g.pad ? (1u << 24) : kFastGuard;  // g.pad: test hook, widens the guard band
-        bool exact = below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
-        const int len = FAST_RLAST + ((mk.y >> 3) & 1);         // bit 35 (k = 36): last sample still mine
-        if (nc < 0 || nc + len > p.blksize) exact = true;
-        __syncthreads();  // tileBase visible
-        mbar_wait(&fsm->mbar, mbarPhase);
-        if (active) {
-            if (!exact) {
-                const long long o = B0 + nc - fsm->tileBase;
-                const unsigned* raw = reinterpret_cast<const unsigned*>(fsm->tile) + (o >> 2);
-                const unsigned sh = (unsigned)(o & 3) * 8u;
-                const int4* wt = tab.w;
-                int Ur, Ui;
-                int SAr = 0, SAi = 0, SBr = 0, SBi = 0, SCr = 0, SCi = 0, H1r = 0, H1i = 0, H2r = 0, H2i = 0;
-                int W1ar = 0, W1ai = 0, W1br = 0, W1bi = 0, W2ar = 0, W2ai = 0, W2br = 0, W2bi = 0;
+    for (int it = 0; it < 4; ++it) j += (tab.thr[j] < Psi);
+    const uint2 mk = tab.mask[j];
+    // near-miss of any decision (including the chip start/end) -> exact path
+    const unsigned below = j > 0 ? Psi - tab.thr[j - 1] : Psi;
+    const unsigned above = j < 36 ? tab.thr[j] - Psi : 0xffffffffu - Psi;
+    bool exact = !tab.valid || below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
+    const int len = FAST_RLAST + ((mk.y >> 3) & 1);          // bit 35 (k = 36): last sample still mine
+    if (nc < 0 || nc + len > p.blksize) exact = true;
+    if (!exact) {
+        const long long o = B0 + nc - tileBase;
+        const unsigned* raw = reinterpret_cast<const unsigned*>(tile) + (o >> 2);
+        const unsigned sh = (unsigned)(o & 3) * 8u;
+        const int4* wt = tab.w;
+        int Ur, Ui;
+        int SAr = 0, SAi = 0, SBr = 0, SBi = 0, SCr = 0, SCi = 0, H1r = 0, H1i = 0, H2r = 0, H2i = 0;
+        int W1ar = 0, W1ai = 0, W1br = 0, W1bi = 0, W2ar = 0, W2ai = 0, W2br = 0, W2bi = 0;
 #define FAST_RAW(i) raw[i]
 #define FAST_FSH(lo, hi) __funnelshift_r(lo, hi, sh)
 #define FAST_WTAB(pi) wt[pi]
 #define FAST_SB(w, b) sext_byte<b>(w)
 #define FAST_SEL(k, s) ((k) <= 32 ? sel_bit<((k)-1) & 31>(s, mk.x) : sel_bit<((k)-33) & 31>(s, mk.y))
-                FAST_CHIP_BODY
+        FAST_CHIP_BODY
 #undef FAST_RAW
 #undef FAST_FSH
 #undef FAST_WTAB
 #undef FAST_SB
 #undef FAST_SEL
-                // ---- chip-level: rotate by exp(-i theta(nc)), combine with chip signs ----
-                const unsigned long long ph = tab.phi0 + (unsigned long long)(long long)nc * tab.dphi;
-                float sn, cs;
-                sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
-                const float rr = cs * (1.0f / 65536.0f), ri = -sn * (1.0f / 65536.0f);
+        // ---- chip-level: rotate by exp(-i theta(nc)), combine with chip signs ----
+        const unsigned long long ph = tab.phi0 + (unsigned long long)(long long)nc * tab.dphi;
+        const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-9f;  // 2*pi / 2^32, |ang| <= pi
+        const float sn = __sinf(ang), cs = __cosf(ang);
+        const float rr = cs * (1.0f / 65536.0f), ri = -sn * (1.0f / 65536.0f);
 #define ROT(N) const float N##x = (float)N##r * rr - (float)N##i * ri, N##y = (float)N##r * ri + (float)N##i * rr;
-                ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
+        ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
 #undef ROT
-                const int cp_ = c == 0 ? 10229 : c - 1, cn_ = c == 10229 ? 0 : c + 1;
-                const float cd = bit_of(bitsData, c) ? -1.f : 1.f, cdp = bit_of(bitsData, cp_) ? -1.f : 1.f,
-                            cdn = bit_of(bitsData, cn_) ? -1.f : 1.f;
-                const float cp = bit_of(bitsPilot, c) ? -1.f : 1.f, cpp = bit_of(bitsPilot, cp_) ? -1.f : 1.f,
-                            cpn = bit_of(bitsPilot, cn_) ? -1.f : 1.f;
-                const float Xx = H2x - H1x, Xy = H2y - H1y;
-                const float XEx = Xx + W1ax - 2.f * W1bx, XEy = Xy + W1ay - 2.f * W1by;
-                const float XLx = Xx + 2.f * W2ax - W2bx, XLy = Xy + 2.f * W2ay - W2by;
-                acc[sum_idx(0, EPL_P, 0)] += cd * Xx;
-                acc[sum_idx(0, EPL_P, 1)] += cd * Xy;
-                acc[sum_idx(0, EPL_E, 0)] += cd * XEx + cdp * W1ax;
-                acc[sum_idx(0, EPL_E, 1)] += cd * XEy + cdp * W1ay;
-                acc[sum_idx(0, EPL_L, 0)] += cd * XLx - cdn * W2bx;
-                acc[sum_idx(0, EPL_L, 1)] += cd * XLy - cdn * W2by;
-                acc[sum_idx(1, EPL_P, 0)] += cp * Xx;
-                acc[sum_idx(1, EPL_P, 1)] += cp * Xy;
-                acc[sum_idx(1, EPL_E, 0)] += cp * XEx + cpp * W1ax;
-                acc[sum_idx(1, EPL_E, 1)] += cp * XEy + cpp * W1ay;
-                acc[sum_idx(1, EPL_L, 0)] += cp * XLx - cpn * W2bx;
-                acc[sum_idx(1, EPL_L, 1)] += cp * XLy - cpn * W2by;
-                const float SPx = SAx + SBx + SCx, SPy = SAy + SBy + SCy;
-                const float SEx = SCx - SAx - SBx, SEy = SCy - SAy - SBy;
-                const float SLx = SAx - SBx - SCx, SLy = SAy - SBy - SCy;
-                acc[sum_idx(2, EPL_P, 0)] += cp * SPx;
-                acc[sum_idx(2, EPL_P, 1)] += cp * SPy;
-                acc[sum_idx(2, EPL_E, 0)] += cp * SEx + (cpp - cp) * W1ax;
-                acc[sum_idx(2, EPL_E, 1)] += cp * SEy + (cpp - cp) * W1ay;
-                acc[sum_idx(2, EPL_L, 0)] += cp * SLx + (cp - cpn) * W2bx;
-                acc[sum_idx(2, EPL_L, 1)] += cp * SLy + (cp - cpn) * W2by;
-            } else {
-                // rare (~1e-5 of chips): keep the fast path's accumulators in registers
-                int k0 = max(0, nc - 2), k1 = min(p.blksize - 1, nc + FAST_RLAST + 2);
-                float tmp[kNSum];
+        const int cp_ = c == 0 ? 10229 : c - 1, cn_ = c == 10229 ? 0 : c + 1;
+        const float cd = bit_of(bitsData, c) ? -1.f : 1.f, cdp = bit_of(bitsData, cp_) ? -1.f : 1.f,
+                    cdn = bit_of(bitsData, cn_) ? -1.f : 1.f;
+        const float cp = bit_of(bitsPilot, c) ? -1.f : 1.f, cpp = bit_of(bitsPilot, cp_) ? -1.f : 1.f,
+                    cpn = bit_of(bitsPilot, cn_) ? -1.f : 1.f;
+        const float Xx = H2x - H1x, Xy = H2y - H1y;
+        const float XEx = Xx + W1ax - 2.f * W1bx, XEy = Xy + W1ay - 2.f * W1by;
+        const float XLx = Xx + 2.f * W2ax - W2bx, XLy = Xy + 2.f * W2ay - W2by;
+        acc[sum_idx(0, EPL_P, 0)] += cd * Xx;
+        acc[sum_idx(0, EPL_P, 1)] += cd * Xy;
+        acc[sum_idx(0, EPL_E, 0)] += cd * XEx + cdp * W1ax;
+        acc[sum_idx(0, EPL_E, 1)] += cd * XEy + cdp * W1ay;
+        acc[sum_idx(0, EPL_L, 0)] += cd * XLx - cdn * W2bx;
+        acc[sum_idx(0, EPL_L, 1)] += cd * XLy - cdn * W2by;
+        acc[sum_idx(1, EPL_P, 0)] += cp * Xx;
+        acc[sum_idx(1, EPL_P, 1)] += cp * Xy;
+        acc[sum_idx(1, EPL_E, 0)] += cp * XEx + cpp * W1ax;
+        acc[sum_idx(1, EPL_E, 1)] += cp * XEy + cpp * W1ay;
+        acc[sum_idx(1, EPL_L, 0)] += cp * XLx - cpn * W2bx;
+        acc[sum_idx(1, EPL_L, 1)] += cp * XLy - cpn * W2by;
+        const float SPx = SAx + SBx + SCx, SPy = SAy + SBy + SCy;
+        const float SEx = SCx - SAx - SBx, SEy = SCy - SAy - SBy;
+        const float SLx = SAx - SBx - SCx, SLy = SAy - SBy - SCy;
+        acc[sum_idx(2, EPL_P, 0)] += cp * SPx;
+        acc[sum_idx(2, EPL_P, 1)] += cp * SPy;
+        acc[sum_idx(2, EPL_E, 0)] += cp * SEx + (cpp - cp) * W1ax;
+        acc[sum_idx(2, EPL_E, 1)] += cp * SEy + (cpp - cp) * W1ay;
+        acc[sum_idx(2, EPL_L, 0)] += cp * SLx + (cp - cpn) * W2bx;
+        acc[sum_idx(2, EPL_L, 1)] += cp * SLy + (cp - cpn) * W2by;
+    } else {
+        // rare (~1e-5 of chips): keep the fast path's accumulators in registers
+        ExactCtx ex;
+        make_exact_ctx(p, dSpacing, fs, ex);
+        const double qe = ((double)(12 * c + 12) - tab.u0) * tab.S;
+        int k0 = max(0, nc - 2), k1 = min(p.blksize - 1, (int)floor(qe) + 3);
+        float tmp[kNSum];
 #pragma unroll
-                for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
-                fast_exact_range(ex, xblk, bitsData, bitsPilot, k0, k1, 12 * c + 1, 12 * c + 12, tmp);
+        for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
+        fast_exact_range(ex, xblk, bitsData, bitsPilot, k0, k1, 12 * c + 1, 12 * c + 12, tmp);
 #pragma unroll
-                for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
-            }
-        }
-        if (g.counters) {  // diagnostics: chips through the fast body / the exact path
-            unsigned bf = __ballot_sync(0xffffffffu, active && !exact), be = __ballot_sync(0xffffffffu, active && exact);
-            if ((t & 31) == 0) {
-                if (bf) atomicAdd(g.counters + 0, (unsigned long long)__popc(bf));
-                if (be) atomicAdd(g.counters + 1, (unsigned long long)__popc(be));
-            }
-        }
-        mbarPhase ^= 1u;
-        __syncthreads();  // everyone done with the tile before the next pass overwrites it
+        for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
     }
+    return exact;
 }
 
 }  // namespace bds

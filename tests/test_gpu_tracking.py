@@ -70,22 +70,39 @@ def test_fast_kernel_rejects_unsupported_config():
         _track.run_tracking("NB", x, ch, util.product_settings(s), n_epochs=2, kernel=L.KERNEL_FAST)
 
 
-def test_closed_loop_fast_matches_general_and_oracle():
+@pytest.mark.parametrize("kernel", ["general", "fast"])
+def test_closed_loop_one_step_parity_wb(kernel):
+    """Every epoch of the device's closed-loop trajectory: sums == oracle correlator at the device's NCO
+    state (1e-4), and the oracle loop closure fed with the device's sums reproduces the device's next
+    state to rounding (util.one_step_parity).  Trajectory-vs-trajectory comparison is only meaningful
+    until the first chip-edge flip, see the module docstring."""
+    s, sats, x, ch = util.record("WB", 2, 0.23)
+    ps = util.product_settings(s)
+    kern = L.KERNEL_GENERAL if kernel == "general" else L.KERNEL_FAST
+    got, _ = _track.run_tracking("WB", x, ch, ps, n_epochs=20, kernel=kern, raw=True)
+    fast_chips, exact_chips, general_slices, _ = _track.run_tracking.last_counters
+    if kernel == "fast":
+        assert general_slices == 0 and fast_chips + exact_chips == 2 * 20 * 10230 and exact_chips <= 64
+    else:
+        assert fast_chips == 0 and general_slices > 0
+    for c in range(2):
+        assert got[c].status == "T"
+        worst = util.one_step_parity("WB", s, x, ch[c], got[c], 20)
+        assert worst <= 1e-4
+
+
+def test_closed_loop_fast_tracks_oracle_trajectory():
     s, sats, x, ch = util.record("WB", 2, 0.13)
     ps = util.product_settings(s)
     tr, raw = util.oracle_track("WB", s, x, ch, 10)
-    gen, _ = _track.run_tracking("WB", x, ch, ps, n_epochs=10, kernel=L.KERNEL_GENERAL, raw=True)
     fast, _ = _track.run_tracking("WB", x, ch, ps, n_epochs=10, kernel=L.KERNEL_FAST, raw=True)
     for c in range(2):
-        sc = util.family_scale(raw[c])
-        for got in (gen[c], fast[c]):
-            err = np.abs(got.raw - raw[c]) / sc
-            assert np.max(err) <= 1e-3 and np.mean(err <= 1e-4) >= 0.99, np.max(err)
         np.testing.assert_array_equal(fast[c].absoluteSample, tr[c].absoluteSample)
-        np.testing.assert_allclose(fast[c].carrFreq, tr[c].carrFreq, rtol=1e-9)
-        assert fast[c].status == "T"
-    fast_chips, exact_chips, general_slices, _ = _track.run_tracking.last_counters
-    assert general_slices == 0 and fast_chips >= 2 * 10 * 10230 - 64
+        np.testing.assert_allclose(fast[c].carrFreq, tr[c].carrFreq, rtol=0, atol=0.01)      # Hz
+        np.testing.assert_allclose(fast[c].remCodePhase, tr[c].remCodePhase, rtol=0, atol=1e-4)  # chips
+        err = np.abs(fast[c].raw - raw[c]) / util.family_scale(raw[c])
+        assert np.max(err[:3]) <= 1e-4          # before any chip-edge flip the trajectories coincide
+        assert np.max(err) <= 2e-2
 
 
 def test_open_loop_first_epoch_t0_sample():

@@ -72,3 +72,44 @@ def family_scale(raw):
         for k in range(6):
             sc[..., fam * 6 + k] = m
     return sc
+
+
+def one_step_parity(mode, s, x, ch_c, g, n_epochs, tol_sums=1e-4):
+    """Closed-loop parity that is insensitive to trajectory chaos (a single sample crossing a chip edge
+    changes the following epochs at the 1e-3 level for ~1/loop-bandwidth seconds).  For every epoch of the
+    device's own trajectory ``g``:
+      (a) the 18 sums equal the oracle correlator evaluated at the device's NCO state (tol_sums * scale);
+      (b) feeding the device's sums to the oracle's loop closure reproduces the device's next state
+          (carrFreq, codeFreq, discriminators, remCodePhase, remCarrPhase) to float64 rounding.
+    Returns the worst relative sum error."""
+    import math
+    codes = O.make_track_codes(mode, s, ch_c.PRN)
+    coef = O.loop_coefficients(mode, s)
+    st = O.LoopState(codeFreq=ch_c.codeFreq, carrFreq=ch_c.acquiredFreq, carrFreqBasis=ch_c.acquiredFreq,
+                     pos=int(s.skipNumberOfBytes + ch_c.codePhase - 1))
+    worst = 0.0
+    for e in range(n_epochs):
+        assert g.absoluteSample[e] == st.pos
+        np.testing.assert_allclose([g.codeFreq[e], g.carrFreq[e]], [st.codeFreq, st.carrFreq], rtol=1e-13)
+        np.testing.assert_allclose([g.remCodePhase[e], g.remCarrPhase[e]], [st.remCodePhase, st.remCarrPhase],
+                                   rtol=0, atol=1e-9)
+        # take the device's state (identical up to rounding) so the comparison stays one-step
+        st.codeFreq, st.carrFreq = float(g.codeFreq[e]), float(g.carrFreq[e])
+        st.remCodePhase, st.remCarrPhase = float(g.remCodePhase[e]), float(g.remCarrPhase[e])
+        step = st.codeFreq / s.samplingFreq
+        blk = int(math.ceil((s.codeLength - st.remCodePhase) / step))
+        out, rc, rp = c_oracle.correlate_epoch(mode, s, x[st.pos: st.pos + blk], codes, st.remCodePhase, step,
+                                               st.carrFreq, st.remCarrPhase)
+        ref = np.array([out.get(k, 0.0) for k in RAW_NAMES])
+        err = np.abs(g.raw[e] - ref) / family_scale(ref[None, :])[0]
+        worst = max(worst, float(np.max(err)))
+        assert np.max(err) <= tol_sums, (e, float(np.max(err)))
+        sums = {k: float(g.raw[e][i]) for i, k in enumerate(RAW_NAMES) if k in out}
+        st.remCodePhase, st.remCarrPhase = rc, rp
+        st.pos += blk
+        o = O.close_loops(mode, s, sums, st, coef, ch_c.codeFreq)
+        for f in ("dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt"):
+            np.testing.assert_allclose(g[f][e], o[f], rtol=1e-9, atol=1e-13)
+        for f in [k for k in o if k.startswith("Pilot_") or k in ("I_P", "Q_P", "I_E", "Q_E", "I_L", "Q_L")]:
+            np.testing.assert_allclose(g[f][e], o[f], rtol=1e-12, atol=1e-6)
+    return worst
