@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libbdsgpu.so")
+_LIB_PATH = os.path.join(_HERE, os.environ.get("BDS_LIB_NAME", "libbdsgpu.so"))  # BDS_LIB_NAME: developer A/B builds
 
 
 class BdsError(RuntimeError):
@@ -66,7 +66,7 @@ ERR_NO_DEVICE = -2
 EXPORTS = ["bds_abi_version", "bds_init", "bds_shutdown", "bds_last_error", "bds_launch_count", "bds_device_ok",
            "bds_gen_code", "bds_make_code_table", "bds_acquire", "bds_track_open", "bds_track_open_file",
            "bds_track_feed", "bds_track_run", "bds_track_run_async", "bds_track_sync", "bds_track_fetch",
-           "bds_track_device_block", "bds_track_stats", "bds_track_counters", "bds_track_reset", "bds_track_close",
+           "bds_track_device_block", "bds_track_stats", "bds_track_counters", "bds_track_dump_trace", "bds_track_reset", "bds_track_close",
            "bds_track_correlate_open_loop", "bds_synth_if", "bds_dev_alloc", "bds_dev_free",
            "bds_host_alloc_pinned", "bds_host_free_pinned", "bds_memcpy_h2d", "bds_memcpy_d2h", "bds_dev_sync"]
 
@@ -106,6 +106,7 @@ def lib():
                                          C.POINTER(C.c_int)]
     L.bds_track_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_float)]
     L.bds_track_counters.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.bds_track_dump_trace.argtypes = [vp, C.c_char_p]
     L.bds_track_reset.argtypes = [vp]
     L.bds_track_close.argtypes = [vp]
     L.bds_track_close.restype = None

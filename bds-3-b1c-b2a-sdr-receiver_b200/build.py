@@ -15,7 +15,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libbdsgpu.so")
+LIB = os.path.join(HERE, os.environ.get("BDS_LIB_NAME", "libbdsgpu.so"))
+OBJ = OBJ + os.environ.get("BDS_OBJ_SUFFIX", "")
 SOURCES = ["bds_api.cu", "bds_codes.cpp", "bds_track.cu", "bds_acq.cu", "bds_synth.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -49,7 +50,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, os.path.splitext(s)[0] + ".o")
         objs.append(obj)
         if force or _newer(src, obj):
-            cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-x", "cu", "-c", src, "-o", obj]
+            cmd = [nvcc, *ARCH, *NVCC_FLAGS, *os.environ.get("BDS_EXTRA_FLAGS", "").split(), "-x", "cu", "-c", src, "-o", obj]
             jobs.append((s, cmd))
 
     def run(job):

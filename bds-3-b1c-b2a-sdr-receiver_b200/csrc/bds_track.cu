@@ -250,7 +250,29 @@ __device__ bool next_params(const TrkDev& g, const ChanState& st, EpochParams& n
     return off >= 0 && off + np.blksize <= g.winLen && np.blksize > 0;
 }
 
-__device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 sums*/, EpochParams& npOut, int& npOk) {
+// The five expensive scalar pieces of the WB loop closure, one per lane (lanes 0..4).
+__device__ double close_pre_wb(const TrkDev& g, int c, int e, const double* s, int lane) {
+    const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
+    auto pI = [&](int o) { return -ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)]; };
+    auto pQ = [&](int o) { return -ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)]; };
+    switch (lane) {
+        case 0: return atan(s[sum_idx(0, EPL_P, 1)] / s[sum_idx(0, EPL_P, 0)]);
+        case 1: return atan(pQ(EPL_P) / pI(EPL_P));
+        case 2: return dll_disc(s[sum_idx(0, EPL_E, 0)], s[sum_idx(0, EPL_E, 1)], s[sum_idx(0, EPL_L, 0)], s[sum_idx(0, EPL_L, 1)]);
+        case 3: return dll_disc(pI(EPL_E), pQ(EPL_E), pI(EPL_L), pQ(EPL_L));
+        case 4: {
+            const EpochParams p = load_cg(g.params + c * 2 + (e & 1));
+            double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
+            return fmod(trig, 6.283185307179586476925286766559);
+        }
+        default: return 0.0;
+    }
+}
+
+// pre (optional, WB with pilot only): {atan(Q_P/I_P), atan(pQ_P/pI_P), dll(data), dll(pilot), fmod(trig,2pi)}
+// evaluated in parallel by other lanes of the closing warp (close_pre_wb); same expressions as below.
+__device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 sums*/, EpochParams& npOut, int& npOk,
+                            const double* pre = nullptr) {
     ChanState st = load_cg(g.st + c);
     const EpochParams p = load_cg(g.params + c * 2 + (e & 1));
     double* out = g.out + (size_t)c * kNFields * g.capacity;
@@ -268,15 +290,15 @@ __device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 
     double base = (double)(p.blksize - 1) * p.step + p.rem;
     st.remCodePhase = base + p.step - g.L;
     double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
-    st.remCarrPhase = fmod(trig, twopi);  // rem(trigarg(blksize+1), 2*pi), WB:337
+    st.remCarrPhase = pre ? pre[4] : fmod(trig, twopi);  // rem(trigarg(blksize+1), 2*pi), WB:337
     st.pos = p.pos + p.blksize;
     st.samples += p.blksize;
 
     double I_E = s[sum_idx(0, EPL_E, 0)], Q_E = s[sum_idx(0, EPL_E, 1)];
     double I_P = s[sum_idx(0, EPL_P, 0)], Q_P = s[sum_idx(0, EPL_P, 1)];
     double I_L = s[sum_idx(0, EPL_L, 0)], Q_L = s[sum_idx(0, EPL_L, 1)];
-    double carrError = atan(Q_P / I_P) / twopi;
-    double codeError = dll_disc(I_E, Q_E, I_L, Q_L);
+    double carrError = (pre ? pre[0] : atan(Q_P / I_P)) / twopi;
+    double codeError = pre ? pre[2] : dll_disc(I_E, Q_E, I_L, Q_L);
     if (b1c) codeError = codeError * (1.0 - g.d);
     if (g.mode == BDS_TRK_B1C_WB && g.hasPilot) {
         const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
@@ -286,9 +308,9 @@ __device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 
             pI[o] = -ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)];
             pQ[o] = -ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)];
         }
-        double pe = atan(pQ[EPL_P] / pI[EPL_P]) / twopi;
+        double pe = (pre ? pre[1] : atan(pQ[EPL_P] / pI[EPL_P])) / twopi;
         carrError = (carrError * 1 + pe * 3) / 4;
-        double pc = dll_disc(pI[EPL_E], pQ[EPL_E], pI[EPL_L], pQ[EPL_L]) * (1.0 - g.d);
+        double pc = (pre ? pre[3] : dll_disc(pI[EPL_E], pQ[EPL_E], pI[EPL_L], pQ[EPL_L])) * (1.0 - g.d);
         codeError = codeError * g.factor + pc * (1.0 - g.factor);
         out[F_PI_P * cap + e] = pI[EPL_P];
         out[F_PI_E * cap + e] = pI[EPL_E];
@@ -599,9 +621,14 @@ struct bds_trk {
     double* dOut = nullptr;
     double* dCno = nullptr;
     int capacity = 0, cnoCap = 0;
-    int S = 0, nAct = 0, gridBlocks = 0;
+    int S = 0, nAct = 0, gridBlocks = 0, nCompute = 0;
     int* dAct = nullptr;
     unsigned long long* dCounters = nullptr;
+    unsigned long long* dQueue = nullptr;
+    unsigned* dQctl = nullptr;
+    unsigned qSize = 0;
+    unsigned long long* dTrace = nullptr;
+    unsigned traceCap = 0;
     FastTab* dFastTab = nullptr;
     bool fast = false;
     size_t smemBytes = 0;
@@ -655,6 +682,19 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.act = h->dAct;
     g.fastTab = h->dFastTab;
     g.counters = h->dCounters;
+    g.queue = h->dQueue;
+    g.qctl = h->dQctl;
+    g.qMask = h->qSize ? h->qSize - 1 : 0;
+    g.pubTime = getenv("BDS_TRK_TIMING") ? (unsigned long long*)(h->dCounters + 32) : nullptr;
+    g.trace = h->dTrace;
+    g.traceCap = h->traceCap;
+    g.nCompute = h->nCompute;
+    g.stages = 3;
+    g.tune = 0;
+    g.ahead = 1;
+    if (const char* e = getenv("BDS_TRK_AHEAD")) g.ahead = atoi(e);
+    if (const char* e = getenv("BDS_TRK_STAGES")) g.stages = std::max(2, std::min(kFwStages, atoi(e)));
+    if (const char* e = getenv("BDS_TRK_TUNE")) g.tune = atoi(e);
     g.maxEpochs = maxEpochs;
     g.capacity = h->capacity;
     g.cnoCap = h->cnoCap;
@@ -694,7 +734,9 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
     return BDS_OK;
 }
 
-size_t smem_bytes(bool fast) { return fast ? sizeof(FwSmem) : sizeof(TrkSmem); }
+size_t smem_bytes(bool fast) {
+    return fast ? std::max(sizeof(FwSmem), sizeof(FwCloseScratch) * (kFwThreads / 32)) : sizeof(TrkSmem);
+}
 
 int init_state(bds_trk* h) {
     std::vector<ChanConst> cc(h->nCh);
@@ -785,6 +827,9 @@ int plan_grid(bds_trk* h) {
         BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_fw_kernel, kFwThreads, h->smemBytes));
         if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
         h->gridBlocks = g_num_sms;
+        // a few CTAs only close loops: one warp per channel (16 warps per CTA)
+        int nCloser = (h->nAct + (kFwThreads / 32) - 1) / (kFwThreads / 32);
+        h->nCompute = std::max(1, h->gridBlocks - nCloser);
         // slices of 448*k chips (one chip per compute thread and pass); >= ~2.5 work items per CTA and round
         int k = 4;
         while (k > 1 && (long long)h->nAct * ((10230 + kFwChips * k - 1) / (kFwChips * k)) * 2 < 5LL * h->gridBlocks) --k;
@@ -845,8 +890,8 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
     TRY(cudaMalloc(&h->dCount, sizeof(int) * n_ch));
     TRY(cudaMalloc(&h->dPartial, sizeof(double) * (size_t)n_ch * h->S * kNSum));
     TRY(cudaMalloc(&h->dAct, sizeof(int) * n_ch));
-    TRY(cudaMalloc(&h->dCounters, 32));
-    TRY(cudaMemset(h->dCounters, 0, 32));
+    TRY(cudaMalloc(&h->dCounters, 256 + 8 * 128));
+    TRY(cudaMemset(h->dCounters, 0, 256 + 8 * 128));
     {
         std::vector<int> act;
         for (int c = 0; c < n_ch; ++c)
@@ -854,7 +899,19 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
         act.resize(n_ch, 0);
         TRY(cudaMemcpy(h->dAct, act.data(), sizeof(int) * n_ch, cudaMemcpyHostToDevice));
     }
-    if (h->fast) TRY(cudaMalloc(&h->dFastTab, sizeof(FastTab) * (size_t)n_ch * 2));
+    if (h->fast) {
+        TRY(cudaMalloc(&h->dFastTab, sizeof(FastTab) * (size_t)n_ch * 2));
+        unsigned need = (unsigned)(2 * n_ch * h->S + h->gridBlocks + 64);
+        h->qSize = 1024;
+        while (h->qSize < need) h->qSize <<= 1;
+        TRY(cudaMalloc(&h->dQueue, sizeof(unsigned long long) * h->qSize));
+        TRY(cudaMalloc(&h->dQctl, 64));
+        if (const char* e = getenv("BDS_TRK_TRACE")) {
+            h->traceCap = (unsigned)atoi(e);
+            TRY(cudaMalloc(&h->dTrace, sizeof(unsigned long long) * 8 * h->traceCap));
+            TRY(cudaMemset(h->dTrace, 0, sizeof(unsigned long long) * 8 * h->traceCap));
+        }
+    }
 #undef TRY
     rc = init_state(h);
     if (rc) return fail(rc);
@@ -950,8 +1007,10 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
     if (rc) return rc;
     TrkDev g;
     fill_dev(h, g, n_epochs);
-    if (h->fast) fw_prepare_kernel<<<(h->nCh + 3) / 4, 128, 0, h->stream>>>(g);
-    else trk_prepare_kernel<<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
+    if (h->fast) {
+        BDS_CUDA(cudaMemsetAsync(h->dQueue, 0, sizeof(unsigned long long) * h->qSize, h->stream));
+        fw_prepare_kernel<<<1, 1024, 0, h->stream>>>(g, h->nCompute);
+    } else trk_prepare_kernel<<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
     count_launch();
     BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
     void* args[] = {&g};
@@ -1060,9 +1119,30 @@ int bds_track_counters(bds_trk* h, long long* out4) {
         return BDS_OK;
     }
     BDS_CUDA(cudaStreamSynchronize(h->stream));
-    unsigned long long v[4];
-    BDS_CUDA(cudaMemcpy(v, h->dCounters, 32, cudaMemcpyDeviceToHost));
+    unsigned long long v[24];
+    BDS_CUDA(cudaMemcpy(v, h->dCounters, 192, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 4; ++i) out4[i] = (long long)v[i];
+    if (getenv("BDS_TRK_TIMING"))  // developer breakdown (SM cycles summed over CTAs)
+        fprintf(stderr, "[bds timing] producer: queue %llu empty %llu total %llu | compute(w2): full-wait %llu res-wait %llu | closer: closure %llu epilogue %llu closures %llu\n",
+                v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+    if (getenv("BDS_TRK_TIMING") && v[11])
+        fprintf(stderr, "[bds timing] per closure: publish->slices done %.2f us, closure %.2f us\n",
+                (double)v[12] / (double)v[11] * 1e-3, (double)v[13] / (double)v[11] * 1e-3);
+    if (getenv("BDS_TRK_TIMING") && v[11])
+        fprintf(stderr, "[bds timing] closure cycles: reduce %.0f, close_epoch %.0f, build_tab %.0f, fence+publish %.0f\n",
+                (double)v[14] / v[11], (double)v[15] / v[11], (double)v[16] / v[11], (double)v[17] / v[11]);
+    return BDS_OK;
+}
+
+int bds_track_dump_trace(bds_trk* h, const char* path) {
+    if (!h || !h->dTrace || !path) return set_error(BDS_ERR_ARG, "no trace");
+    BDS_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<unsigned long long> t((size_t)h->traceCap * 8);
+    BDS_CUDA(cudaMemcpy(t.data(), h->dTrace, t.size() * 8, cudaMemcpyDeviceToHost));
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_error(BDS_ERR_IO, "cannot write %s", path);
+    fwrite(t.data(), 8, t.size(), f);
+    fclose(f);
     return BDS_OK;
 }
 
@@ -1095,6 +1175,9 @@ void bds_track_close(bds_trk* h) {
     cudaFree(h->dCno);
     cudaFree(h->dAct);
     cudaFree(h->dCounters);
+    cudaFree(h->dQueue);
+    cudaFree(h->dQctl);
+    cudaFree(h->dTrace);
     cudaFree(h->dFastTab);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1180,8 +1263,8 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     g.codeBits = dBits;
     g.S = S;
     g.pad = cfg->reserved & 1;
-    TRYC(cudaMalloc(&dCnt, 32));
-    TRYC(cudaMemset(dCnt, 0, 32));
+    TRYC(cudaMalloc(&dCnt, 128));
+    TRYC(cudaMemset(dCnt, 0, 128));
     g.counters = dCnt;
     size_t smem = smem_bytes(fast);
     if (fast) {
@@ -1194,6 +1277,10 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         g.olParams = dP;
         g.olEpochs = n_epochs;
         g.olCount = nce;
+        g.nCompute = g_num_sms;
+        g.stages = 3;
+        g.tune = 0;
+        g.ahead = -1;
         trk_fw_kernel<<<g_num_sms, kFwThreads, smem>>>(g);
     } else {
         trk_open_loop_kernel<<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);

@@ -77,6 +77,15 @@ struct TrkDev {
     unsigned long long* counters;  // [4] diagnostics: fast chips, exact-path chips, general-kernel slices
     const EpochParams* olParams;   // open loop (teacher forced): params per channel-epoch, else null
     int olEpochs, olCount;         // open loop: epochs per channel, number of channel-epochs
+    unsigned long long* queue;     // ready-task ring of the warp-specialised kernel ((ticket+1)<<32 | payload)
+    unsigned* qctl;                // [0] head, [1] tail, [2] channels still running in this launch
+    unsigned qMask;                // ring size - 1
+    unsigned long long* pubTime;   // [nCh] developer timing: globaltimer of the last publication
+    unsigned long long* trace;     // developer tracing: [traceCap][8] timestamps per queue ticket
+    unsigned traceCap;
+    int nCompute;                  // CTAs [0,nCompute) correlate, the rest close loops
+    int ahead;                     // pop a new work item only when <= ahead passes are still pending (-1: no limit)
+    int stages, tune;              // pipeline stages in use; tuning bits (1: pop only with a free stage, 2: parallel closure)
 };
 
 }  // namespace bds

@@ -28,7 +28,7 @@ constexpr int kFastBins = 128;
 constexpr unsigned kFastGuard = 16u;  // fixed-point guard band (2^-32 units of one sample)
 
 struct __align__(16) FastTab {
-    int4 w[(FAST_NSAMP + 2) / 2];       // {wr_r, wi_r, wr_{r+1}, wi_{r+1}}, Q16, exp(-i 2 pi r dphi)
+    int4 w[FAST_NWORDS + 1];            // per 4-sample word: {wr01, wr23, wi01, wi23}, int16 pairs, Q15 exp(-i 2 pi r dphi)
     unsigned thr[40];                   // sorted thresholds (2^32 fixed point), thr[36..] = 0xffffffff
     uint2 mask[40];                     // decision masks by rank
     unsigned char binStart[kFastBins + 16];
@@ -53,13 +53,13 @@ __device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double 
     double r = np.carrFreq / fs;
     r -= floor(r);
     const unsigned long long dphi = __double2ull_rn(r * 18446744073709551616.0);
-    int* w = reinterpret_cast<int*>(tab->w);
-    for (int t = lane; t < FAST_NSAMP + 1; t += 32) {
+    short* w = reinterpret_cast<short*>(tab->w);   // word i: [wr(4i..4i+3) | wi(4i..4i+3)] as int16
+    for (int t = lane; t < 4 * (FAST_NWORDS + 1); t += 32) {
         unsigned long long ph = (unsigned long long)t * dphi;
-        double sn, cs;
-        sincospi((double)(long long)ph * (1.0 / 9223372036854775808.0), &sn, &cs);
-        w[2 * t + 0] = __double2int_rn(cs * 65536.0);
-        w[2 * t + 1] = __double2int_rn(-sn * 65536.0);
+        float sn, cs;  // fp32 sincospi: 1e-7 accuracy, far below the Q15 quantisation step
+        sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+        w[(t >> 2) * 8 + (t & 3)] = (short)__float2int_rn(cs * 32767.0f);
+        w[(t >> 2) * 8 + 4 + (t & 3)] = (short)__float2int_rn(-sn * 32767.0f);
     }
     unsigned* thr = scratch;        // [36] unsorted thresholds
     unsigned* pos = scratch + 40;   // [36] sorted position of threshold k-1
@@ -221,6 +221,15 @@ __device__ __forceinline__ int sext_byte(unsigned w) {
     asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "n"(B | ((B | 8) << 4) | ((B | 8) << 8) | ((B | 8) << 12)));
     return r;
 }
+// v (a constant) if bit BIT of m is set, else 0
+template <int BIT>
+__device__ __forceinline__ unsigned sel_bit_u(unsigned v, unsigned m) {
+    unsigned r;
+    asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %2, %3;\n setp.ne.u32 p, t, 0;\n selp.u32 %0, %1, 0, p;\n}"
+        : "=r"(r)
+        : "r"(v), "r"(m), "n"(1u << BIT));
+    return r;
+}
 // s if bit BIT of m is set, else 0 (LOP3 with predicate result + SEL)
 template <int BIT>
 __device__ __forceinline__ int sel_bit(int s, unsigned m) {
@@ -259,25 +268,26 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
         const unsigned* raw = reinterpret_cast<const unsigned*>(tile) + (o >> 2);
         const unsigned sh = (unsigned)(o & 3) * 8u;
         const int4* wt = tab.w;
-        int Ur, Ui;
-        int SAr = 0, SAi = 0, SBr = 0, SBi = 0, SCr = 0, SCi = 0, H1r = 0, H1i = 0, H2r = 0, H2i = 0;
-        int W1ar = 0, W1ai = 0, W1br = 0, W1bi = 0, W2ar = 0, W2ai = 0, W2br = 0, W2bi = 0;
+        FAST_DECL_ACCS
 #define FAST_RAW(i) raw[i]
 #define FAST_FSH(lo, hi) __funnelshift_r(lo, hi, sh)
-#define FAST_WTAB(pi) wt[pi]
-#define FAST_SB(w, b) sext_byte<b>(w)
-#define FAST_SEL(k, s) ((k) <= 32 ? sel_bit<((k)-1) & 31>(s, mk.x) : sel_bit<((k)-33) & 31>(s, mk.y))
+#define FAST_WTAB(i) wt[i]
+#define FAST_DP_LO(a, b, c) __dp2a_lo((int)(a), (int)(b), (c))
+#define FAST_DP_HI(a, b, c) __dp2a_hi((int)(a), (int)(b), (c))
+#define FAST_SELU(k, v) ((k) <= 32 ? sel_bit_u<((k)-1) & 31>(v, mk.x) : sel_bit_u<((k)-33) & 31>(v, mk.y))
         FAST_CHIP_BODY
+        FAST_COMBINE
 #undef FAST_RAW
 #undef FAST_FSH
 #undef FAST_WTAB
-#undef FAST_SB
-#undef FAST_SEL
+#undef FAST_DP_LO
+#undef FAST_DP_HI
+#undef FAST_SELU
         // ---- chip-level: rotate by exp(-i theta(nc)), combine with chip signs ----
         const unsigned long long ph = tab.phi0 + (unsigned long long)(long long)nc * tab.dphi;
         const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-9f;  // 2*pi / 2^32, |ang| <= pi
         const float sn = __sinf(ang), cs = __cosf(ang);
-        const float rr = cs * (1.0f / 65536.0f), ri = -sn * (1.0f / 65536.0f);
+        const float rr = cs * (1.0f / 32767.0f), ri = -sn * (1.0f / 32767.0f);
 #define ROT(N) const float N##x = (float)N##r * rr - (float)N##i * ri, N##y = (float)N##r * ri + (float)N##i * rr;
         ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
 #undef ROT

@@ -258,6 +258,10 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - t0
     launches = B.launch_count() - launches0
+    if os.environ.get('BDS_TRK_TIMING'):
+        sess.counters()
+    if os.environ.get('BDS_TRK_TRACE'):
+        L.check(L.lib().bds_track_dump_trace(sess.h, os.path.join(ROOT, 'gpurun_out', 'trace.bin').encode()))
     clocks = sampler.stop() if rank == 0 else None
     # device time: max over ranks of the CUDA-event time of the persistent kernel, per step
     dev_ms = sum(kernel_ms) / len(kernel_ms)

@@ -193,6 +193,8 @@ int bds_track_stats(bds_trk* h, long long* channel_samples, int* epochs_run, flo
  * per-sample path, slices run by the general kernel, 0}.  h == NULL: counters of the last
  * bds_track_correlate_open_loop call. */
 int bds_track_counters(bds_trk* h, long long* out4);
+/* developer tracing (env BDS_TRK_TRACE=<n tickets>): dump per-work-item timestamps */
+int bds_track_dump_trace(bds_trk* h, const char* path);
 /* reset loop state to the initial channel state (re-run the same record) */
 int bds_track_reset(bds_trk* h);
 void bds_track_close(bds_trk* h);
