@@ -54,6 +54,18 @@ def settings_b1c(n_ch, seconds):
                               msToProcess=int(round(seconds * 1000)))
 
 
+def measured_traffic(kernel, channels, seconds, world):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    exact configuration (profiles/traffic.json), else None."""
+    try:
+        for e in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))):
+            if (e["kernel"], e["channels"], e["seconds"], e["n_gpus"]) == (kernel, channels, seconds, world):
+                return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -169,7 +181,7 @@ def run_b200(args):
     import numpy as np
     import torch
     import bds3_b200 as B
-    from bds3_b200 import _lib as L, _track, synth
+    from bds3_b200 import _lib as L, _shard, _track, synth
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -195,7 +207,7 @@ def run_b200(args):
     synth.synth_device("B1C", st, sats, n_samples, out_ptr=x_dev.data_ptr())
     torch.cuda.synchronize()
     # ---- channel shard of this rank (round robin)
-    mine = [c for i, c in enumerate(chans) if i % world == rank]
+    mine = _shard.shard_list(chans, rank, world)
     st_local = st.copy()
     st_local.numberOfChannels = len(mine)
     sess = _track.TrackSession("WB", st_local, mine, kernel=kern, device_ptr=x_dev.data_ptr(), n_samples=n_samples)
@@ -216,24 +228,14 @@ def run_b200(args):
         if dist is None:
             return None
         p, nbytes, nf, cap = sess.device_block()
-        n = nbytes // 8
-        t = _as_tensor(p, n)   # the library's device block, wrapped without a copy
-        pad = max_block_elems - n
-        if pad:
-            t = torch.cat([t, torch.zeros(pad, dtype=torch.float64, device="cuda")])
-        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, out, dst=0)
-        return out
+        t = _as_tensor(p, nbytes // 8)   # the library's device block, wrapped without a copy
+        return _shard.gather_blocks(t, max_block_elems, dist, dst=0)
 
     # size of the largest rank block (ranks differ by at most one channel)
     sess.run_async(n_epochs)
     sess.sync()
     _, nbytes0, _, _ = sess.device_block()
-    max_block_elems = nbytes0 // 8
-    if dist is not None:
-        t = torch.tensor([max_block_elems], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        max_block_elems = int(t.item())
+    max_block_elems = _shard.max_block_elems(nbytes0 // 8, dist)
 
     def step():
         sess.reset()
@@ -307,9 +309,10 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        # algorithmic bytes: 1 byte per channel-sample; dominant kernel = trk_persistent_kernel
+        # algorithmic bytes: 1 byte per channel-sample; dominant kernel = trk_fw_kernel
         per_launch_bytes = total_ch_samples / world  # per-GPU launch
         achieved = per_launch_bytes / (dev_ms_max * 1e-3) / 1e9
+        kname = "trk_fw_kernel" if args.kernel != "general" else "trk_persistent_kernel"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32 accumulate / f64 loop closure (int8 IF)", "data": "synthetic",
@@ -319,8 +322,10 @@ def run_b200(args):
                            "l2": f"input {n_samples / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
                            "kernel": args.kernel, "x_realtime": value / (FS / 1e6)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": None,
-                             "peak_source": peak_src, "kernel": "trk_persistent_kernel",
+                             "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
+                             "traffic": measured_traffic(kname, args.channels, args.seconds, world),
+                             "peak_source": peak_src,
+                             "kernel": kname,
                              "kernel_ms_per_launch": dev_ms_max,
                              "algorithmic_bytes_per_launch": per_launch_bytes},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}

@@ -1,0 +1,20 @@
+function acqResults = acquisition(longSignal, settings)
+%ACQUISITION  Drop-in for BDS-3_B1C/acquisition.m, GPU_acquisition.m and BDS-3_B2a/acquisition.m
+%   acqResults = acquisition(longSignal, settings)
+% Put this directory ahead of the reference's on the MATLAB path.  The search itself runs in
+% libbdsgpu (bds_acquire); the struct layout is the reference's (acquisition.m:161-165):
+% carrFreq, codePhase, peakMetric, each 1 x max(acqSatelliteList), zero = not found.
+isB2a = settings.codeFreqBasis > 5e6;            % B2a: 10.23 Mcps, B1C: 1.023 Mcps
+if settings.resamplingflag == 1 && settings.samplingFreq > settings.resamplingThreshold
+    error('bds:unsupported', 'resampling pre-conditioner is not part of the GPU path; set resamplingflag = 0');
+end
+cfg = [settings.samplingFreq, settings.IF, settings.codeFreqBasis, settings.codeLength, ...
+       settings.acqSearchBand, settings.acqStep, settings.acqThreshold, 0, 0, 0];
+if isB2a
+    cfg(10) = settings.fineNoncoh;  signal = 2;
+else
+    cfg(8) = settings.acqCohT;  cfg(9) = settings.pilotACQflag;  signal = 1;
+end
+[acqResults.carrFreq, acqResults.codePhase, acqResults.peakMetric] = ...
+    bds_mex('acquire', signal, int8(longSignal), cfg, double(settings.acqSatelliteList));
+end

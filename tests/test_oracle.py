@@ -1,0 +1,315 @@
+"""CPU tests (no GPU): the oracle against structural known answers, its independent C restatement,
+the committed golden fixtures, and the library's host-side integer code (bds_gen_code /
+bds_make_code_table run on the host and must equal the oracle bit for bit).
+
+The reference ships no golden vectors: these checks are what pins the oracle.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings as hsettings, strategies as hst
+
+import bds_oracle as O
+import c_oracle
+import util
+import bds3_b200 as B
+from bds3_b200 import _lib as L, codes, loopcoef, synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden.npz")
+
+
+# ---- a7: B1C codes ---------------------------------------------------------------------------------
+def test_legendre_sequence_by_euler_criterion():
+    leg = O.legendre_sequence()
+    assert leg[0] == 0 and leg.size == 10243
+    want = np.array([0] + [1 if pow(k, (10243 - 1) // 2, 10243) == 1 else 0 for k in range(1, 10243)])
+    np.testing.assert_array_equal(leg, want)
+    assert leg.sum() == (10243 - 1) // 2
+
+
+@pytest.mark.parametrize("prn", [1, 19, 20, 63])
+def test_weil_code_structure(prn):
+    d, p = O.b1c_data_primary(prn), O.b1c_pilot_primary(prn)
+    for c in (d, p):
+        assert c.size == 10230 and set(np.unique(c)) == {-1.0, 1.0}
+        assert abs(c.sum()) < 300            # Weil codes are nearly balanced
+    # definition, written independently: chip n = L(k) xor L(k+w), k = (n+p-1) mod N  (generateDataBOC11.m:76-79)
+    leg = O.legendre_sequence()
+    w, pp = O.B1C_DATA_W[prn - 1], O.B1C_DATA_P[prn - 1]
+    for n in (0, 1, 5000, 10229):
+        k = (n + pp - 1) % 10243
+        assert d[n] == 1 - 2 * (leg[k] ^ leg[(k + w) % 10243])
+    assert abs(np.dot(d, p)) < 500           # data / pilot are different codes
+    # periodic autocorrelation: peak = length, sidelobes small
+    f = np.fft.fft(d)
+    ac = np.fft.ifft(f * np.conj(f)).real
+    assert round(ac[0]) == 10230 and np.max(np.abs(ac[1:])) < 500
+
+
+def test_boc_expansion_pattern():
+    prim = O.b1c_pilot_primary(7)
+    b11 = O.generatePilotBOC11(None, 7)
+    b61 = O.generatePilotBOC61(None, 7)
+    assert b11.size == 20460 and b61.size == 122760
+    np.testing.assert_array_equal(b11[0::2], -prim)          # chip c -> [-c, +c]
+    np.testing.assert_array_equal(b11[1::2], prim)
+    sub = b61.reshape(10230, 12)
+    for ii in range(12):                                      # chip c -> (-1)^ii c, ii = 1..12
+        np.testing.assert_array_equal(sub[:, ii], prim * (-1.0) ** (ii + 1))
+
+
+# ---- a8: B2a codes ---------------------------------------------------------------------------------
+def _b2a_lfsr_bits(g2_init, taps1, taps2):
+    """Independent logic-level (0/1, xor) implementation of the two 13-stage registers."""
+    r1 = [1] * 13
+    r2 = [(g2_init >> k) & 1 for k in range(13)]
+    out = []
+    for ind in range(1, 10231):
+        out.append(r1[12] ^ r2[12])
+        f1 = 0
+        for t in taps1:
+            f1 ^= r1[t - 1]
+        f2 = 0
+        for t in taps2:
+            f2 ^= r2[t - 1]
+        r1 = [f1] + r1[:12]
+        r2 = [f2] + r2[:12]
+        if ind == 8190:
+            r1 = [1] * 13
+    return np.array(out)
+
+
+@pytest.mark.parametrize("prn", [1, 30, 61, 63])
+def test_b2a_codes_against_logic_level_lfsr(prn):
+    d = O.generateB2aDataCode(prn)
+    p = O.generateB2aPilotCode(prn)
+    np.testing.assert_array_equal(d, 1 - 2 * _b2a_lfsr_bits(O.B2A_DATA_G2[prn - 1], (1, 5, 11, 13), (3, 5, 9, 11, 12, 13)))
+    np.testing.assert_array_equal(p, 1 - 2 * _b2a_lfsr_bits(O.B2A_PILOT_G2[prn - 1], (3, 6, 7, 13), (1, 5, 7, 8, 12, 13)))
+    # register 1 has period 8191 and is reset after chip 8190: chips 8190.. replay register 1 from its start
+    assert d.size == 10230 and abs(d.sum()) < 400 and abs(np.dot(d, p)) < 600
+
+
+def test_b2a_reg2_tables_rows_61_63_differ():
+    assert O.B2A_DATA_G2[:60] == O.B2A_PILOT_G2[:60]
+    assert all(a != b for a, b in zip(O.B2A_DATA_G2[60:], O.B2A_PILOT_G2[60:]))
+
+
+# ---- library host code == oracle, bit exact (all 63 PRNs) --------------------------------------------
+def test_library_codegen_bit_exact_all_prns():
+    for prn in range(1, 64):
+        np.testing.assert_array_equal(codes.gen_code(L.CODE_B1C_DATA_PRIMARY, prn), O.b1c_data_primary(prn))
+        np.testing.assert_array_equal(codes.gen_code(L.CODE_B1C_PILOT_PRIMARY, prn), O.b1c_pilot_primary(prn))
+        np.testing.assert_array_equal(codes.gen_code(L.CODE_B2A_DATA, prn), O.generateB2aDataCode(prn))
+        np.testing.assert_array_equal(codes.gen_code(L.CODE_B2A_PILOT, prn), O.generateB2aPilotCode(prn))
+    for prn in (1, 33, 63):
+        np.testing.assert_array_equal(codes.generateDataBOC11(None, prn), O.generateDataBOC11(None, prn))
+        np.testing.assert_array_equal(codes.generatePilotBOC11(None, prn), O.generatePilotBOC11(None, prn))
+        np.testing.assert_array_equal(codes.generatePilotBOC61(None, prn), O.generatePilotBOC61(None, prn))
+
+
+def test_library_codegen_rejects_bad_arguments():
+    out = np.empty(10230, dtype=np.int8)
+    assert L.lib().bds_gen_code(L.CODE_B2A_DATA, 64, L.ptr(out), out.size) == -1
+    assert L.lib().bds_gen_code(L.CODE_B2A_DATA, 1, L.ptr(out), 100) == -1
+    assert b"" != L.lib().bds_last_error()
+
+
+@pytest.mark.parametrize("fs", [99.375e6, 53e6])
+def test_library_code_tables_bit_exact(fs):
+    s1 = O.initSettings_B1C(samplingFreq=fs)
+    p1 = B.Settings(dict(s1))
+    for prn in (1, 20):
+        t = O.makeDataTable(s1, prn)
+        assert t.size == O.samples_per_code(s1)
+        np.testing.assert_array_equal(codes.makeDataTable(p1, prn), t)
+        np.testing.assert_array_equal(codes.makePilotTable(p1, prn), O.makePilotTable(s1, prn))
+    s2 = O.initSettings_B2a(samplingFreq=fs)
+    p2 = B.Settings(dict(s2))
+    for prn in (4, 62):
+        np.testing.assert_array_equal(codes.makeB2aDataTable(prn, p2), O.makeB2aDataTable(prn, s2))
+        np.testing.assert_array_equal(codes.makeB2aPilotTable(prn, p2), O.makeB2aPilotTable(prn, s2))
+
+
+def test_code_table_quirks():
+    """makeDataTable.m:49-63: index = ceil(ts*k/tc), first forced to 1, last forced to 20460."""
+    s = O.initSettings_B1C(samplingFreq=99.375e6)
+    t = O.makeDataTable(s, 1)
+    c = O.generateDataBOC11(s, 1)
+    assert t.size == 993750 and t[0] == c[0] and t[-1] == c[-1]
+    # exact-integer boundary every 6625 samples (fc/fs = 682/6625): sample k=6625 -> ceil(1364.0) = 1364
+    assert t[6624] == c[1363]
+
+
+# ---- a13: loop constants -----------------------------------------------------------------------------
+def test_loop_constants_match_survey_values():
+    s = O.initSettings_B1C(samplingFreq=99.375e6)
+    tau1, tau2 = O.calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)
+    assert abs(tau1 - 0.279388) < 1e-6 and abs(tau2 - 0.74) < 1e-12
+    np.testing.assert_allclose(O.calcLoopCoefCarr(s), (0.298598, 4.1472, 28.8), rtol=2e-6)
+    s2 = O.initSettings_B2a()
+    tau1, tau2 = O.calcLoopCoef(s2.dllNoiseBandwidth, s2.dllDampingRatio, 1.0)
+    assert abs(tau1 - 0.069847) < 1e-6 and abs(tau2 - 0.37) < 1e-12
+    np.testing.assert_allclose(O.calcLoopCoefCarr(s2), (0.013824, 1.152, 48), rtol=1e-9)
+    assert abs(O.CalcWeighingFactor(s) - 0.163502) < 2e-6
+
+
+def test_product_loop_constants_equal_oracle():
+    for s in (O.initSettings_B1C(samplingFreq=99.375e6), O.initSettings_B2a()):
+        p = B.Settings(dict(s))
+        assert loopcoef.calcLoopCoef(p.dllNoiseBandwidth, p.dllDampingRatio, 1.0) == \
+            O.calcLoopCoef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)
+        assert loopcoef.calcLoopCoefCarr(p) == O.calcLoopCoefCarr(s)
+    s = O.initSettings_B1C(samplingFreq=99.375e6)
+    # two different quadratures (scipy quad vs composite Gauss-Legendre) of the same integrals
+    assert abs(loopcoef.CalcWeighingFactor(B.Settings(dict(s))) - O.CalcWeighingFactor(s)) < 1e-9
+
+
+# ---- MATLAB colon ------------------------------------------------------------------------------------
+@given(rem=hst.floats(0.0, 0.999), dcode=hst.floats(-6.0, 6.0))
+@hsettings(max_examples=60, deadline=None)
+def test_blksize_and_remcodephase_invariants(rem, dcode):
+    """0 <= remCodePhase_next < step, and the colon vector has exactly blksize elements whose last
+    element is the stop expression (SURVEY §8c item 4, quirk ii)."""
+    fs, L_ = 99.375e6, 10230
+    step = (1.023e6 + dcode) / fs
+    rem = rem * step
+    blk = int(math.ceil((L_ - rem) / step))
+    stop = ((blk - 1) * step + rem) * 2
+    t = O.colon(rem * 2, step * 2, stop, blk)
+    assert t.size == blk and t[-1] == stop and t[0] == rem * 2
+    nxt = t[-1] / 2 + step - L_
+    assert -1e-9 <= nxt < step + 1e-9
+    assert np.all(np.diff(t) > 0)
+
+
+# ---- a9-a11: C restatement == numpy oracle -----------------------------------------------------------
+@pytest.mark.parametrize("mode,seconds", [("WB", 0.025), ("NB", 0.025), ("B2a", 0.004)])
+def test_c_oracle_equals_numpy_oracle(mode, seconds):
+    s, sats, x, ch = util.record(mode, 2, seconds)
+    c = ch[0]
+    cod = O.make_track_codes(mode, s, c.PRN)
+    pos = int(c.codePhase - 1)
+    for rem, carr_err in ((0.0, 0.0), (0.0123, 3.0)):
+        step = c.codeFreq / s.samplingFreq
+        blk = int(math.ceil((s.codeLength - rem) / step))
+        raw = x[pos: pos + blk]
+        a, ra, pa = O.correlate_epoch(mode, s, raw, cod, rem, step, c.acquiredFreq + carr_err, 0.3)
+        b, rb, pb = c_oracle.correlate_epoch(mode, s, raw, cod, rem, step, c.acquiredFreq + carr_err, 0.3)
+        assert set(a) == set(b) and len(a) == (18 if mode == "WB" else 12)
+        scale = max(abs(v) for v in a.values())
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-9 * scale, (k, a[k], b[k])
+        assert ra == rb and abs(pa - pb) < 1e-9
+
+
+def test_sign_conventions_b1c_vs_b2a():
+    """B1C mixes with exp(-i theta), I = real; B2a with exp(+i theta), I = imag."""
+    s, sats, x, ch = util.record("NB", 1, 0.012, sigma=0.0)
+    c = ch[0]
+    step = c.codeFreq / s.samplingFreq
+    blk = int(math.ceil(s.codeLength / step))
+    pos = int(c.codePhase - 1)
+    out, _, _ = O.correlate_epoch("NB", s, x[pos:pos + blk], O.make_track_codes("NB", s, c.PRN), 0.0, step,
+                                  c.acquiredFreq - 2.0, 0.0)
+    # noise-free, frequency-exact: data power lands in (d_I, d_Q), pilot BOC(1,1) 90 degrees away
+    d = complex(out["d_I_P"], out["d_Q_P"])
+    p = complex(out["p_I_P"], out["p_Q_P"])
+    assert abs(d) > 1e5 and abs(p) > 1e5
+    ang = np.angle(p / d)
+    assert abs(abs(ang) - np.pi / 2) < 0.05
+
+
+# ---- acquisition oracle recovers what was injected ---------------------------------------------------
+def test_b2a_acquisition_oracle_recovers_injected():
+    s = O.initSettings_B2a(acqSatelliteList=[4, 9])
+    sats = synth.make_sats(1, s, "B2a", seed=3, prns=[4], cn0=47.0)
+    x = synth.synth_numpy("B2a", s, sats, 17 * 99375, seed=3)
+    acq, dbg = O.acquisition_B2a(x, s, return_debug=True)
+    assert acq.carrFreq[3] != 0 and acq.carrFreq[8] == 0
+    assert acq.peakMetric[3] > s.acqThreshold > acq.peakMetric[8]
+    assert abs(acq.carrFreq[3] - (s.IF + sats[0].doppler)) <= 25
+    spc = O.samples_per_code(s)
+    d = (acq.codePhase[3] - 1 - sats[0].codeDelay) % spc
+    assert min(d, spc - d) <= 1.5
+
+
+def test_b1c_acquisition_oracle_recovers_injected():
+    s = O.initSettings_B1C(samplingFreq=util.FS, acqSearchBand=100, acqSatelliteList=[1, 2])
+    sats = synth.make_sats(1, s, "B1C", seed=5, max_doppler=40.0, cn0=47.0)
+    x = synth.synth_numpy("B1C", s, sats, int(0.0305 * util.FS), seed=5)
+    acq = O.acquisition_B1C(x, s)
+    assert acq.carrFreq[0] != 0 and acq.carrFreq[1] == 0
+    assert abs(acq.carrFreq[0] - (s.IF + sats[0].doppler)) <= 25
+    spc = O.samples_per_code(s)
+    d = (acq.codePhase[0] - 1 - sats[0].codeDelay) % spc
+    assert min(d, spc - d) <= 1.5
+
+
+# ---- tracking oracle: loops lock on the synthetic signal ---------------------------------------------
+def test_tracking_oracle_locks_and_decodes_symbols():
+    s, sats, x, ch = util.record("WB", 1, 0.42)
+    s = s.copy()
+    s.CNoInterval = 10
+    tr, _ = util.oracle_track("WB", s, x, ch, 40, record_nco=False)
+    r = tr[0]
+    assert r.status == "T"
+    assert np.all(np.abs(r.dllDiscr[10:]) < 0.2)
+    assert np.abs(r.carrFreq[-1] - (s.IF + sats[0].doppler)) < 1.0      # 2 Hz initial error pulled in
+    assert r.PilotPLD[-1] > 0.9 and r.DataPLD[-1] > 0.5
+    assert 40.0 < r.B1C_CNo[-1] < 50.0                                    # injected 45 dB-Hz
+    assert np.all(np.hypot(r.I_P[20:], r.Q_P[20:]) > 1e5)
+
+
+def test_cno_first_point_is_half_scale():
+    """WB_tracking.m:467-481: stored value = 0.5*new + 0.5*previous interval's (0 for the first)."""
+    s, sats, x, ch = util.record("NB", 1, 0.13)
+    s = s.copy()
+    s.CNoInterval = 5
+    tr, _ = util.oracle_track("NB", s, x, ch, 10, record_nco=False)
+    r = tr[0]
+    cno, _ = O.Calc_CNo_PLD(r, s, 5, "NB")
+    assert r.DataCNo[0] == pytest.approx(0.5 * cno[0])
+
+
+# ---- golden regression fixtures (generated by tests/golden/make_golden.py from the oracle) -----------
+def test_golden_fixtures():
+    g = np.load(GOLDEN)
+    import hashlib
+
+    def h(a):
+        return hashlib.sha256(np.ascontiguousarray(a, dtype=np.int8).tobytes()).hexdigest()
+
+    names = list(g["code_names"])
+    digests = list(g["code_sha256"])
+    for name, dig in zip(names, digests):
+        comp, prn = name.split(":")
+        fn = {"b1c_data": O.b1c_data_primary, "b1c_pilot": O.b1c_pilot_primary,
+              "b2a_data": O.generateB2aDataCode, "b2a_pilot": O.generateB2aPilotCode}[comp]
+        assert h(fn(int(prn))) == dig, name
+    # first 24 chips of PRN 1..4 (the quantity the reference's commented-out self-test prints,
+    # generatePilotBOC61.m:98-106)
+    for comp, fn in (("b1c_data", O.b1c_data_primary), ("b2a_data", O.generateB2aDataCode)):
+        for prn in range(1, 5):
+            np.testing.assert_array_equal(g[f"head24_{comp}"][prn - 1], fn(prn)[:24])
+    # one tracking epoch per mode on the committed 12 ms int8 record
+    x = g["if_b1c"]
+    s = O.initSettings_B1C(samplingFreq=util.FS)
+    for mode in ("WB", "NB"):
+        s.pilotTRKflag = 2 if mode == "WB" else 1
+        cod = O.make_track_codes(mode, s, int(g["trk_prn"]))
+        nco = g["trk_nco"]
+        out, rc, rp = O.correlate_epoch(mode, s, x[int(nco[0]): int(nco[0]) + int(nco[1])], cod, nco[2], nco[3],
+                                        nco[4], nco[5])
+        got = np.array([out.get(k, 0.0) for k in util.RAW_NAMES])
+        np.testing.assert_allclose(got, g[f"trk_sums_{mode}"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose([rc, rp], g[f"trk_next_{mode}"], rtol=0, atol=1e-12)
+    xb = g["if_b2a"]
+    s2 = O.initSettings_B2a()
+    cod = O.make_track_codes("B2a", s2, int(g["trk_prn"]))
+    nco = g["trk_nco_b2a"]
+    out, rc, rp = O.correlate_epoch("B2a", s2, xb[int(nco[0]): int(nco[0]) + int(nco[1])], cod, nco[2], nco[3],
+                                    nco[4], nco[5])
+    got = np.array([out.get(k, 0.0) for k in util.RAW_NAMES])
+    np.testing.assert_allclose(got, g["trk_sums_B2a"], rtol=0, atol=1e-6)
