@@ -78,6 +78,9 @@ class TrackSession:
     """Thin RAII wrapper over bds_trk* (bds_track_open / run / fetch / close)."""
 
     def __init__(self, mode, settings, channel, source=None, kernel=L.KERNEL_AUTO, device_ptr=None, n_samples=None):
+        """``source``: host samples (array / np.memmap) or a file / path (the reference's ``fid``); they are
+        streamed to the device under the tracking kernel by the first ``run_async``.  ``device_ptr``: a record
+        already resident in HBM (used in place)."""
         self.mode, self.settings = mode, settings
         self.nch = len(channel)
         self.cfg = make_cfg(mode, settings, kernel)
@@ -85,7 +88,7 @@ class TrackSession:
         self.h = C.c_void_p()
         lib = L.lib()
         skip = int(settings.get("skipNumberOfBytes", 0))
-        self._keep = None
+        self._host = self._keep = None
         if device_ptr is not None:
             L.check(lib.bds_track_open(_MODE[mode], C.byref(self.cfg), C.c_void_p(device_ptr), int(n_samples),
                                        L.LOC_DEVICE, skip, self.chs, self.nch, C.byref(self.h)))
@@ -94,10 +97,10 @@ class TrackSession:
             L.check(lib.bds_track_open_file(_MODE[mode], C.byref(self.cfg), path.encode(), skip, 0, self.chs, self.nch,
                                             C.byref(self.h)))
         else:
-            x = L.as_int8(source)
-            self._keep = x
-            L.check(lib.bds_track_open(_MODE[mode], C.byref(self.cfg), L.ptr(x), x.size, L.LOC_HOST, skip, self.chs,
+            L.check(lib.bds_track_open(_MODE[mode], C.byref(self.cfg), None, 0, L.LOC_HOST, skip, self.chs,
                                        self.nch, C.byref(self.h)))
+            if source is not None:
+                self._host = L.as_int8(source)
 
     def close(self):
         if self.h:
@@ -122,10 +125,19 @@ class TrackSession:
         else:
             x = L.as_int8(x)
             self._keep = x
+            self._host = None
             L.check(L.lib().bds_track_feed(self.h, L.ptr(x), x.size, L.LOC_HOST, int(first_sample)))
 
     def run_async(self, n_epochs):
-        L.check(L.lib().bds_track_run_async(self.h, int(n_epochs)))
+        if self._host is not None:      # host record not uploaded yet: stream it under the kernel
+            x, self._host, self._keep = self._host, None, self._host
+            L.check(L.lib().bds_track_run_streamed(self.h, L.ptr(x), x.size, 0, int(n_epochs)))
+        else:
+            L.check(L.lib().bds_track_run_async(self.h, int(n_epochs)))
+
+    def run_streamed(self, host_ptr, n, n_epochs, chunk_bytes=0):
+        """Track a host record given by address (e.g. pinned memory): H2D in chunks overlapped with tracking."""
+        L.check(L.lib().bds_track_run_streamed(self.h, C.c_void_p(host_ptr), int(n), int(chunk_bytes), int(n_epochs)))
 
     def sync(self):
         L.check(L.lib().bds_track_sync(self.h))
@@ -146,12 +158,14 @@ class TrackSession:
         L.check(L.lib().bds_track_device_block(self.h, C.byref(p), C.byref(b), C.byref(nf), C.byref(cap)))
         return p.value, b.value, nf.value, cap.value
 
-    def fetch(self, N, raw=False):
-        """-> dict of [nch, N] planes (+ CNo planes [nch, N//CNoInterval], raw [nch,N,18], epochsDone [nch])."""
+    def fetch(self, N, raw=False, into=None):
+        """-> dict of [nch, N] planes (+ CNo planes [nch, N//CNoInterval], raw [nch,N,18], epochsDone [nch]).
+        ``into``: dict name -> preallocated float64 [nch, N] arrays (e.g. pinned memory) to receive the planes."""
         out = L.bds_trk_out()
         planes = {}
         for name in L.TRK_PLANES:
-            a = np.empty((self.nch, N))
+            a = into[name] if into is not None else np.empty((self.nch, N))
+            assert a.shape == (self.nch, N) and a.dtype == np.float64 and a.flags.c_contiguous
             planes[name] = a
             setattr(out, name, a.ctypes.data_as(L._PD))
         nc = N // int(self.settings.CNoInterval)

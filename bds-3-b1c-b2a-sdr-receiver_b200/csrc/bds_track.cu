@@ -250,54 +250,38 @@ __device__ bool next_params(const TrkDev& g, const ChanState& st, EpochParams& n
     return off >= 0 && off + np.blksize <= g.winLen && np.blksize > 0;
 }
 
-// The five expensive scalar pieces of the WB loop closure, one per lane (lanes 0..4).
-__device__ double close_pre_wb(const TrkDev& g, int c, int e, const double* s, int lane) {
-    const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
-    auto pI = [&](int o) { return -ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)]; };
-    auto pQ = [&](int o) { return -ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)]; };
-    switch (lane) {
-        case 0: return atan(s[sum_idx(0, EPL_P, 1)] / s[sum_idx(0, EPL_P, 0)]);
-        case 1: return atan(pQ(EPL_P) / pI(EPL_P));
-        case 2: return dll_disc(s[sum_idx(0, EPL_E, 0)], s[sum_idx(0, EPL_E, 1)], s[sum_idx(0, EPL_L, 0)], s[sum_idx(0, EPL_L, 1)]);
-        case 3: return dll_disc(pI(EPL_E), pQ(EPL_E), pI(EPL_L), pQ(EPL_L));
-        case 4: {
-            const EpochParams p = load_cg(g.params + c * 2 + (e & 1));
-            double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
-            return fmod(trig, 6.283185307179586476925286766559);
-        }
-        default: return 0.0;
-    }
-}
-
-// pre (optional, WB with pilot only): {atan(Q_P/I_P), atan(pQ_P/pI_P), dll(data), dll(pilot), fmod(trig,2pi)}
-// evaluated in parallel by other lanes of the closing warp (close_pre_wb); same expressions as below.
-__device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 sums*/, EpochParams& npOut, int& npOk,
-                            const double* pre = nullptr) {
-    ChanState st = load_cg(g.st + c);
-    const EpochParams p = load_cg(g.params + c * 2 + (e & 1));
-    double* out = g.out + (size_t)c * kNFields * g.capacity;
-    const int cap = g.capacity;
+// Loop-closure arithmetic of one epoch (no memory traffic): discriminators, loop filters, state update.
+//   s[18]  correlator sums;  p  the epoch's NCO parameters;  st  channel state (updated in place);
+//   outv[kNFields]  receives the value of every trackResults plane for this epoch (plus the raw sums);
+//   pre (optional, WB with pilot only) = {atan(Q_P/I_P)/2pi, atan(pQ_P/pI_P)/2pi, dll(data), dll(pilot), fmod(trig,2pi)}
+//   already evaluated with the expressions below by other lanes of a closing warp.
+__device__ void close_core(const TrkDev& g, const double* s, const EpochParams& p, double chCodeFreq, ChanState& st,
+                           double* outv, const double* pre = nullptr) {
     const double twopi = 6.283185307179586476925286766559;
     const bool b1c = g.mode != BDS_TRK_B2A;
-
-    out[F_ABS * cap + e] = (double)p.pos;           // WB:254
-    out[F_REMCODE * cap + e] = p.rem;               // WB:287
-    out[F_REMCARR * cap + e] = p.remCarr;           // WB:332
 #pragma unroll
-    for (int i = 0; i < kNSum; ++i) out[(F_RAW0 + i) * cap + e] = s[i];
+    for (int i = 0; i < kNFields; ++i) outv[i] = 0.0;
+    outv[F_ABS] = (double)p.pos;           // WB:254
+    outv[F_REMCODE] = p.rem;               // WB:287
+    outv[F_REMCARR] = p.remCarr;           // WB:332
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) outv[F_RAW0 + i] = s[i];
 
     // remCodePhase / remCarrPhase updates (WB:327,335-337; B2a:295,303-305)
     double base = (double)(p.blksize - 1) * p.step + p.rem;
     st.remCodePhase = base + p.step - g.L;
-    double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
-    st.remCarrPhase = pre ? pre[4] : fmod(trig, twopi);  // rem(trigarg(blksize+1), 2*pi), WB:337
+    if (pre) st.remCarrPhase = pre[4];
+    else {
+        double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
+        st.remCarrPhase = fmod(trig, twopi);  // rem(trigarg(blksize+1), 2*pi), WB:337
+    }
     st.pos = p.pos + p.blksize;
     st.samples += p.blksize;
 
     double I_E = s[sum_idx(0, EPL_E, 0)], Q_E = s[sum_idx(0, EPL_E, 1)];
     double I_P = s[sum_idx(0, EPL_P, 0)], Q_P = s[sum_idx(0, EPL_P, 1)];
     double I_L = s[sum_idx(0, EPL_L, 0)], Q_L = s[sum_idx(0, EPL_L, 1)];
-    double carrError = (pre ? pre[0] : atan(Q_P / I_P)) / twopi;
+    double carrError = pre ? pre[0] : atan(Q_P / I_P) / twopi;
     double codeError = pre ? pre[2] : dll_disc(I_E, Q_E, I_L, Q_L);
     if (b1c) codeError = codeError * (1.0 - g.d);
     if (g.mode == BDS_TRK_B1C_WB && g.hasPilot) {
@@ -308,16 +292,16 @@ __device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 
             pI[o] = -ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)];
             pQ[o] = -ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)];
         }
-        double pe = (pre ? pre[1] : atan(pQ[EPL_P] / pI[EPL_P])) / twopi;
+        double pe = pre ? pre[1] : atan(pQ[EPL_P] / pI[EPL_P]) / twopi;
         carrError = (carrError * 1 + pe * 3) / 4;
         double pc = (pre ? pre[3] : dll_disc(pI[EPL_E], pQ[EPL_E], pI[EPL_L], pQ[EPL_L])) * (1.0 - g.d);
         codeError = codeError * g.factor + pc * (1.0 - g.factor);
-        out[F_PI_P * cap + e] = pI[EPL_P];
-        out[F_PI_E * cap + e] = pI[EPL_E];
-        out[F_PI_L * cap + e] = pI[EPL_L];
-        out[F_PQ_P * cap + e] = pQ[EPL_P];
-        out[F_PQ_E * cap + e] = pQ[EPL_E];
-        out[F_PQ_L * cap + e] = pQ[EPL_L];
+        outv[F_PI_P] = pI[EPL_P];
+        outv[F_PI_E] = pI[EPL_E];
+        outv[F_PI_L] = pI[EPL_L];
+        outv[F_PQ_P] = pQ[EPL_P];
+        outv[F_PQ_E] = pQ[EPL_E];
+        outv[F_PQ_L] = pQ[EPL_L];
     } else if (g.hasPilot) {
         double pIP = s[sum_idx(1, EPL_P, 0)], pQP = s[sum_idx(1, EPL_P, 1)];
         double pc = dll_disc(s[sum_idx(1, EPL_E, 0)], s[sum_idx(1, EPL_E, 1)], s[sum_idx(1, EPL_L, 0)],
@@ -333,69 +317,96 @@ __device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 
             carrError = (carrError + pe) / 2;
             codeError = (codeError + pc) / 2;
         }
-        out[F_PI_P * cap + e] = pIP;
-        out[F_PQ_P * cap + e] = pQP;
+        outv[F_PI_P] = pIP;
+        outv[F_PQ_P] = pQP;
     }
     // PLL filter WB:399-406
     st.d2CarrError = st.d2CarrError + carrError * g.pf3;
     st.dCarrError = st.d2CarrError + carrError * g.pf2 + st.dCarrError;
     double carrNco = st.dCarrError + carrError * g.pf1;
-    out[F_CARRFREQ * cap + e] = st.carrFreq;
+    outv[F_CARRFREQ] = st.carrFreq;
     st.carrFreq = st.carrFreqBasis + carrNco;
     // DLL filter WB:422-430
-    double codeNco = st.oldCodeNco + (g.tau2 / g.tau1) * (codeError - st.oldCodeError) + codeError * (g.PDI / g.tau1);
+    double codeNco = st.oldCodeNco + g.tau2over1 * (codeError - st.oldCodeError) + codeError * g.PDIoverTau1;  // (tau2/tau1), (PDI/tau1)
     st.oldCodeNco = codeNco;
     st.oldCodeError = codeError;
-    out[F_CODEFREQ * cap + e] = st.codeFreq;
-    st.codeFreq = g.cc[c].chCodeFreq - codeNco;
-    out[F_DLL * cap + e] = codeError;
-    out[F_DLLF * cap + e] = codeNco;
-    out[F_PLL * cap + e] = carrError;
-    out[F_PLLF * cap + e] = carrNco;
-    out[F_I_E * cap + e] = I_E;
-    out[F_I_P * cap + e] = I_P;
-    out[F_I_L * cap + e] = I_L;
-    out[F_Q_E * cap + e] = Q_E;
-    out[F_Q_P * cap + e] = Q_P;
-    out[F_Q_L * cap + e] = Q_L;
+    outv[F_CODEFREQ] = st.codeFreq;
+    st.codeFreq = chCodeFreq - codeNco;
+    outv[F_DLL] = codeError;
+    outv[F_DLLF] = codeNco;
+    outv[F_PLL] = carrError;
+    outv[F_PLLF] = carrNco;
+    outv[F_I_E] = I_E;
+    outv[F_I_P] = I_P;
+    outv[F_I_L] = I_L;
+    outv[F_Q_E] = Q_E;
+    outv[F_Q_P] = Q_P;
+    outv[F_Q_L] = Q_L;
+}
 
-    // C/N0 + lock detector every CNoInterval epochs (WB:459-481)
-    if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
-        int ci = (e + 1) / g.cnoInterval - 1;
-        if (ci < g.cnoCap) {
-            __threadfence();
-            int n = g.cnoInterval, e0 = e + 1 - n;
-            double* cn = g.cno + (size_t)c * kNCno * g.cnoCap;
-            double d, dp, pv = 0, pp = 0;
-            cno_pld(out + F_I_P * cap + e0, out + F_Q_P * cap + e0, n, g.PDI, d, dp);
-            double c0 = 10.0 * log10(d), c1 = 0;
-            if (g.hasPilot) {
-                if (g.mode == BDS_TRK_B1C_WB)
-                    cno_pld(out + F_PI_P * cap + e0, out + F_PQ_P * cap + e0, n, g.PDI, pv, pp);
-                else  // NB / B2a swap pilot I and Q (Calc_CNo_PLD.m:80-88)
-                    cno_pld(out + F_PQ_P * cap + e0, out + F_PI_P * cap + e0, n, g.PDI, pv, pp);
-                c1 = 10.0 * log10(pv);
-            }
-            double c2 = 10.0 * log10(d + pv);
-            cn[0 * g.cnoCap + ci] = c0 * 0.5 + st.cnoPrev[0] * 0.5;
-            cn[1 * g.cnoCap + ci] = dp;
-            if (g.hasPilot) {
-                cn[2 * g.cnoCap + ci] = c1 * 0.5 + st.cnoPrev[1] * 0.5;
-                cn[3 * g.cnoCap + ci] = pp;
-                cn[4 * g.cnoCap + ci] = c2 * 0.5 + st.cnoPrev[2] * 0.5;
-            }
-            st.cnoPrev[0] = c0;
-            st.cnoPrev[1] = c1;
-            st.cnoPrev[2] = c2;
-        }
+// planes a mode does not produce keep their preallocation values (NB / B2a have no E/L pilot planes, data-only
+// modes no pilot planes at all)
+__device__ __forceinline__ bool field_written(const TrkDev& g, int f) {
+    if (f >= F_PI_P && f <= F_PQ_L) {
+        if (!g.hasPilot) return false;
+        if (g.mode != BDS_TRK_B1C_WB) return f == F_PI_P || f == F_PQ_P;
     }
+    return true;
+}
+
+// C/N0 + lock detector every CNoInterval epochs (WB:459-481), single thread
+__device__ void close_cno(const TrkDev& g, int c, int e, ChanState& st) {
+    if (!(g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0)) return;
+    const int ci = (e + 1) / g.cnoInterval - 1;
+    if (ci >= g.cnoCap) return;
+    const int cap = g.capacity;
+    const double* out = g.out + (size_t)c * kNFields * cap;
+    const int n = g.cnoInterval, e0 = e + 1 - n;
+    double* cn = g.cno + (size_t)c * kNCno * g.cnoCap;
+    double d, dp, pv = 0, pp = 0;
+    cno_pld(out + F_I_P * cap + e0, out + F_Q_P * cap + e0, n, g.PDI, d, dp);
+    double c0 = 10.0 * log10(d), c1 = 0;
+    if (g.hasPilot) {
+        if (g.mode == BDS_TRK_B1C_WB)
+            cno_pld(out + F_PI_P * cap + e0, out + F_PQ_P * cap + e0, n, g.PDI, pv, pp);
+        else  // NB / B2a swap pilot I and Q (Calc_CNo_PLD.m:80-88)
+            cno_pld(out + F_PQ_P * cap + e0, out + F_PI_P * cap + e0, n, g.PDI, pv, pp);
+        c1 = 10.0 * log10(pv);
+    }
+    double c2 = 10.0 * log10(d + pv);
+    cn[0 * g.cnoCap + ci] = c0 * 0.5 + st.cnoPrev[0] * 0.5;
+    cn[1 * g.cnoCap + ci] = dp;
+    if (g.hasPilot) {
+        cn[2 * g.cnoCap + ci] = c1 * 0.5 + st.cnoPrev[1] * 0.5;
+        cn[3 * g.cnoCap + ci] = pp;
+        cn[4 * g.cnoCap + ci] = c2 * 0.5 + st.cnoPrev[2] * 0.5;
+    }
+    st.cnoPrev[0] = c0;
+    st.cnoPrev[1] = c1;
+    st.cnoPrev[2] = c2;
+}
+
+// Single-thread closure used by the general kernel: loads state, closes the loops, stores outputs + state and
+// stages the next epoch's params (published by the CTA, publish_next).
+__device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 sums*/, EpochParams& npOut, int& npOk) {
+    ChanState st = load_cg(g.st + c);
+    const EpochParams p = load_cg(g.params + c * 2 + (e & 1));
+    double* out = g.out + (size_t)c * kNFields * g.capacity;
+    const int cap = g.capacity;
+    double outv[kNFields];
+    close_core(g, s, p, g.cc[c].chCodeFreq, st, outv);
+#pragma unroll
+    for (int f = 0; f < kNFields; ++f)
+        if (field_written(g, f)) out[(size_t)f * cap + e] = outv[f];
+    __threadfence();
+    close_cno(g, c, e, st);
     st.epoch = e + 1;
     store_cg(g.st + c, st);
 
     // stage the next epoch's params; the CTA publishes them (publish_next)
     EpochParams np;
-    bool ok = next_params(g, st, np) && e + 1 < g.capacity;
-    if (!ok && e + 1 < g.capacity) out[F_ABS * cap + e + 1] = (double)st.pos;  // WB_tracking.m:254 precedes the failed read
+    bool ok = next_params(g, st, np) && e + 1 < g.epochLimit;
+    if (!ok && e + 1 < g.epochLimit) out[F_ABS * cap + e + 1] = (double)st.pos;  // WB_tracking.m:254 precedes the failed read
     npOut = np;
     npOk = ok;
 }
@@ -548,8 +559,8 @@ __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
         g.count[c] = 0;
         ChanState st = g.st[c];
         g.cc[c].pad = st.epoch;
-        sm.npOk = next_params(g, st, sm.np) && st.epoch < g.capacity;
-        if (!sm.npOk && st.epoch < g.capacity)
+        sm.npOk = next_params(g, st, sm.np) && st.epoch < g.epochLimit;
+        if (!sm.npOk && st.epoch < g.epochLimit)
             g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
         g.ready[c] = st.epoch - 1;
         g.stop[c] = INT_MAX;
@@ -618,6 +629,7 @@ struct bds_trk {
     EpochParams* dParams = nullptr;
     int *dReady = nullptr, *dStop = nullptr, *dCount = nullptr;
     double* dPartial = nullptr;
+    double* dAcc = nullptr;
     double* dOut = nullptr;
     double* dCno = nullptr;
     int capacity = 0, cnoCap = 0;
@@ -633,7 +645,8 @@ struct bds_trk {
     bool fast = false;
     size_t smemBytes = 0;
     int epochsRun = 0;  // max over channels, as seen by the host
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copyStream = nullptr;
+    std::vector<cudaEvent_t> chunkEv;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float lastMs = 0.f;
     bool pending = false;
@@ -641,6 +654,7 @@ struct bds_trk {
     // mmap'd file
     void* map = nullptr;
     size_t mapLen = 0;
+    bool mapUploaded = false;
 };
 
 namespace {
@@ -689,14 +703,16 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.trace = h->dTrace;
     g.traceCap = h->traceCap;
     g.nCompute = h->nCompute;
-    g.stages = 3;
+    g.stages = kFwStages;
     g.tune = 0;
-    g.ahead = 1;
+    g.ahead = 2;
     if (const char* e = getenv("BDS_TRK_AHEAD")) g.ahead = atoi(e);
     if (const char* e = getenv("BDS_TRK_STAGES")) g.stages = std::max(2, std::min(kFwStages, atoi(e)));
+    g.ahead = std::max(0, std::min(g.ahead, g.stages - 1));   // more passes in flight than stages would deadlock the producer
     if (const char* e = getenv("BDS_TRK_TUNE")) g.tune = atoi(e);
     g.maxEpochs = maxEpochs;
     g.capacity = h->capacity;
+    g.epochLimit = h->capacity;
     g.cnoCap = h->cnoCap;
     g.cnoInterval = h->cfg.CNoInterval;
     g.kernelKind = h->fast ? BDS_KERNEL_FAST : BDS_KERNEL_GENERAL;
@@ -707,6 +723,8 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.PDI = h->cfg.intTime;
     g.tau1 = h->cfg.tau1code;
     g.tau2 = h->cfg.tau2code;
+    g.tau2over1 = h->cfg.tau2code / h->cfg.tau1code;   // same IEEE divisions as WB_tracking.m:422-424, hoisted
+    g.PDIoverTau1 = h->cfg.intTime / h->cfg.tau1code;
     g.pf1 = h->cfg.pf1;
     g.pf2 = h->cfg.pf2;
     g.pf3 = h->cfg.pf3;
@@ -719,6 +737,7 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.stop = h->dStop;
     g.count = h->dCount;
     g.partial = h->dPartial;
+    g.acc = h->dAcc;
     g.out = h->dOut;
     g.cno = h->dCno;
 }
@@ -830,9 +849,9 @@ int plan_grid(bds_trk* h) {
         // a few CTAs only close loops: one warp per channel (16 warps per CTA)
         int nCloser = (h->nAct + (kFwThreads / 32) - 1) / (kFwThreads / 32);
         h->nCompute = std::max(1, h->gridBlocks - nCloser);
-        // slices of 448*k chips (one chip per compute thread and pass); >= ~2.5 work items per CTA and round
+        // slices of kFwChips*k chips (one chip per compute thread and pass); >= ~4 work items per CTA and round
         int k = 4;
-        while (k > 1 && (long long)h->nAct * ((10230 + kFwChips * k - 1) / (kFwChips * k)) * 2 < 5LL * h->gridBlocks) --k;
+        while (k > 1 && (long long)h->nAct * ((10230 + kFwChips * k - 1) / (kFwChips * k)) < 4LL * h->gridBlocks) --k;
         if (const char* e = getenv("BDS_TRK_PASSES")) k = std::max(1, std::min(8, atoi(e)));  // tuning knob
         h->S = (10230 + kFwChips * k - 1) / (kFwChips * k);
     } else {
@@ -889,6 +908,8 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
     TRY(cudaMalloc(&h->dStop, sizeof(int) * n_ch));
     TRY(cudaMalloc(&h->dCount, sizeof(int) * n_ch));
     TRY(cudaMalloc(&h->dPartial, sizeof(double) * (size_t)n_ch * h->S * kNSum));
+    TRY(cudaMalloc(&h->dAcc, sizeof(double) * (size_t)n_ch * kNSum));
+    TRY(cudaMemset(h->dAcc, 0, sizeof(double) * (size_t)n_ch * kNSum));
     TRY(cudaMalloc(&h->dAct, sizeof(int) * n_ch));
     TRY(cudaMalloc(&h->dCounters, 256 + 8 * 128));
     TRY(cudaMemset(h->dCounters, 0, 256 + 8 * 128));
@@ -978,15 +999,18 @@ int bds_track_open_file(int mode, const bds_trk_cfg* cfg, const char* path, long
     void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
     ::close(fd);
     if (m == MAP_FAILED) return set_error(BDS_ERR_IO, "mmap of %s failed", path);
+    madvise(m, len, MADV_SEQUENTIAL);
     bds_trk* h = nullptr;
     int rc = open_common(mode, cfg, skip, ch, n_ch, &h);
-    if (rc == BDS_OK) rc = set_window(h, (const int8_t*)m, len, BDS_LOC_HOST, 0);
-    if (rc == BDS_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = set_error(BDS_ERR_CUDA, "H2D copy failed");
-    munmap(m, len);
+    if (rc == BDS_OK) rc = set_window(h, nullptr, 0, BDS_LOC_HOST, 0);
     if (rc) {
+        munmap(m, len);
         if (h) bds_track_close(h);
         return rc;
     }
+    // the mapping is uploaded by the first run, streamed chunk by chunk under the tracking kernel
+    h->map = m;
+    h->mapLen = len;
     *out = h;
     return BDS_OK;
 }
@@ -996,23 +1020,19 @@ int bds_track_feed(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long f
     return set_window(h, x, n, x_loc, first_sample);
 }
 
-int bds_track_run_async(bds_trk* h, int n_epochs) {
-    if (!h || n_epochs <= 0) return set_error(BDS_ERR_ARG, "bds_track_run: bad arguments");
-    int rc = BDS_OK;
-    if (h->pending) {  // the output block may be re-allocated below: finish the previous run first
-        rc = bds_track_sync(h);
-        if (rc) return rc;
-    }
-    rc = ensure_capacity(h, h->epochsRun + n_epochs);
-    if (rc) return rc;
+int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs);
+
+// One launch of the persistent kernel on the session's stream: up to maxEpochs more epochs per channel,
+// no epoch index >= epochLimit, over the currently resident window.
+static int launch_run(bds_trk* h, int maxEpochs, int epochLimit) {
     TrkDev g;
-    fill_dev(h, g, n_epochs);
+    fill_dev(h, g, maxEpochs);
+    g.epochLimit = std::min(epochLimit, h->capacity);
     if (h->fast) {
         BDS_CUDA(cudaMemsetAsync(h->dQueue, 0, sizeof(unsigned long long) * h->qSize, h->stream));
         fw_prepare_kernel<<<1, 1024, 0, h->stream>>>(g, h->nCompute);
     } else trk_prepare_kernel<<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
     count_launch();
-    BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
     void* args[] = {&g};
     if (h->fast)
         BDS_CUDA(cudaLaunchCooperativeKernel((const void*)trk_fw_kernel, dim3(h->gridBlocks), dim3(kFwThreads), args,
@@ -1021,6 +1041,81 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
         BDS_CUDA(cudaLaunchCooperativeKernel((const void*)trk_persistent_kernel, dim3(h->gridBlocks), dim3(kTrkThreads),
                                              args, h->smemBytes, h->stream));
     count_launch();
+    return BDS_OK;
+}
+
+int bds_track_run_async(bds_trk* h, int n_epochs) {
+    if (!h || n_epochs <= 0) return set_error(BDS_ERR_ARG, "bds_track_run: bad arguments");
+    if (h->map && !h->mapUploaded) {  // file-backed session: first run streams the mapping to the device
+        h->mapUploaded = true;
+        return bds_track_run_streamed(h, (const int8_t*)h->map, h->mapLen, 0, n_epochs);
+    }
+    int rc = BDS_OK;
+    if (h->pending) {  // the output block may be re-allocated below: finish the previous run first
+        rc = bds_track_sync(h);
+        if (rc) return rc;
+    }
+    rc = ensure_capacity(h, h->epochsRun + n_epochs);
+    if (rc) return rc;
+    BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = launch_run(h, n_epochs, h->capacity);
+    if (rc) return rc;
+    BDS_CUDA(cudaEventRecord(h->ev1, h->stream));
+    h->pending = true;
+    return BDS_OK;
+}
+
+// Streams a HOST record into HBM in chunks on a copy stream while the persistent kernel tracks the
+// part that has already arrived: launch i runs every channel as far as chunks 0..i allow (a channel that
+// runs out of samples stops exactly like a short read and is resumed from its device-side state by the
+// next launch).  Loop state never leaves the device between launches.
+int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs) {
+    if (!h || !x || n == 0 || n_epochs <= 0) return set_error(BDS_ERR_ARG, "bds_track_run_streamed: bad arguments");
+    int rc = BDS_OK;
+    if (h->pending) {
+        rc = bds_track_sync(h);
+        if (rc) return rc;
+    }
+    rc = ensure_capacity(h, h->epochsRun + n_epochs);
+    if (rc) return rc;
+    if (chunk_bytes == 0) chunk_bytes = (size_t)128 << 20;
+    chunk_bytes = (chunk_bytes + 4095) & ~(size_t)4095;
+    if (!h->ownX || h->xCap < n + 64) {
+        if (h->ownX && h->dX) cudaFree(h->dX);
+        h->dX = nullptr;
+        h->ownX = true;
+        h->xCap = n + 64;
+        BDS_CUDA(cudaMalloc(&h->dX, h->xCap));
+    }
+    if (!h->copyStream) BDS_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    const size_t nChunks = (n + chunk_bytes - 1) / chunk_bytes;
+    while (h->chunkEv.size() < nChunks) {
+        cudaEvent_t e;
+        BDS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->chunkEv.push_back(e);
+    }
+    const int limit = h->epochsRun + n_epochs;
+    auto copy_chunk = [&](size_t i) -> int {
+        const size_t o = i * chunk_bytes, len = std::min(chunk_bytes, n - o);
+        BDS_CUDA(cudaMemcpyAsync(h->dX + o, x + o, len, cudaMemcpyHostToDevice, h->copyStream));
+        if (i + 1 == nChunks) BDS_CUDA(cudaMemsetAsync(h->dX + n, 0, 64, h->copyStream));
+        BDS_CUDA(cudaEventRecord(h->chunkEv[i], h->copyStream));
+        return BDS_OK;
+    };
+    h->winFirst = 0;
+    BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = copy_chunk(0);
+    if (rc) return rc;
+    for (size_t i = 0; i < nChunks; ++i) {
+        if (i + 1 < nChunks) {
+            rc = copy_chunk(i + 1);
+            if (rc) return rc;
+        }
+        BDS_CUDA(cudaStreamWaitEvent(h->stream, h->chunkEv[i], 0));
+        h->winLen = (long long)std::min(n, (i + 1) * chunk_bytes);
+        rc = launch_run(h, n_epochs, limit);
+        if (rc) return rc;
+    }
     BDS_CUDA(cudaEventRecord(h->ev1, h->stream));
     h->pending = true;
     return BDS_OK;
@@ -1046,31 +1141,47 @@ int bds_track_fetch(bds_trk* h, const bds_trk_out* o, int stride) {
     if (rc) return rc;
     if (stride < h->epochsRun) return set_error(BDS_ERR_ARG, "out_stride %d < epochs run %d", stride, h->epochsRun);
     // entries past the last completed epoch carry the reference's preallocation values
-    int nE = std::min(stride, h->capacity);
+    const int nE = std::min(stride, h->capacity);
     if (nE == 0) return BDS_OK;
-    std::vector<double> host((size_t)h->nCh * kNFields * h->capacity);
-    BDS_CUDA(cudaMemcpy(host.data(), h->dOut, host.size() * sizeof(double), cudaMemcpyDeviceToHost));
     double* planes[kNFieldsLoop] = {o->absoluteSample, o->codeFreq, o->carrFreq, o->I_P, o->I_E, o->I_L, o->Q_E,
                                     o->Q_P, o->Q_L, o->Pilot_I_P, o->Pilot_I_E, o->Pilot_I_L, o->Pilot_Q_E,
                                     o->Pilot_Q_P, o->Pilot_Q_L, o->dllDiscr, o->dllDiscrFilt, o->pllDiscr,
                                     o->pllDiscrFilt, o->remCodePhase, o->remCarrPhase};
-    for (int c = 0; c < h->nCh; ++c) {
-        const double* base = host.data() + (size_t)c * kNFields * h->capacity;
-        for (int f = 0; f < kNFieldsLoop; ++f)
-            if (planes[f]) std::memcpy(planes[f] + (size_t)c * stride, base + (size_t)f * h->capacity, sizeof(double) * nE);
-        if (o->raw)
+    // device block [c][field][capacity] -> caller plane [c][stride]: one strided copy per requested plane, straight
+    // into the caller's memory (pinned destinations run at full PCIe rate)
+    const size_t srcPitch = sizeof(double) * (size_t)kNFields * h->capacity;
+    for (int f = 0; f < kNFieldsLoop; ++f)
+        if (planes[f])
+            BDS_CUDA(cudaMemcpy2DAsync(planes[f], sizeof(double) * (size_t)stride, h->dOut + (size_t)f * h->capacity,
+                                       srcPitch, sizeof(double) * (size_t)nE, (size_t)h->nCh, cudaMemcpyDeviceToHost,
+                                       h->stream));
+    std::vector<double> raw;
+    if (o->raw) {
+        raw.resize((size_t)h->nCh * kNSum * nE);
+        for (int c = 0; c < h->nCh; ++c)
+            for (int k = 0; k < kNSum; ++k)
+                BDS_CUDA(cudaMemcpyAsync(raw.data() + ((size_t)c * kNSum + k) * nE,
+                                         h->dOut + ((size_t)c * kNFields + F_RAW0 + k) * h->capacity,
+                                         sizeof(double) * (size_t)nE, cudaMemcpyDeviceToHost, h->stream));
+    }
+    const int ci = std::max(1, h->cfg.CNoInterval);
+    const int nC = stride / ci;
+    std::vector<double> cn;
+    if (nC > 0 && (o->DataCNo || o->DataPLD || o->PilotCNo || o->PilotPLD || o->TotalCNo)) {
+        cn.resize((size_t)h->nCh * kNCno * h->cnoCap);
+        BDS_CUDA(cudaMemcpyAsync(cn.data(), h->dCno, cn.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    BDS_CUDA(cudaStreamSynchronize(h->stream));
+    if (o->raw)
+        for (int c = 0; c < h->nCh; ++c)
             for (int e = 0; e < nE; ++e)
                 for (int k = 0; k < kNSum; ++k)
-                    o->raw[((size_t)c * stride + e) * kNSum + k] = base[(size_t)(F_RAW0 + k) * h->capacity + e];
-        if (o->epochsDone) o->epochsDone[c] = h->hSt[c].epoch;
-    }
-    int ci = std::max(1, h->cfg.CNoInterval);
-    int nC = stride / ci;
-    if (nC > 0 && (o->DataCNo || o->DataPLD || o->PilotCNo || o->PilotPLD || o->TotalCNo)) {
-        std::vector<double> cn((size_t)h->nCh * kNCno * h->cnoCap);
-        BDS_CUDA(cudaMemcpy(cn.data(), h->dCno, cn.size() * sizeof(double), cudaMemcpyDeviceToHost));
+                    o->raw[((size_t)c * stride + e) * kNSum + k] = raw[((size_t)c * kNSum + k) * nE + e];
+    if (o->epochsDone)
+        for (int c = 0; c < h->nCh; ++c) o->epochsDone[c] = h->hSt[c].epoch;
+    if (!cn.empty()) {
         double* cp[kNCno] = {o->DataCNo, o->DataPLD, o->PilotCNo, o->PilotPLD, o->TotalCNo};
-        int n = std::min(nC, h->cnoCap);
+        const int n = std::min(nC, h->cnoCap);
         for (int c = 0; c < h->nCh; ++c)
             for (int f = 0; f < kNCno; ++f)
                 if (cp[f]) {
@@ -1161,7 +1272,9 @@ int bds_track_reset(bds_trk* h) {
 
 void bds_track_close(bds_trk* h) {
     if (!h) return;
+    if (h->copyStream) cudaStreamSynchronize(h->copyStream);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->map) munmap(h->map, h->mapLen);
     if (h->ownX && h->dX) cudaFree(h->dX);
     cudaFree(h->dBits);
     cudaFree(h->dCC);
@@ -1171,6 +1284,7 @@ void bds_track_close(bds_trk* h) {
     cudaFree(h->dStop);
     cudaFree(h->dCount);
     cudaFree(h->dPartial);
+    cudaFree(h->dAcc);
     cudaFree(h->dOut);
     cudaFree(h->dCno);
     cudaFree(h->dAct);
@@ -1181,6 +1295,8 @@ void bds_track_close(bds_trk* h) {
     cudaFree(h->dFastTab);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (auto e : h->chunkEv) cudaEventDestroy(e);
+    if (h->copyStream) cudaStreamDestroy(h->copyStream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1278,7 +1394,7 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         g.olEpochs = n_epochs;
         g.olCount = nce;
         g.nCompute = g_num_sms;
-        g.stages = 3;
+        g.stages = kFwStages;
         g.tune = 0;
         g.ahead = -1;
         trk_fw_kernel<<<g_num_sms, kFwThreads, smem>>>(g);

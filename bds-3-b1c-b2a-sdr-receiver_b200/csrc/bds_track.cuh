@@ -62,6 +62,7 @@ struct TrkDev {
     int S, nAct, maxEpochs, capacity;
     int cnoCap, cnoInterval, kernelKind, pad;
     double fs, L, d, PDI, tau1, tau2, pf1, pf2, pf3, factor;
+    double tau2over1, PDIoverTau1;   // tau2/tau1 and PDI/tau1 (loop invariant)
     const uint32_t* codeBits;  // [nCh][3][320] packed primaries: data, pilot, (unused)
     ChanConst* cc;
     ChanState* st;
@@ -70,6 +71,7 @@ struct TrkDev {
     int* stop;                 // [nCh] first epoch that cannot run (INT_MAX while running)
     int* count;                // [nCh] slice arrival counter
     double* partial;           // [nCh][S][18]
+    double* acc;               // [nCh][18] slice sums of the epoch in flight (warp-specialised kernel, RED.ADD.F64)
     double* out;               // [nCh][kNFields][capacity]
     double* cno;               // [nCh][kNCno][cnoCap]
     const int* act;            // [nAct] indices of the active channels
@@ -86,6 +88,7 @@ struct TrkDev {
     int nCompute;                  // CTAs [0,nCompute) correlate, the rest close loops
     int ahead;                     // pop a new work item only when <= ahead passes are still pending (-1: no limit)
     int stages, tune;              // pipeline stages in use; tuning bits (1: pop only with a free stage, 2: parallel closure)
+    int epochLimit;                // no channel runs an epoch with index >= epochLimit (<= capacity)
 };
 
 }  // namespace bds

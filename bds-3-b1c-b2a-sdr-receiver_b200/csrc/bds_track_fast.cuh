@@ -32,6 +32,7 @@ struct __align__(16) FastTab {
     unsigned thr[40];                   // sorted thresholds (2^32 fixed point), thr[36..] = 0xffffffff
     uint2 mask[40];                     // decision masks by rank
     unsigned char binStart[kFastBins + 16];
+    unsigned char posbin[80];           // [0..35] sorted position of threshold k-1, [40..75] its bin (thr >> 25)
     double u0, sigma, S;                // 12*rem, 12*step, 1/sigma
     unsigned long long dphi, phi0;      // carrier NCO, 2^-64 turns
     int valid;
@@ -45,14 +46,22 @@ inline bool fast_wb_supported(int mode, int hasP61, double fs, double fc, int co
 }
 
 // ---- per-epoch table construction (one warp) -------------------------------------------------
-// tab lives in global memory (one per channel and epoch parity); scratch: >= 128 words of shared
-// memory private to the calling warp.
-__device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double fs, unsigned* scratch) {
+// tab lives in global memory (one per channel, rewritten in place: every slice of epoch e has finished before
+// epoch e+1's table is built); scratch: >= 128 words of shared memory private to the calling warp.
+// prev (optional, shared memory): the posbin[] array of the table being replaced.  The sorted order of the 36
+// thresholds and their bins almost never change from one epoch to the next (the code rate moves by ~1e-9), in
+// which case masks / binStart / posbin are still right and only the threshold values, the carrier rotation
+// table and the scalars are rewritten.
+__device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double fs, unsigned* scratch,
+                                    const unsigned char* prev = nullptr) {
     const int lane = threadIdx.x & 31;
     const double sigma = 12.0 * np.step, S = 1.0 / sigma;
     double r = np.carrFreq / fs;
     r -= floor(r);
     const unsigned long long dphi = __double2ull_rn(r * 18446744073709551616.0);
+    double r0 = np.remCarr / 6.283185307179586476925286766559;   // independent of the above: overlaps its latency
+    r0 -= floor(r0);
+    const unsigned long long phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
     short* w = reinterpret_cast<short*>(tab->w);   // word i: [wr(4i..4i+3) | wi(4i..4i+3)] as int16
     for (int t = lane; t < 4 * (FAST_NWORDS + 1); t += 32) {
         unsigned long long ph = (unsigned long long)t * dphi;
@@ -63,6 +72,7 @@ __device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double 
     }
     unsigned* thr = scratch;        // [36] unsorted thresholds
     unsigned* pos = scratch + 40;   // [36] sorted position of threshold k-1
+    unsigned* srt = scratch + 80;   // [36] thresholds in sorted order (reuse path)
     int ok = 1;
     for (int t = lane; t < 36; t += 32) {
         const int k = t + 1;
@@ -71,49 +81,68 @@ __device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double 
         th = fmin(fmax(th, 0.0), 1.0);
         thr[t] = (unsigned)fmin(th * 4294967296.0, 4294967295.0);
     }
-    __syncwarp();
-    for (int t = lane; t < 40; t += 32) {
-        if (t < 36) {  // rank sort (ties broken by index)
-            const unsigned v = thr[t];
-            int rank = 0;
-            for (int j = 0; j < 36; ++j) rank += (thr[j] < v) || (thr[j] == v && j < t);
-            tab->thr[rank] = v;
-            pos[t] = rank;
-        } else {
-            tab->thr[t] = 0xffffffffu;
-        }
-    }
-    __syncwarp();
-    for (int t = lane; t < 37; t += 32) {
-        // mask[j]: bit (k-1) set  <=>  boundary sample R_k belongs to the OLD segment  <=>  Theta_k >= Psi
-        //          <=> sorted position of k >= j   (j = number of thresholds < Psi)
-        unsigned lo = 0, hi = 0;
-        for (int k = 1; k <= 36; ++k)
-            if ((int)pos[k - 1] >= t) {
-                if (k <= 32) lo |= 1u << (k - 1);
-                else hi |= 1u << (k - 33);
-            }
-        tab->mask[t] = make_uint2(lo, hi);
-    }
-    for (int t = lane; t < kFastBins + 1; t += 32) {
-        int cnt = 0, here = 0;
-        for (int j = 0; j < 36; ++j) {
-            cnt += (thr[j] >> 25) < (unsigned)t;
-            here += (thr[j] >> 25) == (unsigned)t;
-        }
-        tab->binStart[t] = (unsigned char)cnt;
-        ok &= here <= 4;  // the rank refinement in the correlator does 4 steps
-    }
     ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    bool reuse = prev != nullptr && ok;
+    if (reuse) {   // same order, same bins as the table being replaced?
+        int same = 1;
+        for (int t = lane; t < 36; t += 32) {
+            const unsigned p = prev[t];
+            same &= p < 36u && (thr[t] >> 25) == (unsigned)prev[40 + t];
+            srt[p < 36u ? p : 0] = thr[t];
+        }
+        same = __all_sync(0xffffffffu, same);
+        __syncwarp();
+        for (int t = lane; t < 35; t += 32) same &= srt[t] < srt[t + 1];
+        reuse = __all_sync(0xffffffffu, same);
+    }
+    if (reuse) {
+        for (int t = lane; t < 36; t += 32) tab->thr[t] = srt[t];
+    } else {
+        for (int t = lane; t < 40; t += 32) {
+            if (t < 36) {  // rank sort (ties broken by index)
+                const unsigned v = thr[t];
+                int rank = 0;
+                for (int j = 0; j < 36; ++j) rank += (thr[j] < v) || (thr[j] == v && j < t);
+                tab->thr[rank] = v;
+                pos[t] = rank;
+                tab->posbin[t] = (unsigned char)rank;
+                tab->posbin[40 + t] = (unsigned char)(v >> 25);
+            } else {
+                tab->thr[t] = 0xffffffffu;
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < 37; t += 32) {
+            // mask[j]: bit (k-1) set  <=>  boundary sample R_k belongs to the OLD segment  <=>  Theta_k >= Psi
+            //          <=> sorted position of k >= j   (j = number of thresholds < Psi)
+            unsigned lo = 0, hi = 0;
+            for (int k = 1; k <= 36; ++k)
+                if ((int)pos[k - 1] >= t) {
+                    if (k <= 32) lo |= 1u << (k - 1);
+                    else hi |= 1u << (k - 33);
+                }
+            tab->mask[t] = make_uint2(lo, hi);
+        }
+        for (int t = lane; t < kFastBins + 1; t += 32) {
+            int cnt = 0, here = 0;
+            for (int j = 0; j < 36; ++j) {
+                cnt += (thr[j] >> 25) < (unsigned)t;
+                here += (thr[j] >> 25) == (unsigned)t;
+            }
+            tab->binStart[t] = (unsigned char)cnt;
+            ok &= here <= 4;  // the rank refinement in the correlator does 4 steps
+        }
+        ok = __all_sync(0xffffffffu, ok);
+    }
     if (lane == 0) {
-        double r0 = np.remCarr / 6.283185307179586476925286766559;
-        r0 -= floor(r0);
         tab->u0 = 12.0 * np.rem;
         tab->sigma = sigma;
         tab->S = S;
         tab->dphi = dphi;
-        tab->phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
-        tab->valid = ok;
+        tab->phi0 = phi0;
+        // reuse: `here <= 4` held for the replaced table (same bins), whose valid flag is left in place
+        if (!reuse) tab->valid = ok;
     }
     __syncwarp();
 }

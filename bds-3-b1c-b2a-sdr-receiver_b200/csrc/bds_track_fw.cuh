@@ -18,13 +18,29 @@
 
 namespace bds {
 
+// Default build: 16 compute warps (4 per SM sub-partition) at 112 registers + one service warpgroup at 24
+// (BDS_FW_SETMAXNREG).  -DBDS_FW_COMPUTE_WARPS=14 -DBDS_FW_NO_SETMAXNREG gives the 14 + 2 warp, 128-register variant.
 #ifndef BDS_FW_COMPUTE_WARPS
-#define BDS_FW_COMPUTE_WARPS 14
+#define BDS_FW_COMPUTE_WARPS 16
+#endif
+#if !defined(BDS_FW_SETMAXNREG) && !defined(BDS_FW_NO_SETMAXNREG)
+#define BDS_FW_SETMAXNREG 112
 #endif
 constexpr int kFwCompute = BDS_FW_COMPUTE_WARPS;   // compute warps
-constexpr int kFwThreads = (kFwCompute + 2) * 32;
+// BDS_FW_SETMAXNREG = R: warp-specialised register budgets (setmaxnreg, as in producer/consumer GEMMs): the
+// service warps form one warpgroup of 4 (producer, epilogue, 2 idle) that drops to 24 registers so that the
+// compute warpgroups can grow to R.
+#ifdef BDS_FW_SETMAXNREG
+constexpr int kFwService = 4;
+#else
+constexpr int kFwService = 2;
+#endif
+constexpr int kFwThreads = (kFwCompute + kFwService) * 32;
 constexpr int kFwChips = kFwCompute * 32;      // chips per pass
-constexpr int kFwStages = 3;   // compiled-in maximum; g.stages (2..3) are used
+#ifndef BDS_FW_STAGES
+#define BDS_FW_STAGES 4
+#endif
+constexpr int kFwStages = BDS_FW_STAGES;   // compiled-in maximum; g.stages (2..kFwStages) are used
 constexpr int kFwTile = ((kFwChips * 98 + 512 + 127) / 128) * 128;   // chips * 97.2 samples + margins
 constexpr int kFwBitsBytes = 2 * kPackedWordsDev * 4;
 
@@ -54,11 +70,18 @@ struct __align__(128) FwSmem {
 
 // scratch of one loop-closing warp (closer CTAs overlay an array of these on the dynamic smem)
 struct __align__(16) FwCloseScratch {
+    ChanState st;                 // channel state (loaded / stored once per closure)
+    EpochParams p, np;            // this epoch's and the next epoch's NCO parameters
     double sums[kNSum];
     double pre[8];
+    double v[12];                 // {data, composite pilot} x {E, L, P} x {I, Q}
+    double outv[kNFields + 1];    // values of every output plane for this epoch
+    double chCodeFreq;
+    double pad_;
     unsigned scratch[128];
-    EpochParams np;
+    unsigned char posbin[80];
 };
+static_assert(sizeof(FwCloseScratch) % 16 == 0, "FwCloseScratch must be a 16-byte multiple");
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -106,6 +129,27 @@ __device__ void fw_push_slices(const TrkDev& g, int c, int e, int lane) {
     for (int s = lane; s < g.S; s += 32)
         st_release_u64(g.queue + ((base + s) & g.qMask), ((unsigned long long)(base + s + 1) << 32) | fw_payload(c, s, e));
 }
+constexpr unsigned kFwSkip = 0xfffffffeu;   // reserved-but-unused queue slot: consumers pop the next ticket
+// fill S slots reserved earlier at `base` (atomicAdd on qctl[1]) with the slices of (c, e), or with skip entries
+// (the caller has issued a gpu-scope release fence after its last write the consumers will read; consumers
+// ld.acquire the slot)
+__device__ void fw_fill_slices(const TrkDev& g, unsigned base, int c, int e, int lane, bool skip) {
+    for (int s = lane; s < g.S; s += 32) {
+        const unsigned long long v = ((unsigned long long)(base + s + 1) << 32) | (skip ? kFwSkip : fw_payload(c, s, e));
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(g.queue + ((base + s) & g.qMask)), "l"(v) : "memory");
+    }
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// exact fmod(x, y) for 0 <= x, 0 < y, x/y < 2^52: the result x - n*y is representable, so one fma is exact;
+// the +-y steps repair a quotient that rounded across an integer.  (libdevice fmod iterates ~20 times here.)
+__device__ __forceinline__ double fmod_pos(double x, double y) {
+    if (!(x >= 0.0)) return fmod(x, y);
+    const double n = floor(x / y);
+    double r = fma(-n, y, x);
+    if (r < 0.0) r += y;
+    if (r >= y) r -= y;
+    return r;
+}
 __device__ void fw_push_terminate(const TrkDev& g, int n, int lane) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(g.qctl + 1, (unsigned)n);
@@ -127,56 +171,153 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
     return t;
 }
 
-// ---- closure by one warp ----------------------------------------------------------------------
-// returns true if another epoch of the channel was published
-__device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e) {
+// C/N0 + lock detector over n stored prompts, whole warp (Calc_CNo_PLD.m:52-73; var() normalises by N-1)
+__device__ void cno_pld_warp(const double* ip, const double* qp, int n, double T, double& cno, double& pld) {
     const int lane = threadIdx.x & 31;
-    const unsigned long long tIn = gtimer_ns();
+    double zs = 0;
+    for (int i = lane; i < n; i += 32) {
+        double a = __ldcg(ip + i), b = __ldcg(qp + i);
+        zs += a * a + b * b;
+    }
+    const double zm = warp_sum(zs) / n;
+    double zv = 0, pos = 0, neg = 0, sq = 0;
+    for (int i = lane; i < n; i += 32) {
+        double a = __ldcg(ip + i), b = __ldcg(qp + i);
+        double z = a * a + b * b - zm;
+        zv += z * z;
+        if (a > 0) pos += a;
+        if (a < 0) neg += a;
+        sq += b;
+    }
+    zv = warp_sum(zv) / (n - 1);
+    pos = warp_sum(pos);
+    neg = warp_sum(neg);
+    sq = warp_sum(sq);
+    double pav = sqrt(zm * zm - zv);
+    double nv = 0.5 * (zm - pav);
+    cno = fabs((1.0 / T) * pav / (2.0 * nv));
+    double aa = (pos - neg) * (pos - neg), qq = sq * sq;
+    pld = (aa - qq) / (aa + qq);
+}
+
+// ---- closure by one warp ----------------------------------------------------------------------
+// All S slices of (c, e) have arrived.  Critical path (everything the next epoch's slices wait for):
+//   one L2 round trip (sums read-and-zero, state, params, previous table order; the next epoch's queue slots
+//   are reserved in the same round trip) -> discriminator pieces in parallel lanes -> sequential loop filters
+//   on lane 0 -> next table -> fence -> publish.  Output planes, C/N0 and the state write-back follow
+//   after the publication.  Returns true if another epoch of the channel was published.
+__device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, int e0 /* first epoch of this launch */) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long tIn = g.pubTime ? gtimer_ns() : 0ull;
     const long long tcIn = clock64();
     if (lane == 0 && g.counters && g.pubTime) {  // developer timing: publish -> all slices done
         unsigned long long t0 = g.pubTime[c];
         if (t0) atomicAdd(g.counters + 12, tIn - t0);
     }
-    if (lane < kNSum) {  // fixed summation order over the S slices (deterministic)
-        const double* part = g.partial + (size_t)c * g.S * kNSum;
-        double a = 0;
-        for (int s = 0; s < g.S; ++s) a += __ldcg(part + (size_t)s * kNSum + lane);
-        sm.sums[lane] = a;
-    }
+    FastTab* tab = g.fastTab + (size_t)c * 2;
+    unsigned qbase = 0;
+    if (lane == 31) qbase = atomicAdd(g.qctl + 1, (unsigned)g.S);
+    if (lane < kNSum) {      // slice sums were accumulated with exact fp64 RED.ADDs (multiples of 2^-8 below 2^45)
+        sm.sums[lane] = __ldcg(g.acc + (size_t)c * kNSum + lane);
+        __stcg(g.acc + (size_t)c * kNSum + lane, 0.0);   // ordered before the next epoch's REDs by the publication
+    } else if (lane < kNSum + 8)
+        reinterpret_cast<uint4*>(&sm.st)[lane - kNSum] = __ldcg(reinterpret_cast<const uint4*>(g.st + c) + (lane - kNSum));
+    else if (lane < kNSum + 11)
+        reinterpret_cast<uint4*>(&sm.p)[lane - kNSum - 8] = __ldcg(reinterpret_cast<const uint4*>(g.params + c * 2 + (e & 1)) + (lane - kNSum - 8));
+    else if (lane == 29) sm.chCodeFreq = g.cc[c].chCodeFreq;
+    if (lane < 5) reinterpret_cast<uint4*>(sm.posbin)[lane] = __ldcg(reinterpret_cast<const uint4*>(tab->posbin) + lane);
     __syncwarp();
     const long long tc0 = clock64();
-    const bool par = (g.tune & 2) != 0;
-    if (par) {   // expensive scalar pieces in parallel lanes, then the sequential filter update on lane 0
-        const double v = close_pre_wb(g, c, e, sm.sums, lane);
-        if (lane < 5) sm.pre[lane] = v;
+    // ---- discriminator pieces, one per lane, uniform control flow (same expressions as close_core) ----
+    {
+        const double* s = sm.sums;
+        const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
+        if (lane < 6) {   // v[2k], v[2k+1] = (I, Q) of data E, L, P
+            const int o = lane >> 1 == 0 ? EPL_E : (lane >> 1 == 1 ? EPL_L : EPL_P);
+            sm.v[lane] = s[sum_idx(0, o, lane & 1)];
+        } else if (lane < 12) {   // composite pilot (WB:375-380) E, L, P
+            const int k = lane - 6;
+            const int o = k >> 1 == 0 ? EPL_E : (k >> 1 == 1 ? EPL_L : EPL_P);
+            sm.v[lane] = (k & 1) ? (-ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)])
+                                 : (-ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)]);
+        }
+        __syncwarp();
+        // lanes 0..5: (A, B) = data E, data L, data P, pilot E, pilot L, pilot P
+        const int l6 = lane < 6 ? lane : 0;
+        const double A = sm.v[2 * l6], B = sm.v[2 * l6 + 1];
+        const double mag = sqrt(A * A + B * B);
+        const double ang = atan(B / A) / 6.283185307179586476925286766559;   // WB:386,392
+        const double magN = __shfl_down_sync(0xffffffffu, mag, 1);
+        const double disc = (mag - magN) / (mag + magN);
+        const EpochParams& p = sm.p;
+        const double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
+        const double fm = fmod_pos(trig, 6.283185307179586476925286766559);   // == rem(trig, 2*pi), WB:337 (trig >= 0)
+        if (lane == 2) sm.pre[0] = ang;
+        if (lane == 5) sm.pre[1] = ang;
+        if (lane == 0) sm.pre[2] = disc;
+        if (lane == 3) sm.pre[3] = disc;
+        if (lane == 6) sm.pre[4] = fm;
     }
     __syncwarp();
     int ok = 0;
     if (lane == 0) {
-        int npOk;
-        close_epoch(g, c, e, sm.sums, sm.np, npOk, par ? sm.pre : nullptr);
-        ok = npOk;
+        close_core(g, sm.sums, sm.p, sm.chCodeFreq, sm.st, sm.outv, sm.pre);
+        sm.st.epoch = e + 1;
+        ok = next_params(g, sm.st, sm.np) && e + 1 < g.epochLimit;
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
     __syncwarp();
     const long long tc1 = clock64();
-    const bool more = ok && (e + 1 - g.cc[c].pad) < g.maxEpochs;  // another epoch of this channel in this launch?
+    const bool more = ok && (e + 1 - e0) < g.maxEpochs;  // another epoch of this channel in this launch?
     if (more) {
-        fast_build_tab_warp(g.fastTab + (size_t)c * 2 + ((e + 1) & 1), sm.np, g.fs, sm.scratch);
-        if (lane == 0) store_cg(g.params + c * 2 + ((e + 1) & 1), sm.np);
+        fast_build_tab_warp(tab, sm.np, g.fs, sm.scratch, sm.posbin);
+        if (lane < 3) __stcg(reinterpret_cast<uint4*>(g.params + c * 2 + ((e + 1) & 1)) + lane, reinterpret_cast<const uint4*>(&sm.np)[lane]);
     }
     const long long tc2 = clock64();
-    __threadfence();
     __syncwarp();
-    if (lane == 0) {
-        if (ok) st_release(g.ready + c, e + 1);
-        else st_release(g.stop + c, e + 1);
+    fence_acq_rel_gpu();
+    qbase = __shfl_sync(0xffffffffu, qbase, 31);
+    fw_fill_slices(g, qbase, c, e + 1, lane, !more);
+    if (lane == 0) {   // bookkeeping for the next launch's prepare kernel
+        if (ok) g.ready[c] = e + 1;
+        else g.stop[c] = e + 1;
+    }
+    const long long tc3 = clock64();
+    // ---- off the critical path: output planes, C/N0 + lock detector, state write-back ----
+    {
+        const int cap = g.capacity;
+        double* out = g.out + (size_t)c * kNFields * cap;
+        for (int f = lane; f < kNFields; f += 32)
+            if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
+        if (lane == 0 && !ok && e + 1 < g.epochLimit) out[(size_t)F_ABS * cap + e + 1] = (double)sm.st.pos;  // WB_tracking.m:254
+        if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0 && (e + 1) / g.cnoInterval - 1 < g.cnoCap) {
+            __threadfence();   // the prompts of this interval were stored by different lanes of this warp
+            __syncwarp();
+            const int ci = (e + 1) / g.cnoInterval - 1, n = g.cnoInterval, e0 = e + 1 - n;
+            double* cn = g.cno + (size_t)c * kNCno * g.cnoCap;
+            double d, dp, pv, pp;   // fast kernel = wide band with pilot: (I, Q) as stored (Calc_CNo_PLD.m:80-88)
+            cno_pld_warp(out + (size_t)F_I_P * cap + e0, out + (size_t)F_Q_P * cap + e0, n, g.PDI, d, dp);
+            cno_pld_warp(out + (size_t)F_PI_P * cap + e0, out + (size_t)F_PQ_P * cap + e0, n, g.PDI, pv, pp);
+            if (lane == 0) {
+                const double c0 = 10.0 * log10(d), c1 = 10.0 * log10(pv), c2 = 10.0 * log10(d + pv);
+                cn[0 * g.cnoCap + ci] = c0 * 0.5 + sm.st.cnoPrev[0] * 0.5;
+                cn[1 * g.cnoCap + ci] = dp;
+                cn[2 * g.cnoCap + ci] = c1 * 0.5 + sm.st.cnoPrev[1] * 0.5;
+                cn[3 * g.cnoCap + ci] = pp;
+                cn[4 * g.cnoCap + ci] = c2 * 0.5 + sm.st.cnoPrev[2] * 0.5;
+                sm.st.cnoPrev[0] = c0;
+                sm.st.cnoPrev[1] = c1;
+                sm.st.cnoPrev[2] = c2;
+            }
+            __syncwarp();
+        }
+        if (lane < 8) __stcg(reinterpret_cast<uint4*>(g.st + c) + lane, reinterpret_cast<const uint4*>(&sm.st)[lane]);
     }
     if (lane == 0 && g.counters) {
         atomicAdd(g.counters + 14, (unsigned long long)(tc0 - tcIn));
         atomicAdd(g.counters + 15, (unsigned long long)(tc1 - tc0));
         atomicAdd(g.counters + 16, (unsigned long long)(tc2 - tc1));
-        atomicAdd(g.counters + 17, (unsigned long long)(clock64() - tc2));
+        atomicAdd(g.counters + 17, (unsigned long long)(tc3 - tc2));
     }
     if (lane == 0 && g.pubTime) {
         const unsigned long long tOut = gtimer_ns();
@@ -186,8 +327,8 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e) {
             atomicAdd(g.counters + 11, 1ull);
         }
     }
-    if (more) fw_push_slices(g, c, e + 1, lane);
-    else fw_channel_done(g, lane, g.nCompute);
+    if (!more) fw_channel_done(g, lane, g.nCompute);
+    __syncwarp();
     return more;
 }
 
@@ -221,13 +362,13 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         FwCloseScratch* cs = reinterpret_cast<FwCloseScratch*>(dyn_smem) + warp;
         const int nCw = ((int)gridDim.x - g.nCompute) * (kFwThreads / 32);
         const int me = ((int)blockIdx.x - g.nCompute) * (kFwThreads / 32) + warp;
-        int chan[8], ep[8], n = 0;
+        int chan[8], ep[8], ep0[8], n = 0;
         for (int i = me; i < g.nAct && n < 8; i += nCw) {
             const int c = g.act[i];
             // channels that could not start were already retired by the prepare kernel (stop <= first epoch)
             if (g.stop[c] > g.cc[c].pad) {
                 chan[n] = c;
-                ep[n] = g.cc[c].pad;
+                ep[n] = ep0[n] = g.cc[c].pad;
                 ++n;
             }
         }
@@ -241,12 +382,13 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 fired = true;
                 if (lane == 0) g.count[chan[i]] = 0;
                 __syncwarp();
-                const bool more = fw_closure(g, *cs, chan[i], ep[i]);
+                const bool more = fw_closure(g, *cs, chan[i], ep[i], ep0[i]);
                 if (more) {
                     ++ep[i];
                 } else {
                     chan[i] = chan[n - 1];
                     ep[i] = ep[n - 1];
+                    ep0[i] = ep0[n - 1];
                     --n;
                     --i;
                 }
@@ -255,6 +397,10 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         }
         return;
     }
+    if (warp < kFwService) {
+#ifdef BDS_FW_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+#endif
     if (warp == 0) {
         // ================================ producer ================================
         if (lane != 0) return;
@@ -296,11 +442,15 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 }
                 const unsigned pl = (unsigned)ent;
                 if (pl == 0xffffffffu) break;
+                if (pl == kFwSkip) continue;
+                // params / table / codes were written with generic-proxy stores by a closer warp and are read
+                // below through the async proxy (TMA)
+                asm volatile("fence.proxy.async.global;" ::: "memory");
                 c = (int)(pl & 127u);
                 sl = (int)((pl >> 7) & 63u);
                 e = (int)(pl >> 13);
                 gp = g.params + c * 2 + (e & 1);
-                gt = g.fastTab + (size_t)c * 2 + (e & 1);
+                gt = g.fastTab + (size_t)c * 2;
             }
             const int cLo = sl * cps, cHi = min(10230, cLo + cps);  // host guarantees S = ceil(10230 / cps): never empty
             const EpochParams p = load_cg(gp);
@@ -392,8 +542,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 if (lane < kNSum) g.partial[((size_t)ce * g.S + sl) * kNSum + lane] = v;
                 continue;
             }
-            if (lane < kNSum) {
-                g.partial[((size_t)c * g.S + sl) * kNSum + lane] = v;
+            if (lane < kNSum) {   // exact: every partial is an integer multiple of 2^-8, |sum| < 2^45
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(g.acc + (size_t)c * kNSum + lane), "d"(v) : "memory");
                 __threadfence();
             }
             __syncwarp();
@@ -403,9 +553,13 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 if (g.trace && (unsigned)ce < g.traceCap) g.trace[(size_t)ce * 8 + 5] = gtimer_ns();
             }
         }
+    }
     } else {
         // ================================ compute ================================
-        const int cw = warp - 2;
+#ifdef BDS_FW_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BDS_FW_SETMAXNREG));
+#endif
+        const int cw = warp - kFwService;
         float acc[kNSum];
 #pragma unroll
         for (int i = 0; i < kNSum; ++i) acc[i] = 0.f;
@@ -502,6 +656,7 @@ __global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
     __shared__ unsigned scratch[32][128];
     __shared__ EpochParams nps[32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < g.nCh * kNSum; i += blockDim.x) g.acc[i] = 0.0;
     if (threadIdx.x == 0) {
         g.qctl[0] = 0;
         g.qctl[1] = 0;
@@ -516,8 +671,8 @@ __global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
                 ChanState st = g.st[c];
                 g.cc[c].pad = st.epoch;
                 e = st.epoch;
-                ok = next_params(g, st, nps[w]) && st.epoch < g.capacity && g.maxEpochs > 0;
-                if (!ok && st.epoch < g.capacity)
+                ok = next_params(g, st, nps[w]) && st.epoch < g.epochLimit && g.maxEpochs > 0;
+                if (!ok && st.epoch < g.epochLimit)
                     g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
                 g.ready[c] = ok ? e : e - 1;
                 g.stop[c] = ok ? INT_MAX : e;
@@ -530,7 +685,7 @@ __global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
         e = __shfl_sync(0xffffffffu, e, 0);
         __syncwarp();
         if (ok) {
-            fast_build_tab_warp(g.fastTab + (size_t)c * 2 + (e & 1), nps[w], g.fs, scratch[w]);
+            fast_build_tab_warp(g.fastTab + (size_t)c * 2, nps[w], g.fs, scratch[w]);
             if (lane == 0) store_cg(g.params + c * 2 + (e & 1), nps[w]);
             __threadfence();
             __syncwarp();

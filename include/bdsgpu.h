@@ -183,6 +183,12 @@ int bds_track_run(bds_trk* h, int n_epochs, const bds_trk_out* out, int out_stri
  * bds_track_fetch.  Used by bench.py for the HBM-resident timing and by the
  * multi-GPU path (NCCL gather of the packed device block). */
 int bds_track_run_async(bds_trk* h, int n_epochs);
+/* Host-record variant of bds_track_run_async for the end-to-end path (the reference streams the file
+ * with one fread per epoch, WB_tracking.m:265): x[n] (host; pinned memory gives full PCIe rate) is
+ * copied to the device in chunk_bytes pieces (0 = 128 MiB) on a copy stream while the persistent
+ * kernel tracks what has already arrived; n_epochs = total epochs per channel.  Replaces the
+ * session's resident record.  x must stay valid until bds_track_sync / bds_track_fetch returns. */
+int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs);
 int bds_track_sync(bds_trk* h);
 int bds_track_fetch(bds_trk* h, const bds_trk_out* out, int out_stride);
 /* packed device result block: [n_ch][n_fields=21+18][capacity] doubles */

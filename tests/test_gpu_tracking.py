@@ -186,3 +186,52 @@ def test_cno_and_lock_detector():
             np.testing.assert_allclose(got[c][f], tr[c][f], atol=0.02)
         for f in ("DataPLD", "PilotPLD"):
             np.testing.assert_allclose(got[c][f], tr[c][f], atol=2e-3)
+
+
+@pytest.mark.parametrize("kernel", ["general", "fast"])
+def test_streamed_host_record_equals_resident_record(kernel, tmp_path):
+    """bds_track_run_streamed (chunked H2D under the kernel; channels stop at the end of the arrived data and
+    are resumed by the next launch) gives bit-identical results to tracking the fully resident record, for
+    a host array, a file path (bds_track_open_file) and odd chunk sizes."""
+    s, sats, x, ch = util.record("WB", 2, 0.13)
+    ps = util.product_settings(s)
+    kern = L.KERNEL_GENERAL if kernel == "general" else L.KERNEL_FAST
+    N = 9
+    with _track.TrackSession("WB", ps, ch, kernel=kern) as ses:        # resident: one copy, then one launch
+        ses.feed(x)
+        ses.run_async(N)
+        want = ses.fetch(N, raw=True)
+    outs = []
+    for chunk in (1 << 20, 3 * 4096 + 4096 * 777):
+        with _track.TrackSession("WB", ps, ch, kernel=kern) as ses:
+            ses.run_streamed(x.ctypes.data, x.size, N, chunk_bytes=chunk)
+            outs.append(ses.fetch(N, raw=True))
+    path = tmp_path / "if.bin"
+    x.tofile(path)
+    with _track.TrackSession("WB", ps, ch, source=str(path), kernel=kern) as ses:
+        ses.run_async(N)
+        outs.append(ses.fetch(N, raw=True))
+    got_api, _ = _track.run_tracking("WB", x, ch, ps, n_epochs=N, kernel=kern, raw=True)
+    for o in outs:
+        assert list(o["epochsDone"]) == [N, N]
+        for k in want:
+            np.testing.assert_array_equal(o[k], want[k], err_msg=k)
+    np.testing.assert_array_equal(got_api[0].raw, want["raw"][0])
+
+
+def test_golden_fixture_open_loop():
+    """The committed golden record / sums (tests/golden, generated from the oracle) through both kernels."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
+    x = g["if_b1c"]
+    for mode, kernels in (("WB", (L.KERNEL_GENERAL, L.KERNEL_FAST)), ("NB", (L.KERNEL_GENERAL,))):
+        s = util.settings_for(mode)
+        want = g[f"trk_sums_{mode}"]
+        for kern in kernels:
+            got = open_loop(mode, s, x, [int(g["trk_prn"])], g["trk_nco"].reshape(1, 1, 6), kern)[0, 0]
+            err = np.abs(got - want) / util.family_scale(want[None, :])[0]
+            assert np.max(err) <= 1e-4, (mode, kern, float(np.max(err)))
+    s = util.settings_for("B2a")
+    got = open_loop("B2a", s, g["if_b2a"], [int(g["trk_prn"])], g["trk_nco_b2a"].reshape(1, 1, 6), L.KERNEL_GENERAL)[0, 0]
+    want = g["trk_sums_B2a"]
+    assert np.max(np.abs(got - want) / util.family_scale(want[None, :])[0]) <= 1e-4
