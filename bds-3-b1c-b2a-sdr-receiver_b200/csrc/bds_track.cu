@@ -306,8 +306,9 @@ __device__ void close_core(const TrkDev& g, const double* s, const EpochParams& 
         double pIP = s[sum_idx(1, EPL_P, 0)], pQP = s[sum_idx(1, EPL_P, 1)];
         double pc = dll_disc(s[sum_idx(1, EPL_E, 0)], s[sum_idx(1, EPL_E, 1)], s[sum_idx(1, EPL_L, 0)],
                              s[sum_idx(1, EPL_L, 1)]);
+        if (pre) pc = pre[3];
         if (g.mode == BDS_TRK_B1C_NB) {
-            double pe = atan(-pIP / pQP) / twopi;   // NB:357
+            double pe = pre ? pre[1] : atan(-pIP / pQP) / twopi;   // NB:357
             carrError = (carrError * 11 + pe * 29) / 40;
             codeError = (codeError * 11 + pc * (1.0 - g.d) * 29) / 40;
         } else {
@@ -660,6 +661,7 @@ struct bds_trk {
 namespace {
 
 unsigned long long g_open_loop_counters[4] = {0, 0, 0, 0};
+unsigned long long g_open_loop_us = 0;   // device time of the last open-loop chip-synchronous kernel launch
 
 bool mode_flags(int mode, int flag, int& hasPilot, int& hasP61) {
     hasPilot = (mode == BDS_TRK_B1C_WB && flag == 2) || (mode != BDS_TRK_B1C_WB && flag == 1);
@@ -707,7 +709,6 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.tune = 0;
     g.ahead = 2;
     if (const char* e = getenv("BDS_TRK_AHEAD")) g.ahead = atoi(e);
-    if (const char* e = getenv("BDS_TRK_STAGES")) g.stages = std::max(2, std::min(kFwStages, atoi(e)));
     g.ahead = std::max(0, std::min(g.ahead, g.stages - 1));   // more passes in flight than stages would deadlock the producer
     if (const char* e = getenv("BDS_TRK_TUNE")) g.tune = atoi(e);
     g.maxEpochs = maxEpochs;
@@ -745,7 +746,7 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
 int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
     int hasPilot, hasP61;
     mode_flags(mode, cfg->pilotTRKflag, hasPilot, hasP61);
-    bool can = fast_wb_supported(mode, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
+    bool can = fast_wb_supported(mode, hasPilot, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
                                  cfg->dllCorrelatorSpacing);
     if (cfg->kernel == BDS_KERNEL_FAST && !can)
         return set_error(BDS_ERR_UNSUPPORTED, "fast tracking kernel does not support this configuration");
@@ -922,10 +923,10 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
     }
     if (h->fast) {
         TRY(cudaMalloc(&h->dFastTab, sizeof(FastTab) * (size_t)n_ch * 2));
-        unsigned need = (unsigned)(2 * n_ch * h->S + h->gridBlocks + 64);
+        unsigned need = (unsigned)(2 * n_ch * h->S + 2 * h->gridBlocks + 64);
         h->qSize = 1024;
         while (h->qSize < need) h->qSize <<= 1;
-        TRY(cudaMalloc(&h->dQueue, sizeof(unsigned long long) * h->qSize));
+        TRY(cudaMalloc(&h->dQueue, sizeof(unsigned long long) * 2 * h->qSize));   // 16-byte entries
         TRY(cudaMalloc(&h->dQctl, 64));
         if (const char* e = getenv("BDS_TRK_TRACE")) {
             h->traceCap = (unsigned)atoi(e);
@@ -1029,7 +1030,7 @@ static int launch_run(bds_trk* h, int maxEpochs, int epochLimit) {
     fill_dev(h, g, maxEpochs);
     g.epochLimit = std::min(epochLimit, h->capacity);
     if (h->fast) {
-        BDS_CUDA(cudaMemsetAsync(h->dQueue, 0, sizeof(unsigned long long) * h->qSize, h->stream));
+        BDS_CUDA(cudaMemsetAsync(h->dQueue, 0, sizeof(unsigned long long) * 2 * h->qSize, h->stream));
         fw_prepare_kernel<<<1, 1024, 0, h->stream>>>(g, h->nCompute);
     } else trk_prepare_kernel<<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
     count_launch();
@@ -1236,6 +1237,8 @@ int bds_track_counters(bds_trk* h, long long* out4) {
     if (getenv("BDS_TRK_TIMING"))  // developer breakdown (SM cycles summed over CTAs)
         fprintf(stderr, "[bds timing] producer: queue %llu empty %llu total %llu | compute(w2): full-wait %llu res-wait %llu | closer: closure %llu epilogue %llu closures %llu\n",
                 v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+    if (getenv("BDS_TRK_TIMING"))
+        fprintf(stderr, "[bds timing] producer detail: ticket atomic %llu, proxy fence %llu, pass issue %llu\n", v[18], v[19], v[20]);
     if (getenv("BDS_TRK_TIMING") && v[11])
         fprintf(stderr, "[bds timing] per closure: publish->slices done %.2f us, closure %.2f us\n",
                 (double)v[12] / (double)v[11] * 1e-3, (double)v[13] / (double)v[11] * 1e-3);
@@ -1397,7 +1400,18 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         g.stages = kFwStages;
         g.tune = 0;
         g.ahead = -1;
+        cudaEvent_t e0, e1;
+        TRYC(cudaEventCreate(&e0));
+        TRYC(cudaEventCreate(&e1));
+        TRYC(cudaEventRecord(e0, 0));
         trk_fw_kernel<<<g_num_sms, kFwThreads, smem>>>(g);
+        TRYC(cudaEventRecord(e1, 0));
+        TRYC(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        g_open_loop_us = (unsigned long long)(ms * 1000.f);
     } else {
         trk_open_loop_kernel<<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);
     }
@@ -1407,6 +1421,7 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     TRYC(cudaGetLastError());
     TRYC(cudaMemcpy(sums, dSums, sizeof(double) * (size_t)nce * kNSum, cudaMemcpyDeviceToHost));
     TRYC(cudaMemcpy(g_open_loop_counters, dCnt, 32, cudaMemcpyDeviceToHost));
+    g_open_loop_counters[3] = g_open_loop_us;
 #undef TRYC
     cleanup();
     return BDS_OK;

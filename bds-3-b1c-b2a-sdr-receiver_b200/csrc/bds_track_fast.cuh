@@ -40,9 +40,11 @@ struct __align__(16) FastTab {
 };
 static_assert(sizeof(FastTab) % 16 == 0, "FastTab must be a 16-byte multiple");
 
-inline bool fast_wb_supported(int mode, int hasP61, double fs, double fc, int codeLength, double d) {
-    return mode == BDS_TRK_B1C_WB && hasP61 && codeLength == 10230 && fs == FAST_FS_HZ && fc == FAST_FC_HZ &&
-           d == FAST_D;
+// B1C with a pilot: wide band (data + BOC(1,1) + BOC(6,1) pilot, 18 sums) or narrow band (the same minus the
+// BOC(6,1) replica, 12 sums — the unused sums are zeroed by the epilogue warp).
+inline bool fast_wb_supported(int mode, int hasPilot, int hasP61, double fs, double fc, int codeLength, double d) {
+    const bool modeOk = (mode == BDS_TRK_B1C_WB && hasP61) || (mode == BDS_TRK_B1C_NB && hasPilot);
+    return modeOk && codeLength == 10230 && fs == FAST_FS_HZ && fc == FAST_FC_HZ && d == FAST_D;
 }
 
 // ---- per-epoch table construction (one warp) -------------------------------------------------
@@ -275,7 +277,7 @@ __device__ __forceinline__ int sel_bit(int s, unsigned m) {
 // chip went through the exact per-sample path.
 __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams& p, const uint32_t* bitsData,
                                           const uint32_t* bitsPilot, const unsigned char* tile, long long tileBase,
-                                          long long B0, const int8_t* xblk, double dSpacing, double fs, int c,
+                                          int tileBytes, long long B0, const int8_t* xblk, double dSpacing, double fs, int c,
                                           unsigned guard, float* acc) {
     // ---- per-chip phase bookkeeping (fp64) ----
     const double q = ((double)(12 * c) - tab.u0) * tab.S;  // sample position of the chip start
@@ -292,8 +294,9 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
     bool exact = !tab.valid || below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
     const int len = FAST_RLAST + ((mk.y >> 3) & 1);          // bit 35 (k = 36): last sample still mine
     if (nc < 0 || nc + len > p.blksize) exact = true;
+    const long long o = B0 + nc - tileBase;   // the chip's first sample inside the staged bytes
+    if (o < 0 || o + 4 * (FAST_NWORDS + 1) > (long long)tileBytes) exact = true;
     if (!exact) {
-        const long long o = B0 + nc - tileBase;
         const unsigned* raw = reinterpret_cast<const unsigned*>(tile) + (o >> 2);
         const unsigned sh = (unsigned)(o & 3) * 8u;
         const int4* wt = tab.w;

@@ -49,6 +49,7 @@ struct FwUnit {
     int c0, cEnd;          // chip range of this pass
     int first, last;       // first / last pass of the task
     int ce, ticket;        // open loop: channel-epoch index; queue ticket (developer tracing)
+    int tileBytes, pad_;   // bytes staged in tile[]
     long long tileBase;    // window byte offset of tile[0]
     long long B0;          // window byte offset of the block start
 };
@@ -111,35 +112,59 @@ __host__ __device__ inline int fw_chips_per_slice(int S) {
 }
 
 // ---- ready-task queue -----------------------------------------------------------------------------
-// payload: channel (7 bits) | slice (6 bits) << 7 | epoch (19 bits) << 13 ; 0xffffffff = terminate
+// Ring of 16-byte entries {tag, info}: tag = (ticket + 1) << 32 | payload, info = lap << 48 | block start (absolute
+// sample index, 48 bits).  payload: channel (7 bits) | slice (6 bits) << 7 | epoch (19 bits) << 13; 0xffffffff =
+// terminate, 0xfffffffe = skip.  A consumer reads an entry with ONE 16-byte load and accepts it when the tag carries
+// its ticket and info carries the ring lap of that ticket (so a torn read can never be mistaken for a valid entry);
+// everything it needs to start the TMA copies is in the entry, so popping a task costs one L2 round trip.
 __device__ __forceinline__ unsigned fw_payload(int c, int sl, int e) { return (unsigned)c | ((unsigned)sl << 7) | ((unsigned)e << 13); }
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+constexpr unsigned kFwSkip = 0xfffffffeu;   // reserved-but-unused queue slot: consumers pop the next ticket
+constexpr unsigned kFwTerminate = 0xffffffffu;
+__device__ __forceinline__ unsigned fw_lap(const TrkDev& g, unsigned ticket) { return (ticket >> __popc(g.qMask)) & 0xffffu; }
+__device__ __forceinline__ void fw_put(const TrkDev& g, unsigned ticket, unsigned payload, long long pos) {
+    const unsigned long long tag = ((unsigned long long)(ticket + 1u) << 32) | payload;
+    const unsigned long long info = ((unsigned long long)fw_lap(g, ticket) << 48) | ((unsigned long long)pos & 0xffffffffffffull);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(g.queue + 2 * (size_t)(ticket & g.qMask)), "l"(tag), "l"(info)
+                 : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+// one poll of the slot of `ticket`; true when the entry is there
+__device__ __forceinline__ bool fw_peek(const TrkDev& g, unsigned ticket, unsigned& payload, long long& pos) {
+    unsigned long long tag, info;
+    asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(tag), "=l"(info)
+                 : "l"(g.queue + 2 * (size_t)(ticket & g.qMask))
+                 : "memory");
+    payload = (unsigned)tag;
+    pos = (long long)(info & 0xffffffffffffull);
+    return (tag >> 32) == (unsigned long long)ticket + 1ull && (unsigned)(info >> 48) == fw_lap(g, ticket);
 }
-// push the S slices of (c, e); caller has fenced its prior writes (params, tables)
-__device__ void fw_push_slices(const TrkDev& g, int c, int e, int lane) {
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Writers issue a gpu-scope release fence after the last write the consumers will read, then fw_put; fw_peek is an
+// acquire load.
+// push the S slices of (c, e) at freshly reserved tickets
+__device__ void fw_push_slices(const TrkDev& g, int c, int e, long long pos, int lane) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(g.qctl + 1, (unsigned)g.S);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (int s = lane; s < g.S; s += 32)
-        st_release_u64(g.queue + ((base + s) & g.qMask), ((unsigned long long)(base + s + 1) << 32) | fw_payload(c, s, e));
+    for (int s = lane; s < g.S; s += 32) fw_put(g, base + s, fw_payload(c, s, e), pos);
 }
-constexpr unsigned kFwSkip = 0xfffffffeu;   // reserved-but-unused queue slot: consumers pop the next ticket
 // fill S slots reserved earlier at `base` (atomicAdd on qctl[1]) with the slices of (c, e), or with skip entries
-// (the caller has issued a gpu-scope release fence after its last write the consumers will read; consumers
-// ld.acquire the slot)
-__device__ void fw_fill_slices(const TrkDev& g, unsigned base, int c, int e, int lane, bool skip) {
-    for (int s = lane; s < g.S; s += 32) {
-        const unsigned long long v = ((unsigned long long)(base + s + 1) << 32) | (skip ? kFwSkip : fw_payload(c, s, e));
-        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(g.queue + ((base + s) & g.qMask)), "l"(v) : "memory");
-    }
+__device__ void fw_fill_slices(const TrkDev& g, unsigned base, int c, int e, long long pos, int lane, bool skip) {
+    for (int s = lane; s < g.S; s += 32) fw_put(g, base + s, skip ? kFwSkip : fw_payload(c, s, e), pos);
 }
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ void fw_push_terminate(const TrkDev& g, int n, int lane) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(g.qctl + 1, (unsigned)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int s = lane; s < n; s += 32) fw_put(g, base + s, kFwTerminate, 0);
+}
+// a channel has no further epoch in this launch: the last one to end shuts the grid down
+__device__ void fw_channel_done(const TrkDev& g, int lane, int nCtas) {
+    unsigned left = 0;
+    if (lane == 0) left = atomicSub(g.qctl + 2, 1u) - 1u;
+    left = __shfl_sync(0xffffffffu, left, 0);
+    if (left == 0) fw_push_terminate(g, 2 * nCtas, lane);   // a producer may hold one prefetched ticket at the end
+}
 // exact fmod(x, y) for 0 <= x, 0 < y, x/y < 2^52: the result x - n*y is representable, so one fma is exact;
 // the +-y steps repair a quotient that rounded across an integer.  (libdevice fmod iterates ~20 times here.)
 __device__ __forceinline__ double fmod_pos(double x, double y) {
@@ -149,20 +174,6 @@ __device__ __forceinline__ double fmod_pos(double x, double y) {
     if (r < 0.0) r += y;
     if (r >= y) r -= y;
     return r;
-}
-__device__ void fw_push_terminate(const TrkDev& g, int n, int lane) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(g.qctl + 1, (unsigned)n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (int s = lane; s < n; s += 32)
-        st_release_u64(g.queue + ((base + s) & g.qMask), ((unsigned long long)(base + s + 1) << 32) | 0xffffffffull);
-}
-// a channel has no further epoch in this launch: the last one to end shuts the grid down
-__device__ void fw_channel_done(const TrkDev& g, int lane, int nCtas) {
-    unsigned left = 0;
-    if (lane == 0) left = atomicSub(g.qctl + 2, 1u) - 1u;
-    left = __shfl_sync(0xffffffffu, left, 0);
-    if (left == 0) fw_push_terminate(g, nCtas, lane);
 }
 
 __device__ __forceinline__ unsigned long long gtimer_ns() {
@@ -232,19 +243,28 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     {
         const double* s = sm.sums;
         const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
+        const bool wb = g.mode == BDS_TRK_B1C_WB;
         if (lane < 6) {   // v[2k], v[2k+1] = (I, Q) of data E, L, P
             const int o = lane >> 1 == 0 ? EPL_E : (lane >> 1 == 1 ? EPL_L : EPL_P);
             sm.v[lane] = s[sum_idx(0, o, lane & 1)];
-        } else if (lane < 12) {   // composite pilot (WB:375-380) E, L, P
+        } else if (lane < 12) {   // pilot E, L, P: composite (WB:375-380) or the BOC(1,1) pilot itself (NB)
             const int k = lane - 6;
             const int o = k >> 1 == 0 ? EPL_E : (k >> 1 == 1 ? EPL_L : EPL_P);
-            sm.v[lane] = (k & 1) ? (-ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)])
-                                 : (-ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)]);
+            if (wb)
+                sm.v[lane] = (k & 1) ? (-ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)])
+                                     : (-ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)]);
+            else
+                sm.v[lane] = s[sum_idx(1, o, k & 1)];
         }
         __syncwarp();
         // lanes 0..5: (A, B) = data E, data L, data P, pilot E, pilot L, pilot P
         const int l6 = lane < 6 ? lane : 0;
-        const double A = sm.v[2 * l6], B = sm.v[2 * l6 + 1];
+        double A = sm.v[2 * l6], B = sm.v[2 * l6 + 1];
+        if (!wb && lane == 5) {   // narrow band pilot PLL discriminator: atan(-p11_I_P / p11_Q_P), NB:357
+            const double t = A;
+            A = B;
+            B = -t;
+        }
         const double mag = sqrt(A * A + B * B);
         const double ang = atan(B / A) / 6.283185307179586476925286766559;   // WB:386,392
         const double magN = __shfl_down_sync(0xffffffffu, mag, 1);
@@ -277,7 +297,7 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     __syncwarp();
     fence_acq_rel_gpu();
     qbase = __shfl_sync(0xffffffffu, qbase, 31);
-    fw_fill_slices(g, qbase, c, e + 1, lane, !more);
+    fw_fill_slices(g, qbase, c, e + 1, sm.np.pos, lane, !more);
     if (lane == 0) {   // bookkeeping for the next launch's prepare kernel
         if (ok) g.ready[c] = e + 1;
         else g.stop[c] = e + 1;
@@ -295,9 +315,10 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
             __syncwarp();
             const int ci = (e + 1) / g.cnoInterval - 1, n = g.cnoInterval, e0 = e + 1 - n;
             double* cn = g.cno + (size_t)c * kNCno * g.cnoCap;
-            double d, dp, pv, pp;   // fast kernel = wide band with pilot: (I, Q) as stored (Calc_CNo_PLD.m:80-88)
+            double d, dp, pv, pp;   // pilot (I, Q) as stored for wide band, swapped for narrow band (Calc_CNo_PLD.m:80-88)
             cno_pld_warp(out + (size_t)F_I_P * cap + e0, out + (size_t)F_Q_P * cap + e0, n, g.PDI, d, dp);
-            cno_pld_warp(out + (size_t)F_PI_P * cap + e0, out + (size_t)F_PQ_P * cap + e0, n, g.PDI, pv, pp);
+            const int fpi = g.mode == BDS_TRK_B1C_WB ? F_PI_P : F_PQ_P, fpq = g.mode == BDS_TRK_B1C_WB ? F_PQ_P : F_PI_P;
+            cno_pld_warp(out + (size_t)fpi * cap + e0, out + (size_t)fpq * cap + e0, n, g.PDI, pv, pp);
             if (lane == 0) {
                 const double c0 = 10.0 * log10(d), c1 = 10.0 * log10(pv), c2 = 10.0 * log10(d + pv);
                 cn[0 * g.cnoCap + ci] = c0 * 0.5 + sm.st.cnoPrev[0] * 0.5;
@@ -352,7 +373,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
     const long long perRound = openLoop ? (long long)g.S : (long long)g.nAct * g.S;
     const long long total = openLoop ? (long long)g.olCount * g.S : perRound * g.maxEpochs;
     const int cps = fw_chips_per_slice(g.S);
-    const unsigned nst = (unsigned)g.stages;
+    constexpr unsigned nst = (unsigned)kFwStages;   // compile-time: u % nst, u / nst become mask / shift
 
     if (!openLoop && (int)blockIdx.x >= g.nCompute) {
         // ================================ closer CTA ================================
@@ -406,12 +427,16 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         if (lane != 0) return;
         unsigned u = 0;
         int seq = 0;
-        long long tQueue = 0, tEmpty = 0, tStart = clock64();
-        unsigned curTicket = 0;
+        long long tQueue = 0, tEmpty = 0, tStart = clock64(), tTicket = 0, tFence = 0, tIssue = 0;
+        unsigned curTicket = 0, nextTicket = 0;
+        bool haveNext = false;
         for (long long t = blockIdx.x;; t += gridDim.x) {
             int c, e, sl, ce = 0;
             const EpochParams* gp;
             const FastTab* gt;
+            long long B0;
+            bool nominal = true;          // tile bounds from the nominal chip rate (no dependence on the epoch's NCO)
+            double u0 = 0, Ss = 0;
             if (openLoop) {
                 if (t >= total) break;
                 ce = (int)(t / g.S);
@@ -420,6 +445,11 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 e = ce - c * g.olEpochs;
                 gp = g.olParams + ce;
                 gt = g.fastTab + ce;
+                const EpochParams p = load_cg(gp);
+                u0 = 12.0 * p.rem;
+                Ss = 1.0 / (12.0 * p.step);   // == tab.u0, tab.S (same expressions)
+                B0 = p.pos - g.winFirst;
+                nominal = false;
             } else {
                 // take work only when a stage is free for it (tasks are scarce while channels sit in loop
                 // closure, so a CTA must not hoard them), then pop the next ready (channel, epoch, slice)
@@ -430,36 +460,46 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                     tEmpty += clock64() - t1;
                 }
                 long long t0 = clock64();
-                const unsigned ticket = atomicAdd(g.qctl + 0, 1u);
-                unsigned long long ent;
-                while (((ent = ld_acquire_u64(g.queue + (ticket & g.qMask))) >> 32) != (unsigned long long)ticket + 1ull)
+                const unsigned ticket = haveNext ? nextTicket : atomicAdd(g.qctl + 0, 1u);
+                haveNext = false;
+                tTicket += clock64() - t0;
+                unsigned pl;
+                long long pos;
+                bool waited = false;
+                while (!fw_peek(g, ticket, pl, pos)) {
+                    waited = true;
                     __nanosleep(64);
+                }
+                // backlog (the entry was already there): take the next ticket now so that its round trip overlaps this
+                // task; starved (we had to wait): take tickets on demand so that no ready task sits behind a busy CTA
+                if ((g.tune & 8) && !waited && pl != kFwTerminate) {
+                    nextTicket = atomicAdd(g.qctl + 0, 1u);
+                    haveNext = true;
+                }
                 tQueue += clock64() - t0;
                 curTicket = ticket;
                 if (g.trace && ticket < g.traceCap) {
-                    g.trace[(size_t)ticket * 8 + 0] = ((unsigned long long)blockIdx.x << 32) | (unsigned)ent;
+                    g.trace[(size_t)ticket * 8 + 0] = ((unsigned long long)blockIdx.x << 32) | pl;
                     g.trace[(size_t)ticket * 8 + 1] = gtimer_ns();
                 }
-                const unsigned pl = (unsigned)ent;
-                if (pl == 0xffffffffu) break;
+                if (pl == kFwTerminate) break;
                 if (pl == kFwSkip) continue;
-                // params / table / codes were written with generic-proxy stores by a closer warp and are read
-                // below through the async proxy (TMA)
-                asm volatile("fence.proxy.async.global;" ::: "memory");
+                // params / table were written with generic-proxy stores by a closer warp (made visible by its release
+                // fence + the acquire load above) and are read below through the async proxy (TMA)
+                {
+                    long long tf = clock64();
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    tFence += clock64() - tf;
+                }
                 c = (int)(pl & 127u);
                 sl = (int)((pl >> 7) & 63u);
                 e = (int)(pl >> 13);
                 gp = g.params + c * 2 + (e & 1);
                 gt = g.fastTab + (size_t)c * 2;
+                B0 = pos - g.winFirst;
             }
             const int cLo = sl * cps, cHi = min(10230, cLo + cps);  // host guarantees S = ceil(10230 / cps): never empty
-            const EpochParams p = load_cg(gp);
-            double u0 = 12.0 * p.rem, Ss = 1.0 / (12.0 * p.step);  // == tab.u0, tab.S (same expressions)
-            if (g.tune & 4) {
-                u0 = __ldcg(&gt->u0);
-                Ss = __ldcg(&gt->S);
-            }
-            const long long B0 = p.pos - g.winFirst;
+            const long long gMax = (g.winLen + 16) & ~15LL;         // every IF buffer has >= 16 bytes of slack past winLen
             int c0 = cLo;
             do {
                 const int cEnd = min(c0 + kFwChips, cHi);
@@ -467,25 +507,35 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 long long t1 = clock64();
                 mbar_wait(&sm.empty[stage], ((u / nst) & 1) ^ 1);
                 tEmpty += clock64() - t1;
+                const long long ti0 = clock64();
                 FwStage& st = sm.st[stage];
-                long long na = 0, nb = 0;
-                if (cEnd > c0) {
-                    double qa = ((double)(12 * c0) - u0) * Ss, qb = ((double)(12 * cEnd) - u0) * Ss;
+                long long na, nb;
+                if (nominal) {
+                    // chip c starts (c - rem) / step samples into the block: rem < 1 sample and the code rate is within
+                    // ~1e-5 of nominal, i.e. within ~11 samples of c * fs/fc.  A chip that nevertheless falls outside
+                    // the staged bytes is detected by the compute thread and evaluated from global memory.
+                    na = (long long)c0 * (long long)(FAST_FS_HZ / 1000.0) / (long long)(FAST_FC_HZ / 1000.0) - 32;
+                    nb = (long long)cEnd * (long long)(FAST_FS_HZ / 1000.0) / (long long)(FAST_FC_HZ / 1000.0) + 40;
+                } else {
+                    const double qa = ((double)(12 * c0) - u0) * Ss, qb = ((double)(12 * cEnd) - u0) * Ss;
                     na = (long long)floor(qa) - 2;
-                    nb = (long long)floor(qb) + 4;
-                    if (na < 0) na = 0;
-                    if (nb > p.blksize) nb = p.blksize;
-                    if (nb < na) nb = na;
+                    nb = (long long)floor(qb) + 12;   // a chip reads 26 aligned words from its first sample
                 }
-                const long long gA = (B0 + na) & ~15LL;
+                if (na < 0) na = 0;
+                if (nb < na) nb = na;
+                long long gA = (B0 + na) & ~15LL;
+                if (gA < 0) gA = 0;
                 long long gE = (B0 + nb + 15) & ~15LL;
+                if (gE > gMax) gE = gMax;
                 if (gE - gA > kFwTile) gE = gA + kFwTile;
+                if (gE < gA) gE = gA;
                 const unsigned bytes = (unsigned)(gE - gA);
                 FwUnit d;
                 d.c = c; d.e = e; d.sl = sl; d.seq = seq;
                 d.c0 = c0; d.cEnd = cEnd;
                 d.first = (c0 == cLo); d.last = (cEnd >= cHi);
                 d.ce = ce; d.ticket = (int)curTicket;
+                d.tileBytes = (int)bytes; d.pad_ = 0;
                 d.tileBase = gA; d.B0 = B0;
                 st.u = d;
                 mbar_expect_tx(&sm.full[stage], bytes + (unsigned)sizeof(FastTab) + kFwBitsBytes + (unsigned)sizeof(EpochParams));
@@ -496,6 +546,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 if (g.trace && d.first && curTicket < g.traceCap && !openLoop) g.trace[(size_t)curTicket * 8 + 2] = gtimer_ns();
                 ++u;
                 c0 = cEnd;
+                tIssue += clock64() - ti0;
             } while (c0 < cHi);
             ++seq;
         }
@@ -509,6 +560,9 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
             atomicAdd(g.counters + 4, (unsigned long long)tQueue);
             atomicAdd(g.counters + 5, (unsigned long long)tEmpty);
             atomicAdd(g.counters + 6, (unsigned long long)(clock64() - tStart));
+            atomicAdd(g.counters + 18, (unsigned long long)tTicket);
+            atomicAdd(g.counters + 19, (unsigned long long)tFence);
+            atomicAdd(g.counters + 20, (unsigned long long)tIssue);
         }
     } else if (warp == 1) {
         // ================================ epilogue warp ================================
@@ -526,7 +580,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 long long a = 0;
 #pragma unroll
                 for (int w = 0; w < kFwCompute; ++w) a += sm.res[rs][w][lane];
-                v = (double)a * (1.0 / 256.0);
+                v = (lane >= 12 && !g.hasP61) ? 0.0 : (double)a * (1.0 / 256.0);   // narrow band: no BOC(6,1) sums
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.resEmpty[rs]);
@@ -564,12 +618,19 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
 #pragma unroll
         for (int i = 0; i < kNSum; ++i) acc[i] = 0.f;
         const unsigned guard = g.pad ? (1u << 24) : kFastGuard;  // g.pad: test hook, widens the guard band
+        unsigned nFast = 0, nExact = 0;   // diagnostics (bds_track_counters), flushed once per task
+#ifdef BDS_FW_DEV
         long long tFull = 0, tRes = 0;
+#endif
         for (unsigned u = 0;; ++u) {
             const int stage = u % nst;
+#ifdef BDS_FW_DEV
             long long t0 = clock64();
+#endif
             mbar_wait(&sm.full[stage], (u / nst) & 1);
+#ifdef BDS_FW_DEV
             tFull += clock64() - t0;
+#endif
             const FwStage& st = sm.st[stage];
             const FwUnit d = st.u;
             if (d.c < 0) {  // terminate: forward to the closer through the result channel
@@ -578,20 +639,25 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                     mbar_wait(&sm.resEmpty[rs], ((d.seq >> 1) & 1) ^ 1);
                     if (cw == 0) sm.resTask[rs][0] = -1;
                     mbar_arrive(&sm.resFull[rs]);
+#ifdef BDS_FW_DEV
                     if (cw == 0 && g.counters) {
                         atomicAdd(g.counters + 7, (unsigned long long)tFull);
                         atomicAdd(g.counters + 8, (unsigned long long)tRes);
                     }
+#endif
                 }
                 break;
             }
             const int c = d.c0 + cw * 32 + lane;
             const bool active = c < d.cEnd;
             bool exact = false;
+#ifdef BDS_FW_DEV
             const bool tr = g.trace && cw == 0 && lane == 0 && (unsigned)d.ticket < g.traceCap && !openLoop;
             if (tr && d.first) g.trace[(size_t)d.ticket * 8 + 3] = gtimer_ns();
+#endif
             if (d.first && d.sl == 0 && cw == 0 && lane == 0 && st.p.rem == 0.0) {
-                // the t = 0 sample takes the previous period's last chip (SURVEY quirk i)
+                // first pass of slice 0 of an epoch with remCodePhase == 0: the t = 0 sample takes the previous
+                // period's last chip (SURVEY quirk i)
                 ExactCtx ex;
                 make_exact_ctx(st.p, g.d, g.fs, ex);
                 float tmp[kNSum];
@@ -602,31 +668,38 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
             }
             if (active)
-                exact = fast_chip(st.tab, st.p, st.bits[0], st.bits[1], st.tile, d.tileBase, d.B0, g.x + d.B0, g.d, g.fs,
-                                  c, guard, acc);
-            if (g.counters) {
-                unsigned bf = __ballot_sync(0xffffffffu, active && !exact), be = __ballot_sync(0xffffffffu, active && exact);
-                if (lane == 0) {
-                    if (bf) atomicAdd(g.counters + 0, (unsigned long long)__popc(bf));
-                    if (be) atomicAdd(g.counters + 1, (unsigned long long)__popc(be));
-                }
-            }
+                exact = fast_chip(st.tab, st.p, st.bits[0], st.bits[1], st.tile, d.tileBase, d.tileBytes, d.B0, g.x + d.B0, g.d,
+                                  g.fs, c, guard, acc);
+            nFast += active && !exact;
+            nExact += active && exact;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
+#ifdef BDS_FW_DEV
             if (tr && d.last) g.trace[(size_t)d.ticket * 8 + 4] = gtimer_ns();
+#endif
             if (d.last) {
                 const int rs = d.seq & 1;
-                int mine = 0;
+#ifdef BDS_FW_DEV
+                long long t2 = clock64();
+#endif
+                mbar_wait(&sm.resEmpty[rs], ((d.seq >> 1) & 1) ^ 1);
+#ifdef BDS_FW_DEV
+                tRes += clock64() - t2;
+#endif
 #pragma unroll
-                for (int i = 0; i < kNSum; ++i) {
-                    int s = __reduce_add_sync(0xffffffffu, __float2int_rn(acc[i] * 256.f));
-                    if (lane == i) mine = s;
+                for (int i = 0; i < kNSum; ++i) {   // warp sums in Q8 fixed point (exact integer adds from here on)
+                    const int s = __reduce_add_sync(0xffffffffu, __float2int_rn(acc[i] * 256.f));
+                    if (lane == 0) sm.res[rs][cw][i] = s;
                     acc[i] = 0.f;
                 }
-                long long t2 = clock64();
-                mbar_wait(&sm.resEmpty[rs], ((d.seq >> 1) & 1) ^ 1);
-                tRes += clock64() - t2;
-                if (lane < kNSum) sm.res[rs][cw][lane] = mine;
+                if (g.counters) {
+                    const unsigned tf = __reduce_add_sync(0xffffffffu, nFast), te = __reduce_add_sync(0xffffffffu, nExact);
+                    if (lane == 0) {
+                        if (tf) atomicAdd(g.counters + 0, (unsigned long long)tf);
+                        if (te) atomicAdd(g.counters + 1, (unsigned long long)te);
+                    }
+                    nFast = nExact = 0;
+                }
                 if (cw == 0 && lane == 0) {
                     sm.resTask[rs][0] = d.c;
                     sm.resTask[rs][1] = d.e;
@@ -689,7 +762,7 @@ __global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
             if (lane == 0) store_cg(g.params + c * 2 + (e & 1), nps[w]);
             __threadfence();
             __syncwarp();
-            fw_push_slices(g, c, e, lane);
+            fw_push_slices(g, c, e, nps[w].pos, lane);
         } else {
             fw_channel_done(g, lane, nCtas);
         }

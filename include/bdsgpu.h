@@ -197,7 +197,7 @@ int bds_track_device_block(bds_trk* h, void** dev_ptr, size_t* bytes, int* n_fie
 int bds_track_stats(bds_trk* h, long long* channel_samples, int* epochs_run, float* last_kernel_ms);
 /* diagnostics: out4 = {chips integrated by the chip-synchronous body, chips re-evaluated by its exact
  * per-sample path, slices run by the general kernel, 0}.  h == NULL: counters of the last
- * bds_track_correlate_open_loop call. */
+ * bds_track_correlate_open_loop call (out4[3] = device microseconds of its correlator kernel). */
 int bds_track_counters(bds_trk* h, long long* out4);
 /* developer tracing (env BDS_TRK_TRACE=<n tickets>): dump per-work-item timestamps */
 int bds_track_dump_trace(bds_trk* h, const char* path);

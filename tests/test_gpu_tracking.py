@@ -65,9 +65,35 @@ def test_open_loop_parity_fast(wide_guard):
 
 
 def test_fast_kernel_rejects_unsupported_config():
+    s, sats, x, ch = util.record("B2a", 2, 0.012)
+    with pytest.raises(L.BdsError):
+        _track.run_tracking("B2a", x, ch, util.product_settings(s), n_epochs=2, kernel=L.KERNEL_FAST)
     s, sats, x, ch = util.record("NB", 2, 0.06)
+    s = s.copy()
+    s.pilotTRKflag = 0            # data-only narrow band has no fast path
     with pytest.raises(L.BdsError):
         _track.run_tracking("NB", x, ch, util.product_settings(s), n_epochs=2, kernel=L.KERNEL_FAST)
+
+
+def test_narrow_band_fast_kernel():
+    """NB_tracking.m on the chip-synchronous kernel: open-loop sums (BOC(6,1) family exactly zero) and the
+    closed loop one step at a time against the oracle's NB loop closure."""
+    s, sats, x, ch = util.record("NB", 2, 0.23)
+    tr, raw = util.oracle_track("NB", s, x, ch, 3)
+    nco = np.stack([t.nco for t in tr])
+    got = open_loop("NB", s, x, [c.PRN for c in ch], nco, L.KERNEL_FAST)
+    assert np.max(np.abs(got - raw) / util.family_scale(raw)) <= 1e-4
+    assert np.all(got[..., 12:] == 0.0)
+    ps = util.product_settings(s)
+    res, _ = _track.run_tracking("NB", x, ch, ps, n_epochs=20, kernel=L.KERNEL_FAST, raw=True)
+    fast_chips, exact_chips, general_slices, _ = _track.run_tracking.last_counters
+    assert general_slices == 0 and fast_chips + exact_chips == 2 * 20 * 10230
+    for c in range(2):
+        assert res[c].status == "T" and "Pilot_I_E" not in res[c]
+        assert util.one_step_parity("NB", s, x, ch[c], res[c], 20) <= 1e-4
+    auto, _ = _track.run_tracking("NB", x, ch, ps, n_epochs=20, raw=True)       # AUTO now picks the fast kernel
+    assert _track.run_tracking.last_counters[2] == 0
+    np.testing.assert_array_equal(auto[0].raw, res[0].raw)
 
 
 @pytest.mark.parametrize("kernel", ["general", "fast"])
@@ -175,12 +201,14 @@ def test_short_read_stops_like_reference():
     assert np.all(np.isinf(tr[1].carrFreq))
 
 
-def test_cno_and_lock_detector():
-    s, sats, x, ch = util.record("WB", 2, 0.13)
+@pytest.mark.parametrize("mode,kernel", [("WB", "general"), ("WB", "fast"), ("NB", "general"), ("NB", "fast")])
+def test_cno_and_lock_detector(mode, kernel):
+    s, sats, x, ch = util.record(mode, 2, 0.13)
     s = s.copy()
     s.CNoInterval = 5
-    tr, _ = util.oracle_track("WB", s, x, ch, 10)
-    got, _ = _track.run_tracking("WB", x, ch, util.product_settings(s), n_epochs=10, kernel=L.KERNEL_GENERAL)
+    tr, _ = util.oracle_track(mode, s, x, ch, 10)
+    kern = L.KERNEL_GENERAL if kernel == "general" else L.KERNEL_FAST
+    got, _ = _track.run_tracking(mode, x, ch, util.product_settings(s), n_epochs=10, kernel=kern)
     for c in range(2):
         for f in ("DataCNo", "PilotCNo", "B1C_CNo"):
             np.testing.assert_allclose(got[c][f], tr[c][f], atol=0.02)
