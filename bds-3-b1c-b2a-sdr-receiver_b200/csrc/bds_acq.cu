@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "bds_codes.h"
@@ -29,6 +31,7 @@ namespace bds {
 constexpr int kTwN = 4096;           // butterfly twiddle table size (covers sub-FFTs <= 4096)
 constexpr int kColTile = 8;          // columns per CTA in the column passes
 constexpr int kAcqThreads = 512;
+constexpr int kRowTile = 4;          // rows per CTA in the row passes (more work between barriers)
 
 struct AcqPlan {
     int log2P, log2P1, log2P2;   // P = P1*P2 ; P1 = column (strided) length, P2 = row length
@@ -49,37 +52,115 @@ __device__ __forceinline__ float2 twiddleP(const AcqPlan& pl, unsigned m) {
     return cmul(hi, lo);
 }
 
-// In-place radix-2 FFT over `len` = 2^lg elements for `batch` independent sequences held in
-// shared memory: element (i, b) at buf[i*si + b*sb].  kInv=false: DIF forward (natural ->
-// bit reversed).  kInv=true: DIT inverse (bit reversed -> natural), unnormalised.
-template <bool kInv>
+// In-place FFT over `len` = 2^lg elements for `batch` (a power of two) independent sequences held in shared
+// memory: element (i, b) at buf[i*si + b*sb].  kInv=false: DIF forward (natural -> bit reversed).  kInv=true: DIT
+// inverse (bit reversed -> natural), unnormalised.  Two radix-2 stages are fused into one radix-4 step on four
+// elements held in registers (half the barriers and half the shared-memory traffic of a radix-2 sweep); an odd
+// stage count leaves one radix-2 step.  kBatchInner: consecutive threads take consecutive b (column tiles, sb = 1);
+// otherwise consecutive butterflies of one sequence (rows, si = 1) - either way the accesses of a warp are contiguous.
+// Row transforms (kBatchInner = false) use a padded layout, element i of a row at i + (i >> 4): the strided accesses
+// of the short-span stages (lane stride 4 or 16 elements) would otherwise hit the same banks 4 times over.
+__device__ __forceinline__ int row_pad(int i) { return i + (i >> 4); }
+template <bool kInv, bool kBatchInner>
 __device__ void smem_fft(float2* buf, int lg, int batch, int si, int sb, const float2* tw) {
-    const int len = 1 << lg, half = len >> 1;
-    const int total = half * batch;
-    for (int s = 0; s < lg; ++s) {
-        const int lh = kInv ? s : (lg - 1 - s);  // log2 of the half span
+#define EL(base_, i_) ((base_) + (kBatchInner ? (i_) * si : row_pad(i_)))
+    const int len = 1 << lg;
+    const int lgBatch = 31 - __clz(batch);
+    int s = 0;
+    while (s < lg) {
+        const bool pair = kInv ? (s + 1 < lg) : (lg - 1 - s >= 1);
+        const int lh = kInv ? s : (lg - 1 - s);  // log2 of the (first) half span
         const int h = 1 << lh;
-        const int twStride = kTwN >> (lh + 1);
-        for (int u = threadIdx.x; u < total; u += blockDim.x) {
-            int b = u % batch, v = u / batch;
-            int j = v & (h - 1);
-            int i0 = ((v >> lh) << (lh + 1)) + j;
-            float2* pa = buf + i0 * si + b * sb;
-            float2* pb = pa + h * si;
-            float2 a = *pa, c = *pb;
-            float2 w = __ldg(tw + j * twStride);
-            if (kInv) {
-                float2 t = cmulc(c, w);
-                *pa = make_float2(a.x + t.x, a.y + t.y);
-                *pb = make_float2(a.x - t.x, a.y - t.y);
-            } else {
-                float2 d = make_float2(a.x - c.x, a.y - c.y);
-                *pa = make_float2(a.x + c.x, a.y + c.y);
-                *pb = cmul(d, w);
+        if (pair) {
+            const int quarter = len >> 2, total = quarter * batch;
+            for (int u = threadIdx.x; u < total; u += blockDim.x) {
+                int b, v;
+                if (kBatchInner) {
+                    b = u & (batch - 1);
+                    v = u >> lgBatch;
+                } else {
+                    b = u >> (lg - 2);
+                    v = u & (quarter - 1);
+                }
+                float2* base = buf + b * sb;
+                if (!kInv) {
+                    // DIF: half spans h then h/2 on elements i, i+h/2, i+h, i+3h/2
+                    const int hh = h >> 1;
+                    const int j = v & (hh - 1);
+                    const int i = ((v >> (lh - 1)) << (lh + 1)) + j;
+                    float2* p0 = EL(base, i);
+                    float2* p1 = EL(base, i + hh);
+                    float2* p2 = EL(base, i + h);
+                    float2* p3 = EL(base, i + h + hh);
+                    const float2 x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+                    const float2 w1 = __ldg(tw + j * (kTwN >> (lh + 1)));   // W_{2h}^j
+                    const float2 w2 = __ldg(tw + j * (kTwN >> lh));         // W_{h}^j
+                    const float2 y0 = make_float2(x0.x + x2.x, x0.y + x2.y);
+                    const float2 y2 = cmul(make_float2(x0.x - x2.x, x0.y - x2.y), w1);
+                    const float2 y1 = make_float2(x1.x + x3.x, x1.y + x3.y);
+                    const float2 d3 = cmul(make_float2(x1.x - x3.x, x1.y - x3.y), w1);
+                    const float2 y3 = make_float2(d3.y, -d3.x);             // * (-i) = W_{2h}^{h/2}
+                    *p0 = make_float2(y0.x + y1.x, y0.y + y1.y);
+                    *p1 = cmul(make_float2(y0.x - y1.x, y0.y - y1.y), w2);
+                    *p2 = make_float2(y2.x + y3.x, y2.y + y3.y);
+                    *p3 = cmul(make_float2(y2.x - y3.x, y2.y - y3.y), w2);
+                } else {
+                    // DIT: half spans h then 2h on elements i, i+h, i+2h, i+3h
+                    const int j = v & (h - 1);
+                    const int i = ((v >> lh) << (lh + 2)) + j;
+                    float2* p0 = EL(base, i);
+                    float2* p1 = EL(base, i + h);
+                    float2* p2 = EL(base, i + 2 * h);
+                    float2* p3 = EL(base, i + 3 * h);
+                    const float2 x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+                    const float2 w1 = __ldg(tw + j * (kTwN >> (lh + 1)));   // W_{2h}^j
+                    const float2 w2 = __ldg(tw + j * (kTwN >> (lh + 2)));   // W_{4h}^j
+                    const float2 t1 = cmulc(x1, w1), t3 = cmulc(x3, w1);
+                    const float2 y0 = make_float2(x0.x + t1.x, x0.y + t1.y), y1 = make_float2(x0.x - t1.x, x0.y - t1.y);
+                    const float2 y2 = make_float2(x2.x + t3.x, x2.y + t3.y), y3 = make_float2(x2.x - t3.x, x2.y - t3.y);
+                    const float2 u2 = cmulc(y2, w2);
+                    const float2 q3 = cmulc(y3, w2);
+                    const float2 u3 = make_float2(-q3.y, q3.x);             // * (+i) = conj(W_{4h}^{h})
+                    *p0 = make_float2(y0.x + u2.x, y0.y + u2.y);
+                    *p2 = make_float2(y0.x - u2.x, y0.y - u2.y);
+                    *p1 = make_float2(y1.x + u3.x, y1.y + u3.y);
+                    *p3 = make_float2(y1.x - u3.x, y1.y - u3.y);
+                }
             }
+            s += 2;
+        } else {
+            const int half = len >> 1, total = half * batch;
+            const int twStride = kTwN >> (lh + 1);
+            for (int u = threadIdx.x; u < total; u += blockDim.x) {
+                int b, v;
+                if (kBatchInner) {
+                    b = u & (batch - 1);
+                    v = u >> lgBatch;
+                } else {
+                    b = u >> (lg - 1);
+                    v = u & (half - 1);
+                }
+                const int j = v & (h - 1);
+                const int i0 = ((v >> lh) << (lh + 1)) + j;
+                float2* pa = EL(buf + b * sb, i0);
+                float2* pb = EL(buf + b * sb, i0 + h);
+                const float2 a = *pa, c = *pb;
+                const float2 w = __ldg(tw + j * twStride);
+                if (kInv) {
+                    const float2 t = cmulc(c, w);
+                    *pa = make_float2(a.x + t.x, a.y + t.y);
+                    *pb = make_float2(a.x - t.x, a.y - t.y);
+                } else {
+                    const float2 d = make_float2(a.x - c.x, a.y - c.y);
+                    *pa = make_float2(a.x + c.x, a.y + c.y);
+                    *pb = cmul(d, w);
+                }
+            }
+            s += 1;
         }
         __syncthreads();
     }
+#undef EL
 }
 
 // ---- forward column pass -------------------------------------------------------------
@@ -116,7 +197,7 @@ __global__ void __launch_bounds__(kAcqThreads) acq_fwd_col_kernel(AcqPlan pl, in
         buf[e] = v;
     }
     __syncthreads();
-    smem_fft<false>(buf, pl.log2P1, kColTile, kColTile, 1, pl.tw);
+    smem_fft<false, true>(buf, pl.log2P1, kColTile, kColTile, 1, pl.tw);
     float2* out = spec + (size_t)bi * pl.P;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         int c = e & (kColTile - 1), r = e >> 3;
@@ -129,39 +210,44 @@ __global__ void __launch_bounds__(kAcqThreads) acq_fwd_col_kernel(AcqPlan pl, in
 
 // ---- forward row pass (in place) -----------------------------------------------------
 // conjScale != 0: store conj(X) * conjScale (code spectra: acquisition.m:180 with the 1/P of
-// the inverse transform folded in).
+// the inverse transform folded in).  grid = (P1 / kRowTile, batch); kRowTile rows per CTA.
 __global__ void __launch_bounds__(kAcqThreads) acq_fwd_row_kernel(AcqPlan pl, float2* spec, float conjScale) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
-    float2* row = spec + (size_t)blockIdx.y * pl.P + (size_t)blockIdx.x * pl.P2;
-    for (int i = threadIdx.x; i < pl.P2; i += blockDim.x) buf[i] = row[i];
+    float2* rows = spec + (size_t)blockIdx.y * pl.P + (size_t)blockIdx.x * kRowTile * pl.P2;   // kRowTile contiguous rows
+    const int total = kRowTile * pl.P2, rowStride = pl.P2 + (pl.P2 >> 4);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) buf[(i >> pl.log2P2) * rowStride + row_pad(i & (pl.P2 - 1))] = rows[i];
     __syncthreads();
-    smem_fft<false>(buf, pl.log2P2, 1, 1, 0, pl.tw);
-    for (int i = threadIdx.x; i < pl.P2; i += blockDim.x) {
-        float2 v = buf[i];
+    smem_fft<false, false>(buf, pl.log2P2, kRowTile, 1, rowStride, pl.tw);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        float2 v = buf[(i >> pl.log2P2) * rowStride + row_pad(i & (pl.P2 - 1))];
         if (conjScale != 0.f) v = make_float2(v.x * conjScale, -v.y * conjScale);
-        row[i] = v;
+        rows[i] = v;
     }
 }
 
 // ---- inverse row pass ------------------------------------------------------------------
 // work[bin][dp] row r = IDFT_row( sig[bin] row r .* code[dp] row r ) .* W_P^{-n2 k1}
-// grid = (P1, nbins, ncodes)
+// grid = (P1 / kRowTile, nbins, ncodes); binMap (optional): Doppler bin of batch entry blockIdx.y
 __global__ void __launch_bounds__(kAcqThreads) acq_inv_row_kernel(AcqPlan pl, const float2* sig, const float2* code,
-                                                                  float2* work, int ncodes) {
+                                                                  float2* work, int ncodes, const int* binMap) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
-    const int r = blockIdx.x, bin = blockIdx.y, dp = blockIdx.z;
-    const float2* srow = sig + (size_t)bin * pl.P + (size_t)r * pl.P2;
-    const float2* crow = code + (size_t)dp * pl.P + (size_t)r * pl.P2;
-    for (int i = threadIdx.x; i < pl.P2; i += blockDim.x) buf[i] = cmul(srow[i], __ldg(crow + i));
+    const int r0 = blockIdx.x * kRowTile, bi = blockIdx.y, dp = blockIdx.z;
+    const int bin = binMap ? binMap[bi] : bi;
+    const float2* srow = sig + (size_t)bin * pl.P + (size_t)r0 * pl.P2;
+    const float2* crow = code + (size_t)dp * pl.P + (size_t)r0 * pl.P2;
+    const int total = kRowTile * pl.P2, rowStride = pl.P2 + (pl.P2 >> 4);
+    for (int i = threadIdx.x; i < total; i += blockDim.x)
+        buf[(i >> pl.log2P2) * rowStride + row_pad(i & (pl.P2 - 1))] = cmul(srow[i], __ldg(crow + i));
     __syncthreads();
-    smem_fft<true>(buf, pl.log2P2, 1, 1, 0, pl.tw);
-    const unsigned k1 = __brev((unsigned)r) >> (32 - pl.log2P1);
-    float2* orow = work + ((size_t)bin * ncodes + dp) * pl.P + (size_t)r * pl.P2;
-    for (int i = threadIdx.x; i < pl.P2; i += blockDim.x) {
-        float2 w = twiddleP(pl, k1 * (unsigned)i);
-        orow[i] = cmulc(buf[i], w);
+    smem_fft<true, false>(buf, pl.log2P2, kRowTile, 1, rowStride, pl.tw);
+    float2* orow = work + ((size_t)bi * ncodes + dp) * pl.P + (size_t)r0 * pl.P2;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = r0 + (i >> pl.log2P2), n2 = i & (pl.P2 - 1);
+        const unsigned k1 = __brev((unsigned)r) >> (32 - pl.log2P1);
+        float2 w = twiddleP(pl, k1 * (unsigned)n2);
+        orow[i] = cmulc(buf[(i >> pl.log2P2) * rowStride + row_pad(n2)], w);
     }
 }
 
@@ -189,7 +275,7 @@ __global__ void __launch_bounds__(kAcqThreads) acq_inv_col_kernel(AcqPlan pl, co
             buf[e] = w[(size_t)r * pl.P2 + col0 + c];
         }
         __syncthreads();
-        smem_fft<true>(buf, pl.log2P1, kColTile, kColTile, 1, pl.tw);
+        smem_fft<true, true>(buf, pl.log2P1, kColTile, kColTile, 1, pl.tw);
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
             float2 v = buf[e];
             float m = sqrtf(v.x * v.x + v.y * v.y);
@@ -241,6 +327,14 @@ __global__ void __launch_bounds__(kAcqThreads) acq_inv_col_kernel(AcqPlan pl, co
     }
 }
 
+// Sampled code tables on the device: table[t][k] = code[t][idx[k] - 1]  (makeDataTable.m:49-66; idx is computed once on
+// the host with the reference's own expression, it does not depend on the PRN).  grid = (blocks, tables)
+__global__ void acq_sample_tables_kernel(const int32_t* idx, const int8_t* codes, int codeLen, int spc, int8_t* tables) {
+    const int8_t* code = codes + (size_t)blockIdx.y * codeLen;
+    int8_t* out = tables + (size_t)blockIdx.y * spc;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < spc; k += gridDim.x * blockDim.x) out[k] = code[__ldg(idx + k) - 1];
+}
+
 // per-bin reduction of the column-group peaks
 __global__ void acq_peak_reduce_kernel(const AcqPeak* peaks, int groups, AcqPeak* binPeak) {
     int bin = blockIdx.x;
@@ -253,16 +347,26 @@ __global__ void acq_peak_reduce_kernel(const AcqPeak* peaks, int groups, AcqPeak
             bl = p.lag;
         }
     }
-    __shared__ float sv[256];
-    __shared__ int sl[256];
-    sv[threadIdx.x] = best;
-    sl[threadIdx.x] = bl;
+    for (int o = 16; o > 0; o >>= 1) {   // max value, then min lag (first index wins, acquisition.m:229-232)
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (ov > best || (ov == best && ol < bl)) {
+            best = ov;
+            bl = ol;
+        }
+    }
+    __shared__ float sv[8];
+    __shared__ int sl[8];
+    if ((threadIdx.x & 31) == 0) {
+        sv[threadIdx.x >> 5] = best;
+        sl[threadIdx.x >> 5] = bl;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int t = 1; t < (int)blockDim.x; ++t)
-            if (sv[t] > best || (sv[t] == best && sl[t] < bl)) {
-                best = sv[t];
-                bl = sl[t];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (sv[w] > best || (sv[w] == best && sl[w] < bl)) {
+                best = sv[w];
+                bl = sl[w];
             }
         binPeak[bin] = AcqPeak{best, bl};
     }
@@ -372,10 +476,16 @@ unsigned long long freq_to_dphi(double f, double fs) {
 
 long mround(double x) { return std::lround(x); }
 
-int sampled_table(int component, int prn, double fs, double fcb, int L, std::vector<int8_t>& t) {
-    long spc = mround(fs / (fcb / L));
-    t.resize(spc);
-    return bds_make_code_table(component, prn, fs, fcb, L, t.data(), (int)spc);
+// The ranging codes are constants of the signal: generate each (component, PRN) once per process.
+const std::vector<int8_t>* cached_component(int component, int prn) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::vector<int8_t>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({component, prn});
+    if (it != cache.end()) return &it->second;
+    std::vector<int8_t> v;
+    if (!gen_component(component, prn, v)) return nullptr;
+    return &cache.emplace(std::make_pair(component, prn), std::move(v)).first->second;
 }
 
 }  // namespace
@@ -482,7 +592,7 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     TRYA(dSig.alloc(specBytes * nbins));
     const size_t smemCol = sizeof(float2) * pl.P1 * kColTile;
     const size_t smemColInv = smemCol + sizeof(float) * pl.P1 * kColTile;
-    const size_t smemRow = sizeof(float2) * pl.P2;
+    const size_t smemRow = sizeof(float2) * (pl.P2 + (pl.P2 >> 4)) * kRowTile;   // padded rows, see row_pad()
     TRYA(cudaFuncSetAttribute(acq_fwd_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCol));
     TRYA(cudaFuncSetAttribute(acq_inv_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemColInv));
     TRYA(cudaFuncSetAttribute(acq_fwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRow));
@@ -490,7 +600,7 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     const int colGroups = pl.P2 / kColTile;
     acq_fwd_col_kernel<<<dim3(colGroups, nbins), kAcqThreads, smemCol>>>(pl, 0, dx, 0, dDphi.as<unsigned long long>(),
                                                                        dSig.as<float2>());
-    acq_fwd_row_kernel<<<dim3(pl.P1, nbins), kAcqThreads, smemRow>>>(pl, dSig.as<float2>(), 0.f);
+    acq_fwd_row_kernel<<<dim3(pl.P1 / kRowTile, nbins), kAcqThreads, smemRow>>>(pl, dSig.as<float2>(), 0.f);
     count_launch(2);
     TRYA(cudaGetLastError());
 
@@ -508,185 +618,267 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
         sigPower = std::sqrt(var * (double)M);
     }
 
-    // ---- per-PRN buffers; work buffer sized to the free memory (bins per batch)
-    TRYA(dCode.alloc(specBytes * ncodes));
-    TRYA(dTab.alloc((size_t)spc * ncodes));
+    // ---- the PRN list is processed in chunks whose code spectra fit comfortably in HBM; inside a chunk every
+    //      phase queues the kernels of all its PRNs back to back and synchronises once (no host round trip per PRN)
+    const int nSelAll = std::max(0, prn_hi - prn_lo);
     size_t freeB = 0, totalB = 0;
     TRYA(cudaMemGetInfo(&freeB, &totalB));
-    int binsPerBatch = (int)std::min<size_t>(nbins, std::max<size_t>(1, (freeB / 2) / (specBytes * ncodes)));
-    binsPerBatch = std::min(binsPerBatch, 8);
+    const size_t perPrn = specBytes * ncodes + (size_t)spc * ncodes;
+    const int chunkMax = (int)std::max<size_t>(1, std::min<size_t>(64, (freeB / 3) / perPrn));
+    // bins per batch: keep the inverse-row output of a batch resident in L2 for the inverse-column pass
+    const int binsPerBatch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nbins, (size_t)8, ((size_t)96 << 20) / (specBytes * ncodes)}));
     TRYA(dWork.alloc(specBytes * ncodes * binsPerBatch));
     TRYA(dPeaks.alloc(sizeof(AcqPeak) * (size_t)colGroups * binsPerBatch));
-    TRYA(dBinPeak.alloc(sizeof(AcqPeak) * nbins));
-    std::vector<AcqPeak> binPeak(nbins);
-    std::vector<int8_t> tabD, tabP;
-
-    for (int li = prn_lo; li < prn_hi; ++li) {
-        const int PRN = prn[li];
-        // code tables and their (conjugated, 1/P scaled) spectra
-        rc = sampled_table(b1c ? BDS_CODE_B1C_DATA_BOC11 : BDS_CODE_B2A_DATA, PRN, fs, cfg->codeFreqBasis, cfg->codeLength, tabD);
-        if (rc) return rc;
-        TRYA(cudaMemcpy(dTab.p, tabD.data(), spc, cudaMemcpyHostToDevice));
-        if (ncodes == 2) {
-            rc = sampled_table(b1c ? BDS_CODE_B1C_PILOT_BOC11 : BDS_CODE_B2A_PILOT, PRN, fs, cfg->codeFreqBasis, cfg->codeLength, tabP);
-            if (rc) return rc;
-            TRYA(cudaMemcpy(dTab.as<int8_t>() + spc, tabP.data(), spc, cudaMemcpyHostToDevice));
+    DevBuf dBinMap, dSecond, dIdx;
+    {   // makeDataTable.m:49-63 / makeB2aDataTable.m:46-62: idx = ceil((ts*k)/tc), k = 1..spc; idx(end) forced to the last
+        // element; B1C also forces idx(1) = 1  (same expression as bds_make_code_table)
+        std::vector<int32_t> idx(spc);
+        const double ts = 1.0 / fs;
+        const double tc = b1c ? (1.0 / cfg->codeFreqBasis) / 2.0 : 1.0 / cfg->codeFreqBasis;
+        const long last = b1c ? 2L * cfg->codeLength : (long)cfg->codeLength;
+        for (long k = 1; k <= spc; ++k) {
+            long v = (long)std::ceil((ts * (double)k) / tc);
+            if (k == spc) v = last;
+            if (b1c && k == 1) v = 1;
+            if (v < 1 || v > last) return set_error(BDS_ERR_ARG, "code index out of range (fs/codeFreqBasis mismatch)");
+            idx[k - 1] = (int32_t)v;
         }
-        acq_fwd_col_kernel<<<dim3(colGroups, ncodes), kAcqThreads, smemCol>>>(pl, 1, dTab.as<int8_t>(), (size_t)spc, nullptr,
-                                                                            dCode.as<float2>());
-        acq_fwd_row_kernel<<<dim3(pl.P1, ncodes), kAcqThreads, smemRow>>>(pl, dCode.as<float2>(), 1.0f / (float)pl.P);
+        TRYA(dIdx.alloc(sizeof(int32_t) * spc));
+        TRYA(cudaMemcpy(dIdx.p, idx.data(), sizeof(int32_t) * spc, cudaMemcpyHostToDevice));
+    }
+    struct Cand {
+        int PRN, bestBin;
+        long cp;
+        float peak;
+        double metric, norm;
+    };
+    for (int c0 = 0; c0 < nSelAll; c0 += chunkMax) {
+        const int nSel = std::min(chunkMax, nSelAll - c0);
+        // ---- phase 0: sampled code tables of the chunk (host, integer) and their conjugated, 1/P-scaled spectra
+        const int compD = b1c ? BDS_CODE_B1C_DATA_BOC11 : BDS_CODE_B2A_DATA, compP = b1c ? BDS_CODE_B1C_PILOT_BOC11 : BDS_CODE_B2A_PILOT;
+        const int codeLen = component_length(compD);
+        std::vector<int8_t> codes((size_t)nSel * ncodes * codeLen);
+        for (int i = 0; i < nSel; ++i) {
+            const int PRN = prn[prn_lo + c0 + i];
+            for (int dp = 0; dp < ncodes; ++dp) {
+                const std::vector<int8_t>* cc = cached_component(dp == 0 ? compD : compP, PRN);
+                if (!cc) return set_error(BDS_ERR_ARG, "PRN %d out of range 1..63", PRN);
+                std::memcpy(&codes[((size_t)i * ncodes + dp) * codeLen], cc->data(), codeLen);
+            }
+        }
+        DevBuf dCodes;
+        TRYA(dCodes.alloc(codes.size()));
+        TRYA(cudaMemcpy(dCodes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+        TRYA(dTab.alloc((size_t)nSel * ncodes * spc));
+        acq_sample_tables_kernel<<<dim3(std::max(1L, std::min(64L, spc / 4096)), nSel * ncodes), 256>>>(
+            dIdx.as<int32_t>(), dCodes.as<int8_t>(), codeLen, (int)spc, dTab.as<int8_t>());
+        count_launch();
+        TRYA(dCode.alloc(specBytes * ncodes * nSel));
+        acq_fwd_col_kernel<<<dim3(colGroups, ncodes * nSel), kAcqThreads, smemCol>>>(pl, 1, dTab.as<int8_t>(), (size_t)spc, nullptr,
+                                                                                   dCode.as<float2>());
+        acq_fwd_row_kernel<<<dim3(pl.P1 / kRowTile, ncodes * nSel), kAcqThreads, smemRow>>>(pl, dCode.as<float2>(), 1.0f / (float)pl.P);
         count_launch(2);
-        for (int b0 = 0; b0 < nbins; b0 += binsPerBatch) {
-            int nb = std::min(binsPerBatch, nbins - b0);
-            acq_inv_row_kernel<<<dim3(pl.P1, nb, ncodes), kAcqThreads, smemRow>>>(
-                pl, dSig.as<float2>() + (size_t)b0 * pl.P, dCode.as<float2>(), dWork.as<float2>(), ncodes);
-            acq_inv_col_kernel<<<dim3(colGroups, nb), kAcqThreads, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, 0, 0,
-                                                                               0, 0, 0, dPeaks.as<AcqPeak>());
-            acq_peak_reduce_kernel<<<nb, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dBinPeak.as<AcqPeak>() + b0);
-            count_launch(3);
+        // ---- phase 1: coarse PRN x Doppler grid; per (PRN, bin) peak and first lag
+        TRYA(dBinPeak.alloc(sizeof(AcqPeak) * (size_t)nbins * nSel));
+        for (int i = 0; i < nSel; ++i) {
+            const float2* code = dCode.as<float2>() + (size_t)i * ncodes * pl.P;
+            for (int b0 = 0; b0 < nbins; b0 += binsPerBatch) {
+                const int nb = std::min(binsPerBatch, nbins - b0);
+                acq_inv_row_kernel<<<dim3(pl.P1 / kRowTile, nb, ncodes), kAcqThreads, smemRow>>>(
+                    pl, dSig.as<float2>() + (size_t)b0 * pl.P, code, dWork.as<float2>(), ncodes, nullptr);
+                acq_inv_col_kernel<<<dim3(colGroups, nb), kAcqThreads, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, 0, 0,
+                                                                                   0, 0, 0, dPeaks.as<AcqPeak>());
+                acq_peak_reduce_kernel<<<nb, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dBinPeak.as<AcqPeak>() + (size_t)i * nbins + b0);
+                count_launch(3);
+            }
         }
         TRYA(cudaGetLastError());
-        TRYA(cudaMemcpy(binPeak.data(), dBinPeak.p, sizeof(AcqPeak) * nbins, cudaMemcpyDeviceToHost));
-        // [~, bin] = max(max(results,[],2)); [peak, codePhase] = max(max(results))  (first index wins)
-        float peak = -1.f;
-        int bestBin = 0;
-        for (int k = 0; k < nbins; ++k)
-            if (binPeak[k].val > peak) {
-                peak = binPeak[k].val;
-                bestBin = k;
-            }
-        int lag = 0x7fffffff;
-        for (int k = 0; k < nbins; ++k)
-            if (binPeak[k].val == peak) lag = std::min(lag, binPeak[k].lag);
-        long cp = (long)lag + 1;  // 1-based
-        double metric, norm;
+        std::vector<AcqPeak> binPeak((size_t)nbins * nSel);
+        TRYA(cudaMemcpy(binPeak.data(), dBinPeak.p, sizeof(AcqPeak) * binPeak.size(), cudaMemcpyDeviceToHost));
+        std::vector<Cand> cand(nSel);
+        for (int i = 0; i < nSel; ++i) {
+            // [~, bin] = max(max(results,[],2)); [peak, codePhase] = max(max(results))  (first index wins)
+            const AcqPeak* bp = &binPeak[(size_t)i * nbins];
+            float peak = -1.f;
+            int bestBin = 0;
+            for (int k = 0; k < nbins; ++k)
+                if (bp[k].val > peak) {
+                    peak = bp[k].val;
+                    bestBin = k;
+                }
+            int lag = 0x7fffffff;
+            for (int k = 0; k < nbins; ++k)
+                if (bp[k].val == peak) lag = std::min(lag, bp[k].lag);
+            cand[i] = Cand{prn[prn_lo + c0 + i], bestBin, (long)lag + 1 /* 1-based */, peak, 0.0, 0.0};
+        }
+        // ---- phase 2: metric normaliser
         if (b1c) {
-            norm = sigPower;
-            metric = (double)peak / sigPower;                       // acquisition.m:235
+            for (auto& cd : cand) {
+                cd.norm = sigPower;
+                cd.metric = (double)cd.peak / sigPower;                       // acquisition.m:235
+            }
         } else {
             // second peak in the best bin's row, excluding +-samples2CodeChip around the peak and
             // its one-period image   (B2a acquisition.m:224-252)
-            long s2cc = (long)std::ceil(fs / cfg->codeFreqBasis) * 2;
-            long e1 = cp - s2cc, e2 = cp + s2cc, e3 = cp - spc + s2cc, e4 = cp + spc - s2cc;
-            int lo0 = 1, hi0 = 0, lo1 = 1, hi1 = 0;  // empty
-            if (e1 >= 1) {
-                lo0 = (int)std::max(1L, e3) - 1;
-                hi0 = (int)e1 - 1;
-            }
-            if (e2 < N) {
-                lo1 = (int)e2 - 1;
-                hi1 = (int)std::min(e4, N) - 1;
-            }
-            acq_inv_row_kernel<<<dim3(pl.P1, 1, ncodes), kAcqThreads, smemRow>>>(
-                pl, dSig.as<float2>() + (size_t)bestBin * pl.P, dCode.as<float2>(), dWork.as<float2>(), ncodes);
-            acq_inv_col_kernel<<<dim3(colGroups, 1), kAcqThreads, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0,
-                                                                              hi0, lo1, hi1, 1, dPeaks.as<AcqPeak>());
-            acq_peak_reduce_kernel<<<1, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dBinPeak.as<AcqPeak>());
-            count_launch(3);
-            AcqPeak second;
-            TRYA(cudaMemcpy(&second, dBinPeak.p, sizeof(AcqPeak), cudaMemcpyDeviceToHost));
-            norm = second.val;
-            metric = (double)peak / (double)second.val;
-        }
-        peakMetric[PRN - 1] = metric;
-        if (b1c && cp + spc - 1 > (long)n) cp -= spc;               // acquisition.m:239-241
-        if (dbg) {
-            dbg[(PRN - 1) * 4 + 0] = bestBin;
-            dbg[(PRN - 1) * 4 + 1] = (double)cp;
-            dbg[(PRN - 1) * 4 + 2] = peak;
-            dbg[(PRN - 1) * 4 + 3] = norm;
-        }
-        if (!(metric > cfg->acqThreshold)) continue;
-        if (cp < 1) continue;  // the reference would index longSignal(<=0) here and abort
-
-        if (b1c) {
-            // ---- fine search, acquisition.m:253-307
-            if ((size_t)(cp - 1 + spc) > n) continue;
-            const int nfine = (int)mround(cfg->acqStep / 25) * 2 + 1;
-            std::vector<double> ff(nfine);
-            std::vector<unsigned long long> fd(nfine);
-            for (int j = 0; j < nfine; ++j) {
-                ff[j] = frq[bestBin] - cfg->acqStep + 25.0 * j;
-                fd[j] = freq_to_dphi(ff[j], fs);
-            }
-            TRYA(dFineDphi.alloc(sizeof(unsigned long long) * nfine));
-            TRYA(cudaMemcpy(dFineDphi.p, fd.data(), sizeof(unsigned long long) * nfine, cudaMemcpyHostToDevice));
-            TRYA(dFine.alloc(sizeof(double) * nfine * ncodes * 4));
-            TRYA(cudaMemset(dFine.p, 0, sizeof(double) * nfine * ncodes * 4));
-            TRYA(cudaMemset(dSums.p, 0, 16));
-            acq_power_kernel<<<g_num_sms * 4, 256>>>(dx + (cp - 1), (int)spc, dSums.as<long long>());
-            acq_fine_b1c_kernel<<<dim3(g_num_sms, nfine, ncodes), 256>>>(dx + (cp - 1), dTab.as<int8_t>(), (int)spc,
-                                                                        dFineDphi.as<unsigned long long>(), ncodes,
-                                                                        dFine.as<double>());
-            count_launch(2);
-            long long hs[2];
-            TRYA(cudaMemcpy(hs, dSums.p, 16, cudaMemcpyDeviceToHost));
-            std::vector<double> fo((size_t)nfine * ncodes * 4);
-            TRYA(cudaMemcpy(fo.data(), dFine.p, fo.size() * 8, cudaMemcpyDeviceToHost));
-            const double mean = (double)hs[0] / (double)spc;
-            int best = 0;
-            double bestV = -1;
-            for (int j = 0; j < nfine; ++j) {
-                double v[2] = {0, 0};
-                for (int dp = 0; dp < ncodes; ++dp) {
-                    const double* o = &fo[((size_t)j * ncodes + dp) * 4];
-                    v[dp] = std::hypot(o[0] - mean * o[2], o[1] - mean * o[3]);
+            TRYA(dSecond.alloc(sizeof(AcqPeak) * nSel));
+            TRYA(dBinMap.alloc(sizeof(int) * nSel));
+            std::vector<int> bm(nSel);
+            for (int i = 0; i < nSel; ++i) bm[i] = cand[i].bestBin;
+            TRYA(cudaMemcpy(dBinMap.p, bm.data(), sizeof(int) * nSel, cudaMemcpyHostToDevice));
+            const long s2cc = (long)std::ceil(fs / cfg->codeFreqBasis) * 2;
+            for (int i = 0; i < nSel; ++i) {
+                const long cp = cand[i].cp;
+                const long e1 = cp - s2cc, e2 = cp + s2cc, e3 = cp - spc + s2cc, e4 = cp + spc - s2cc;
+                int lo0 = 1, hi0 = 0, lo1 = 1, hi1 = 0;  // empty
+                if (e1 >= 1) {
+                    lo0 = (int)std::max(1L, e3) - 1;
+                    hi0 = (int)e1 - 1;
                 }
-                double r = ncodes == 2 ? (v[0] * 11 + v[1] * 29) / 40 : v[0];
-                if (r > bestV) {
-                    bestV = r;
-                    best = j;
+                if (e2 < N) {
+                    lo1 = (int)e2 - 1;
+                    hi1 = (int)std::min(e4, N) - 1;
                 }
+                acq_inv_row_kernel<<<dim3(pl.P1 / kRowTile, 1, ncodes), kAcqThreads, smemRow>>>(
+                    pl, dSig.as<float2>(), dCode.as<float2>() + (size_t)i * ncodes * pl.P, dWork.as<float2>(), ncodes,
+                    dBinMap.as<int>() + i);
+                acq_inv_col_kernel<<<dim3(colGroups, 1), kAcqThreads, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0,
+                                                                                  hi0, lo1, hi1, 1, dPeaks.as<AcqPeak>());
+                acq_peak_reduce_kernel<<<1, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dSecond.as<AcqPeak>() + i);
+                count_launch(3);
             }
-            carrFreq[PRN - 1] = ff[best];
-        } else {
-            // ---- fine search, B2a acquisition.m:256-335
-            const int nseg = cfg->fineNoncoh;
-            if (nseg <= 0 || (size_t)(cp - 1 + (long)nseg * spc) > n) continue;
-            const int nfine = (int)mround(cfg->acqStep / 25) + 1;
-            std::vector<double> ff(nfine);
-            std::vector<unsigned long long> fd(nfine);
-            for (int j = 0; j < nfine; ++j) {
-                ff[j] = frq[bestBin] - cfg->acqStep / 2 + 25.0 * j;
-                fd[j] = freq_to_dphi(ff[j], fs);
+            std::vector<AcqPeak> second(nSel);
+            TRYA(cudaMemcpy(second.data(), dSecond.p, sizeof(AcqPeak) * nSel, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < nSel; ++i) {
+                cand[i].norm = second[i].val;
+                cand[i].metric = (double)cand[i].peak / (double)second[i].val;
             }
-            std::vector<uint32_t> bits(2 * kPackedWords);
-            std::vector<uint8_t> chips;
-            primary_bits(BDS_CODE_B2A_DATA, PRN, chips);
-            pack_bits(chips, bits.data());
-            primary_bits(BDS_CODE_B2A_PILOT, PRN, chips);
-            pack_bits(chips, bits.data() + kPackedWords);
-            TRYA(dBits.alloc(bits.size() * 4));
-            TRYA(cudaMemcpy(dBits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
-            TRYA(dFineDphi.alloc(sizeof(unsigned long long) * nfine));
-            TRYA(cudaMemcpy(dFineDphi.p, fd.data(), sizeof(unsigned long long) * nfine, cudaMemcpyHostToDevice));
-            const size_t no = (size_t)nfine * 2 * nseg * 2;
-            TRYA(dFine.alloc(sizeof(double) * no));
-            TRYA(cudaMemset(dFine.p, 0, sizeof(double) * no));
-            acq_fine_b2a_kernel<<<dim3(32, nfine, nseg), 256>>>(dx + (cp - 1), dBits.as<uint32_t>(), (int)spc, 1.0 / fs,
-                                                               1.0 / cfg->codeFreqBasis,
-                                                               dFineDphi.as<unsigned long long>(), nseg, dFine.as<double>());
-            count_launch();
-            std::vector<double> fo(no);
-            TRYA(cudaMemcpy(fo.data(), dFine.p, no * 8, cudaMemcpyDeviceToHost));
-            int best = 0;
-            double bestV = -1;
-            for (int j = 0; j < nfine; ++j) {
-                double r = 0;
-                for (int dp = 0; dp < 2; ++dp)
-                    for (int s = 0; s < nseg; ++s) {
-                        const double* o = &fo[(((size_t)j * 2 + dp) * nseg + s) * 2];
-                        r += std::hypot(o[0], o[1]);
+        }
+        // ---- phase 3: threshold, fine frequency search of the detected PRNs (queued together, one sync)
+        struct FineJob {
+            int i, nfine;
+            size_t off;        // offset into dFine (doubles)
+            long cp;
+            std::vector<double> ff;
+        };
+        std::vector<FineJob> jobs;
+        size_t fineDoubles = 0, fineDphis = 0;
+        const int nseg = cfg->fineNoncoh;
+        for (int i = 0; i < nSel; ++i) {
+            Cand& cd = cand[i];
+            const int PRN = cd.PRN;
+            peakMetric[PRN - 1] = cd.metric;
+            if (b1c && cd.cp + spc - 1 > (long)n) cd.cp -= spc;               // acquisition.m:239-241
+            if (dbg) {
+                dbg[(PRN - 1) * 4 + 0] = cd.bestBin;
+                dbg[(PRN - 1) * 4 + 1] = (double)cd.cp;
+                dbg[(PRN - 1) * 4 + 2] = cd.peak;
+                dbg[(PRN - 1) * 4 + 3] = cd.norm;
+            }
+            if (!(cd.metric > cfg->acqThreshold)) continue;
+            if (cd.cp < 1) continue;  // the reference would index longSignal(<=0) here and abort
+            FineJob j;
+            j.i = i;
+            j.cp = cd.cp;
+            if (b1c) {
+                if ((size_t)(cd.cp - 1 + spc) > n) continue;
+                j.nfine = (int)mround(cfg->acqStep / 25) * 2 + 1;             // acquisition.m:266-267
+                for (int q = 0; q < j.nfine; ++q) j.ff.push_back(frq[cd.bestBin] - cfg->acqStep + 25.0 * q);
+                j.off = fineDoubles;
+                fineDoubles += (size_t)j.nfine * ncodes * 4 + 2;              // + 2 slots for the power sums (as long long)
+            } else {
+                if (nseg <= 0 || (size_t)(cd.cp - 1 + (long)nseg * spc) > n) continue;
+                j.nfine = (int)mround(cfg->acqStep / 25) + 1;                 // B2a acquisition.m:265
+                for (int q = 0; q < j.nfine; ++q) j.ff.push_back(frq[cd.bestBin] - cfg->acqStep / 2 + 25.0 * q);
+                j.off = fineDoubles;
+                fineDoubles += (size_t)j.nfine * 2 * nseg * 2;
+            }
+            fineDphis += j.nfine;
+            jobs.push_back(std::move(j));
+        }
+        if (!jobs.empty()) {
+            std::vector<unsigned long long> fd;
+            fd.reserve(fineDphis);
+            for (auto& j : jobs)
+                for (double f : j.ff) fd.push_back(freq_to_dphi(f, fs));
+            TRYA(dFineDphi.alloc(sizeof(unsigned long long) * fd.size()));
+            TRYA(cudaMemcpy(dFineDphi.p, fd.data(), sizeof(unsigned long long) * fd.size(), cudaMemcpyHostToDevice));
+            TRYA(dFine.alloc(sizeof(double) * fineDoubles));
+            TRYA(cudaMemset(dFine.p, 0, sizeof(double) * fineDoubles));
+            std::vector<uint32_t> bitsAll;
+            if (!b1c) {
+                bitsAll.resize((size_t)jobs.size() * 2 * kPackedWords);
+                std::vector<uint8_t> chips;
+                for (size_t q = 0; q < jobs.size(); ++q) {
+                    const int PRN = cand[jobs[q].i].PRN;
+                    primary_bits(BDS_CODE_B2A_DATA, PRN, chips);
+                    pack_bits(chips, &bitsAll[(q * 2 + 0) * kPackedWords]);
+                    primary_bits(BDS_CODE_B2A_PILOT, PRN, chips);
+                    pack_bits(chips, &bitsAll[(q * 2 + 1) * kPackedWords]);
+                }
+                TRYA(dBits.alloc(bitsAll.size() * 4));
+                TRYA(cudaMemcpy(dBits.p, bitsAll.data(), bitsAll.size() * 4, cudaMemcpyHostToDevice));
+            }
+            size_t dphiOff = 0;
+            for (size_t q = 0; q < jobs.size(); ++q) {
+                const FineJob& j = jobs[q];
+                double* out = dFine.as<double>() + j.off;
+                const unsigned long long* dph = dFineDphi.as<unsigned long long>() + dphiOff;
+                if (b1c) {   // acquisition.m:253-307
+                    long long* pw = reinterpret_cast<long long*>(out + (size_t)j.nfine * ncodes * 4);
+                    acq_power_kernel<<<g_num_sms * 4, 256>>>(dx + (j.cp - 1), (int)spc, pw);
+                    acq_fine_b1c_kernel<<<dim3(g_num_sms, j.nfine, ncodes), 256>>>(
+                        dx + (j.cp - 1), dTab.as<int8_t>() + (size_t)j.i * ncodes * spc, (int)spc, dph, ncodes, out);
+                    count_launch(2);
+                } else {     // B2a acquisition.m:256-335
+                    acq_fine_b2a_kernel<<<dim3(32, j.nfine, nseg), 256>>>(dx + (j.cp - 1), dBits.as<uint32_t>() + q * 2 * kPackedWords,
+                                                                         (int)spc, 1.0 / fs, 1.0 / cfg->codeFreqBasis, dph, nseg, out);
+                    count_launch();
+                }
+                dphiOff += j.nfine;
+            }
+            TRYA(cudaGetLastError());
+            std::vector<double> fo(fineDoubles);
+            TRYA(cudaMemcpy(fo.data(), dFine.p, sizeof(double) * fineDoubles, cudaMemcpyDeviceToHost));
+            for (const FineJob& j : jobs) {
+                const int PRN = cand[j.i].PRN;
+                const double* o0 = &fo[j.off];
+                int best = 0;
+                double bestV = -1;
+                if (b1c) {
+                    long long hs[2];
+                    std::memcpy(hs, o0 + (size_t)j.nfine * ncodes * 4, 16);
+                    const double mean = (double)hs[0] / (double)spc;
+                    for (int q = 0; q < j.nfine; ++q) {
+                        double v[2] = {0, 0};
+                        for (int dp = 0; dp < ncodes; ++dp) {
+                            const double* o = o0 + ((size_t)q * ncodes + dp) * 4;
+                            v[dp] = std::hypot(o[0] - mean * o[2], o[1] - mean * o[3]);
+                        }
+                        const double r = ncodes == 2 ? (v[0] * 11 + v[1] * 29) / 40 : v[0];
+                        if (r > bestV) {
+                            bestV = r;
+                            best = q;
+                        }
                     }
-                if (r > bestV) {
-                    bestV = r;
-                    best = j;
+                } else {
+                    for (int q = 0; q < j.nfine; ++q) {
+                        double r = 0;
+                        for (int dp = 0; dp < 2; ++dp)
+                            for (int sg = 0; sg < nseg; ++sg) {
+                                const double* o = o0 + (((size_t)q * 2 + dp) * nseg + sg) * 2;
+                                r += std::hypot(o[0], o[1]);
+                            }
+                        if (r > bestV) {
+                            bestV = r;
+                            best = q;
+                        }
+                    }
                 }
+                carrFreq[PRN - 1] = j.ff[best];
+                if (carrFreq[PRN - 1] == 0) carrFreq[PRN - 1] = 1;          // acquisition.m:303-305
+                codePhase[PRN - 1] = (double)j.cp;
             }
-            carrFreq[PRN - 1] = ff[best];
         }
-        if (carrFreq[PRN - 1] == 0) carrFreq[PRN - 1] = 1;          // acquisition.m:303-305
-        codePhase[PRN - 1] = (double)cp;
     }
     TRYA(cudaDeviceSynchronize());
 #undef TRYA

@@ -91,7 +91,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -100,9 +100,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample (call at the start / end of the timed region)"""
+        return len(self.rows)
+
+    def stop(self, i0=0, i1=None):
+        """summary of the samples [i0, i1) = the ones taken during the timed region (the sampler is started before
+        the warm-up so that nvidia-smi is already streaming when the timed region begins)"""
         if self.proc:
             self.proc.terminate()
+        rows = self.rows[i0:i1] if i1 is not None else self.rows[i0:]
+        if not rows:            # timed region shorter than one sampling period: the samples right before it (same load)
+            rows = self.rows[max(0, i0 - 3):i0 + 1]
+        self.rows = rows
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = []
@@ -247,13 +257,14 @@ def run_b200(args):
         gather_block()
         return sess.stats()
 
-    for _ in range(args.warmup):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
     launches0 = B.launch_count()
     barrier()
+    s0 = sampler.mark()
     t0 = time.perf_counter()
     kernel_ms, ch_samples = [], 0
     for _ in range(args.steps):
@@ -262,12 +273,13 @@ def run_b200(args):
         ch_samples = cs
     barrier()
     wall = time.perf_counter() - t0
+    s1 = sampler.mark()
     launches = B.launch_count() - launches0
     if os.environ.get('BDS_TRK_TIMING'):
         sess.counters()
     if os.environ.get('BDS_TRK_TRACE'):
         L.check(L.lib().bds_track_dump_trace(sess.h, os.path.join(ROOT, 'gpurun_out', 'trace.bin').encode()))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(s0, s1) if rank == 0 else None
     # device time: max over ranks of the CUDA-event time of the persistent kernel, per step
     dev_ms = sum(kernel_ms) / len(kernel_ms)
     tmax = torch.tensor([dev_ms, wall * 1e3 / args.steps], device="cuda", dtype=torch.float64)
@@ -405,9 +417,13 @@ def run_acq_b2a(args):
             fn()
         barrier()
         t0 = time.perf_counter()
+        per = []
         for _ in range(args.steps):
+            t1 = time.perf_counter()
             r = fn()
+            per.append(round((time.perf_counter() - t1) * 1e3, 1))
         barrier()
+        print("acq step ms:", per, file=sys.stderr)
         return (time.perf_counter() - t0) / args.steps, r
 
     l0 = B.launch_count()
