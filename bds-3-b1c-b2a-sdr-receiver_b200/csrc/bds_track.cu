@@ -707,7 +707,10 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.nCompute = h->nCompute;
     g.stages = kFwStages;
     g.tune = 0;
-    g.ahead = 2;
+    // passes a producer may have in flight before it takes its next task: deep prefetch when the queue has a backlog
+    // (many channels), none when tasks are scarce (a ready task must not wait behind a busy CTA)
+    const long long tasksPerRound = (long long)h->nAct * h->S;
+    g.ahead = tasksPerRound >= 3LL * h->gridBlocks ? 2 : (2 * tasksPerRound >= 3LL * h->gridBlocks ? 1 : 0);
     if (const char* e = getenv("BDS_TRK_AHEAD")) g.ahead = atoi(e);
     g.ahead = std::max(0, std::min(g.ahead, g.stages - 1));   // more passes in flight than stages would deadlock the producer
     if (const char* e = getenv("BDS_TRK_TUNE")) g.tune = atoi(e);

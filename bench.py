@@ -448,7 +448,7 @@ def run_acq_b2a(args):
                                                   "prns_found": found, "injected": [s_.PRN for s_ in sats]},
                 "roofline": {"bound": "hbm", "achieved": alg / float(tt[0]) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg / float(tt[0]) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "acq_inv_row_kernel + acq_inv_col_kernel (whole bds_acquire call, host sync per PRN included)",
+                             "kernel": "acq_inv_row_kernel + acq_inv_col_kernel (whole bds_acquire call: host code generation, allocation and the three phase synchronisations included)",
                              "algorithmic_bytes_per_launch": alg},
                 "e2e": {"value": cells / float(tt[1]), "unit": "cells/s", "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": 3 * 63 * 8},
                 "gpu_launches": int(launches)}
