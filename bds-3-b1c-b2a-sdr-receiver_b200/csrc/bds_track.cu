@@ -1092,7 +1092,13 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
         BDS_CUDA(cudaMalloc(&h->dX, h->xCap));
     }
     if (!h->copyStream) BDS_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
-    const size_t nChunks = (n + chunk_bytes - 1) / chunk_bytes;
+    // chunk boundaries: the first chunks are small (16 MiB, doubling) so that tracking starts almost at once
+    std::vector<size_t> ends;
+    for (size_t o = 0, c = std::min(chunk_bytes, (size_t)16 << 20); o < n; c = std::min(chunk_bytes, c * 2)) {
+        o = std::min(n, o + c);
+        ends.push_back(o);
+    }
+    const size_t nChunks = ends.size();
     while (h->chunkEv.size() < nChunks) {
         cudaEvent_t e;
         BDS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1100,7 +1106,7 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
     }
     const int limit = h->epochsRun + n_epochs;
     auto copy_chunk = [&](size_t i) -> int {
-        const size_t o = i * chunk_bytes, len = std::min(chunk_bytes, n - o);
+        const size_t o = i ? ends[i - 1] : 0, len = ends[i] - o;
         BDS_CUDA(cudaMemcpyAsync(h->dX + o, x + o, len, cudaMemcpyHostToDevice, h->copyStream));
         if (i + 1 == nChunks) BDS_CUDA(cudaMemsetAsync(h->dX + n, 0, 64, h->copyStream));
         BDS_CUDA(cudaEventRecord(h->chunkEv[i], h->copyStream));
@@ -1116,7 +1122,7 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
             if (rc) return rc;
         }
         BDS_CUDA(cudaStreamWaitEvent(h->stream, h->chunkEv[i], 0));
-        h->winLen = (long long)std::min(n, (i + 1) * chunk_bytes);
+        h->winLen = (long long)ends[i];
         rc = launch_run(h, n_epochs, limit);
         if (rc) return rc;
     }
@@ -1374,7 +1380,9 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     std::memset(&g, 0, sizeof(g));
     g.x = dX;
     g.winFirst = 0;
-    g.winLen = (long long)n;
+    // staged tiles may extend 16 bytes past winLen: a host record was copied with 64 bytes of slack, a caller-owned
+    // device buffer has none
+    g.winLen = x_loc == BDS_LOC_HOST ? (long long)n : (long long)n - 16;
     g.mode = mode;
     g.hasPilot = hp;
     g.hasP61 = h6;

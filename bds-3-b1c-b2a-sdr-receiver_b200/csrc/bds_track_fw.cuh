@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 while (!mbar_test(&sm.resFull[rs], (k >> 1) & 1)) __nanosleep(100);
             long long t0 = clock64();
             __syncwarp();
+            mbar_wait(&sm.resFull[rs], (k >> 1) & 1);   // every lane observes the completed phase itself (succeeds at once)
             const int c = sm.resTask[rs][0], sl = sm.resTask[rs][2], ce = sm.resTask[rs][3];
             double v = 0;
             if (lane < kNSum && c >= 0) {
