@@ -31,10 +31,11 @@ namespace bds {
 constexpr int kTwN = 4096;           // butterfly twiddle table size (covers sub-FFTs <= 4096)
 constexpr int kColTile = 8;          // columns per CTA in the column passes
 constexpr int kAcqThreads = 512;
-constexpr int kRowTile = 4;          // rows per CTA in the row passes (more work between barriers)
+constexpr int kLgColTile = 3;        // log2(kColTile)
 
 struct AcqPlan {
     int log2P, log2P1, log2P2;   // P = P1*P2 ; P1 = column (strided) length, P2 = row length
+    int lgRowTile;               // log2 of the rows per CTA in the row passes
     int P, P1, P2;
     int N, M, Next;              // circular length, code length, N+M-1
     const float2* tw;            // exp(-2 pi i k / kTwN)
@@ -52,115 +53,125 @@ __device__ __forceinline__ float2 twiddleP(const AcqPlan& pl, unsigned m) {
     return cmul(hi, lo);
 }
 
-// In-place FFT over `len` = 2^lg elements for `batch` (a power of two) independent sequences held in shared
-// memory: element (i, b) at buf[i*si + b*sb].  kInv=false: DIF forward (natural -> bit reversed).  kInv=true: DIT
-// inverse (bit reversed -> natural), unnormalised.  Two radix-2 stages are fused into one radix-4 step on four
-// elements held in registers (half the barriers and half the shared-memory traffic of a radix-2 sweep); an odd
-// stage count leaves one radix-2 step.  kBatchInner: consecutive threads take consecutive b (column tiles, sb = 1);
-// otherwise consecutive butterflies of one sequence (rows, si = 1) - either way the accesses of a warp are contiguous.
-// Row transforms (kBatchInner = false) use a padded layout, element i of a row at i + (i >> 4): the strided accesses
-// of the short-span stages (lane stride 4 or 16 elements) would otherwise hit the same banks 4 times over.
-__device__ __forceinline__ int row_pad(int i) { return i + (i >> 4); }
-template <bool kInv, bool kBatchInner>
-__device__ void smem_fft(float2* buf, int lg, int batch, int si, int sb, const float2* tw) {
-#define EL(base_, i_) ((base_) + (kBatchInner ? (i_) * si : row_pad(i_)))
-    const int len = 1 << lg;
-    const int lgBatch = 31 - __clz(batch);
-    int s = 0;
-    while (s < lg) {
-        const bool pair = kInv ? (s + 1 < lg) : (lg - 1 - s >= 1);
-        const int lh = kInv ? s : (lg - 1 - s);  // log2 of the (first) half span
-        const int h = 1 << lh;
-        if (pair) {
-            const int quarter = len >> 2, total = quarter * batch;
-            for (int u = threadIdx.x; u < total; u += blockDim.x) {
-                int b, v;
-                if (kBatchInner) {
-                    b = u & (batch - 1);
-                    v = u >> lgBatch;
-                } else {
-                    b = u >> (lg - 2);
-                    v = u & (quarter - 1);
-                }
-                float2* base = buf + b * sb;
-                if (!kInv) {
-                    // DIF: half spans h then h/2 on elements i, i+h/2, i+h, i+3h/2
-                    const int hh = h >> 1;
-                    const int j = v & (hh - 1);
-                    const int i = ((v >> (lh - 1)) << (lh + 1)) + j;
-                    float2* p0 = EL(base, i);
-                    float2* p1 = EL(base, i + hh);
-                    float2* p2 = EL(base, i + h);
-                    float2* p3 = EL(base, i + h + hh);
-                    const float2 x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
-                    const float2 w1 = __ldg(tw + j * (kTwN >> (lh + 1)));   // W_{2h}^j
-                    const float2 w2 = __ldg(tw + j * (kTwN >> lh));         // W_{h}^j
-                    const float2 y0 = make_float2(x0.x + x2.x, x0.y + x2.y);
-                    const float2 y2 = cmul(make_float2(x0.x - x2.x, x0.y - x2.y), w1);
-                    const float2 y1 = make_float2(x1.x + x3.x, x1.y + x3.y);
-                    const float2 d3 = cmul(make_float2(x1.x - x3.x, x1.y - x3.y), w1);
-                    const float2 y3 = make_float2(d3.y, -d3.x);             // * (-i) = W_{2h}^{h/2}
-                    *p0 = make_float2(y0.x + y1.x, y0.y + y1.y);
-                    *p1 = cmul(make_float2(y0.x - y1.x, y0.y - y1.y), w2);
-                    *p2 = make_float2(y2.x + y3.x, y2.y + y3.y);
-                    *p3 = cmul(make_float2(y2.x - y3.x, y2.y - y3.y), w2);
-                } else {
-                    // DIT: half spans h then 2h on elements i, i+h, i+2h, i+3h
-                    const int j = v & (h - 1);
-                    const int i = ((v >> lh) << (lh + 2)) + j;
-                    float2* p0 = EL(base, i);
-                    float2* p1 = EL(base, i + h);
-                    float2* p2 = EL(base, i + 2 * h);
-                    float2* p3 = EL(base, i + 3 * h);
-                    const float2 x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
-                    const float2 w1 = __ldg(tw + j * (kTwN >> (lh + 1)));   // W_{2h}^j
-                    const float2 w2 = __ldg(tw + j * (kTwN >> (lh + 2)));   // W_{4h}^j
-                    const float2 t1 = cmulc(x1, w1), t3 = cmulc(x3, w1);
-                    const float2 y0 = make_float2(x0.x + t1.x, x0.y + t1.y), y1 = make_float2(x0.x - t1.x, x0.y - t1.y);
-                    const float2 y2 = make_float2(x2.x + t3.x, x2.y + t3.y), y3 = make_float2(x2.x - t3.x, x2.y - t3.y);
-                    const float2 u2 = cmulc(y2, w2);
-                    const float2 q3 = cmulc(y3, w2);
-                    const float2 u3 = make_float2(-q3.y, q3.x);             // * (+i) = conj(W_{4h}^{h})
-                    *p0 = make_float2(y0.x + u2.x, y0.y + u2.y);
-                    *p2 = make_float2(y0.x - u2.x, y0.y - u2.y);
-                    *p1 = make_float2(y1.x + u3.x, y1.y + u3.y);
-                    *p3 = make_float2(y1.x - u3.x, y1.y - u3.y);
-                }
+// ---- shared-memory FFT ---------------------------------------------------------------
+// In-place FFT over len = 2^lg elements for 2^lgBatch independent sequences held in shared memory.
+// kInv=false: DIF forward (natural -> bit reversed).  kInv=true: DIT inverse (bit reversed -> natural), unnormalised.
+// Up to four radix-2 stages are fused into one step on 16 elements held in registers, so a 2048-point
+// transform makes three trips through shared memory (4 + 4 + 3 stages) instead of eleven.  Within a step the
+// twiddle of a butterfly factors into a per-thread part W_{2h}^j (table lookup, one per stage) and a
+// compile-time 16th root of unity.
+// Layout: element i of a sequence sits at the padded index pidx(i) = i + (i >> 4), which makes both the
+// stride-1 steps (a thread owns 16 consecutive elements) and the strided ones bank-conflict free:
+//   kCols = false (rows)   : element (i, b) at buf[b * seqStride + pidx(i)]
+//   kCols = true  (columns): element (i, b) at buf[pidx(i) * 2^lgBatch + b]
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+
+// x * exp(-2 pi i k / 16), k = 0..7; k is a compile-time constant after unrolling, the switch folds away
+__device__ __forceinline__ float2 mul_w16(float2 x, int k) {
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+    switch (k) {
+        case 0: return x;
+        case 1: return make_float2(x.x * c1 + x.y * s1, x.y * c1 - x.x * s1);
+        case 2: return make_float2((x.x + x.y) * r2, (x.y - x.x) * r2);
+        case 3: return make_float2(x.x * s1 + x.y * c1, x.y * s1 - x.x * c1);
+        case 4: return make_float2(x.y, -x.x);
+        case 5: return make_float2(x.y * c1 - x.x * s1, -x.y * s1 - x.x * c1);
+        case 6: return make_float2((x.y - x.x) * r2, -(x.x + x.y) * r2);
+        default: return make_float2(x.y * s1 - x.x * c1, -x.y * c1 - x.x * s1);   // 7
+    }
+}
+// x * exp(+2 pi i k / 16)
+__device__ __forceinline__ float2 mul_w16c(float2 x, int k) {
+    const float2 y = mul_w16(make_float2(x.x, -x.y), k);   // conj(conj(x) * w) = x * conj(w)
+    return make_float2(y.x, -y.y);
+}
+
+// Q fused radix-2 stages on N = 2^Q register values; w[l] = W_{2 h_l}^j of stage l
+template <bool kInv, int Q>
+__device__ __forceinline__ void fft_regs(float2* r, const float2* w) {
+    constexpr int N = 1 << Q;
+#pragma unroll
+    for (int l = 0; l < Q; ++l) {
+        const int dist = kInv ? (1 << l) : (N >> (l + 1));
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            if (m & dist) continue;
+            const int k = (m & (dist - 1)) * (8 / dist);     // exp(-+2 pi i mp / (2 dist)) as a 16th root of unity
+            const float2 a = r[m], b = r[m + dist];
+            if (!kInv) {
+                r[m] = make_float2(a.x + b.x, a.y + b.y);
+                r[m + dist] = cmul(mul_w16(make_float2(a.x - b.x, a.y - b.y), k), w[l]);
+            } else {
+                const float2 t = cmulc(mul_w16c(b, k), w[l]);
+                r[m] = make_float2(a.x + t.x, a.y + t.y);
+                r[m + dist] = make_float2(a.x - t.x, a.y - t.y);
             }
-            s += 2;
-        } else {
-            const int half = len >> 1, total = half * batch;
-            const int twStride = kTwN >> (lh + 1);
-            for (int u = threadIdx.x; u < total; u += blockDim.x) {
-                int b, v;
-                if (kBatchInner) {
-                    b = u & (batch - 1);
-                    v = u >> lgBatch;
-                } else {
-                    b = u >> (lg - 1);
-                    v = u & (half - 1);
-                }
-                const int j = v & (h - 1);
-                const int i0 = ((v >> lh) << (lh + 1)) + j;
-                float2* pa = EL(buf + b * sb, i0);
-                float2* pb = EL(buf + b * sb, i0 + h);
-                const float2 a = *pa, c = *pb;
-                const float2 w = __ldg(tw + j * twStride);
-                if (kInv) {
-                    const float2 t = cmulc(c, w);
-                    *pa = make_float2(a.x + t.x, a.y + t.y);
-                    *pb = make_float2(a.x - t.x, a.y - t.y);
-                } else {
-                    const float2 d = make_float2(a.x - c.x, a.y - c.y);
-                    *pa = make_float2(a.x + c.x, a.y + c.y);
-                    *pb = cmul(d, w);
-                }
-            }
-            s += 1;
         }
+    }
+}
+
+// one fused step of Q stages; `done` stages have been applied before it
+template <bool kInv, bool kCols, int Q>
+__device__ __forceinline__ void fft_step(float2* buf, int lg, int lgBatch, int seqStride, int done, const float2* tw) {
+    constexpr int N = 1 << Q;
+    const int lgItems = lg - Q;                       // groups per sequence
+    const int items = 1 << (lgItems + lgBatch);
+    for (int u = threadIdx.x; u < items; u += blockDim.x) {
+        int b, v;
+        if (kCols) {
+            b = u & ((1 << lgBatch) - 1);
+            v = u >> lgBatch;
+        } else {
+            b = u >> lgItems;
+            v = u & ((1 << lgItems) - 1);
+        }
+        int i, lstride, j, lh;
+        if (!kInv) {     // DIF: half spans h, h/2, .. ; elements i + m * (h >> (Q-1))
+            lh = lg - 1 - done;
+            lstride = lh - (Q - 1);
+            j = v & ((1 << lstride) - 1);
+            i = ((v >> lstride) << (lh + 1)) + j;
+        } else {         // DIT: half spans h, 2h, .. ; elements i + m * h
+            lh = done;
+            lstride = lh;
+            j = v & ((1 << lh) - 1);
+            i = ((v >> lh) << (lh + Q)) + j;
+        }
+        float2 w[Q];
+#pragma unroll
+        for (int l = 0; l < Q; ++l) {
+            const int l2h = kInv ? (lh + l + 1) : (lh - l + 1);          // log2 of the full span of stage l
+            w[l] = __ldg(tw + ((unsigned)j << (12 - l2h)));               // W_{2h_l}^j, kTwN = 4096
+        }
+        float2 r[N];
+        float2* base = kCols ? buf + b : buf + b * seqStride;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            const int e = pidx(i + (m << lstride));
+            r[m] = kCols ? base[e << lgBatch] : base[e];
+        }
+        fft_regs<kInv, Q>(r, w);
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            const int e = pidx(i + (m << lstride));
+            if (kCols) base[e << lgBatch] = r[m];
+            else base[e] = r[m];
+        }
+    }
+}
+
+template <bool kInv, bool kCols>
+__device__ void smem_fft(float2* buf, int lg, int lgBatch, int seqStride, const float2* tw) {
+    int done = 0;
+    while (done < lg) {
+        const int q = min(4, lg - done);
+        if (q == 4) fft_step<kInv, kCols, 4>(buf, lg, lgBatch, seqStride, done, tw);
+        else if (q == 3) fft_step<kInv, kCols, 3>(buf, lg, lgBatch, seqStride, done, tw);
+        else if (q == 2) fft_step<kInv, kCols, 2>(buf, lg, lgBatch, seqStride, done, tw);
+        else fft_step<kInv, kCols, 1>(buf, lg, lgBatch, seqStride, done, tw);
+        done += q;
         __syncthreads();
     }
-#undef EL
 }
 
 // ---- forward column pass -------------------------------------------------------------
@@ -168,7 +179,7 @@ __device__ void smem_fft(float2* buf, int lg, int batch, int si, int sb, const f
 //                 (acquisition.m:194-205; periodic extension see file header)
 // kind 1: code    y[n] = table[n] for n < M else 0   (acquisition.m:176-180)
 // grid = (P2/kColTile, batch); batch index selects the Doppler bin / code table.
-__global__ void __launch_bounds__(kAcqThreads) acq_fwd_col_kernel(AcqPlan pl, int kind, const int8_t* src,
+__global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_col_kernel(AcqPlan pl, int kind, const int8_t* src,
                                                                   size_t srcStride, const unsigned long long* dphi,
                                                                   float2* spec) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -194,33 +205,33 @@ __global__ void __launch_bounds__(kAcqThreads) acq_fwd_col_kernel(AcqPlan pl, in
         } else if (n < (unsigned)pl.M) {
             v.x = (float)x[n];
         }
-        buf[e] = v;
+        buf[pidx(r) * kColTile + c] = v;
     }
     __syncthreads();
-    smem_fft<false, true>(buf, pl.log2P1, kColTile, kColTile, 1, pl.tw);
+    smem_fft<false, true>(buf, pl.log2P1, kLgColTile, 0, pl.tw);
     float2* out = spec + (size_t)bi * pl.P;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         int c = e & (kColTile - 1), r = e >> 3;
         unsigned k1 = __brev((unsigned)r) >> (32 - pl.log2P1);
         unsigned n2 = col0 + c;
         float2 w = twiddleP(pl, k1 * n2);
-        out[(size_t)r * pl.P2 + n2] = cmul(buf[e], w);
+        out[(size_t)r * pl.P2 + n2] = cmul(buf[pidx(r) * kColTile + c], w);
     }
 }
 
 // ---- forward row pass (in place) -----------------------------------------------------
 // conjScale != 0: store conj(X) * conjScale (code spectra: acquisition.m:180 with the 1/P of
-// the inverse transform folded in).  grid = (P1 / kRowTile, batch); kRowTile rows per CTA.
-__global__ void __launch_bounds__(kAcqThreads) acq_fwd_row_kernel(AcqPlan pl, float2* spec, float conjScale) {
+// the inverse transform folded in).  grid = (P1 >> lgRowTile, batch).
+__global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_row_kernel(AcqPlan pl, float2* spec, float conjScale) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
-    float2* rows = spec + (size_t)blockIdx.y * pl.P + (size_t)blockIdx.x * kRowTile * pl.P2;   // kRowTile contiguous rows
-    const int total = kRowTile * pl.P2, rowStride = pl.P2 + (pl.P2 >> 4);
-    for (int i = threadIdx.x; i < total; i += blockDim.x) buf[(i >> pl.log2P2) * rowStride + row_pad(i & (pl.P2 - 1))] = rows[i];
+    float2* rows = spec + (size_t)blockIdx.y * pl.P + ((size_t)blockIdx.x << pl.lgRowTile) * pl.P2;   // 2^lgRowTile contiguous rows
+    const int total = pl.P2 << pl.lgRowTile, rowStride = pl.P2 + (pl.P2 >> 4);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))] = rows[i];
     __syncthreads();
-    smem_fft<false, false>(buf, pl.log2P2, kRowTile, 1, rowStride, pl.tw);
+    smem_fft<false, false>(buf, pl.log2P2, pl.lgRowTile, rowStride, pl.tw);
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        float2 v = buf[(i >> pl.log2P2) * rowStride + row_pad(i & (pl.P2 - 1))];
+        float2 v = buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))];
         if (conjScale != 0.f) v = make_float2(v.x * conjScale, -v.y * conjScale);
         rows[i] = v;
     }
@@ -228,26 +239,26 @@ __global__ void __launch_bounds__(kAcqThreads) acq_fwd_row_kernel(AcqPlan pl, fl
 
 // ---- inverse row pass ------------------------------------------------------------------
 // work[bin][dp] row r = IDFT_row( sig[bin] row r .* code[dp] row r ) .* W_P^{-n2 k1}
-// grid = (P1 / kRowTile, nbins, ncodes); binMap (optional): Doppler bin of batch entry blockIdx.y
-__global__ void __launch_bounds__(kAcqThreads) acq_inv_row_kernel(AcqPlan pl, const float2* sig, const float2* code,
+// grid = (P1 >> lgRowTile, nbins, ncodes); binMap (optional): Doppler bin of batch entry blockIdx.y
+__global__ void __launch_bounds__(kAcqThreads, 2) acq_inv_row_kernel(AcqPlan pl, const float2* sig, const float2* code,
                                                                   float2* work, int ncodes, const int* binMap) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
-    const int r0 = blockIdx.x * kRowTile, bi = blockIdx.y, dp = blockIdx.z;
+    const int r0 = blockIdx.x << pl.lgRowTile, bi = blockIdx.y, dp = blockIdx.z;
     const int bin = binMap ? binMap[bi] : bi;
     const float2* srow = sig + (size_t)bin * pl.P + (size_t)r0 * pl.P2;
     const float2* crow = code + (size_t)dp * pl.P + (size_t)r0 * pl.P2;
-    const int total = kRowTile * pl.P2, rowStride = pl.P2 + (pl.P2 >> 4);
+    const int total = pl.P2 << pl.lgRowTile, rowStride = pl.P2 + (pl.P2 >> 4);
     for (int i = threadIdx.x; i < total; i += blockDim.x)
-        buf[(i >> pl.log2P2) * rowStride + row_pad(i & (pl.P2 - 1))] = cmul(srow[i], __ldg(crow + i));
+        buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))] = cmul(srow[i], __ldg(crow + i));
     __syncthreads();
-    smem_fft<true, false>(buf, pl.log2P2, kRowTile, 1, rowStride, pl.tw);
+    smem_fft<true, false>(buf, pl.log2P2, pl.lgRowTile, rowStride, pl.tw);
     float2* orow = work + ((size_t)bi * ncodes + dp) * pl.P + (size_t)r0 * pl.P2;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int r = r0 + (i >> pl.log2P2), n2 = i & (pl.P2 - 1);
         const unsigned k1 = __brev((unsigned)r) >> (32 - pl.log2P1);
         float2 w = twiddleP(pl, k1 * (unsigned)n2);
-        orow[i] = cmulc(buf[(i >> pl.log2P2) * rowStride + row_pad(n2)], w);
+        orow[i] = cmulc(buf[(i >> pl.log2P2) * rowStride + pidx(n2)], w);
     }
 }
 
@@ -260,24 +271,25 @@ struct AcqPeak {
 //          2 B2a |d|+|p| (B2a acquisition.m:205-209)
 // Lags are restricted to [0,N) and, when ex0 <= ex1 (second-peak search, B2a
 // acquisition.m:224-249, 0-based inclusive bounds), to [lo0,hi0] U [lo1,hi1].
-__global__ void __launch_bounds__(kAcqThreads) acq_inv_col_kernel(AcqPlan pl, const float2* work, int ncodes,
+__global__ void __launch_bounds__(kAcqThreads, 2) acq_inv_col_kernel(AcqPlan pl, const float2* work, int ncodes,
                                                                   int combine, int lo0, int hi0, int lo1, int hi1,
                                                                   int useRanges, AcqPeak* peaks /*[bin][gridDim.x]*/) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
     const int total = pl.P1 * kColTile;
-    float* mag = reinterpret_cast<float*>(buf + total);
+    float* mag = reinterpret_cast<float*>(buf + (pl.P1 + (pl.P1 >> 4)) * kColTile);   // after the padded FFT buffer
     const int col0 = blockIdx.x * kColTile, bin = blockIdx.y;
     for (int dp = 0; dp < ncodes; ++dp) {
         const float2* w = work + ((size_t)bin * ncodes + dp) * pl.P;
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
             int c = e & (kColTile - 1), r = e >> 3;
-            buf[e] = w[(size_t)r * pl.P2 + col0 + c];
+            buf[pidx(r) * kColTile + c] = w[(size_t)r * pl.P2 + col0 + c];
         }
         __syncthreads();
-        smem_fft<true, true>(buf, pl.log2P1, kColTile, kColTile, 1, pl.tw);
+        smem_fft<true, true>(buf, pl.log2P1, kLgColTile, 0, pl.tw);
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            float2 v = buf[e];
+            const int c = e & (kColTile - 1), r = e >> 3;
+            float2 v = buf[pidx(r) * kColTile + c];
             float m = sqrtf(v.x * v.x + v.y * v.y);
             if (dp == 0)
                 mag[e] = m;
@@ -456,15 +468,53 @@ using namespace bds;
 
 namespace {
 
+// Work buffers come from a small process-wide pool: cudaMalloc / cudaFree of the 0.7 - 10 GB an acquisition needs
+// costs tens of milliseconds (and varies wildly), more than the search itself.  The pool is emptied by bds_shutdown.
+struct PoolBlock {
+    void* p;
+    size_t cap;
+};
+std::mutex g_poolMu;
+std::vector<PoolBlock> g_pool;
+
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
+    size_t cap = 0;
+    ~DevBuf() { release(); }
     template <typename T>
     T* as() { return reinterpret_cast<T*>(p); }
-    cudaError_t alloc(size_t bytes) {
-        cudaFree(p);
+    void release() {
+        if (!p) return;
+        std::lock_guard<std::mutex> lock(g_poolMu);
+        g_pool.push_back(PoolBlock{p, cap});
         p = nullptr;
-        return cudaMalloc(&p, bytes);
+        cap = 0;
+    }
+    cudaError_t alloc(size_t bytes) {
+        release();
+        if (bytes == 0) bytes = 16;
+        {
+            std::lock_guard<std::mutex> lock(g_poolMu);
+            int best = -1;
+            for (int i = 0; i < (int)g_pool.size(); ++i)   // smallest block that fits, but not one wastefully larger
+                if (g_pool[i].cap >= bytes && g_pool[i].cap <= 2 * bytes + (1 << 20) && (best < 0 || g_pool[i].cap < g_pool[best].cap))
+                    best = i;
+            if (best >= 0) {
+                p = g_pool[best].p;
+                cap = g_pool[best].cap;
+                g_pool.erase(g_pool.begin() + best);
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {   // out of memory: give the pooled blocks back and retry once
+            cudaGetLastError();
+            bds::acq_pool_release();
+            e = cudaMalloc(&p, bytes);
+        }
+        cap = e == cudaSuccess ? bytes : 0;
+        if (e != cudaSuccess) p = nullptr;
+        return e;
     }
 };
 
@@ -528,8 +578,10 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     if (lgP > 23 || lgP < 8) return set_error(BDS_ERR_UNSUPPORTED, "FFT length 2^%d out of range", lgP);
     AcqPlan pl{};
     pl.log2P = lgP;
-    pl.log2P1 = lgP / 2;
-    pl.log2P2 = lgP - pl.log2P1;
+    // long transforms: shorter columns (more column tiles per launch, two CTAs per SM) and 4096-point rows
+    pl.log2P2 = lgP >= 21 ? std::min(12, lgP - lgP / 2 + 1) : lgP - lgP / 2;
+    pl.log2P1 = lgP - pl.log2P2;
+    pl.lgRowTile = pl.log2P2 >= 12 ? 1 : 2;
     pl.P = 1 << lgP;
     pl.P1 = 1 << pl.log2P1;
     pl.P2 = 1 << pl.log2P2;
@@ -590,17 +642,21 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     // ---- forward FFT of every bin, resident for all PRNs (the reference recomputes it per PRN)
     const size_t specBytes = sizeof(float2) * (size_t)pl.P;
     TRYA(dSig.alloc(specBytes * nbins));
-    const size_t smemCol = sizeof(float2) * pl.P1 * kColTile;
+    const size_t smemCol = sizeof(float2) * (pl.P1 + (pl.P1 >> 4)) * kColTile;   // padded, see pidx()
     const size_t smemColInv = smemCol + sizeof(float) * pl.P1 * kColTile;
-    const size_t smemRow = sizeof(float2) * (pl.P2 + (pl.P2 >> 4)) * kRowTile;   // padded rows, see row_pad()
+    const int rowTile = 1 << pl.lgRowTile;
+    const size_t smemRow = sizeof(float2) * (pl.P2 + (pl.P2 >> 4)) * rowTile;   // padded rows, see pidx()
     TRYA(cudaFuncSetAttribute(acq_fwd_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemCol));
     TRYA(cudaFuncSetAttribute(acq_inv_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemColInv));
     TRYA(cudaFuncSetAttribute(acq_fwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRow));
     TRYA(cudaFuncSetAttribute(acq_inv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRow));
     const int colGroups = pl.P2 / kColTile;
-    acq_fwd_col_kernel<<<dim3(colGroups, nbins), kAcqThreads, smemCol>>>(pl, 0, dx, 0, dDphi.as<unsigned long long>(),
+    // one thread per 16-element register group (fewer for the short B2a transforms)
+    const int thrRow = std::min(kAcqThreads, std::max(128, (pl.P2 >> 4) * rowTile));
+    const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
+    acq_fwd_col_kernel<<<dim3(colGroups, nbins), thrCol, smemCol>>>(pl, 0, dx, 0, dDphi.as<unsigned long long>(),
                                                                        dSig.as<float2>());
-    acq_fwd_row_kernel<<<dim3(pl.P1 / kRowTile, nbins), kAcqThreads, smemRow>>>(pl, dSig.as<float2>(), 0.f);
+    acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, nbins), thrRow, smemRow>>>(pl, dSig.as<float2>(), 0.f);
     count_launch(2);
     TRYA(cudaGetLastError());
 
@@ -674,9 +730,9 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
             dIdx.as<int32_t>(), dCodes.as<int8_t>(), codeLen, (int)spc, dTab.as<int8_t>());
         count_launch();
         TRYA(dCode.alloc(specBytes * ncodes * nSel));
-        acq_fwd_col_kernel<<<dim3(colGroups, ncodes * nSel), kAcqThreads, smemCol>>>(pl, 1, dTab.as<int8_t>(), (size_t)spc, nullptr,
+        acq_fwd_col_kernel<<<dim3(colGroups, ncodes * nSel), thrCol, smemCol>>>(pl, 1, dTab.as<int8_t>(), (size_t)spc, nullptr,
                                                                                    dCode.as<float2>());
-        acq_fwd_row_kernel<<<dim3(pl.P1 / kRowTile, ncodes * nSel), kAcqThreads, smemRow>>>(pl, dCode.as<float2>(), 1.0f / (float)pl.P);
+        acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, ncodes * nSel), thrRow, smemRow>>>(pl, dCode.as<float2>(), 1.0f / (float)pl.P);
         count_launch(2);
         // ---- phase 1: coarse PRN x Doppler grid; per (PRN, bin) peak and first lag
         TRYA(dBinPeak.alloc(sizeof(AcqPeak) * (size_t)nbins * nSel));
@@ -684,9 +740,9 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
             const float2* code = dCode.as<float2>() + (size_t)i * ncodes * pl.P;
             for (int b0 = 0; b0 < nbins; b0 += binsPerBatch) {
                 const int nb = std::min(binsPerBatch, nbins - b0);
-                acq_inv_row_kernel<<<dim3(pl.P1 / kRowTile, nb, ncodes), kAcqThreads, smemRow>>>(
+                acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, nb, ncodes), thrRow, smemRow>>>(
                     pl, dSig.as<float2>() + (size_t)b0 * pl.P, code, dWork.as<float2>(), ncodes, nullptr);
-                acq_inv_col_kernel<<<dim3(colGroups, nb), kAcqThreads, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, 0, 0,
+                acq_inv_col_kernel<<<dim3(colGroups, nb), thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, 0, 0,
                                                                                    0, 0, 0, dPeaks.as<AcqPeak>());
                 acq_peak_reduce_kernel<<<nb, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dBinPeak.as<AcqPeak>() + (size_t)i * nbins + b0);
                 count_launch(3);
@@ -738,10 +794,10 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
                     lo1 = (int)e2 - 1;
                     hi1 = (int)std::min(e4, N) - 1;
                 }
-                acq_inv_row_kernel<<<dim3(pl.P1 / kRowTile, 1, ncodes), kAcqThreads, smemRow>>>(
+                acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, 1, ncodes), thrRow, smemRow>>>(
                     pl, dSig.as<float2>(), dCode.as<float2>() + (size_t)i * ncodes * pl.P, dWork.as<float2>(), ncodes,
                     dBinMap.as<int>() + i);
-                acq_inv_col_kernel<<<dim3(colGroups, 1), kAcqThreads, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0,
+                acq_inv_col_kernel<<<dim3(colGroups, 1), thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0,
                                                                                   hi0, lo1, hi1, 1, dPeaks.as<AcqPeak>());
                 acq_peak_reduce_kernel<<<1, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dSecond.as<AcqPeak>() + i);
                 count_launch(3);
@@ -884,3 +940,11 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
 #undef TRYA
     return BDS_OK;
 }
+
+namespace bds {
+void acq_pool_release() {
+    std::lock_guard<std::mutex> lock(g_poolMu);
+    for (auto& b : g_pool) cudaFree(b.p);
+    g_pool.clear();
+}
+}  // namespace bds

@@ -61,7 +61,10 @@ int bds_init(int device) {
 }
 
 void bds_shutdown(void) {
-    if (g_device >= 0) cudaDeviceSynchronize();
+    if (g_device >= 0) {
+        cudaDeviceSynchronize();
+        acq_pool_release();
+    }
     g_device = -1;
 }
 

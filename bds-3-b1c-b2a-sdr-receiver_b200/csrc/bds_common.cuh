@@ -29,6 +29,9 @@ int require_device();
                                     cudaGetErrorString(_e), __FILE__, __LINE__);              \
     } while (0)
 
+// frees the device work buffers pooled by bds_acquire (bds_acq.cu)
+void acq_pool_release();
+
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- device-side memory-model helpers --------------------------------------------------
