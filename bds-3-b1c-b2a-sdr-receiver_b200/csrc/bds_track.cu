@@ -858,6 +858,10 @@ int plan_grid(bds_trk* h) {
         while (k > 1 && (long long)h->nAct * ((10230 + kFwChips * k - 1) / (kFwChips * k)) < 4LL * h->gridBlocks) --k;
         if (const char* e = getenv("BDS_TRK_PASSES")) k = std::max(1, std::min(8, atoi(e)));  // tuning knob
         h->S = (10230 + kFwChips * k - 1) / (kFwChips * k);
+        // queue payload: 7 bits of channel, 6 bits of slice, 19 bits of epoch (fw_payload)
+        if (h->nCh > 127 || h->S > 63)
+            return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: at most 127 channels per session (got %d); "
+                                                  "open several sessions or use BDS_KERNEL_GENERAL", h->nCh);
     } else {
         BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel, kTrkThreads, h->smemBytes));
         if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
@@ -887,6 +891,7 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
         delete h;
         return rc;
     }
+    if (h->fast && cfg->kernel == BDS_KERNEL_AUTO && n_ch > 127) h->fast = false;   // queue payload holds 7 bits of channel
     auto fail = [&](int code) {
         bds_track_close(h);
         return code;
@@ -1059,6 +1064,8 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
         rc = bds_track_sync(h);
         if (rc) return rc;
     }
+    if (h->fast && h->epochsRun + n_epochs > (1 << 19) - 1)
+        return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: at most 524287 epochs per session");
     rc = ensure_capacity(h, h->epochsRun + n_epochs);
     if (rc) return rc;
     BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -1080,6 +1087,8 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
         rc = bds_track_sync(h);
         if (rc) return rc;
     }
+    if (h->fast && h->epochsRun + n_epochs > (1 << 19) - 1)
+        return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: at most 524287 epochs per session");
     rc = ensure_capacity(h, h->epochsRun + n_epochs);
     if (rc) return rc;
     if (chunk_bytes == 0) chunk_bytes = (size_t)128 << 20;
