@@ -758,7 +758,7 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
 }
 
 size_t smem_bytes(bool fast) {
-    return fast ? std::max(sizeof(FwSmem), sizeof(FwCloseScratch) * (kFwThreads / 32)) : sizeof(TrkSmem);
+    return fast ? std::max(sizeof(FwSmem), kFwCloseBase + sizeof(FwCloseScratch) * (kFwThreads / 32)) : sizeof(TrkSmem);
 }
 
 int init_state(bds_trk* h) {

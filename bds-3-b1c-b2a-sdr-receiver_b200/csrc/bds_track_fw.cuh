@@ -83,6 +83,7 @@ struct __align__(16) FwCloseScratch {
     unsigned char posbin[80];
 };
 static_assert(sizeof(FwCloseScratch) % 16 == 0, "FwCloseScratch must be a 16-byte multiple");
+constexpr int kFwCloseBase = 1024;   // closer scratch starts past the (unused, uninitialised) mbarrier area of FwSmem
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -358,7 +359,9 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     FwSmem& sm = *reinterpret_cast<FwSmem*>(dyn_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
+    const bool openLoop = g.olParams != nullptr;
+    const bool closerCta = !openLoop && (int)blockIdx.x >= g.nCompute;
+    if (threadIdx.x == 0 && !closerCta) {   // closer CTAs use their shared memory as plain per-warp scratch: no mbarriers there
         for (int s = 0; s < kFwStages; ++s) {
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], kFwCompute);
@@ -369,18 +372,17 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         }
     }
     __syncthreads();
-    const bool openLoop = g.olParams != nullptr;
     const long long perRound = openLoop ? (long long)g.S : (long long)g.nAct * g.S;
     const long long total = openLoop ? (long long)g.olCount * g.S : perRound * g.maxEpochs;
     const int cps = fw_chips_per_slice(g.S);
     constexpr unsigned nst = (unsigned)kFwStages;   // compile-time: u % nst, u / nst become mask / shift
 
-    if (!openLoop && (int)blockIdx.x >= g.nCompute) {
+    if (closerCta) {
         // ================================ closer CTA ================================
         // Every warp owns the channels c with (index in the active list) % (closer warps) == its id and
         // polls their slice-arrival counters; when all S slices of an epoch have arrived it closes the
         // loops (fp64), builds the next epoch's tables, publishes and queues the next slices.
-        FwCloseScratch* cs = reinterpret_cast<FwCloseScratch*>(dyn_smem) + warp;
+        FwCloseScratch* cs = reinterpret_cast<FwCloseScratch*>(dyn_smem + kFwCloseBase) + warp;
         const int nCw = ((int)gridDim.x - g.nCompute) * (kFwThreads / 32);
         const int me = ((int)blockIdx.x - g.nCompute) * (kFwThreads / 32) + warp;
         int chan[8], ep[8], ep0[8], n = 0;

@@ -280,6 +280,8 @@ def run_b200(args):
     if os.environ.get('BDS_TRK_TRACE'):
         L.check(L.lib().bds_track_dump_trace(sess.h, os.path.join(ROOT, 'gpurun_out', 'trace.bin').encode()))
     clocks = sampler.stop(s0, s1) if rank == 0 else None
+    done_ = sess.fetch(n_epochs)["epochsDone"]      # untimed check: every channel ran every epoch of the timed steps
+    assert int(done_.min()) == n_epochs, f"tracking stopped early: epochsDone min {int(done_.min())} of {n_epochs}"
     # device time: max over ranks of the CUDA-event time of the persistent kernel, per step
     dev_ms = sum(kernel_ms) / len(kernel_ms)
     tmax = torch.tensor([dev_ms, wall * 1e3 / args.steps], device="cuda", dtype=torch.float64)

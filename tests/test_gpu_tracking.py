@@ -263,3 +263,34 @@ def test_golden_fixture_open_loop():
     got = open_loop("B2a", s, g["if_b2a"], [int(g["trk_prn"])], g["trk_nco_b2a"].reshape(1, 1, 6), L.KERNEL_GENERAL)[0, 0]
     want = g["trk_sums_B2a"]
     assert np.max(np.abs(got - want) / util.family_scale(want[None, :])[0]) <= 1e-4
+
+
+def test_closed_loop_is_deterministic_under_load():
+    """24 channels x 58 epochs repeated 60 times on one session (resident and streamed alternately): every channel
+    completes every epoch and every run gives bit-identical outputs (the slice sums are exact integer additions, so
+    the order in which slices arrive cannot matter).  Regression test for a shared-memory overlay bug that corrupted
+    a closer warp's channel state about once per 10^7 loop closures."""
+    import torch
+    from bds3_b200 import synth
+    st = util.product_settings(util.settings_for("WB", numberOfChannels=24))
+    sats = synth.make_sats(24, st, "B1C", seed=5)
+    ch = synth.channels_from_sats(sats, st, "B1C", freq_error=2.0)
+    n = int(0.6 * util.FS)
+    x = synth.synth_device("B1C", st, sats, n, seed=5)
+    ne = 58
+    ref = None
+    with _track.TrackSession("WB", st, ch) as ses:
+        for it in range(60):
+            ses.reset()
+            if it % 2:
+                ses.run_streamed(x.ctypes.data, x.size, ne, chunk_bytes=8 << 20)
+            else:
+                ses.feed(x)
+                ses.run_async(ne)
+            pl = ses.fetch(ne)
+            assert int(pl["epochsDone"].min()) == ne, (it, pl["epochsDone"])
+            key = np.stack([pl["I_P"], pl["Q_P"], pl["carrFreq"], pl["codeFreq"]])
+            if ref is None:
+                ref = key
+            else:
+                np.testing.assert_array_equal(key, ref, err_msg=f"run {it} differs")
