@@ -87,7 +87,7 @@ struct TrkDev {
     unsigned traceCap;
     int nCompute;                  // CTAs [0,nCompute) correlate, the rest close loops
     int ahead;                     // pop a new work item only when <= ahead passes are still pending (-1: no limit)
-    int stages, tune;              // pipeline stages in use; tuning bits (1: pop only with a free stage, 2: parallel closure)
+    int stages, tune;              // pipeline stages (compile-time kFwStages); tune: unused developer bits
     int epochLimit;                // no channel runs an epoch with index >= epochLimit (<= capacity)
 };
 
