@@ -65,7 +65,7 @@ ERR_NO_DEVICE = -2
 # every symbol include/bdsgpu.h declares (tests check that the .so exports all of them)
 EXPORTS = ["bds_abi_version", "bds_init", "bds_shutdown", "bds_last_error", "bds_launch_count", "bds_device_ok",
            "bds_gen_code", "bds_make_code_table", "bds_acquire", "bds_track_open", "bds_track_open_file",
-           "bds_track_feed", "bds_track_run", "bds_track_run_async", "bds_track_run_streamed", "bds_track_sync", "bds_track_fetch",
+           "bds_track_feed", "bds_track_run", "bds_track_run_async", "bds_track_run_streamed", "bds_track_run_window", "bds_track_sync", "bds_track_fetch",
            "bds_track_device_block", "bds_track_stats", "bds_track_counters", "bds_track_dump_trace", "bds_track_reset", "bds_track_close",
            "bds_track_correlate_open_loop", "bds_synth_if", "bds_dev_alloc", "bds_dev_free",
            "bds_host_alloc_pinned", "bds_host_free_pinned", "bds_memcpy_h2d", "bds_memcpy_d2h", "bds_dev_sync"]
@@ -101,6 +101,7 @@ def lib():
     L.bds_track_run.argtypes = [vp, C.c_int, C.POINTER(bds_trk_out), C.c_int]
     L.bds_track_run_async.argtypes = [vp, C.c_int]
     L.bds_track_run_streamed.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int]
+    L.bds_track_run_window.argtypes = [vp, vp, C.c_size_t, C.c_int]
     L.bds_track_sync.argtypes = [vp]
     L.bds_track_fetch.argtypes = [vp, C.POINTER(bds_trk_out), C.c_int]
     L.bds_track_device_block.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int),

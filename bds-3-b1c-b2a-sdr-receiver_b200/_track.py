@@ -139,6 +139,10 @@ class TrackSession:
         """Track a host record given by address (e.g. pinned memory): H2D in chunks overlapped with tracking."""
         L.check(L.lib().bds_track_run_streamed(self.h, C.c_void_p(host_ptr), int(n), int(chunk_bytes), int(n_epochs)))
 
+    def run_window(self, device_ptr, n_avail, epoch_limit):
+        """One asynchronous launch over the first ``n_avail`` samples of a device record that is still arriving."""
+        L.check(L.lib().bds_track_run_window(self.h, C.c_void_p(device_ptr), int(n_avail), int(epoch_limit)))
+
     def sync(self):
         L.check(L.lib().bds_track_sync(self.h))
 

@@ -1140,6 +1140,40 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
     return BDS_OK;
 }
 
+// One launch over a caller-filled DEVICE record of which the first n_avail samples are valid (and device-synchronised):
+// every channel runs as far as the data allows, never past epoch index epoch_limit.  Asynchronous; loop state stays on
+// the device, so successive calls with a growing n_avail track a record that is still arriving (e.g. over NVLink).
+int bds_track_run_window(bds_trk* h, const int8_t* x_dev, size_t n_avail, int epoch_limit) {
+    if (!h || !x_dev || epoch_limit <= 0) return set_error(BDS_ERR_ARG, "bds_track_run_window: bad arguments");
+    if (((uintptr_t)x_dev & 15) != 0) return set_error(BDS_ERR_ARG, "device IF buffer must be 16-byte aligned");
+    int rc = BDS_OK;
+    if (epoch_limit > h->capacity) {   // the output block is re-allocated: finish what is in flight first
+        if (h->pending) {
+            rc = bds_track_sync(h);
+            if (rc) return rc;
+        }
+        rc = ensure_capacity(h, epoch_limit);
+        if (rc) return rc;
+    }
+    if (h->fast && epoch_limit > (1 << 19) - 1)
+        return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: at most 524287 epochs per session");
+    if (h->ownX && h->dX) {
+        BDS_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(h->dX);
+    }
+    h->dX = const_cast<int8_t*>(x_dev);
+    h->ownX = false;
+    h->xCap = n_avail;
+    h->winFirst = 0;
+    h->winLen = n_avail > 32 ? (long long)n_avail - 32 : 0;   // kernels read whole 16-byte chunks / TMA tiles
+    if (!h->pending) BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = launch_run(h, epoch_limit, epoch_limit);
+    if (rc) return rc;
+    BDS_CUDA(cudaEventRecord(h->ev1, h->stream));
+    h->pending = true;
+    return BDS_OK;
+}
+
 int bds_track_sync(bds_trk* h) {
     if (!h) return set_error(BDS_ERR_ARG, "null handle");
     BDS_CUDA(cudaStreamSynchronize(h->stream));

@@ -189,6 +189,11 @@ int bds_track_run_async(bds_trk* h, int n_epochs);
  * kernel tracks what has already arrived; n_epochs = total epochs per channel.  Replaces the
  * session's resident record.  x must stay valid until bds_track_sync / bds_track_fetch returns. */
 int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs);
+/* Device-record variant for a record that is still arriving on the device (multi-GPU: every rank uploads 1/N of
+ * each chunk and the ranks all-gather it over NVLink): one asynchronous launch over the first n_avail samples of
+ * x_dev (valid and device-synchronised by the caller); channels stop at the end of the data or at epoch index
+ * epoch_limit and are resumed by the next call with a larger n_avail.  x_dev needs 32 bytes of slack. */
+int bds_track_run_window(bds_trk* h, const int8_t* x_dev, size_t n_avail, int epoch_limit);
 int bds_track_sync(bds_trk* h);
 int bds_track_fetch(bds_trk* h, const bds_trk_out* out, int out_stride);
 /* packed device result block: [n_ch][n_fields=21+18][capacity] doubles */

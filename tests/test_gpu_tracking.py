@@ -294,3 +294,28 @@ def test_closed_loop_is_deterministic_under_load():
                 ref = key
             else:
                 np.testing.assert_array_equal(key, ref, err_msg=f"run {it} differs")
+
+
+def test_run_window_on_an_arriving_device_record():
+    """bds_track_run_window: successive launches over a growing valid prefix of a device buffer (how the multi-GPU
+    end-to-end path tracks a record that arrives over NVLink) equal the one-launch result bit for bit."""
+    import torch
+    s, sats, x, ch = util.record("WB", 2, 0.13)
+    ps = util.product_settings(s)
+    N = 9
+    with _track.TrackSession("WB", ps, ch) as ses:
+        ses.feed(x)
+        ses.run_async(N)
+        want = ses.fetch(N, raw=True)
+    xd = torch.zeros(x.size + 64, dtype=torch.int8, device="cuda")
+    with _track.TrackSession("WB", ps, ch) as ses:
+        for frac in (0.3, 0.55, 0.8, 1.0):
+            n_avail = int(x.size * frac)
+            lo = int(x.size * {0.3: 0.0, 0.55: 0.3, 0.8: 0.55, 1.0: 0.8}[frac])
+            xd[lo:n_avail].copy_(torch.from_numpy(x[lo:n_avail]))
+            torch.cuda.synchronize()
+            ses.run_window(xd.data_ptr(), n_avail if frac < 1.0 else x.size + 32, N)
+        got = ses.fetch(N, raw=True)
+    assert list(got["epochsDone"]) == [N, N]
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
