@@ -1,19 +1,18 @@
-// Warp-specialised persistent kernel for the chip-synchronous B1C wide-band correlator.
-// (included from bds_track.cu after close_epoch / next_params)
+// Warp-specialised persistent kernel for the chip-synchronous B1C correlator (wide band and narrow band).
+// (included from bds_track.cu after close_core / next_params)
 //
-// One CTA of 16 warps per SM:
-//   warp 0      producer : walks this CTA's work items, waits until the item's channel-epoch has
-//                          been published (acquire load), then stages everything a pass needs —
-//                          the IF tile, the per-epoch tables, the packed codes and the NCO params
-//                          — into one of kFwStages shared-memory stages with TMA bulk copies that
-//                          complete on the stage's mbarrier.  It runs ahead of the compute warps,
+// One CTA of 20 warps per SM.  Compute CTAs:
+//   warp 0      producer : pops ready (channel, epoch, slice) tasks from the global ring (one 16-byte acquire load
+//                          per task), then stages everything a pass needs - the IF tile, the per-epoch table, the
+//                          packed codes and the NCO params - into one of kFwStages shared-memory stages with TMA
+//                          bulk copies that complete on the stage's mbarrier.  It runs ahead of the compute warps,
 //                          so global-memory latency is off their critical path.
-//   warp 1      closer   : receives the per-warp sums of a finished slice, stores the slice
-//                          partial, bumps the channel's arrival counter and — if it was the last
-//                          slice — reduces all partials in a fixed order, closes the PLL/DLL in
-//                          fp64 (close_epoch), builds the next epoch's tables and publishes them
-//                          with a release store.
-//   warps 2..15 compute  : one chip per thread and pass (fast_chip); warp sums via REDUX.
+//   warp 1      epilogue : receives the per-warp sums of a finished slice, adds them to the channel's 18 sums
+//                          (exact fp64 RED.ADDs) and bumps the channel's arrival counter (release).
+//   warps 2,3   idle     : they only make the service warps a full warpgroup for setmaxnreg (24 registers).
+//   warps 4..19 compute  : one chip per thread and pass (fast_chip) at 112 registers; warp sums via REDUX.
+// Closer CTAs (the last few of the grid): one warp per channel polls the arrival counter and, when all S slices of
+// an epoch are in, closes the PLL/DLL in fp64 (fw_closure), rewrites the epoch table and queues the next slices.
 #pragma once
 
 namespace bds {
