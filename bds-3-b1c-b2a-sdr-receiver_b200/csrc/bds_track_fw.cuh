@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                     --i;
                 }
             }
-            if (!fired) __nanosleep(100);
+            if (!fired) __nanosleep(20);
         }
         return;
     }
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 tTicket += clock64() - t0;
                 unsigned pl;
                 long long pos;
-                while (!fw_peek(g, ticket, pl, pos)) __nanosleep(64);
+                while (!fw_peek(g, ticket, pl, pos)) __nanosleep(32);
                 tQueue += clock64() - t0;
                 curTicket = ticket;
                 if (g.trace && ticket < g.traceCap) {
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         for (int k = 0;; ++k) {
             const int rs = k & 1;
             if (lane == 0)
-                while (!mbar_test(&sm.resFull[rs], (k >> 1) & 1)) __nanosleep(100);
+                while (!mbar_test(&sm.resFull[rs], (k >> 1) & 1)) __nanosleep(32);
             long long t0 = clock64();
             __syncwarp();
             mbar_wait(&sm.resFull[rs], (k >> 1) & 1);   // every lane observes the completed phase itself (succeeds at once)
