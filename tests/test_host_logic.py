@@ -100,3 +100,24 @@ def test_shard_helpers():
     assert rngs[0][0] == 0 and rngs[-1][1] == 63 and all(a[1] == b[0] for a, b in zip(rngs, rngs[1:]))
     with pytest.raises(ValueError):
         _shard.shard_indices(4, 2, 2)
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback():
+    """bench.py --impl reference runs the CPU restatement (never the product) and prints the contract's JSON line;
+    the product arm refuses to run without a B200 instead of falling back to the CPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--channels", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Msamples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not B.device_ok():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
