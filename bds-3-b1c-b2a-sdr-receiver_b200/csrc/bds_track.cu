@@ -1157,7 +1157,8 @@ int bds_track_run_window(bds_trk* h, const int8_t* x_dev, size_t n_avail, int ep
     }
     if (h->fast && epoch_limit > (1 << 19) - 1)
         return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: at most 524287 epochs per session");
-    if (h->ownX && h->dX) {
+    if (h->ownX && h->dX) {   // a record owned by the session (earlier host / streamed run) is replaced
+        if (h->copyStream) BDS_CUDA(cudaStreamSynchronize(h->copyStream));
         BDS_CUDA(cudaStreamSynchronize(h->stream));
         cudaFree(h->dX);
     }
