@@ -271,6 +271,73 @@ __device__ __forceinline__ int sel_bit(int s, unsigned m) {
     return r;
 }
 
+// ---- packed fp32 pairs (FFMA2 / FADD2 / FMUL2 of sm_100): an (I, Q) pair per instruction -------------
+#ifndef BDS_FAST_F32X2
+#define BDS_FAST_F32X2 0
+#endif
+#ifndef BDS_ABL
+#define BDS_ABL 0   // developer ablations of fast_chip, bit mask (1: no rotation, 2: no rank search, 4: no per-sample body); never shipped
+#endif
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pk(float a, float b) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpk(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    f2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+    f2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+    f2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) {
+    f2_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t f2_sfma(float s, f2_t b, f2_t c) { return f2_fma(f2_pk(s, s), b, c); }   // s * b + c
+
+// the per-thread running sums of the compute warps: 18 floats, or 9 (I, Q) pairs in the packed build
+#if BDS_FAST_F32X2
+typedef f2_t fast_acc_t;
+constexpr int kFastAccN = kNSum / 2;
+__device__ __forceinline__ void fast_acc_zero(fast_acc_t* a) {
+#pragma unroll
+    for (int i = 0; i < kFastAccN; ++i) a[i] = 0ull;
+}
+__device__ __forceinline__ void fast_acc_add(fast_acc_t* a, const float* t) {
+#pragma unroll
+    for (int i = 0; i < kFastAccN; ++i) a[i] = f2_add(a[i], f2_pk(t[2 * i], t[2 * i + 1]));
+}
+__device__ __forceinline__ float fast_acc_get(const fast_acc_t* a, int i) {
+    float x, y;
+    f2_unpk(a[i >> 1], x, y);
+    return (i & 1) ? y : x;
+}
+#else
+typedef float fast_acc_t;
+constexpr int kFastAccN = kNSum;
+__device__ __forceinline__ void fast_acc_zero(fast_acc_t* a) {
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) a[i] = 0.f;
+}
+__device__ __forceinline__ void fast_acc_add(fast_acc_t* a, const float* t) {
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) a[i] += t[i];
+}
+__device__ __forceinline__ float fast_acc_get(const fast_acc_t* a, int i) { return a[i]; }
+#endif
+
 // ---- one chip (one thread) ---------------------------------------------------------------------
 // Integrates chip c of the epoch described by (tab, p) into acc[18].  tile/tileBase: staged IF
 // bytes (window byte offset of tile[0]); xblk = g.x + B0 for the exact path.  Returns true if the
@@ -278,13 +345,17 @@ __device__ __forceinline__ int sel_bit(int s, unsigned m) {
 __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams& p, const uint32_t* bitsData,
                                           const uint32_t* bitsPilot, const unsigned char* tile, long long tileBase,
                                           int tileBytes, long long B0, const int8_t* xblk, double dSpacing, double fs, int c,
-                                          unsigned guard, float* acc) {
+                                          unsigned guard, fast_acc_t* acc) {
     // ---- per-chip phase bookkeeping (fp64) ----
     const double q = ((double)(12 * c) - tab.u0) * tab.S;  // sample position of the chip start
     const int nc = (int)floor(q) + 1;                        // first sample of the chip
     const double psi = (double)nc - q;                       // in (0,1] samples
     const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
     int j = tab.binStart[Psi >> 25];
+#if BDS_ABL & 2   // developer ablation (wrong results): no rank refinement, no guard band
+    const uint2 mk = tab.mask[j];
+    bool exact = !tab.valid;
+#else
 #pragma unroll
     for (int it = 0; it < 4; ++it) j += (tab.thr[j] < Psi);
     const uint2 mk = tab.mask[j];
@@ -292,6 +363,7 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
     const unsigned below = j > 0 ? Psi - tab.thr[j - 1] : Psi;
     const unsigned above = j < 36 ? tab.thr[j] - Psi : 0xffffffffu - Psi;
     bool exact = !tab.valid || below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
+#endif
     const int len = FAST_RLAST + ((mk.y >> 3) & 1);          // bit 35 (k = 36): last sample still mine
     if (nc < 0 || nc + len > p.blksize) exact = true;
     const long long o = B0 + nc - tileBase;   // the chip's first sample inside the staged bytes
@@ -307,19 +379,66 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
 #define FAST_DP_LO(a, b, c) __dp2a_lo((int)(a), (int)(b), (c))
 #define FAST_DP_HI(a, b, c) __dp2a_hi((int)(a), (int)(b), (c))
 #define FAST_SELU(k, v) ((k) <= 32 ? sel_bit_u<((k)-1) & 31>(v, mk.x) : sel_bit_u<((k)-33) & 31>(v, mk.y))
+#if BDS_ABL & 4   // developer ablation (wrong results): no per-sample body, one word of the tile per chip
+        const int v0 = (int)__funnelshift_r(raw[0], raw[1], sh) + wt[0].x;
+        const int SAr = v0, SAi = v0, SBr = v0, SBi = v0, SCr = v0, SCi = v0, H1r = v0, H1i = v0, H2r = v0, H2i = v0,
+                  W1ar = v0, W1ai = v0, W1br = v0, W1bi = v0, W2ar = v0, W2ai = v0, W2br = v0, W2bi = v0;
+        (void)mk;
+#else
         FAST_CHIP_BODY
         FAST_COMBINE
+#endif
 #undef FAST_RAW
 #undef FAST_FSH
 #undef FAST_WTAB
 #undef FAST_DP_LO
 #undef FAST_DP_HI
 #undef FAST_SELU
+#if BDS_ABL & 1   // developer ablation (wrong results): no rotation, no chip-sign combination
+        {
+            float tmp[kNSum] = {(float)SAr, (float)SAi, (float)SBr, (float)SBi, (float)SCr, (float)SCi,
+                                (float)H1r, (float)H1i, (float)H2r, (float)H2i, (float)W1ar, (float)W1ai,
+                                (float)W1br, (float)W1bi, (float)W2ar, (float)W2ai, (float)W2br, (float)W2bi};
+            fast_acc_add(acc, tmp);
+        }
+#else
         // ---- chip-level: rotate by exp(-i theta(nc)), combine with chip signs ----
         const unsigned long long ph = tab.phi0 + (unsigned long long)(long long)nc * tab.dphi;
         const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-9f;  // 2*pi / 2^32, |ang| <= pi
         const float sn = __sinf(ang), cs = __cosf(ang);
         const float rr = cs * (1.0f / 32767.0f), ri = -sn * (1.0f / 32767.0f);
+#if BDS_FAST_F32X2
+        // the same sums with an (I, Q) pair per instruction
+        const f2_t rotA = f2_pk(rr, ri), rotB = f2_pk(-ri, rr);
+#define ROT(N) const f2_t N##p = f2_sfma((float)N##i, rotB, f2_mul(f2_pk((float)N##r, (float)N##r), rotA));
+        ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
+#undef ROT
+        const int cp_ = c == 0 ? 10229 : c - 1, cn_ = c == 10229 ? 0 : c + 1;
+        const float cd = bit_of(bitsData, c) ? -1.f : 1.f, cdp = bit_of(bitsData, cp_) ? -1.f : 1.f,
+                    cdn = bit_of(bitsData, cn_) ? -1.f : 1.f;
+        const float cp = bit_of(bitsPilot, c) ? -1.f : 1.f, cpp = bit_of(bitsPilot, cp_) ? -1.f : 1.f,
+                    cpn = bit_of(bitsPilot, cn_) ? -1.f : 1.f;
+        const f2_t Xp = f2_sub(H2p, H1p);
+        const f2_t XEp = f2_sfma(-2.f, W1bp, f2_add(Xp, W1ap));
+        const f2_t XLp = f2_sfma(2.f, W2ap, f2_sub(Xp, W2bp));
+        const f2_t sAB = f2_add(SAp, SBp), sBC = f2_add(SBp, SCp);
+        const f2_t SPp = f2_add(sAB, SCp), SEp = f2_sub(SCp, sAB), SLp = f2_sub(SAp, sBC);
+#define ACC2(fam, epl, expr)                                       \
+    {                                                              \
+        const f2_t a0 = acc[sum_idx(fam, epl, 0) >> 1];            \
+        acc[sum_idx(fam, epl, 0) >> 1] = expr;                     \
+    }
+        ACC2(0, EPL_P, f2_sfma(cd, Xp, a0))
+        ACC2(0, EPL_E, f2_sfma(cd, XEp, f2_sfma(cdp, W1ap, a0)))
+        ACC2(0, EPL_L, f2_sfma(cd, XLp, f2_sfma(-cdn, W2bp, a0)))
+        ACC2(1, EPL_P, f2_sfma(cp, Xp, a0))
+        ACC2(1, EPL_E, f2_sfma(cp, XEp, f2_sfma(cpp, W1ap, a0)))
+        ACC2(1, EPL_L, f2_sfma(cp, XLp, f2_sfma(-cpn, W2bp, a0)))
+        ACC2(2, EPL_P, f2_sfma(cp, SPp, a0))
+        ACC2(2, EPL_E, f2_sfma(cp, SEp, f2_sfma(cpp - cp, W1ap, a0)))
+        ACC2(2, EPL_L, f2_sfma(cp, SLp, f2_sfma(cp - cpn, W2bp, a0)))
+#undef ACC2
+#else
 #define ROT(N) const float N##x = (float)N##r * rr - (float)N##i * ri, N##y = (float)N##r * ri + (float)N##i * rr;
         ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
 #undef ROT
@@ -352,6 +471,8 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
         acc[sum_idx(2, EPL_E, 1)] += cp * SEy + (cpp - cp) * W1ay;
         acc[sum_idx(2, EPL_L, 0)] += cp * SLx + (cp - cpn) * W2bx;
         acc[sum_idx(2, EPL_L, 1)] += cp * SLy + (cp - cpn) * W2by;
+#endif
+#endif  // BDS_ABL & 1
     } else {
         // rare (~1e-5 of chips): keep the fast path's accumulators in registers
         ExactCtx ex;
@@ -362,8 +483,7 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
 #pragma unroll
         for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
         fast_exact_range(ex, xblk, bitsData, bitsPilot, k0, k1, 12 * c + 1, 12 * c + 12, tmp);
-#pragma unroll
-        for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
+        fast_acc_add(acc, tmp);
     }
     return exact;
 }

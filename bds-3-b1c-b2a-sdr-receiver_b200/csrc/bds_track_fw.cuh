@@ -606,9 +606,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BDS_FW_SETMAXNREG));
 #endif
         const int cw = warp - kFwService;
-        float acc[kNSum];
-#pragma unroll
-        for (int i = 0; i < kNSum; ++i) acc[i] = 0.f;
+        fast_acc_t acc[kFastAccN];
+        fast_acc_zero(acc);
         const unsigned guard = g.pad ? (1u << 24) : kFastGuard;  // g.pad: test hook, widens the guard band
         unsigned nFast = 0, nExact = 0;   // diagnostics (bds_track_counters), flushed once per task
 #ifdef BDS_FW_DEV
@@ -656,8 +655,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
 #pragma unroll
                 for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
                 fast_exact_range(ex, g.x + d.B0, st.bits[0], st.bits[1], 0, 0, -100, 0, tmp);
-#pragma unroll
-                for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
+                fast_acc_add(acc, tmp);
             }
             if (active)
                 exact = fast_chip(st.tab, st.p, st.bits[0], st.bits[1], st.tile, d.tileBase, d.tileBytes, d.B0, g.x + d.B0, g.d,
@@ -680,10 +678,10 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
 #endif
 #pragma unroll
                 for (int i = 0; i < kNSum; ++i) {   // warp sums in Q8 fixed point (exact integer adds from here on)
-                    const int s = __reduce_add_sync(0xffffffffu, __float2int_rn(acc[i] * 256.f));
+                    const int s = __reduce_add_sync(0xffffffffu, __float2int_rn(fast_acc_get(acc, i) * 256.f));
                     if (lane == 0) sm.res[rs][cw][i] = s;
-                    acc[i] = 0.f;
                 }
+                fast_acc_zero(acc);
                 if (g.counters) {
                     const unsigned tf = __reduce_add_sync(0xffffffffu, nFast), te = __reduce_add_sync(0xffffffffu, nExact);
                     if (lane == 0) {
