@@ -15,8 +15,9 @@ import re
 import numpy as np
 import pytest
 
-INC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                   "bds-3-b1c-b2a-sdr-receiver_b200", "csrc", "bds_track_fast_gen.inc")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bds-3-b1c-b2a-sdr-receiver_b200", "csrc")
+INC = os.path.join(CSRC, "bds_track_fast_gen.inc")
+INC_B2A = os.path.join(CSRC, "bds_track_fast_b2a_gen.inc")   # gen_fast_b2a.py: ten B2a chips per thread
 
 
 def _macro(text, name):
@@ -47,14 +48,16 @@ def dp2a(lo, a, b, c):
 
 
 class Gen:
-    def __init__(self):
-        text = open(INC).read()
-        self.R = [int(v) for v in re.search(r"kFastR\[37\] = \{(.*?)\}", text).group(1).split(",")]
-        self.beta = [float(v) for v in re.search(r"kFastBeta\[37\] = \{(.*?)\}", text).group(1).split(",")]
-        self.nwords = int(re.search(r"#define FAST_NWORDS (\d+)", text).group(1))
-        self.names = re.findall(r"(\w+)r = 0", _macro(text, "FAST_DECL_ACCS"))
-        self.body = self._to_python(_macro(text, "FAST_CHIP_BODY"))
-        self.combine = self._to_python(_macro(text, "FAST_COMBINE"))
+    def __init__(self, inc=INC, prefix="FAST", tab="kFast"):
+        text = open(inc).read()
+        self.prefix = prefix
+        self.R = [int(v) for v in re.search(tab + r"R\[\d+\] = \{(.*?)\}", text).group(1).split(",")]
+        self.beta = [float(v) for v in re.search(tab + r"Beta\[\d+\] = \{(.*?)\}", text).group(1).split(",")]
+        self.nb = len(self.R) - 1                                     # boundaries = segments per thread unit
+        self.nwords = int(re.search(r"#define %s_NWORDS (\d+)" % prefix, text).group(1))
+        self.names = re.findall(r"(\w+)r = 0", _macro(text, prefix + "_DECL_ACCS"))
+        self.body = self._to_python(_macro(text, prefix + "_CHIP_BODY"))
+        self.combine = self._to_python(_macro(text, prefix + "_COMBINE"))
 
     @staticmethod
     def _to_python(c):
@@ -76,17 +79,19 @@ class Gen:
                 out.append(ln)
         return "\n".join(out)
 
-    def run(self, raw_words, table, sh, mk):
+    def run(self, raw_words, table, sh, mk, extra=None):
         """one chip: raw_words = 32-bit words starting at the aligned word of the first sample, sh = 8 * (offset & 3),
-        table[i] = (wr01, wr23, wi01, wi23) packed int16 pairs, mk = 36-bit jitter mask"""
+        table[i] = (wr01, wr23, wi01, wi23) packed int16 pairs, mk = jitter mask (bit k-1: boundary k)"""
         env = {n + c: 0 for n in self.names for c in "ri"}
-        env.update(
-            FAST_RAW=lambda i: raw_words[i],
-            FAST_FSH=lambda lo, hi: ((lo | (hi << 32)) >> sh) & 0xFFFFFFFF,
-            FAST_WTAB=lambda i: table[i],
-            FAST_DP_LO=lambda a, b, c: dp2a(True, a, b, c),
-            FAST_DP_HI=lambda a, b, c: dp2a(False, a, b, c),
-            FAST_SELU=lambda k, v: v if (mk >> (k - 1)) & 1 else 0)
+        p = self.prefix
+        env.update({
+            p + "_RAW": lambda i: raw_words[i],
+            p + "_FSH": lambda lo, hi: ((lo | (hi << 32)) >> sh) & 0xFFFFFFFF,
+            p + "_WTAB": lambda i: table[i],
+            p + "_DP_LO": lambda a, b, c: dp2a(True, a, b, c),
+            p + "_DP_HI": lambda a, b, c: dp2a(False, a, b, c),
+            p + "_SELU": lambda k, v: v if (mk >> (k - 1)) & 1 else 0})
+        env.update(extra or {})
         exec(self.body, env)
         exec(self.combine, env)
         return env
@@ -103,16 +108,17 @@ def _class_of_segment(k):
     return special.get((j, cls), "%s%d%s" % ("E" if j % 2 == 0 else "O", 1 if j <= 6 else 2, "ABC"[cls]))
 
 
-def _random_chip(rng, off):
-    x = rng.integers(-127, 128, size=4 * (GEN.nwords + 2)).astype(np.int64)      # int8 samples from the aligned word on
-    wr = rng.integers(-32767, 32768, size=4 * (GEN.nwords + 1)).astype(np.int64)
-    wi = rng.integers(-32767, 32768, size=4 * (GEN.nwords + 1)).astype(np.int64)
+def _random_chip(rng, off, gen=None):
+    gen = gen or GEN
+    x = rng.integers(-127, 128, size=4 * (gen.nwords + 2)).astype(np.int64)      # int8 samples from the aligned word on
+    wr = rng.integers(-32767, 32768, size=4 * (gen.nwords + 1)).astype(np.int64)
+    wi = rng.integers(-32767, 32768, size=4 * (gen.nwords + 1)).astype(np.int64)
     b = (x & 0xFF).astype(np.uint64)
     words = [int(b[4 * i] | (b[4 * i + 1] << np.uint64(8)) | (b[4 * i + 2] << np.uint64(16)) | (b[4 * i + 3] << np.uint64(24)))
-             for i in range(GEN.nwords + 2)]
+             for i in range(gen.nwords + 2)]
     pk = lambda a, c: int((int(a) & 0xFFFF) | ((int(c) & 0xFFFF) << 16))
     table = [(pk(wr[4 * i], wr[4 * i + 1]), pk(wr[4 * i + 2], wr[4 * i + 3]), pk(wi[4 * i], wi[4 * i + 1]),
-              pk(wi[4 * i + 2], wi[4 * i + 3])) for i in range(GEN.nwords + 1)]
+              pk(wi[4 * i + 2], wi[4 * i + 3])) for i in range(gen.nwords + 1)]
     xs = x[off:]                                                                # sample r of the chip = x[off + r]
     return words, table, xs, wr, wi
 
@@ -188,3 +194,69 @@ def test_basis_sums_and_chip_signs_reproduce_the_nine_replicas():
                ("p61", "L"): cp * (SA - SB - SC) + (cp - cpn) * W2b}
         for key in got:
             assert got[key] == want[key], (key, psi, off)
+
+
+# ---- B2a: ten chips per thread, 20 half-chip segments (gen_fast_b2a.py; not wired into a kernel yet) ------------
+GENB = Gen(INC_B2A, "FASTB", "kFastb")
+
+
+def test_b2a_generator_output_is_current():
+    """the committed .inc files are what the generators write"""
+    import subprocess
+    import sys
+    for gen, inc in (("gen_fast_wb.py", INC), ("gen_fast_b2a.py", INC_B2A)):
+        out = subprocess.run([sys.executable, os.path.join(CSRC, gen)], capture_output=True, text=True, check=True).stdout
+        assert out == open(inc).read(), gen
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_b2a_body_equals_per_sample_segment_sums(seed):
+    rng = np.random.default_rng(100 + seed)
+    R, nb = GENB.R, GENB.nb
+    assert nb == 20 and GENB.names == ["H%d" % k for k in range(20)]
+    for _ in range(12):
+        off = int(rng.integers(0, 4))
+        mk = int(rng.integers(0, 1 << nb))
+        words, table, xs, wr, wi = _random_chip(rng, off, GENB)
+        env = GENB.run(words, table, 8 * off, mk, {"FASTB_CD": lambda j: 1, "FASTB_CP": lambda j: 1})
+        want = {n + c: 0 for n in GENB.names for c in "ri"}
+        last = R[nb] + ((mk >> (nb - 1)) & 1)
+        for r in range(last):
+            k = 0
+            for kk in range(1, nb):
+                if r > R[kk] or (r == R[kk] and not (mk >> (kk - 1)) & 1):
+                    k = kk
+            want["H%dr" % k] += int(xs[r]) * int(wr[r])
+            want["H%di" % k] += int(xs[r]) * int(wi[r])
+        for n in want:
+            assert env[n] == want[n], (n, off, hex(mk))
+
+
+def test_b2a_combination_reproduces_the_six_replicas():
+    """FASTB_COMBINE with the chip signs == early / prompt / late of the data and the pilot code evaluated sample by
+    sample with the reference's indexing (tracking.m:262-296: code(ceil(t -+ d) + 1) on the table extended by one chip
+    on either side, d = 0.5)."""
+    import math
+    rng = np.random.default_rng(7)
+    S = 99.375e6 / (2 * 10.23e6)                              # samples per half chip
+    nb = GENB.nb
+    for _ in range(40):
+        psi = float(rng.uniform(0.02, 0.98))
+        off = int(rng.integers(0, 4))
+        words, table, xs, wr, wi = _random_chip(rng, off, GENB)
+        mk = 0
+        for k in range(1, nb + 1):
+            if GENB.R[k] < GENB.beta[k] * S - psi:
+                mk |= 1 << (k - 1)
+        cd = {j: int(v) for j, v in zip(range(-1, 11), rng.choice([-1, 1], size=12))}
+        cp = {j: int(v) for j, v in zip(range(-1, 11), rng.choice([-1, 1], size=12))}
+        env = GENB.run(words, table, 8 * off, mk, {"FASTB_CD": lambda j: cd[j], "FASTB_CP": lambda j: cp[j]})
+        n = GENB.R[nb] + ((mk >> (nb - 1)) & 1)
+        for fam, code in (("D", cd), ("P", cp)):
+            for name, shift in (("E", -0.5), ("P", 0.0), ("L", 0.5)):
+                acc = 0
+                for r in range(n):
+                    t = (r + psi) / (2 * S) + shift           # code phase in chips from the start of the unit
+                    acc += code[math.ceil(t) - 1] * complex(int(xs[r]) * int(wr[r]), int(xs[r]) * int(wi[r]))
+                got = complex(env[fam + name + "r"], env[fam + name + "i"])
+                assert got == acc, (fam, name, psi, off)
