@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
 
 }  // namespace bds
 #include "bds_track_fw.cuh"
+#include "bds_track_b2a.cuh"
 namespace bds {
 
 // ======================================================================================
@@ -644,6 +645,7 @@ struct bds_trk {
     unsigned traceCap = 0;
     FastTab* dFastTab = nullptr;
     bool fast = false;
+    bool b2aUnit = false;   // B2a on the per-channel chip-synchronous kernel (opt-in: BDS_TRK_B2A_UNIT=1)
     size_t smemBytes = 0;
     int epochsRun = 0;  // max over channels, as seen by the host
     cudaStream_t stream = nullptr, copyStream = nullptr;
@@ -757,6 +759,13 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
     return BDS_OK;
 }
 
+// The per-channel B2a kernel is opt-in until it has been validated on hardware.
+bool b2a_unit_enabled(int mode, const bds_trk_cfg* cfg) {
+    const char* e = getenv("BDS_TRK_B2A_UNIT");
+    return e && atoi(e) != 0 && cfg->kernel != BDS_KERNEL_GENERAL &&
+           fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing);
+}
+
 size_t smem_bytes(bool fast) {
     return fast ? std::max(sizeof(FwSmem), kFwCloseBase + sizeof(FwCloseScratch) * (kFwThreads / 32)) : sizeof(TrkSmem);
 }
@@ -845,7 +854,14 @@ int plan_grid(bds_trk* h) {
     int nAct = 0;
     for (auto& c : h->ch) nAct += c.PRN != 0;
     h->nAct = std::max(nAct, 1);
-    if (h->fast) {
+    if (h->b2aUnit) {
+        h->smemBytes = sizeof(B2aSmem);
+        BDS_CUDA(cudaFuncSetAttribute(trk_b2a_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_b2a_unit_kernel, kB2aThreads, h->smemBytes));
+        if (occ < 1) return set_error(BDS_ERR_CUDA, "B2a tracking kernel does not fit on an SM");
+        h->gridBlocks = h->nAct;   // one CTA per channel, no co-residency requirement
+        h->S = 1;
+    } else if (h->fast) {
         BDS_CUDA(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
         BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_fw_kernel, kFwThreads, h->smemBytes));
         if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
@@ -892,6 +908,7 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
         return rc;
     }
     if (h->fast && cfg->kernel == BDS_KERNEL_AUTO && n_ch > 127) h->fast = false;   // queue payload holds 7 bits of channel
+    h->b2aUnit = !h->fast && b2a_unit_enabled(mode, cfg);
     auto fail = [&](int code) {
         bds_track_close(h);
         return code;
@@ -1037,6 +1054,12 @@ static int launch_run(bds_trk* h, int maxEpochs, int epochLimit) {
     TrkDev g;
     fill_dev(h, g, maxEpochs);
     g.epochLimit = std::min(epochLimit, h->capacity);
+    if (h->b2aUnit) {   // self-contained: every CTA starts from its channel's device-side state
+        trk_b2a_unit_kernel<<<h->nAct, kB2aThreads, h->smemBytes, h->stream>>>(g);
+        count_launch();
+        BDS_CUDA(cudaGetLastError());
+        return BDS_OK;
+    }
     if (h->fast) {
         BDS_CUDA(cudaMemsetAsync(h->dQueue, 0, sizeof(unsigned long long) * 2 * h->qSize, h->stream));
         fw_prepare_kernel<<<1, 1024, 0, h->stream>>>(g, h->nCompute);
@@ -1441,7 +1464,12 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     TRYC(cudaMemset(dCnt, 0, 128));
     g.counters = dCnt;
     size_t smem = smem_bytes(fast);
-    if (fast) {
+    const bool b2aUnit = !fast && b2a_unit_enabled(mode, cfg);
+    if (b2aUnit) {
+        smem = sizeof(B2aSmem);
+        TRYC(cudaFuncSetAttribute(trk_b2a_unit_open_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        trk_b2a_unit_open_kernel<<<nce, kB2aThreads, smem>>>(g, dP, n_epochs, dSums);
+    } else if (fast) {
         TRYC(cudaMalloc(&dTabs, sizeof(FastTab) * (size_t)nce));
         TRYC(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fw_tab_kernel<<<(nce + 3) / 4, 128>>>(dP, nce, g.fs, dTabs);
@@ -1471,8 +1499,10 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         trk_open_loop_kernel<<<dim3(S, nce), kTrkThreads, smem>>>(g, dP, n_epochs, dPart);
     }
     count_launch();
-    trk_open_loop_reduce_kernel<<<(nce * kNSum + 127) / 128, 128>>>(dPart, S, nce, dSums);
-    count_launch();
+    if (!b2aUnit) {
+        trk_open_loop_reduce_kernel<<<(nce * kNSum + 127) / 128, 128>>>(dPart, S, nce, dSums);
+        count_launch();
+    }
     TRYC(cudaGetLastError());
     TRYC(cudaMemcpy(sums, dSums, sizeof(double) * (size_t)nce * kNSum, cudaMemcpyDeviceToHost));
     TRYC(cudaMemcpy(g_open_loop_counters, dCnt, 32, cudaMemcpyDeviceToHost));

@@ -1,0 +1,449 @@
+// Chip-synchronous B2a tracking (sm_100a): one CTA per channel, epoch and loop closure inside the CTA.
+//
+// BDS-3_B2a/tracking.m integrates 1 ms (10 230 chips, 99 375 samples at 99.375 MHz) per loop update, so a channel
+// closes its loops 1000 times per second of signal: the latency of one closure bounds the speed, not the arithmetic.
+// The multi-CTA scheduler of the B1C kernel (slices of an epoch on many SMs, a closer CTA, three L2 round trips per
+// closure) is the wrong shape for that; here a channel owns one SM:
+//   * the epoch's samples (99 KB) are staged into shared memory with one TMA bulk copy, issued for epoch e+1 as soon
+//     as the correlator has finished reading epoch e (the start of the next block is known before the loops close);
+//   * 512 threads integrate the 1 023 ten-chip units of the epoch (two per thread) with the generated IDP.2A body
+//     of gen_fast_b2a.py: 20 half-chip segments per unit, the chip signs applied by integer adds at the end of the
+//     unit, one fp32 rotation per unit and replica;
+//   * warp sums in Q8 fixed point (REDUX) -> warp 0 -> thread 0 runs the same close_core / close_cno as the general
+//     kernel, writes the trackResults planes and the next epoch's NCO parameters; warp 0 rebuilds the per-epoch table.
+// Segment-edge decisions use the same fixed-point thresholds + guard band as the B1C body; units that come within
+// the guard band of a decision, or that touch the ends of the block, are evaluated sample by sample with the float64
+// expressions of the general kernel (tracking.m:262-296 incl. the two-ended colon), so chip lookups are the oracle's.
+//
+// Status: OPT-IN (BDS_TRK_B2A_UNIT=1).  The generated body and the chip-sign combination are verified on the CPU
+// (tests/test_fast_body_emulation.py); the kernel has not run on a GPU yet, so AUTO keeps B2a on the general kernel.
+#pragma once
+#include "bds_track_fast.cuh"
+
+namespace bds {
+
+#include "bds_track_fast_b2a_gen.inc"
+
+constexpr int kB2aThreads = 512;
+constexpr int kB2aUnits = 10230 / FASTB_CHIPS;   // thread units per epoch
+constexpr int kB2aTileBytes = 99584;             // one block (<= 99 380 samples) + 16-byte alignment + the word reads of
+                                                 // the last unit; a multiple of 128
+static_assert(kB2aUnits * FASTB_CHIPS == 10230, "unit size must divide the code length");
+
+struct __align__(16) FastbTab {
+    int4 w[FASTB_NWORDS + 1];           // per 4-sample word: {wr01, wr23, wi01, wi23}, int16 pairs, Q15 exp(-i 2 pi r dphi)
+    unsigned thr[24];                   // sorted thresholds (2^32 fixed point), thr[20..] = 0xffffffff
+    unsigned mask[24];                  // decision masks by rank: bit k-1 set <=> sample R_k stays in the old segment
+    unsigned char binStart[kFastBins + 16];
+    double u0, sigma, S;                // 2*rem, 2*step, 1/sigma (half-chip units)
+    unsigned long long dphi, phi0;      // carrier NCO, 2^-64 turns
+    int valid;
+    int pad[3];
+};
+
+inline bool fastb_supported(int mode, double fs, double fc, int codeLength, double d) {
+    return mode == BDS_TRK_B2A && codeLength == 10230 && fs == FASTB_FS_HZ && fc == FASTB_FC_HZ && d == FASTB_D;
+}
+
+// ---- per-epoch table (one warp; tab and scratch (>= 64 words) in shared memory) ------------------------------
+__device__ void fastb_build_tab_warp(FastbTab* tab, const EpochParams& np, double fs, unsigned* scratch) {
+    const int lane = threadIdx.x & 31;
+    const double sigma = 2.0 * np.step, S = 1.0 / sigma;
+    double r = np.carrFreq / fs;
+    r -= floor(r);
+    const unsigned long long dphi = __double2ull_rn(r * 18446744073709551616.0);
+    double r0 = np.remCarr / 6.283185307179586476925286766559;
+    r0 -= floor(r0);
+    const unsigned long long phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
+    short* w = reinterpret_cast<short*>(tab->w);   // word i: [wr(4i..4i+3) | wi(4i..4i+3)] as int16
+    for (int t = lane; t < 4 * (FASTB_NWORDS + 1); t += 32) {
+        unsigned long long ph = (unsigned long long)t * dphi;
+        float sn, cs;
+        sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+        w[(t >> 2) * 8 + (t & 3)] = (short)__float2int_rn(cs * 32767.0f);
+        w[(t >> 2) * 8 + 4 + (t & 3)] = (short)__float2int_rn(-sn * 32767.0f);
+    }
+    unsigned* thr = scratch;        // [20] unsorted thresholds
+    unsigned* pos = scratch + 32;   // [20] sorted position of threshold k-1
+    int ok = 1;
+    if (lane < FASTB_NSEG) {
+        const int k = lane + 1;
+        double th = kFastbBeta[k] * S - (double)kFastbR[k];  // theta_k / sigma
+        ok = (th > 1e-6 && th < 1.0 - 1e-6);
+        th = fmin(fmax(th, 0.0), 1.0);
+        thr[lane] = (unsigned)fmin(th * 4294967296.0, 4294967295.0);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    if (lane < FASTB_NSEG) {  // rank sort (ties broken by index)
+        const unsigned v = thr[lane];
+        int rank = 0;
+        for (int j = 0; j < FASTB_NSEG; ++j) rank += (thr[j] < v) || (thr[j] == v && j < lane);
+        tab->thr[rank] = v;
+        pos[lane] = rank;
+    } else if (lane < 24) {
+        tab->thr[lane] = 0xffffffffu;
+    }
+    __syncwarp();
+    if (lane <= FASTB_NSEG) {
+        // mask[j]: bit (k-1) set <=> Theta_k >= Psi <=> sorted position of k >= j (j = number of thresholds < Psi)
+        unsigned m = 0;
+        for (int k = 1; k <= FASTB_NSEG; ++k)
+            if ((int)pos[k - 1] >= lane) m |= 1u << (k - 1);
+        tab->mask[lane] = m;
+    }
+    for (int t = lane; t < kFastBins + 1; t += 32) {
+        int cnt = 0, here = 0;
+        for (int j = 0; j < FASTB_NSEG; ++j) {
+            cnt += (thr[j] >> 25) < (unsigned)t;
+            here += (thr[j] >> 25) == (unsigned)t;
+        }
+        tab->binStart[t] = (unsigned char)cnt;
+        ok &= here <= 4;  // the rank refinement in the correlator does 4 steps
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        tab->u0 = 2.0 * np.rem;
+        tab->sigma = sigma;
+        tab->S = S;
+        tab->dphi = dphi;
+        tab->phi0 = phi0;
+        tab->valid = ok;
+    }
+    __syncwarp();
+}
+
+// ---- exact per-sample evaluation (the general kernel's B2a arithmetic, bds_track.cu correlate_general) --------
+__device__ inline void make_exact_ctx_b2a(const EpochParams& p, double d, double fs, ExactCtx& c) {
+    c.n = p.blksize - 1;
+    c.dd = p.step;
+    const double base = __dadd_rn(__dmul_rn((double)c.n, p.step), p.rem);
+    c.a[0] = __dadd_rn(p.rem, -d);
+    c.a[1] = p.rem;
+    c.a[2] = __dadd_rn(p.rem, d);
+    c.stop[0] = __dadd_rn(base, -d);
+    c.stop[1] = base;
+    c.stop[2] = __dadd_rn(base, d);
+    double r = p.carrFreq / fs;
+    r -= floor(r);
+    c.dphi = __double2ull_rn(r * 18446744073709551616.0);
+    double r0 = p.remCarr / 6.283185307179586476925286766559;
+    r0 -= floor(r0);
+    c.phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
+}
+
+// Accumulates block-relative samples k in [k0, k1] whose exact prompt chip index ceil(t) lies in [idxLo, idxHi].
+__device__ __noinline__ void fastb_exact_range(const ExactCtx& c, const int8_t* xblk, const uint32_t* bitsData,
+                                               const uint32_t* bitsPilot, int k0, int k1, int idxLo, int idxHi, float* acc) {
+    for (int k = k0; k <= k1; ++k) {
+        const double tP = colon_elem_f(c.a[1], c.dd, c.stop[1], c.n, k);
+        const int ip = (int)ceil(tP);
+        if (ip < idxLo || ip > idxHi) continue;
+        const float xs = (float)xblk[k];
+        const unsigned long long ph = c.phi0 + (unsigned long long)k * c.dphi;
+        float sn, cs;
+        sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+        const float qB = xs * cs, iB = xs * sn;   // exp(+i theta), I = imag, Q = real: tracking.m:309-314
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const double t = colon_elem_f(c.a[o], c.dd, c.stop[o], c.n, k);
+            int cc = (int)ceil(t) - 1;            // padded table [code(end) code code(1)], tracking.m:262-296
+            if (cc < 0) cc = 10229;
+            if (cc >= 10230) cc = 0;
+            const float sd = bit_of(bitsData, cc) ? -1.f : 1.f;
+            const float sp = bit_of(bitsPilot, cc) ? -1.f : 1.f;
+            acc[sum_idx(0, o, 0)] += sd * iB;
+            acc[sum_idx(0, o, 1)] += sd * qB;
+            acc[sum_idx(1, o, 0)] += sp * iB;
+            acc[sum_idx(1, o, 1)] += sp * qB;
+        }
+    }
+}
+
+// code bits of chips 10u-1 .. 10u+10 (bit j+1 <-> chip 10u+j) from the code rotated by one chip (b2a_load_bits):
+// ext bit n = chip n-1, ext bit 0 = the last chip, ext bit 10231 = the first one, so no unit needs a special case
+__device__ __forceinline__ unsigned fastb_code12(const uint32_t* ext, int u) {
+    const int start = FASTB_CHIPS * u;
+    const int i0 = start >> 5;
+    return __funnelshift_r(ext[i0], ext[min(i0 + 1, kPackedWordsDev - 1)], start & 31) & 0xfffu;
+}
+
+// ---- one unit of ten chips (one thread) ------------------------------------------------------------------------
+// Integrates unit u of the epoch (tab, p) into acc[18] (families 0 = data, 1 = pilot; family 2 stays zero).  Returns
+// true if the unit went through the exact per-sample path.
+__device__ __forceinline__ bool fastb_unit(const FastbTab& tab, const EpochParams& p, const uint32_t* bitsData,
+                                           const uint32_t* bitsPilot, const uint32_t* extData, const uint32_t* extPilot,
+                                           const unsigned char* tile, long long tileBase, int tileBytes, long long B0,
+                                           const int8_t* xblk, double dSpacing, double fs, int u, unsigned guard, float* acc) {
+    const double q = ((double)(2 * FASTB_CHIPS * u) - tab.u0) * tab.S;  // sample position of the unit start
+    const int nc = (int)floor(q) + 1;                                    // first sample of the unit
+    const double psi = (double)nc - q;                                   // in (0,1] samples
+    const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
+    int j = tab.binStart[Psi >> 25];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) j += (tab.thr[j] < Psi);
+    const unsigned mk = tab.mask[j];
+    const unsigned below = j > 0 ? Psi - tab.thr[j - 1] : Psi;
+    const unsigned above = j < FASTB_NSEG ? tab.thr[j] - Psi : 0xffffffffu - Psi;
+    bool exact = !tab.valid || below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
+    const int len = FASTB_RLAST + ((mk >> (FASTB_NSEG - 1)) & 1);        // bit 19 (k = 20): last sample still mine
+    if (nc < 0 || nc + len > p.blksize) exact = true;
+    const long long o = B0 + nc - tileBase;   // the unit's first sample inside the staged bytes
+    if (o < 0 || o + 4 * (FASTB_NWORDS + 1) > (long long)tileBytes) exact = true;
+    if (!exact) {
+        const unsigned* raw = reinterpret_cast<const unsigned*>(tile) + (o >> 2);
+        const unsigned sh = (unsigned)(o & 3) * 8u;
+        const int4* wt = tab.w;
+        FASTB_DECL_ACCS
+#define FASTB_RAW(i) raw[i]
+#define FASTB_FSH(lo, hi) __funnelshift_r(lo, hi, sh)
+#define FASTB_WTAB(i) wt[i]
+#define FASTB_DP_LO(a, b, c) __dp2a_lo((int)(a), (int)(b), (c))
+#define FASTB_DP_HI(a, b, c) __dp2a_hi((int)(a), (int)(b), (c))
+#define FASTB_SELU(k, v) sel_bit_u<((k)-1) & 31>(v, mk)
+        FASTB_CHIP_BODY
+        const unsigned dbits = fastb_code12(extData, u), pbits = fastb_code12(extPilot, u);
+#define FASTB_CD(j) (1 - 2 * (int)((dbits >> ((j) + 1)) & 1u))
+#define FASTB_CP(j) (1 - 2 * (int)((pbits >> ((j) + 1)) & 1u))
+        FASTB_COMBINE
+#undef FASTB_CD
+#undef FASTB_CP
+#undef FASTB_RAW
+#undef FASTB_FSH
+#undef FASTB_WTAB
+#undef FASTB_DP_LO
+#undef FASTB_DP_HI
+#undef FASTB_SELU
+        // ---- unit level: rotate by exp(-i theta(nc)); B2a mixes with exp(+i theta): Q = Re, I = -Im of the conjugate sum
+        const unsigned long long ph = tab.phi0 + (unsigned long long)(long long)nc * tab.dphi;
+        const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-9f;  // 2*pi / 2^32, |ang| <= pi
+        const float sn = __sinf(ang), cs = __cosf(ang);
+        const float rr = cs * (1.0f / 32767.0f), ri = -sn * (1.0f / 32767.0f);
+#define ROTB(N, fam, epl)                                                                    \
+    {                                                                                        \
+        const float x_ = (float)N##r * rr - (float)N##i * ri, y_ = (float)N##r * ri + (float)N##i * rr; \
+        acc[sum_idx(fam, epl, 0)] -= y_;                                                     \
+        acc[sum_idx(fam, epl, 1)] += x_;                                                     \
+    }
+        ROTB(DE, 0, EPL_E) ROTB(DP, 0, EPL_P) ROTB(DL, 0, EPL_L)
+        ROTB(PE, 1, EPL_E) ROTB(PP, 1, EPL_P) ROTB(PL, 1, EPL_L)
+#undef ROTB
+    } else {
+        ExactCtx ex;
+        make_exact_ctx_b2a(p, dSpacing, fs, ex);
+        const double qe = ((double)(2 * FASTB_CHIPS * (u + 1)) - tab.u0) * tab.S;
+        const int k0 = max(0, nc - 2), k1 = min(p.blksize - 1, (int)floor(qe) + 3);
+        float tmp[kNSum];
+#pragma unroll
+        for (int i = 0; i < kNSum; ++i) tmp[i] = 0.f;
+        fastb_exact_range(ex, xblk, bitsData, bitsPilot, k0, k1, FASTB_CHIPS * u + 1, FASTB_CHIPS * u + FASTB_CHIPS, tmp);
+#pragma unroll
+        for (int i = 0; i < kNSum; ++i) acc[i] += tmp[i];
+    }
+    return exact;
+}
+
+// ---- shared memory of the per-channel CTA ------------------------------------------------------------------------
+struct __align__(128) B2aSmem {
+    unsigned char tile[kB2aTileBytes];
+    FastbTab tab;
+    uint32_t bits[2][kPackedWordsDev];  // packed primaries: data, pilot (bit k of word w = chip 32 w + k)
+    uint32_t ext[2][kPackedWordsDev];   // the same rotated by one chip (fastb_code12)
+    int res[kB2aThreads / 32][12];      // warp sums, Q8 fixed point
+    double sums[kNSum];
+    EpochParams p;
+    unsigned scratch[64];
+    unsigned long long full;            // mbarrier: the staged block has arrived
+    long long tileBase;                 // window byte offset of tile[0]
+    int tileBytes;
+    int run;
+};
+
+// whole CTA (no barrier inside): the channel's code bits and their rotated copy
+__device__ __forceinline__ void b2a_load_bits(const TrkDev& g, B2aSmem& sm, int c) {
+    const uint32_t* src = g.codeBits + (size_t)c * 2 * kPackedWordsDev;
+    for (int i = threadIdx.x; i < 2 * kPackedWordsDev; i += kB2aThreads) {
+        const int f = i / kPackedWordsDev, k = i - f * kPackedWordsDev;
+        const uint32_t* w = src + f * kPackedWordsDev;
+        const uint32_t cur = __ldg(w + k);
+        const uint32_t carry = k ? __ldg(w + k - 1) >> 31 : (__ldg(w + (10229 >> 5)) >> (10229 & 31)) & 1u;
+        uint32_t e = (cur << 1) | carry;
+        if (k == (10231 >> 5)) e |= (__ldg(w) & 1u) << (10231 & 31);
+        sm.bits[f][k] = cur;
+        sm.ext[f][k] = e;
+    }
+}
+
+// thread 0: stage the block that starts at absolute sample `pos` (whatever of it the window holds); returns the bytes
+// requested (0: nothing to load, the barrier is not armed)
+__device__ __forceinline__ int b2a_issue_tile(const TrkDev& g, B2aSmem& sm, long long pos) {
+    const long long off = pos - g.winFirst;
+    const long long base = off & ~15LL;
+    const long long lim = (g.winLen + 16) & ~15LL;     // staged tiles may extend 16 bytes past winLen (set_window)
+    long long bytes = lim - base;
+    if (bytes > kB2aTileBytes) bytes = kB2aTileBytes;
+    sm.tileBase = base;
+    if (off < 0 || bytes <= 0) {
+        sm.tileBytes = 0;
+        return 0;
+    }
+    sm.tileBytes = (int)bytes;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was last read through the generic proxy
+    tma_load_1d(sm.tile, g.x + base, (unsigned)bytes, &sm.full);
+    return (int)bytes;
+}
+
+// the correlator part of one epoch, whole CTA: per-warp Q8 sums -> sm.res
+__device__ __forceinline__ void b2a_correlate(const TrkDev& g, B2aSmem& sm, const EpochParams& p, unsigned guard,
+                                              unsigned& nFast, unsigned& nExact) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long B0 = p.pos - g.winFirst;
+    float acc[kNSum];
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) acc[i] = 0.f;
+    if (tid == 0 && p.rem == 0.0) {
+        // remCodePhase == 0: the t = 0 sample reads the padded table's first entry, the previous period's last chip
+        ExactCtx ex;
+        make_exact_ctx_b2a(p, g.d, g.fs, ex);
+        fastb_exact_range(ex, g.x + B0, sm.bits[0], sm.bits[1], 0, 0, -100, 0, acc);
+    }
+    for (int u = tid; u < kB2aUnits; u += kB2aThreads) {
+        const bool ex = fastb_unit(sm.tab, p, sm.bits[0], sm.bits[1], sm.ext[0], sm.ext[1], sm.tile, sm.tileBase,
+                                   sm.tileBytes, B0, g.x + B0, g.d, g.fs, u, guard, acc);
+        nFast += !ex;
+        nExact += ex;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {   // warp sums in Q8 fixed point (exact integer adds from here on)
+        const int s = __reduce_add_sync(0xffffffffu, __float2int_rn(acc[i] * 256.f));
+        if (lane == 0) sm.res[warp][i] = s;
+    }
+}
+
+// warp 0 after the CTA barrier: 12 sums as doubles (the pilot family is zero without a pilot, like the general kernel)
+__device__ __forceinline__ void b2a_collect(const TrkDev& g, B2aSmem& sm) {
+    const int lane = threadIdx.x & 31;
+    if (lane < kNSum) {
+        double v = 0.0;
+        if (lane < 6 || (lane < 12 && g.hasPilot)) {
+            long long t = 0;
+#pragma unroll
+            for (int w = 0; w < kB2aThreads / 32; ++w) t += sm.res[w][lane];
+            v = (double)t * (1.0 / 256.0);
+        }
+        sm.sums[lane] = v;
+    }
+    __syncwarp();
+}
+
+// Closed loop: grid = active channels.  Every launch runs each channel for up to g.maxEpochs epochs from its device-side
+// state, never past epoch index g.epochLimit, as far as the resident window allows (a short read stops the channel
+// exactly like tracking.m:246-251).
+__global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    B2aSmem& sm = *reinterpret_cast<B2aSmem*>(dyn_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = g.act[blockIdx.x];
+    if (!g.cc[c].active) return;
+    b2a_load_bits(g, sm, c);
+    ChanState st;            // thread 0
+    int done = 0, pendingTile = 0;
+    double* const out = g.out + (size_t)c * kNFields * g.capacity;
+    const int cap = g.capacity;
+    const unsigned guard = g.pad ? (1u << 24) : kFastGuard;   // g.pad: test hook, widens the guard band
+    unsigned nFast = 0, nExact = 0;
+    unsigned phase = 0;
+    if (tid == 0) {
+        mbar_init(&sm.full, 1);
+        st = g.st[c];
+        EpochParams np;
+        const bool okp = next_params(g, st, np), lim = st.epoch < g.epochLimit;
+        if (!okp && lim) out[(size_t)F_ABS * cap + st.epoch] = (double)st.pos;   // tracking.m:228 precedes the failed read
+        sm.run = okp && lim && g.maxEpochs > 0;
+        if (sm.run) {
+            sm.p = np;
+            pendingTile = b2a_issue_tile(g, sm, np.pos);
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && sm.run) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
+    __syncthreads();
+    while (sm.run) {
+        const EpochParams p = sm.p;
+        if (sm.tileBytes > 0) mbar_wait(&sm.full, phase), phase ^= 1;
+        b2a_correlate(g, sm, p, guard, nFast, nExact);
+        __syncthreads();   // every warp is done with the tile and the table; warp sums are visible
+        if (warp == 0) {
+            b2a_collect(g, sm);
+            if (lane == 0) {
+                pendingTile = b2a_issue_tile(g, sm, p.pos + p.blksize);   // the next block, while the loops close
+                const int e = st.epoch;
+                double outv[kNFields];
+                close_core(g, sm.sums, p, g.cc[c].chCodeFreq, st, outv);
+#pragma unroll
+                for (int f = 0; f < kNFields; ++f)
+                    if (field_written(g, f)) out[(size_t)f * cap + e] = outv[f];
+                __threadfence();
+                close_cno(g, c, e, st);
+                st.epoch = e + 1;
+                ++done;
+                EpochParams np;
+                const bool okp = next_params(g, st, np), lim = st.epoch < g.epochLimit;
+                if (!okp && lim) out[(size_t)F_ABS * cap + st.epoch] = (double)st.pos;
+                const int run = okp && lim && done < g.maxEpochs;
+                if (run) sm.p = np;
+                sm.run = run;
+            }
+            __syncwarp();
+            if (sm.run) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (pendingTile) mbar_wait(&sm.full, phase);   // never leave with a bulk copy in flight
+        g.st[c] = st;
+    }
+    if (g.counters) {
+        const unsigned tf = __reduce_add_sync(0xffffffffu, nFast), te = __reduce_add_sync(0xffffffffu, nExact);
+        if (lane == 0) {
+            if (tf) atomicAdd(g.counters + 0, (unsigned long long)tf);
+            if (te) atomicAdd(g.counters + 1, (unsigned long long)te);
+        }
+    }
+}
+
+// Open loop (teacher forced): one CTA per channel-epoch, sums[ce][18] written directly.
+__global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_open_kernel(TrkDev g, const EpochParams* params, int nEpochs,
+                                                                         double* sums) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    B2aSmem& sm = *reinterpret_cast<B2aSmem*>(dyn_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ce = blockIdx.x, c = ce / nEpochs;
+    b2a_load_bits(g, sm, c);
+    if (tid == 0) {
+        mbar_init(&sm.full, 1);
+        sm.p = params[ce];
+        b2a_issue_tile(g, sm, sm.p.pos);
+    }
+    __syncthreads();
+    if (warp == 0) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
+    __syncthreads();
+    const EpochParams p = sm.p;
+    if (sm.tileBytes > 0) mbar_wait(&sm.full, 0);
+    unsigned nFast = 0, nExact = 0;
+    b2a_correlate(g, sm, p, g.pad ? (1u << 24) : kFastGuard, nFast, nExact);
+    __syncthreads();
+    if (warp == 0) {
+        b2a_collect(g, sm);
+        if (lane < kNSum) sums[(size_t)ce * kNSum + lane] = sm.sums[lane];
+    }
+    if (g.counters) {
+        const unsigned tf = __reduce_add_sync(0xffffffffu, nFast), te = __reduce_add_sync(0xffffffffu, nExact);
+        if (lane == 0) {
+            if (tf) atomicAdd(g.counters + 0, (unsigned long long)tf);
+            if (te) atomicAdd(g.counters + 1, (unsigned long long)te);
+        }
+    }
+}
+
+}  // namespace bds
