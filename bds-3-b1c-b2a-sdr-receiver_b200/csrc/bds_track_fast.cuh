@@ -24,6 +24,9 @@ namespace bds {
 
 #include "bds_track_fast_gen.inc"
 
+#ifndef BDS_FAST_BINREC
+#define BDS_FAST_BINREC 0   // 1: rank search through a per-bin record (one 8-byte load instead of four dependent ones); opt-in build
+#endif
 constexpr int kFastBins = 128;
 constexpr unsigned kFastGuard = 16u;  // fixed-point guard band (2^-32 units of one sample)
 
@@ -33,6 +36,9 @@ struct __align__(16) FastTab {
     uint2 mask[40];                     // decision masks by rank
     unsigned char binStart[kFastBins + 16];
     unsigned char posbin[80];           // [0..35] sorted position of threshold k-1, [40..75] its bin (thr >> 25)
+#if BDS_FAST_BINREC
+    uint2 rec[kFastBins / 2];           // per pair of bins (Psi >> 26): the (at most two) thresholds inside, else 0xffffffff
+#endif
     double u0, sigma, S;                // 12*rem, 12*step, 1/sigma
     unsigned long long dphi, phi0;      // carrier NCO, 2^-64 turns
     int valid;
@@ -137,6 +143,22 @@ __device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double 
         }
         ok = __all_sync(0xffffffffu, ok);
     }
+#if BDS_FAST_BINREC
+    {
+        __syncwarp();   // tab->thr (sorted) and tab->binStart are complete (this build or the table being reused)
+        int okr = 1;
+        for (int b = lane; b < kFastBins / 2; b += 32) {
+            const int s0 = tab->binStart[2 * b], s1 = tab->binStart[2 * b + 2];
+            tab->rec[b] = make_uint2(s0 < s1 ? tab->thr[s0] : 0xffffffffu, s0 + 1 < s1 ? tab->thr[s0 + 1] : 0xffffffffu);
+            okr &= s1 - s0 <= 2;
+        }
+        okr = __all_sync(0xffffffffu, okr);
+        if (!okr) {   // never with the nominal geometry (thresholds are >= 0.008 apart); keeps the result right regardless
+            ok = 0;
+            reuse = false;
+        }
+    }
+#endif
     if (lane == 0) {
         tab->u0 = 12.0 * np.rem;
         tab->sigma = sigma;
@@ -351,6 +373,16 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
     const int nc = (int)floor(q) + 1;                        // first sample of the chip
     const double psi = (double)nc - q;                       // in (0,1] samples
     const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
+#if BDS_FAST_BINREC
+    // thresholds of this pair of bins come with one load; a threshold of a neighbouring pair within the guard band of
+    // Psi implies that Psi is within the guard band of the pair's edge
+    const uint2 rc = tab.rec[Psi >> 26];
+    const int j = tab.binStart[(Psi >> 26) * 2] + (rc.x < Psi) + (rc.y < Psi);
+    const uint2 mk = tab.mask[j];
+    const unsigned eg = guard < 4096u ? guard : 4096u, low = Psi & 0x3ffffffu;
+    bool exact = !tab.valid || rc.x - Psi + guard <= 2u * guard || rc.y - Psi + guard <= 2u * guard || low <= eg ||
+                 low >= 0x3ffffffu - eg || Psi >= 0xffffffffu - guard;
+#else
     int j = tab.binStart[Psi >> 25];
 #if BDS_ABL & 2   // developer ablation (wrong results): no rank refinement, no guard band
     const uint2 mk = tab.mask[j];
@@ -364,6 +396,7 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
     const unsigned above = j < 36 ? tab.thr[j] - Psi : 0xffffffffu - Psi;
     bool exact = !tab.valid || below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
 #endif
+#endif  // BDS_FAST_BINREC
     const int len = FAST_RLAST + ((mk.y >> 3) & 1);          // bit 35 (k = 36): last sample still mine
     if (nc < 0 || nc + len > p.blksize) exact = true;
     const long long o = B0 + nc - tileBase;   // the chip's first sample inside the staged bytes
