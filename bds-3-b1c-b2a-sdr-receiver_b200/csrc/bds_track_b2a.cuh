@@ -313,6 +313,7 @@ __device__ __forceinline__ void b2a_correlate(const TrkDev& g, B2aSmem& sm, cons
         nFast += !ex;
         nExact += ex;
     }
+    __syncwarp();   // lanes leave the unit loop after one or two units
 #pragma unroll
     for (int i = 0; i < 12; ++i) {   // warp sums in Q8 fixed point (exact integer adds from here on)
         const int s = __reduce_add_sync(0xffffffffu, __float2int_rn(acc[i] * 256.f));
@@ -403,6 +404,7 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
         if (pendingTile) mbar_wait(&sm.full, phase);   // never leave with a bulk copy in flight
         g.st[c] = st;
     }
+    __syncwarp();
     if (g.counters) {
         const unsigned tf = __reduce_add_sync(0xffffffffu, nFast), te = __reduce_add_sync(0xffffffffu, nExact);
         if (lane == 0) {
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_open_kernel(TrkDe
         b2a_collect(g, sm);
         if (lane < kNSum) sums[(size_t)ce * kNSum + lane] = sm.sums[lane];
     }
+    __syncwarp();
     if (g.counters) {
         const unsigned tf = __reduce_add_sync(0xffffffffu, nFast), te = __reduce_add_sync(0xffffffffu, nExact);
         if (lane == 0) {
