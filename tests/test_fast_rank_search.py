@@ -75,3 +75,42 @@ def test_record_search_equals_refinement_search():
                 n_rec += er
             if guard == 16:
                 assert n_rec <= n_def + 5 * 127 + 8          # extra exact chips only at the 127 bin edges probed
+
+
+def test_b1c_chip_bookkeeping_tiles_the_block():
+    """fast_chip's per-chip bookkeeping (first sample nc, sub-sample phase psi, rank -> jitter mask, length) restated in
+    Python for whole epochs: the chips' sample ranges [nc, nc + len) tile the block of blksize samples exactly once
+    (apart from chips the kernel sends to the exact path), and the mask picked through the sorted thresholds equals the
+    mask from the definition (boundary sample R_k stays in the old segment iff it lies before beta_k S - psi)."""
+    import math
+    fs, L = 99.375e6, 10230
+    for rem, code_freq in ((0.0, 1.023e6), (0.0093, 1.023e6 - 2.9), (0.0007, 1.023e6 + 3.1)):
+        step = code_freq / fs
+        blk = int(math.ceil((L - rem) / step))
+        srt, bins, rec = tables(code_freq)
+        pos = {v: i for i, v in enumerate(srt[:36])}
+        S = 1.0 / (12.0 * step)
+        thr_of_k = [int(min((BETA[k] * S - R[k]) * 4294967296.0, 4294967295.0)) for k in range(1, 37)]
+        masks = [sum(1 << (k - 1) for k in range(1, 37) if pos[thr_of_k[k - 1]] >= j) for j in range(37)]
+        cover = np.zeros(blk + 200, dtype=np.int64)
+        n_exact = 0
+        for c in range(L):
+            q = (12.0 * c - 12.0 * rem) * S
+            nc = int(math.floor(q)) + 1
+            psi = nc - q
+            Psi = int(min(psi * 4294967296.0, 4294967295.0))
+            j, near = search_default(srt, bins, Psi, 16)
+            mk = masks[j]
+            ln = R[36] + ((mk >> 35) & 1)
+            if near or nc < 0 or nc + ln > blk:
+                n_exact += 1
+                continue
+            want = sum(1 << (k - 1) for k in range(1, 37) if R[k] < BETA[k] * S - psi)
+            assert mk == want, (c, hex(mk), hex(want))
+            cover[nc:nc + ln] += 1
+        # rem = 0 at exactly the nominal code rate puts (12 c + beta_k) S on an integer for ~1 % of the chips (exact ties,
+        # all sent through the exact path); any real code-rate offset removes them
+        assert n_exact <= (200 if rem == 0.0 else 3), n_exact
+        holes = np.flatnonzero(cover[:blk] != 1)
+        assert cover[blk:].sum() == 0 and holes.size <= 98 * n_exact, (holes[:5], n_exact)
+        assert np.all(cover[:blk] <= 1)
