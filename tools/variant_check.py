@@ -5,6 +5,8 @@ process starts in a second or two on a fresh GPU box).
         60-channel B1C WB closed loop on a synthetic record rendered on the device; prints the kernel time and
         x real time, writes OUT_PREFIX.npz (output planes + the NCO trajectory for the open-loop mode).
     BDS_LIB_NAME=libbds_x.so python tools/variant_check.py open NCO.npz OUT_PREFIX
+    [BDS_TRK_B2A_UNIT=1] python tools/variant_check.py closed_b2a OUT_PREFIX [seconds]
+        60-channel B2a closed loop (general kernel, or the per-channel kernel with BDS_TRK_B2A_UNIT=1)
         the same correlator teacher-forced with that trajectory (no loop closure): usable with ablation builds
         whose sums are wrong on purpose.
 
@@ -45,7 +47,32 @@ def main():
     t00 = time.time()
     L.init(0)
     res = {"lib": os.path.basename(L.lib_path()), "mode": mode}
-    if mode == "closed":
+    if mode == "closed_b2a":
+        out = sys.argv[2]
+        seconds = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+        st = B.b2a.initSettings(numberOfChannels=NCH, msToProcess=int(seconds * 1000))
+        sats = synth.make_sats(NCH, st, "B2a", max_doppler=100.0)
+        ch = synth.channels_from_sats(sats, st, "B2a", freq_error=2.0)
+        n = int(round(seconds * FS))
+        p = C.c_void_p()
+        L.check(L.lib().bds_dev_alloc(C.byref(p), n + 64))
+        synth.synth_device("B2a", st, sats, n, out_ptr=p.value)
+        L.check(L.lib().bds_dev_sync())
+        ne = max(1, int(n // 99376) - 2)
+        s = _track.TrackSession("B2a", st, ch, device_ptr=p.value, n_samples=n)
+        ms = []
+        for _ in range(3):
+            s.reset()
+            s.run_async(ne)
+            s.sync()
+            ms.append(s.stats()[2])
+        pl = s.fetch(ne)
+        cnt = s.counters()
+        res.update(seconds=seconds, epochs=ne, kernel_ms=[round(m, 3) for m in ms], unit_kernel=os.environ.get("BDS_TRK_B2A_UNIT", "0"),
+                   x_realtime=round(ne * 0.001 / max(min(ms[1:]) * 1e-3, 1e-12), 1), epochs_done_min=int(pl["epochsDone"].min()),
+                   fast_units=cnt[0], exact_units=cnt[1], general_slices=cnt[2])
+        np.savez_compressed(out + ".npz", **{k: pl[k] for k in ("I_P", "Q_P", "carrFreq", "codeFreq", "absoluteSample", "epochsDone")})
+    elif mode == "closed":
         out = sys.argv[2]
         seconds = float(sys.argv[3]) if len(sys.argv) > 3 else 5.0
         st, ch, n, xp = render(seconds)
