@@ -183,7 +183,8 @@ class Session:
 
     def run(self, max_epochs, epoch_limit=None, win_len=None):
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
-        self.lib.run_b2a_closed(vp(self.x), C.c_longlong(self.win_len if win_len is None else win_len), C.byref(self.cfg), 1,
+        self.lib.run_b2a_closed(vp(self.x), C.c_longlong(self.win_len if win_len is None else win_len), C.byref(self.cfg),
+                                int(self.s.pilotTRKflag == 1),
                                 vp(self.bits), self.cc, self.st, self.n, vp(self.out), vp(self.cno), self.capacity, self.cno_cap,
                                 int(max_epochs), int(self.capacity if epoch_limit is None else epoch_limit), vp(self.counters))
 
@@ -248,3 +249,20 @@ def test_emulated_kernel_resumes_across_launches_and_stops_at_a_short_read(emu):
     assert [parts.st[c].epoch for c in range(2)] == done
     for c in range(2):                                          # tracking.m:228: absoluteSample of the epoch that could not be read
         assert one.out[c, 0, done[c]] == one.st[c].pos
+
+
+def test_emulated_kernel_data_only(emu):
+    """pilotTRKflag = 0: data-only loops (tracking.m:337-360 without the pilot terms); the pilot sums stay zero like the
+    general kernel's"""
+    s, sats, x, ch = util.record("B2a", 2, 0.03)
+    s = s.copy()
+    s.pilotTRKflag = 0
+    epochs = 12
+    tr, raw = util.oracle_track("B2a", s, x, ch, epochs)
+    sess = Session(emu, s, x, ch, capacity=16)
+    sess.run(epochs)
+    for c in range(2):
+        g = _as_g(sess, c, epochs)
+        np.testing.assert_array_equal(g.absoluteSample, tr[c].absoluteSample)
+        assert np.all(g.raw[:, 6:] == 0.0)
+        assert util.one_step_parity("B2a", s, x, ch[c], g, epochs) <= 1e-4
