@@ -49,7 +49,9 @@ def test_open_loop_parity(wide_guard):
     if wide_guard:
         assert 0.05 < exact_units / (2 * 8 * 1023) < 0.6
     else:
-        assert exact_units <= 2 * 8 + 4
+        # the first epoch of a B2a channel starts at remCodePhase = 0 and exactly the nominal code rate (preRun gives no
+        # code-Doppler aiding), which ties 18 unit phases to a threshold exactly: those go through the exact path
+        assert exact_units <= 2 * 20 + 8
 
 
 def test_closed_loop_matches_oracle_and_general_kernel():
