@@ -49,15 +49,20 @@ def _sym(seed, s, period, k):
     return np.where((h >> np.uint64(40)) & np.uint64(1), -1.0, 1.0)
 
 
-def synth_numpy(signal, settings, sats, n, sigma=25.0, seed=20260101, first_sample=0, chunk=1 << 22):
-    """Float64 host rendering of the same model as bds_synth_if (noise from numpy's generator)."""
+def synth_numpy(signal, settings, sats, n, sigma=25.0, seed=20260101, first_sample=0, chunk=1 << 22, primary_codes=None, noise_seed=None):
+    """Float64 host rendering of the same model as bds_synth_if (noise from numpy's generator).
+    ``primary_codes(prn) -> (data, pilot)`` +-1 primary codes; default: the library's host code generator.  (bench.py's
+    reference arm passes the oracle's generators so that libbdsgpu.so is never loaded in that process.)"""
     fs = settings.samplingFreq
     b1c = signal == "B1C"
     out = np.empty(n, dtype=np.int8)
-    rng = np.random.default_rng(seed + 7919)
+    rng = np.random.default_rng(seed + 7919 if noise_seed is None else noise_seed)
     prim = []
     for st in sats:
-        if b1c:
+        if primary_codes is not None:
+            d_, p_ = primary_codes(st.PRN)
+            prim.append((np.asarray(d_, dtype=np.float64), np.asarray(p_, dtype=np.float64)))
+        elif b1c:
             prim.append((codes.gen_code(L.CODE_B1C_DATA_PRIMARY, st.PRN).astype(np.float64),
                          codes.gen_code(L.CODE_B1C_PILOT_PRIMARY, st.PRN).astype(np.float64)))
         else:

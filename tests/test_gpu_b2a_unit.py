@@ -69,8 +69,14 @@ def test_closed_loop_matches_oracle_and_general_kernel():
         sc = util.family_scale(raw[c])
         err = np.abs(g.raw - raw[c]) / sc
         err = err[np.isfinite(err)]
-        # one sample crossing a chip edge moves a 1 ms sum by a few 1e-3 of the scale; one_step_parity below is the strict check
-        assert np.max(err) <= 5e-3 and np.mean(err <= 1e-4) >= 0.99
+        # Trajectory against trajectory is not the north-star comparison (one_step_parity below is: <= 1e-4 at the device's
+        # own NCO state).  The two closed loops differ by fp rounding in remCodePhase, so now and then ONE sample falls on
+        # the other side of a chip edge: that moves a 1 ms sum by at most 2 * 127 LSB (|x| <= 127, |carrier| <= 1), and the
+        # 2 Hz / 18 Hz loops pass the step on to the following epochs with gain < 1.  Bound = two such samples, derived
+        # from the record, not calibrated; 99 % of all values must meet 1e-4 outright.
+        absdiff = np.abs(g.raw - raw[c])[np.isfinite(np.abs(g.raw - raw[c]) / sc)]
+        assert np.mean(err <= 1e-4) >= 0.99, float(np.mean(err <= 1e-4))
+        assert np.max(absdiff) <= 2 * 2 * 127.0, float(np.max(absdiff))
         for f in ("carrFreq", "codeFreq"):
             np.testing.assert_allclose(g[f], o[f], rtol=1e-9)
         for f in ("remCodePhase", "remCarrPhase", "dllDiscr", "pllDiscr"):

@@ -117,6 +117,9 @@ def test_bench_reference_arm_contract_and_no_cpu_fallback():
     assert line["impl"] == "reference" and line["unit"] == "Msamples/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # nothing of the product is loaded in the reference arm: its input is rendered with numpy + the oracle's generators
+    assert line["native_so_loaded"] and all(p.startswith("oracle/") for p in line["native_so_loaded"]), line["native_so_loaded"]
+    assert "WB tracking" in line["config"]["workload"] and "epochs" in line["config"]["sample"]
     if not B.device_ok():
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                            timeout=300)

@@ -113,3 +113,94 @@ def one_step_parity(mode, s, x, ch_c, g, n_epochs, tol_sums=1e-4):
         for f in [k for k in o if k.startswith("Pilot_") or k in ("I_P", "Q_P", "I_E", "Q_E", "I_L", "Q_L")]:
             np.testing.assert_allclose(g[f][e], o[f], rtol=1e-12, atol=1e-6)
     return worst
+
+
+def replay_loop_chain(mode, s, chans, planes, n_epochs):
+    """Whole-trajectory check of the closed loop's bookkeeping, vectorised over channels (cheap: no correlation).
+
+    From the device's own discriminator history (pllDiscr, dllDiscr) the reference's loop filters
+    (WB_tracking.m:399-406, 422-430) are replayed in float64 and must reproduce the device's carrFreq / codeFreq /
+    filtered discriminators of EVERY epoch; from (codeFreq, remCodePhase, carrFreq, remCarrPhase) of epoch e the
+    reference's block bookkeeping (WB:258-261, 327, 335-337, 254) must give absoluteSample / remCodePhase /
+    remCarrPhase of epoch e+1.  Returns the filter memories per epoch (for one_step_parity_sampled)."""
+    tau1, tau2, pf3, pf2, pf1, _ = O.loop_coefficients(mode, s)
+    nch = len(chans)
+    fs, L, PDI = s.samplingFreq, float(s.codeLength), s.intTime
+    basis = np.array([c.acquiredFreq for c in chans], dtype=np.float64)
+    chcf = np.array([c.codeFreq for c in chans], dtype=np.float64)
+    d2 = np.zeros(nch); d1 = np.zeros(nch); old_nco = np.zeros(nch); old_err = np.zeros(nch)
+    mem = np.zeros((n_epochs, 4, nch))
+    g = planes
+    np.testing.assert_allclose(g["carrFreq"][:, 0], basis, rtol=1e-15)
+    np.testing.assert_allclose(g["codeFreq"][:, 0], chcf, rtol=1e-15)
+    b1c = mode != "B2a"
+    for e in range(n_epochs):
+        mem[e] = (d2, d1, old_nco, old_err)
+        ce = g["pllDiscr"][:, e]
+        d2 = d2 + ce * pf3
+        d1 = d2 + ce * pf2 + d1
+        nco = d1 + ce * pf1
+        np.testing.assert_allclose(g["pllDiscrFilt"][:, e], nco, rtol=1e-12, atol=1e-13)
+        de = g["dllDiscr"][:, e]
+        cn = old_nco + (tau2 / tau1) * (de - old_err) + de * (PDI / tau1)
+        old_nco, old_err = cn, de
+        np.testing.assert_allclose(g["dllDiscrFilt"][:, e], cn, rtol=1e-12, atol=1e-13)
+        step = g["codeFreq"][:, e] / fs
+        rem = g["remCodePhase"][:, e]
+        blk = np.ceil((L - rem) / step)
+        if e + 1 < n_epochs:
+            np.testing.assert_allclose(g["carrFreq"][:, e + 1], basis + nco, rtol=1e-13)
+            np.testing.assert_allclose(g["codeFreq"][:, e + 1], chcf - cn, rtol=1e-13)
+            np.testing.assert_array_equal(g["absoluteSample"][:, e + 1], g["absoluteSample"][:, e] + blk)
+            base = (blk - 1) * step + rem
+            rem_next = (base * 2) / 2 + step - L if b1c else (base + step) - L
+            np.testing.assert_allclose(g["remCodePhase"][:, e + 1], rem_next, rtol=0, atol=1e-9)
+            trig = ((g["carrFreq"][:, e] * 2.0 * np.pi) * (blk / fs)) + g["remCarrPhase"][:, e]
+            diff = np.abs(np.fmod(trig, 2 * np.pi) - g["remCarrPhase"][:, e + 1])
+            assert np.all(np.minimum(diff, 2 * np.pi - diff) <= 1e-8), float(diff.max())
+    return mem
+
+
+def one_step_parity_sampled(mode, s, get_block, ch_c, g, raw_c, mem_c, epochs, tol_sums=1e-4):
+    """one_step_parity for selected epochs of a long run.  ``g``: the channel's planes (dict of 1-D arrays), ``raw_c``
+    [N,18] device sums, ``mem_c`` [N,4] filter memories from replay_loop_chain, ``get_block(pos, n)`` -> int8 samples.
+    (a) device sums == oracle correlator at the device's NCO state (tol_sums x family scale);
+    (b) oracle loop closure fed with the device's sums reproduces the device's discriminators and stored prompts."""
+    import math
+    codes = O.make_track_codes(mode, s, ch_c.PRN)
+    coef = O.loop_coefficients(mode, s)
+    worst = 0.0
+    for e in epochs:
+        step = float(g["codeFreq"][e]) / s.samplingFreq
+        rem = float(g["remCodePhase"][e])
+        blk = int(math.ceil((s.codeLength - rem) / step))
+        pos = int(g["absoluteSample"][e])
+        out, rc, rp = c_oracle.correlate_epoch(mode, s, get_block(pos, blk), codes, rem, step, float(g["carrFreq"][e]),
+                                               float(g["remCarrPhase"][e]))
+        ref = np.array([out.get(k, 0.0) for k in RAW_NAMES])
+        err = np.abs(raw_c[e] - ref) / family_scale(ref[None, :])[0]
+        worst = max(worst, float(np.max(err)))
+        assert np.max(err) <= tol_sums, (ch_c.PRN, e, float(np.max(err)))
+        st = O.LoopState(codeFreq=float(g["codeFreq"][e]), carrFreq=float(g["carrFreq"][e]),
+                         carrFreqBasis=ch_c.acquiredFreq, d2CarrError=float(mem_c[e][0]), dCarrError=float(mem_c[e][1]),
+                         oldCodeNco=float(mem_c[e][2]), oldCodeError=float(mem_c[e][3]))
+        sums = {k: float(raw_c[e][i]) for i, k in enumerate(RAW_NAMES) if k in out}
+        o = O.close_loops(mode, s, sums, st, coef, ch_c.codeFreq)
+        for f in ("dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt"):
+            np.testing.assert_allclose(g[f][e], o[f], rtol=1e-9, atol=1e-13)
+        for f in [k for k in o if k.startswith("Pilot_") or k in ("I_P", "Q_P", "I_E", "Q_E", "I_L", "Q_L")]:
+            np.testing.assert_allclose(g[f][e], o[f], rtol=1e-12, atol=1e-6)
+    return worst
+
+
+def lock_report(mode, s, planes, n_epochs, seconds_tail=10.0, injected_cn0=45.0):
+    """Per-channel lock over the tail of a run: DataPLD / PilotPLD (Calc_CNo_PLD.m:70-73) and the total C/N0
+    (WB_tracking.m:467-477).  The stored C/N0 includes the other satellites of the record as noise."""
+    per = s.intTime * s.CNoInterval
+    nc = n_epochs // int(s.CNoInterval)
+    k = max(1, min(nc - 1, int(round(seconds_tail / per))))   # never the first (half-scale) point
+    sl = slice(nc - k, nc)
+    dpld = planes["DataPLD"][:, sl].min(axis=1)
+    ppld = planes["PilotPLD"][:, sl].min(axis=1)
+    cno = np.median(planes["TotalCNo"][:, sl], axis=1)
+    return {"data_pld_min": dpld, "pilot_pld_min": ppld, "cno_median": cno, "points": k}
