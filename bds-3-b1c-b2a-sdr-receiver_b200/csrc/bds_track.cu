@@ -645,7 +645,7 @@ struct bds_trk {
     unsigned traceCap = 0;
     FastTab* dFastTab = nullptr;
     bool fast = false;
-    bool b2aUnit = false;   // B2a on the per-channel chip-synchronous kernel (opt-in: BDS_TRK_B2A_UNIT=1)
+    bool b2aUnit = false;   // B2a on the per-channel chip-synchronous kernel
     size_t smemBytes = 0;
     int epochsRun = 0;  // max over channels, as seen by the host
     cudaStream_t stream = nullptr, copyStream = nullptr;
@@ -753,16 +753,17 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
     mode_flags(mode, cfg->pilotTRKflag, hasPilot, hasP61);
     bool can = fast_wb_supported(mode, hasPilot, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
                                  cfg->dllCorrelatorSpacing);
-    if (cfg->kernel == BDS_KERNEL_FAST && !can)
+    if (cfg->kernel == BDS_KERNEL_FAST && !can &&
+        !fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing))
         return set_error(BDS_ERR_UNSUPPORTED, "fast tracking kernel does not support this configuration");
-    fast = (cfg->kernel == BDS_KERNEL_FAST) || (cfg->kernel == BDS_KERNEL_AUTO && can);
+    fast = can && cfg->kernel != BDS_KERNEL_GENERAL;   // B1C chip-synchronous kernel; B2a: see b2a_unit_enabled
     return BDS_OK;
 }
 
-// The per-channel B2a kernel is opt-in until it has been validated on hardware.
+// B2a at the supported configuration runs on the per-channel chip-synchronous kernel (validated on hardware against the
+// oracle: tests/test_gpu_b2a_unit.py); BDS_KERNEL_GENERAL selects the exact general kernel.
 bool b2a_unit_enabled(int mode, const bds_trk_cfg* cfg) {
-    const char* e = getenv("BDS_TRK_B2A_UNIT");
-    return e && atoi(e) != 0 && cfg->kernel != BDS_KERNEL_GENERAL &&
+    return cfg->kernel != BDS_KERNEL_GENERAL &&
            fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing);
 }
 

@@ -15,8 +15,8 @@
 // the guard band of a decision, or that touch the ends of the block, are evaluated sample by sample with the float64
 // expressions of the general kernel (tracking.m:262-296 incl. the two-ended colon), so chip lookups are the oracle's.
 //
-// Status: OPT-IN (BDS_TRK_B2A_UNIT=1).  The generated body and the chip-sign combination are verified on the CPU
-// (tests/test_fast_body_emulation.py); the kernel has not run on a GPU yet, so AUTO keeps B2a on the general kernel.
+// Status: the AUTO choice for B2a (validated on a B200 in round 2).  The generated body and the chip-sign combination are verified on the CPU
+// (tests/test_fast_body_emulation.py), the kernel on hardware (tests/test_gpu_b2a_unit.py).
 #pragma once
 #include "bds_track_fast.cuh"
 

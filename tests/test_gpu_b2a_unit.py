@@ -1,8 +1,7 @@
 """GPU parity of the per-channel chip-synchronous B2a kernel (csrc/bds_track_b2a.cuh) against the float64 oracle.
 
-OPT-IN: the kernel is selected by BDS_TRK_B2A_UNIT=1 and has not been validated on hardware yet, so these tests only
-run with BDS_TEST_B2A_UNIT=1 (e.g. `BDS_TEST_B2A_UNIT=1 python -m pytest tests/test_gpu_b2a_unit.py -m gpu`).  The
-arithmetic of its generated body is covered on the CPU by tests/test_fast_body_emulation.py.  Tolerances as in
+KERNEL_AUTO selects it for B2a at fs = 99.375 MHz, d = 0.5 (first run on hardware in round 2: all green).  The arithmetic
+of its generated body is covered on the CPU by tests/test_fast_body_emulation.py.  Tolerances as in
 tests/test_gpu_tracking.py."""
 import ctypes as C
 import os
@@ -13,14 +12,7 @@ import pytest
 import util
 from bds3_b200 import _lib as L, _track
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BDS_TEST_B2A_UNIT") != "1",
-                                 reason="opt-in: per-channel B2a kernel not validated on hardware yet")]
-
-
-@pytest.fixture(autouse=True)
-def _select_unit_kernel(monkeypatch):
-    monkeypatch.setenv("BDS_TRK_B2A_UNIT", "1")
+pytestmark = [pytest.mark.gpu]
 
 
 def _open_loop(s, x, prns, nco, reserved=0):

@@ -66,6 +66,8 @@ def test_open_loop_parity_fast(wide_guard):
 
 def test_fast_kernel_rejects_unsupported_config():
     s, sats, x, ch = util.record("B2a", 2, 0.012)
+    s = s.copy()
+    s.dllCorrelatorSpacing = 0.4  # the B2a chip-synchronous body is generated for the reference's 0.5 chip
     with pytest.raises(L.BdsError):
         _track.run_tracking("B2a", x, ch, util.product_settings(s), n_epochs=2, kernel=L.KERNEL_FAST)
     s, sats, x, ch = util.record("NB", 2, 0.06)
