@@ -28,7 +28,8 @@ class bds_trk_cfg(C.Structure):
                 ("dllCorrelatorSpacing", C.c_double), ("intTime", C.c_double), ("pilotTRKflag", C.c_int32),
                 ("CNoInterval", C.c_int32), ("tau1code", C.c_double), ("tau2code", C.c_double),
                 ("pf3", C.c_double), ("pf2", C.c_double), ("pf1", C.c_double), ("wbFactor", C.c_double),
-                ("kernel", C.c_int32), ("reserved", C.c_int32)]
+                ("kernel", C.c_int32), ("reserved", C.c_int32), ("fwPassesPerTask", C.c_int32),
+                ("fwPrefetch", C.c_int32), ("debug", C.c_int32), ("traceTickets", C.c_int32)]
 
 
 class bds_channel(C.Structure):
@@ -60,6 +61,8 @@ CODE_B1C_DATA_PRIMARY, CODE_B1C_PILOT_PRIMARY, CODE_B1C_DATA_BOC11, CODE_B1C_PIL
 CODE_B1C_PILOT_BOC61, CODE_B2A_DATA, CODE_B2A_PILOT = 5, 6, 7
 LOC_HOST, LOC_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERAL, KERNEL_FAST = 0, 1, 2
+DBG_TIMING, DBG_TRACE = 1, 2
+ABI_VERSION = 2
 ERR_NO_DEVICE = -2
 
 # every symbol include/bdsgpu.h declares (tests check that the .so exports all of them)

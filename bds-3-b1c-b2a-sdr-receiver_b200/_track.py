@@ -27,15 +27,20 @@ def has_pilot(mode, settings) -> bool:
     return (mode == "WB" and f == 2) or (mode in ("NB", "B2a") and f == 1)
 
 
-def make_cfg(mode, settings, kernel=L.KERNEL_AUTO) -> L.bds_trk_cfg:
+def make_cfg(mode, settings, kernel=L.KERNEL_AUTO, tuning=None) -> L.bds_trk_cfg:
+    """``tuning``: optional dict of the bds_trk_cfg tuning / diagnostics fields (fwPassesPerTask, fwPrefetch, debug,
+    traceTickets); the library itself never reads the environment."""
     tau1, tau2 = loopcoef.calcLoopCoef(settings.dllNoiseBandwidth, settings.dllDampingRatio, 1.0)
     pf3, pf2, pf1 = loopcoef.calcLoopCoefCarr(settings)
     factor = loopcoef.CalcWeighingFactor(settings) if mode == "WB" else 0.0   # WB_tracking.m:138
-    return L.bds_trk_cfg(samplingFreq=settings.samplingFreq, codeFreqBasis=settings.codeFreqBasis,
-                         codeLength=int(settings.codeLength), dllCorrelatorSpacing=settings.dllCorrelatorSpacing,
-                         intTime=settings.intTime, pilotTRKflag=int(settings.pilotTRKflag),
-                         CNoInterval=int(settings.CNoInterval), tau1code=tau1, tau2code=tau2, pf3=pf3, pf2=pf2,
-                         pf1=pf1, wbFactor=factor, kernel=int(kernel), reserved=0)
+    cfg = L.bds_trk_cfg(samplingFreq=settings.samplingFreq, codeFreqBasis=settings.codeFreqBasis,
+                        codeLength=int(settings.codeLength), dllCorrelatorSpacing=settings.dllCorrelatorSpacing,
+                        intTime=settings.intTime, pilotTRKflag=int(settings.pilotTRKflag),
+                        CNoInterval=int(settings.CNoInterval), tau1code=tau1, tau2code=tau2, pf3=pf3, pf2=pf2,
+                        pf1=pf1, wbFactor=factor, kernel=int(kernel), reserved=0)
+    for k, v in (tuning or {}).items():
+        setattr(cfg, k, int(v))
+    return cfg
 
 
 def make_channels(channel):
@@ -77,13 +82,14 @@ def template(mode, settings, N) -> Struct:
 class TrackSession:
     """Thin RAII wrapper over bds_trk* (bds_track_open / run / fetch / close)."""
 
-    def __init__(self, mode, settings, channel, source=None, kernel=L.KERNEL_AUTO, device_ptr=None, n_samples=None):
+    def __init__(self, mode, settings, channel, source=None, kernel=L.KERNEL_AUTO, device_ptr=None, n_samples=None,
+                 tuning=None):
         """``source``: host samples (array / np.memmap) or a file / path (the reference's ``fid``); they are
         streamed to the device under the tracking kernel by the first ``run_async``.  ``device_ptr``: a record
         already resident in HBM (used in place)."""
         self.mode, self.settings = mode, settings
         self.nch = len(channel)
-        self.cfg = make_cfg(mode, settings, kernel)
+        self.cfg = make_cfg(mode, settings, kernel, tuning)
         self.chs = make_channels(channel)
         self.h = C.c_void_p()
         lib = L.lib()

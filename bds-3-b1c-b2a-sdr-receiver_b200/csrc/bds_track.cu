@@ -643,7 +643,6 @@ struct bds_trk {
     unsigned qSize = 0;
     unsigned long long* dTrace = nullptr;
     unsigned traceCap = 0;
-    FastTab* dFastTab = nullptr;
     bool fast = false;
     bool b2aUnit = false;   // B2a on the per-channel chip-synchronous kernel
     size_t smemBytes = 0;
@@ -698,12 +697,11 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.S = h->S;
     g.nAct = h->nAct;
     g.act = h->dAct;
-    g.fastTab = h->dFastTab;
     g.counters = h->dCounters;
     g.queue = h->dQueue;
     g.qctl = h->dQctl;
     g.qMask = h->qSize ? h->qSize - 1 : 0;
-    g.pubTime = getenv("BDS_TRK_TIMING") ? (unsigned long long*)(h->dCounters + 32) : nullptr;
+    g.pubTime = (h->cfg.debug & BDS_DBG_TIMING) ? (unsigned long long*)(h->dCounters + 32) : nullptr;
     g.trace = h->dTrace;
     g.traceCap = h->traceCap;
     g.nCompute = h->nCompute;
@@ -713,9 +711,8 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     // (many channels), none when tasks are scarce (a ready task must not wait behind a busy CTA)
     const long long tasksPerRound = (long long)h->nAct * h->S;
     g.ahead = tasksPerRound >= 3LL * h->gridBlocks ? 2 : (2 * tasksPerRound >= 3LL * h->gridBlocks ? 1 : 0);
-    if (const char* e = getenv("BDS_TRK_AHEAD")) g.ahead = atoi(e);
+    if (h->cfg.fwPrefetch > 0) g.ahead = h->cfg.fwPrefetch - 1;   // caller's tuning (bds_trk_cfg)
     g.ahead = std::max(0, std::min(g.ahead, g.stages - 1));   // more passes in flight than stages would deadlock the producer
-    if (const char* e = getenv("BDS_TRK_TUNE")) g.tune = atoi(e);
     g.maxEpochs = maxEpochs;
     g.capacity = h->capacity;
     g.epochLimit = h->capacity;
@@ -873,7 +870,7 @@ int plan_grid(bds_trk* h) {
         // slices of kFwChips*k chips (one chip per compute thread and pass); >= ~4 work items per CTA and round
         int k = 4;
         while (k > 1 && (long long)h->nAct * ((10230 + kFwChips * k - 1) / (kFwChips * k)) < 4LL * h->gridBlocks) --k;
-        if (const char* e = getenv("BDS_TRK_PASSES")) k = std::max(1, std::min(8, atoi(e)));  // tuning knob
+        if (h->cfg.fwPassesPerTask > 0) k = std::max(1, std::min(8, (int)h->cfg.fwPassesPerTask));  // caller's tuning
         h->S = (10230 + kFwChips * k - 1) / (kFwChips * k);
         // queue payload: 7 bits of channel, 6 bits of slice, 19 bits of epoch (fw_payload)
         if (h->nCh > 127 || h->S > 63)
@@ -948,14 +945,13 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
         TRY(cudaMemcpy(h->dAct, act.data(), sizeof(int) * n_ch, cudaMemcpyHostToDevice));
     }
     if (h->fast) {
-        TRY(cudaMalloc(&h->dFastTab, sizeof(FastTab) * (size_t)n_ch * 2));
         unsigned need = (unsigned)(2 * n_ch * h->S + 2 * h->gridBlocks + 64);
         h->qSize = 1024;
         while (h->qSize < need) h->qSize <<= 1;
         TRY(cudaMalloc(&h->dQueue, sizeof(unsigned long long) * 2 * h->qSize));   // 16-byte entries
-        TRY(cudaMalloc(&h->dQctl, 64));
-        if (const char* e = getenv("BDS_TRK_TRACE")) {
-            h->traceCap = (unsigned)atoi(e);
+        TRY(cudaMalloc(&h->dQctl, sizeof(unsigned) * kQWords));
+        if ((cfg->debug & BDS_DBG_TRACE) && cfg->traceTickets > 0) {
+            h->traceCap = (unsigned)cfg->traceTickets;
             TRY(cudaMalloc(&h->dTrace, sizeof(unsigned long long) * 8 * h->traceCap));
             TRY(cudaMemset(h->dTrace, 0, sizeof(unsigned long long) * 8 * h->traceCap));
         }
@@ -1311,15 +1307,15 @@ int bds_track_counters(bds_trk* h, long long* out4) {
     unsigned long long v[24];
     BDS_CUDA(cudaMemcpy(v, h->dCounters, 192, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 4; ++i) out4[i] = (long long)v[i];
-    if (getenv("BDS_TRK_TIMING"))  // developer breakdown (SM cycles summed over CTAs)
+    if (h->cfg.debug & BDS_DBG_TIMING)  // developer breakdown (SM cycles summed over CTAs)
         fprintf(stderr, "[bds timing] producer: queue %llu empty %llu total %llu | compute(w2): full-wait %llu res-wait %llu | closer: closure %llu epilogue %llu closures %llu\n",
                 v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
-    if (getenv("BDS_TRK_TIMING"))
+    if (h->cfg.debug & BDS_DBG_TIMING)
         fprintf(stderr, "[bds timing] producer detail: ticket atomic %llu, proxy fence %llu, pass issue %llu\n", v[18], v[19], v[20]);
-    if (getenv("BDS_TRK_TIMING") && v[11])
+    if ((h->cfg.debug & BDS_DBG_TIMING) && v[11])
         fprintf(stderr, "[bds timing] per closure: publish->slices done %.2f us, closure %.2f us\n",
                 (double)v[12] / (double)v[11] * 1e-3, (double)v[13] / (double)v[11] * 1e-3);
-    if (getenv("BDS_TRK_TIMING") && v[11])
+    if ((h->cfg.debug & BDS_DBG_TIMING) && v[11])
         fprintf(stderr, "[bds timing] closure cycles: reduce %.0f, close_epoch %.0f, build_tab %.0f, fence+publish %.0f\n",
                 (double)v[14] / v[11], (double)v[15] / v[11], (double)v[16] / v[11], (double)v[17] / v[11]);
     return BDS_OK;
@@ -1372,7 +1368,6 @@ void bds_track_close(bds_trk* h) {
     cudaFree(h->dQueue);
     cudaFree(h->dQctl);
     cudaFree(h->dTrace);
-    cudaFree(h->dFastTab);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (auto e : h->chunkEv) cudaEventDestroy(e);
@@ -1414,7 +1409,6 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     uint32_t* dBits = nullptr;
     EpochParams* dP = nullptr;
     double *dPart = nullptr, *dSums = nullptr;
-    FastTab* dTabs = nullptr;
     unsigned long long* dCnt = nullptr;
     const int S = fast ? (10230 + kFwChips * 3 - 1) / (kFwChips * 3) : 32;
     auto cleanup = [&]() {
@@ -1423,7 +1417,6 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         cudaFree(dP);
         cudaFree(dPart);
         cudaFree(dSums);
-        cudaFree(dTabs);
         cudaFree(dCnt);
     };
 #define TRYC(x_)                                                       \
@@ -1471,11 +1464,7 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         TRYC(cudaFuncSetAttribute(trk_b2a_unit_open_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         trk_b2a_unit_open_kernel<<<nce, kB2aThreads, smem>>>(g, dP, n_epochs, dSums);
     } else if (fast) {
-        TRYC(cudaMalloc(&dTabs, sizeof(FastTab) * (size_t)nce));
         TRYC(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fw_tab_kernel<<<(nce + 3) / 4, 128>>>(dP, nce, g.fs, dTabs);
-        count_launch();
-        g.fastTab = dTabs;
         g.partial = dPart;
         g.olParams = dP;
         g.olEpochs = n_epochs;

@@ -3,48 +3,59 @@
 // Same arithmetic as BDS-3_B1C/WB_tracking.m:289-372 (nine +-1 replicas x carrier-wiped
 // samples -> 18 sums), reorganised so that the per-sample work is ~3 instructions:
 //   * one thread integrates one primary-code chip (~97 samples at 99.375 MHz);
-//   * inside a chip all nine replicas are constant on 36 segments (gen_fast_wb.py); the
-//     per-sample work is a fused int8 x Q16-carrier multiply-accumulate into the running
-//     segment sum (2 IMAD + 1 PRMT); segment sums are folded into nine complex
-//     "basis" sums (SA,SB,SC,H1,H2,W1a,W1b,W2a,W2b) from which E/P/L of data, BOC(1,1)
+//   * inside a chip all nine replicas are constant on 36 segments (gen_fast_wb.py); a re-aligned word of four
+//     int8 samples is AND-masked to a segment (one LOP3 with the prefix masks of the segment's boundaries, each a
+//     SEL between two constants on a bit of the rank's decision mask) and multiplied with the Q15 carrier by IDP.2A into the segment's class accumulator; class sums are
+//     folded into nine complex "basis" sums (SA,SB,SC,H1,H2,W1a,W1b,W2a,W2b) from which E/P/L of data, BOC(1,1)
 //     pilot and BOC(6,1) pilot follow by +-1 combinations with the chip signs;
 //   * the carrier is exp(-i theta(n_c)) * exp(-i 2 pi r dphi): a per-epoch table of the
-//     second factor (r = 0..97, Q16) is broadcast from shared memory, the first factor is
+//     second factor (r = 0..103, Q15) is broadcast from shared memory, the first factor is
 //     applied once per chip in fp32;
 //   * the IF samples of a pass are staged into shared memory with one TMA bulk copy.
 // Which of two neighbouring segments the sample at a boundary belongs to depends only on
-// the sub-sample phase psi of the thread's first sample; it is looked up from a per-epoch
-// table of sorted thresholds.  When psi is within 4e-9 of a threshold the chip is
-// re-evaluated sample by sample with the exact float64 expressions of the general kernel,
+// the sub-sample phase psi of the thread's first sample: its rank among the epoch's 36 thresholds (one table
+// lookup + one compare, the thresholds' order being a generation-time constant).  When psi is within 4e-9 of a
+// threshold the chip is re-evaluated sample by sample with the exact float64 expressions of the general kernel,
 // so chip-edge decisions are identical to the oracle's.
+//
+// The file also compiles for the host (tests/test_fast_b1c_hostcompile.py includes it after a shim that gives the
+// CUDA intrinsics host definitions), so the arithmetic of a build is checked against the oracle before it gets GPU time.
 #pragma once
 #include "bds_track.cuh"
 
 namespace bds {
 
+#ifndef FAST_CONST
+#define FAST_CONST static __constant__
+#endif
 #include "bds_track_fast_gen.inc"
 
-#ifndef BDS_FAST_BINREC
-#define BDS_FAST_BINREC 0   // 1: rank search through a per-bin record (one 8-byte load instead of four dependent ones); opt-in build
-#endif
-constexpr int kFastBins = 128;
+constexpr int kFastBins = 128;        // (B2a body: bins of its rank index)
 constexpr unsigned kFastGuard = 16u;  // fixed-point guard band (2^-32 units of one sample)
+constexpr unsigned kFastNomTol = 1u << 22;   // a threshold may sit this far from its nominal value (half a rank bin)
 
+// Per-epoch table of one channel, built in shared memory by the table-builder warp of the consuming CTA from the
+// epoch's NCO parameters alone (48 bytes travel from the loop closure to the correlator, nothing else).
 struct __align__(16) FastTab {
     int4 w[FAST_NWORDS + 1];            // per 4-sample word: {wr01, wr23, wi01, wi23}, int16 pairs, Q15 exp(-i 2 pi r dphi)
-    unsigned thr[40];                   // sorted thresholds (2^32 fixed point), thr[36..] = 0xffffffff
-    uint2 mask[40];                     // decision masks by rank
-    unsigned char binStart[kFastBins + 16];
-    unsigned char posbin[80];           // [0..35] sorted position of threshold k-1, [40..75] its bin (thr >> 25)
-#if BDS_FAST_BINREC
-    uint2 rec[kFastBins / 2];           // per pair of bins (Psi >> 26): the (at most two) thresholds inside, else 0xffffffff
-#endif
+    unsigned thr[40];                   // thresholds in the (generation-time) sorted order, 2^32 fixed point; [36..] = 0xffffffff
     double u0, sigma, S;                // 12*rem, 12*step, 1/sigma
     unsigned long long dphi, phi0;      // carrier NCO, 2^-64 turns
-    int valid;
+    int valid;                          // thresholds within kFastNomTol of nominal (else every chip takes the exact path)
     int pad[3];
 };
 static_assert(sizeof(FastTab) % 16 == 0, "FastTab must be a 16-byte multiple");
+
+// Generation-time tables (gen_fast_wb.py), copied once per CTA into shared memory: lanes index them with different
+// ranks, which constant memory would serialise.
+struct __align__(16) FastStatic {
+    uint2 mask[40];                     // [rank]: bit k-1 set <=> the jitter sample of boundary k is old
+    unsigned thrNom[36];                // nominal sorted thresholds
+    unsigned char rankLo[FAST_RANK_BINS];
+    unsigned char pos[36];              // sorted position of threshold k-1
+    unsigned char pad_[12];
+};
+static_assert(sizeof(FastStatic) % 16 == 0, "FastStatic must be a 16-byte multiple");
 
 // B1C with a pilot: wide band (data + BOC(1,1) + BOC(6,1) pilot, 18 sums) or narrow band (the same minus the
 // BOC(6,1) replica, 12 sums — the unused sums are zeroed by the epilogue warp).
@@ -53,123 +64,69 @@ inline bool fast_wb_supported(int mode, int hasPilot, int hasP61, double fs, dou
     return modeOk && codeLength == 10230 && fs == FAST_FS_HZ && fc == FAST_FC_HZ && d == FAST_D;
 }
 
-// ---- per-epoch table construction (one warp) -------------------------------------------------
-// tab lives in global memory (one per channel, rewritten in place: every slice of epoch e has finished before
-// epoch e+1's table is built); scratch: >= 128 words of shared memory private to the calling warp.
-// prev (optional, shared memory): the posbin[] array of the table being replaced.  The sorted order of the 36
-// thresholds and their bins almost never change from one epoch to the next (the code rate moves by ~1e-9), in
-// which case masks / binStart / posbin are still right and only the threshold values, the carrier rotation
-// table and the scalars are rewritten.
-__device__ void fast_build_tab_warp(FastTab* tab, const EpochParams& np, double fs, unsigned* scratch,
-                                    const unsigned char* prev = nullptr) {
-    const int lane = threadIdx.x & 31;
+// one thread's share of the copy of the static tables (tid = 0 .. nthreads-1; followed by a CTA barrier)
+__device__ inline void fast_load_static(FastStatic* fsx, int tid, int nthreads) {
+    for (int i = tid; i < 37; i += nthreads)
+        fsx->mask[i] = make_uint2((unsigned)kFastMask[i], (unsigned)(kFastMask[i] >> 32));
+    for (int i = tid; i < 36; i += nthreads) {
+        fsx->thrNom[i] = kFastThrNom[i];
+        fsx->pos[i] = kFastPos[i];
+    }
+    for (int i = tid; i < FAST_RANK_BINS; i += nthreads) fsx->rankLo[i] = kFastRankLo[i];
+}
+
+// ---- per-epoch table construction --------------------------------------------------------------
+// One lane's share (lane = 0..31): carrier rotation entries lane, lane+32, ... and thresholds lane+1, lane+33.
+// Returns 0 if one of its thresholds is further than kFastNomTol from nominal.  No cross-lane dependency.
+__device__ inline int fast_build_tab_lane(FastTab* tab, const FastStatic& fsx, const EpochParams& np, double fs, int lane) {
     const double sigma = 12.0 * np.step, S = 1.0 / sigma;
     double r = np.carrFreq / fs;
     r -= floor(r);
     const unsigned long long dphi = __double2ull_rn(r * 18446744073709551616.0);
-    double r0 = np.remCarr / 6.283185307179586476925286766559;   // independent of the above: overlaps its latency
-    r0 -= floor(r0);
-    const unsigned long long phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
     short* w = reinterpret_cast<short*>(tab->w);   // word i: [wr(4i..4i+3) | wi(4i..4i+3)] as int16
     for (int t = lane; t < 4 * (FAST_NWORDS + 1); t += 32) {
-        unsigned long long ph = (unsigned long long)t * dphi;
-        float sn, cs;  // fp32 sincospi: 1e-7 accuracy, far below the Q15 quantisation step
-        sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
-        w[(t >> 2) * 8 + (t & 3)] = (short)__float2int_rn(cs * 32767.0f);
-        w[(t >> 2) * 8 + 4 + (t & 3)] = (short)__float2int_rn(-sn * 32767.0f);
+        // MUFU sine / cosine of the exactly reduced phase (|angle| <= pi, abs. error 4e-7): a tenth of the Q15 step,
+        // i.e. at most the odd last bit of a table entry; this runs once per pass on a service warp, so it is kept short
+        const unsigned long long ph = (unsigned long long)t * dphi;
+        const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-9f;  // 2*pi / 2^32
+        w[(t >> 2) * 8 + (t & 3)] = (short)__float2int_rn(__cosf(ang) * 32767.0f);
+        w[(t >> 2) * 8 + 4 + (t & 3)] = (short)__float2int_rn(-__sinf(ang) * 32767.0f);
     }
-    unsigned* thr = scratch;        // [36] unsorted thresholds
-    unsigned* pos = scratch + 40;   // [36] sorted position of threshold k-1
-    unsigned* srt = scratch + 80;   // [36] thresholds in sorted order (reuse path)
     int ok = 1;
-    for (int t = lane; t < 36; t += 32) {
-        const int k = t + 1;
-        double th = kFastBeta[k] * S - (double)kFastR[k];  // theta_k / sigma
-        ok &= (th > 1e-6 && th < 1.0 - 1e-6);
-        th = fmin(fmax(th, 0.0), 1.0);
-        thr[t] = (unsigned)fmin(th * 4294967296.0, 4294967295.0);
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    __syncwarp();
-    bool reuse = prev != nullptr && ok;
-    if (reuse) {   // same order, same bins as the table being replaced?
-        int same = 1;
-        for (int t = lane; t < 36; t += 32) {
-            const unsigned p = prev[t];
-            same &= p < 36u && (thr[t] >> 25) == (unsigned)prev[40 + t];
-            srt[p < 36u ? p : 0] = thr[t];
-        }
-        same = __all_sync(0xffffffffu, same);
-        __syncwarp();
-        for (int t = lane; t < 35; t += 32) same &= srt[t] < srt[t + 1];
-        reuse = __all_sync(0xffffffffu, same);
-    }
-    if (reuse) {
-        for (int t = lane; t < 36; t += 32) tab->thr[t] = srt[t];
-    } else {
-        for (int t = lane; t < 40; t += 32) {
-            if (t < 36) {  // rank sort (ties broken by index)
-                const unsigned v = thr[t];
-                int rank = 0;
-                for (int j = 0; j < 36; ++j) rank += (thr[j] < v) || (thr[j] == v && j < t);
-                tab->thr[rank] = v;
-                pos[t] = rank;
-                tab->posbin[t] = (unsigned char)rank;
-                tab->posbin[40 + t] = (unsigned char)(v >> 25);
-            } else {
-                tab->thr[t] = 0xffffffffu;
-            }
-        }
-        __syncwarp();
-        for (int t = lane; t < 37; t += 32) {
-            // mask[j]: bit (k-1) set  <=>  boundary sample R_k belongs to the OLD segment  <=>  Theta_k >= Psi
-            //          <=> sorted position of k >= j   (j = number of thresholds < Psi)
-            unsigned lo = 0, hi = 0;
-            for (int k = 1; k <= 36; ++k)
-                if ((int)pos[k - 1] >= t) {
-                    if (k <= 32) lo |= 1u << (k - 1);
-                    else hi |= 1u << (k - 33);
-                }
-            tab->mask[t] = make_uint2(lo, hi);
-        }
-        for (int t = lane; t < kFastBins + 1; t += 32) {
-            int cnt = 0, here = 0;
-            for (int j = 0; j < 36; ++j) {
-                cnt += (thr[j] >> 25) < (unsigned)t;
-                here += (thr[j] >> 25) == (unsigned)t;
-            }
-            tab->binStart[t] = (unsigned char)cnt;
-            ok &= here <= 4;  // the rank refinement in the correlator does 4 steps
-        }
-        ok = __all_sync(0xffffffffu, ok);
-    }
-#if BDS_FAST_BINREC
-    {
-        __syncwarp();   // tab->thr (sorted) and tab->binStart are complete (this build or the table being reused)
-        int okr = 1;
-        for (int b = lane; b < kFastBins / 2; b += 32) {
-            const int s0 = tab->binStart[2 * b], s1 = tab->binStart[2 * b + 2];
-            tab->rec[b] = make_uint2(s0 < s1 ? tab->thr[s0] : 0xffffffffu, s0 + 1 < s1 ? tab->thr[s0 + 1] : 0xffffffffu);
-            okr &= s1 - s0 <= 2;
-        }
-        okr = __all_sync(0xffffffffu, okr);
-        if (!okr) {   // never with the nominal geometry (thresholds are >= 0.008 apart); keeps the result right regardless
-            ok = 0;
-            reuse = false;
+    for (int t = lane; t < 40; t += 32) {
+        if (t < 36) {
+            const int k = t + 1;
+            double th = kFastBeta[k] * S - (double)kFastR[k];  // theta_k / sigma
+            th = fmin(fmax(th, 0.0), 1.0);
+            const unsigned v = (unsigned)fmin(th * 4294967296.0, 4294967295.0);
+            const int p = fsx.pos[t];
+            const unsigned nom = fsx.thrNom[p];
+            ok &= (v - nom + kFastNomTol) < 2u * kFastNomTol;
+            tab->thr[p] = v;
+        } else {
+            tab->thr[t] = 0xffffffffu;
         }
     }
-#endif
     if (lane == 0) {
+        double r0 = np.remCarr / 6.283185307179586476925286766559;
+        r0 -= floor(r0);
         tab->u0 = 12.0 * np.rem;
         tab->sigma = sigma;
         tab->S = S;
         tab->dphi = dphi;
-        tab->phi0 = phi0;
-        // reuse: `here <= 4` held for the replaced table (same bins), whose valid flag is left in place
-        if (!reuse) tab->valid = ok;
+        tab->phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
     }
+    return ok;
+}
+#ifdef __CUDACC__
+// whole warp; tab in shared memory
+__device__ inline void fast_build_tab_warp(FastTab* tab, const FastStatic& fsx, const EpochParams& np, double fs) {
+    const int lane = threadIdx.x & 31;
+    const int ok = __all_sync(0xffffffffu, fast_build_tab_lane(tab, fsx, np, fs, lane));
+    if (lane == 0) tab->valid = ok;
     __syncwarp();
 }
+#endif
 
 // ---- exact per-sample evaluation (shared with the general kernel's arithmetic) --------------
 struct ExactCtx {
@@ -241,6 +198,7 @@ __device__ __noinline__ void fast_exact_range(const ExactCtx& c, const int8_t* x
     }
 }
 
+#ifdef __CUDACC__
 // ---- TMA bulk copy helpers -------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -266,15 +224,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
         : "memory");
 }
 
-// sign-extended byte b of a 32-bit word (PRMT with sign replication)
-// (__byte_perm masks the selector nibbles to 3 bits, so the PTX form is needed for the sign mode)
-template <int B>
-__device__ __forceinline__ int sext_byte(unsigned w) {
-    int r;
-    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "n"(B | ((B | 8) << 4) | ((B | 8) << 8) | ((B | 8) << 12)));
+// hi if bit BIT of m is set, else lo (both constants): R2P + SEL
+template <int BIT>
+__device__ __forceinline__ unsigned fast_psel(unsigned m, unsigned lo, unsigned hi) {
+    unsigned r;
+    asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %3, %4;\n setp.ne.u32 p, t, 0;\n selp.u32 %0, %1, %2, p;\n}"
+        : "=r"(r)
+        : "r"(hi), "r"(lo), "r"(m), "n"(1u << BIT));
     return r;
 }
-// v (a constant) if bit BIT of m is set, else 0
+// v (a constant) if bit BIT of m is set, else 0   (B2a body)
 template <int BIT>
 __device__ __forceinline__ unsigned sel_bit_u(unsigned v, unsigned m) {
     unsigned r;
@@ -283,23 +242,8 @@ __device__ __forceinline__ unsigned sel_bit_u(unsigned v, unsigned m) {
         : "r"(v), "r"(m), "n"(1u << BIT));
     return r;
 }
-// s if bit BIT of m is set, else 0 (LOP3 with predicate result + SEL)
-template <int BIT>
-__device__ __forceinline__ int sel_bit(int s, unsigned m) {
-    int r;
-    asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %2, %3;\n setp.ne.u32 p, t, 0;\n selp.s32 %0, %1, 0, p;\n}"
-        : "=r"(r)
-        : "r"(s), "r"(m), "n"(1u << BIT));
-    return r;
-}
 
 // ---- packed fp32 pairs (FFMA2 / FADD2 / FMUL2 of sm_100): an (I, Q) pair per instruction -------------
-#ifndef BDS_FAST_F32X2
-#define BDS_FAST_F32X2 0
-#endif
-#ifndef BDS_ABL
-#define BDS_ABL 0   // developer ablations of fast_chip, bit mask (1: no rotation, 2: no rank search, 4: no per-sample body); never shipped
-#endif
 typedef unsigned long long f2_t;
 __device__ __forceinline__ f2_t f2_pk(float a, float b) {
     f2_t r;
@@ -327,10 +271,14 @@ __device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+#endif  // __CUDACC__  (the host build brings its own definitions of the helpers above)
 __device__ __forceinline__ f2_t f2_sfma(float s, f2_t b, f2_t c) { return f2_fma(f2_pk(s, s), b, c); }   // s * b + c
 
-// the per-thread running sums of the compute warps: 18 floats, or 9 (I, Q) pairs in the packed build
-#if BDS_FAST_F32X2
+#ifndef BDS_ABL
+#define BDS_ABL 0   // developer ablations of fast_chip, bit mask (1: no rotation, 2: no rank search, 4: no per-sample body); never shipped
+#endif
+
+// the per-thread running sums of the compute warps: 9 (I, Q) pairs
 typedef f2_t fast_acc_t;
 constexpr int kFastAccN = kNSum / 2;
 __device__ __forceinline__ void fast_acc_zero(fast_acc_t* a) {
@@ -346,58 +294,32 @@ __device__ __forceinline__ float fast_acc_get(const fast_acc_t* a, int i) {
     f2_unpk(a[i >> 1], x, y);
     return (i & 1) ? y : x;
 }
-#else
-typedef float fast_acc_t;
-constexpr int kFastAccN = kNSum;
-__device__ __forceinline__ void fast_acc_zero(fast_acc_t* a) {
-#pragma unroll
-    for (int i = 0; i < kNSum; ++i) a[i] = 0.f;
-}
-__device__ __forceinline__ void fast_acc_add(fast_acc_t* a, const float* t) {
-#pragma unroll
-    for (int i = 0; i < kNSum; ++i) a[i] += t[i];
-}
-__device__ __forceinline__ float fast_acc_get(const fast_acc_t* a, int i) { return a[i]; }
-#endif
 
 // ---- one chip (one thread) ---------------------------------------------------------------------
-// Integrates chip c of the epoch described by (tab, p) into acc[18].  tile/tileBase: staged IF
+// Integrates chip c of the epoch described by (tab, p) into acc[9 pairs].  tile/tileBase: staged IF
 // bytes (window byte offset of tile[0]); xblk = g.x + B0 for the exact path.  Returns true if the
 // chip went through the exact per-sample path.
-__device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams& p, const uint32_t* bitsData,
-                                          const uint32_t* bitsPilot, const unsigned char* tile, long long tileBase,
-                                          int tileBytes, long long B0, const int8_t* xblk, double dSpacing, double fs, int c,
-                                          unsigned guard, fast_acc_t* acc) {
+__device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& fsx, const EpochParams& p,
+                                          const uint32_t* bitsData, const uint32_t* bitsPilot, const unsigned char* tile,
+                                          long long tileBase, int tileBytes, long long B0, const int8_t* xblk, double dSpacing,
+                                          double fs, int c, unsigned guard, fast_acc_t* acc) {
     // ---- per-chip phase bookkeeping (fp64) ----
     const double q = ((double)(12 * c) - tab.u0) * tab.S;  // sample position of the chip start
     const int nc = (int)floor(q) + 1;                        // first sample of the chip
     const double psi = (double)nc - q;                       // in (0,1] samples
     const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
-#if BDS_FAST_BINREC
-    // thresholds of this pair of bins come with one load; a threshold of a neighbouring pair within the guard band of
-    // Psi implies that Psi is within the guard band of the pair's edge
-    const uint2 rc = tab.rec[Psi >> 26];
-    const int j = tab.binStart[(Psi >> 26) * 2] + (rc.x < Psi) + (rc.y < Psi);
-    const uint2 mk = tab.mask[j];
-    const unsigned eg = guard < 4096u ? guard : 4096u, low = Psi & 0x3ffffffu;
-    bool exact = !tab.valid || rc.x - Psi + guard <= 2u * guard || rc.y - Psi + guard <= 2u * guard || low <= eg ||
-                 low >= 0x3ffffffu - eg || Psi >= 0xffffffffu - guard;
-#else
-    int j = tab.binStart[Psi >> 25];
-#if BDS_ABL & 2   // developer ablation (wrong results): no rank refinement, no guard band
-    const uint2 mk = tab.mask[j];
-    bool exact = !tab.valid;
-#else
-#pragma unroll
-    for (int it = 0; it < 4; ++it) j += (tab.thr[j] < Psi);
-    const uint2 mk = tab.mask[j];
+    // rank = number of thresholds < Psi.  The thresholds keep their generation-time order and stay within half a
+    // 1/512 bin of nominal (tab.valid), nominal neighbours are > 3 bins apart: the only threshold that can lie within
+    // a bin of Psi - and hence the only one that can decide the rank beyond rankLo, or come within the guard band -
+    // is thr[rankLo[bin]].
+    const int jlo = fsx.rankLo[Psi >> (32 - 9)];
+    static_assert(FAST_RANK_BINS == 512, "rank bins");
+    const unsigned tnear = tab.thr[jlo];
+    const int j = jlo + (tnear < Psi);
+    const uint2 mk = fsx.mask[j];
     // near-miss of any decision (including the chip start/end) -> exact path
-    const unsigned below = j > 0 ? Psi - tab.thr[j - 1] : Psi;
-    const unsigned above = j < 36 ? tab.thr[j] - Psi : 0xffffffffu - Psi;
-    bool exact = !tab.valid || below <= guard || above <= guard || Psi >= 0xffffffffu - guard;
-#endif
-#endif  // BDS_FAST_BINREC
-    const int len = FAST_RLAST + ((mk.y >> 3) & 1);          // bit 35 (k = 36): last sample still mine
+    bool exact = !tab.valid || tnear - Psi + guard <= 2u * guard || Psi <= guard || Psi >= 0xffffffffu - guard;
+    const int len = FAST_RLAST + (j <= FAST_POS_LAST);       // boundary 36 old: the last sample is still mine
     if (nc < 0 || nc + len > p.blksize) exact = true;
     const long long o = B0 + nc - tileBase;   // the chip's first sample inside the staged bytes
     if (o < 0 || o + 4 * (FAST_NWORDS + 1) > (long long)tileBytes) exact = true;
@@ -409,14 +331,13 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
 #define FAST_RAW(i) raw[i]
 #define FAST_FSH(lo, hi) __funnelshift_r(lo, hi, sh)
 #define FAST_WTAB(i) wt[i]
+#define FAST_PSEL(k, lo, hi) ((k) <= 32 ? fast_psel<((k)-1) & 31>(mk.x, lo, hi) : fast_psel<((k)-33) & 31>(mk.y, lo, hi))
 #define FAST_DP_LO(a, b, c) __dp2a_lo((int)(a), (int)(b), (c))
 #define FAST_DP_HI(a, b, c) __dp2a_hi((int)(a), (int)(b), (c))
-#define FAST_SELU(k, v) ((k) <= 32 ? sel_bit_u<((k)-1) & 31>(v, mk.x) : sel_bit_u<((k)-33) & 31>(v, mk.y))
 #if BDS_ABL & 4   // developer ablation (wrong results): no per-sample body, one word of the tile per chip
-        const int v0 = (int)__funnelshift_r(raw[0], raw[1], sh) + wt[0].x;
+        const int v0 = (int)__funnelshift_r(raw[0], raw[1], sh) + wt[0].x + (int)mk.x;
         const int SAr = v0, SAi = v0, SBr = v0, SBi = v0, SCr = v0, SCi = v0, H1r = v0, H1i = v0, H2r = v0, H2i = v0,
                   W1ar = v0, W1ai = v0, W1br = v0, W1bi = v0, W2ar = v0, W2ai = v0, W2br = v0, W2bi = v0;
-        (void)mk;
 #else
         FAST_CHIP_BODY
         FAST_COMBINE
@@ -424,9 +345,9 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
 #undef FAST_RAW
 #undef FAST_FSH
 #undef FAST_WTAB
+#undef FAST_PSEL
 #undef FAST_DP_LO
 #undef FAST_DP_HI
-#undef FAST_SELU
 #if BDS_ABL & 1   // developer ablation (wrong results): no rotation, no chip-sign combination
         {
             float tmp[kNSum] = {(float)SAr, (float)SAi, (float)SBr, (float)SBi, (float)SCr, (float)SCi,
@@ -435,13 +356,11 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
             fast_acc_add(acc, tmp);
         }
 #else
-        // ---- chip-level: rotate by exp(-i theta(nc)), combine with chip signs ----
+        // ---- chip-level: rotate by exp(-i theta(nc)), combine with chip signs; an (I, Q) pair per instruction ----
         const unsigned long long ph = tab.phi0 + (unsigned long long)(long long)nc * tab.dphi;
         const float ang = (float)(int)(ph >> 32) * 1.4629180792671596e-9f;  // 2*pi / 2^32, |ang| <= pi
         const float sn = __sinf(ang), cs = __cosf(ang);
         const float rr = cs * (1.0f / 32767.0f), ri = -sn * (1.0f / 32767.0f);
-#if BDS_FAST_F32X2
-        // the same sums with an (I, Q) pair per instruction
         const f2_t rotA = f2_pk(rr, ri), rotB = f2_pk(-ri, rr);
 #define ROT(N) const f2_t N##p = f2_sfma((float)N##i, rotB, f2_mul(f2_pk((float)N##r, (float)N##r), rotA));
         ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
@@ -471,43 +390,9 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const EpochParams&
         ACC2(2, EPL_E, f2_sfma(cp, SEp, f2_sfma(cpp - cp, W1ap, a0)))
         ACC2(2, EPL_L, f2_sfma(cp, SLp, f2_sfma(cp - cpn, W2bp, a0)))
 #undef ACC2
-#else
-#define ROT(N) const float N##x = (float)N##r * rr - (float)N##i * ri, N##y = (float)N##r * ri + (float)N##i * rr;
-        ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
-#undef ROT
-        const int cp_ = c == 0 ? 10229 : c - 1, cn_ = c == 10229 ? 0 : c + 1;
-        const float cd = bit_of(bitsData, c) ? -1.f : 1.f, cdp = bit_of(bitsData, cp_) ? -1.f : 1.f,
-                    cdn = bit_of(bitsData, cn_) ? -1.f : 1.f;
-        const float cp = bit_of(bitsPilot, c) ? -1.f : 1.f, cpp = bit_of(bitsPilot, cp_) ? -1.f : 1.f,
-                    cpn = bit_of(bitsPilot, cn_) ? -1.f : 1.f;
-        const float Xx = H2x - H1x, Xy = H2y - H1y;
-        const float XEx = Xx + W1ax - 2.f * W1bx, XEy = Xy + W1ay - 2.f * W1by;
-        const float XLx = Xx + 2.f * W2ax - W2bx, XLy = Xy + 2.f * W2ay - W2by;
-        acc[sum_idx(0, EPL_P, 0)] += cd * Xx;
-        acc[sum_idx(0, EPL_P, 1)] += cd * Xy;
-        acc[sum_idx(0, EPL_E, 0)] += cd * XEx + cdp * W1ax;
-        acc[sum_idx(0, EPL_E, 1)] += cd * XEy + cdp * W1ay;
-        acc[sum_idx(0, EPL_L, 0)] += cd * XLx - cdn * W2bx;
-        acc[sum_idx(0, EPL_L, 1)] += cd * XLy - cdn * W2by;
-        acc[sum_idx(1, EPL_P, 0)] += cp * Xx;
-        acc[sum_idx(1, EPL_P, 1)] += cp * Xy;
-        acc[sum_idx(1, EPL_E, 0)] += cp * XEx + cpp * W1ax;
-        acc[sum_idx(1, EPL_E, 1)] += cp * XEy + cpp * W1ay;
-        acc[sum_idx(1, EPL_L, 0)] += cp * XLx - cpn * W2bx;
-        acc[sum_idx(1, EPL_L, 1)] += cp * XLy - cpn * W2by;
-        const float SPx = SAx + SBx + SCx, SPy = SAy + SBy + SCy;
-        const float SEx = SCx - SAx - SBx, SEy = SCy - SAy - SBy;
-        const float SLx = SAx - SBx - SCx, SLy = SAy - SBy - SCy;
-        acc[sum_idx(2, EPL_P, 0)] += cp * SPx;
-        acc[sum_idx(2, EPL_P, 1)] += cp * SPy;
-        acc[sum_idx(2, EPL_E, 0)] += cp * SEx + (cpp - cp) * W1ax;
-        acc[sum_idx(2, EPL_E, 1)] += cp * SEy + (cpp - cp) * W1ay;
-        acc[sum_idx(2, EPL_L, 0)] += cp * SLx + (cp - cpn) * W2bx;
-        acc[sum_idx(2, EPL_L, 1)] += cp * SLy + (cp - cpn) * W2by;
-#endif
 #endif  // BDS_ABL & 1
     } else {
-        // rare (~1e-5 of chips): keep the fast path's accumulators in registers
+        // rare (~1e-6 of chips): keep the fast path's accumulators in registers
         ExactCtx ex;
         make_exact_ctx(p, dSpacing, fs, ex);
         const double qe = ((double)(12 * c + 12) - tab.u0) * tab.S;

@@ -7,9 +7,23 @@ prompt, late and early replicas change sign at offsets j, j+(1-delta) and j+delt
 sub-chip (delta = 12 * dllCorrelatorSpacing, 0.5 < delta < 1), so a chip splits into 36
 segments in which all nine replicas are constant.  For a fixed sampling rate the k-th segment
 boundary falls at sample R_k = floor(beta_k * S) or one later, depending only on the sub-sample
-phase of the thread's first sample ("jitter" sample, decided by a per-thread bit mask).
+phase Psi of the thread's first sample: sample R_k still belongs to the old segment iff
+Psi <= Theta_k = frac(beta_k * S) ("jitter" sample).  The 36 thresholds cut (0, 1] into 37
+intervals ("ranks"); their ORDER is a property of the nominal geometry (the thresholds move by
+< 1e-3 sample over +-15 kHz of Doppler while neighbours are >= 8e-3 apart), so everything that
+depends on the rank only is tabulated here at generation time:
 
-Arithmetic of the body (v2): the int8 samples are never unpacked.  Each re-aligned 32-bit word of
+    kFastMask[rank]         bit k-1 set <=> the jitter sample of boundary k is old.  From it the body forms, with one
+                            SEL between two immediates per boundary, the PREFIX byte mask P_k of the samples of word
+                            (R_k >> 2) that lie before boundary k (bytes 0 .. (R_k & 3) - 1, plus byte (R_k & 3) when
+                            the jitter sample is old); every segment piece of a word is X & P, X & ~P or
+                            X & ~P_k & P_k+1: one LOP3.  (A table of the 36 prefix masks per rank was measured too:
+                            nine conflicting LDS.128 per chip made shared memory the bottleneck, 86 % of its peak.)
+    kFastRankLo[bin]        the rank of the first nominal threshold that can lie in or above the 1/512-wide bin of Psi
+                            (at most one threshold lies within a bin and its neighbours: one compare gives the rank)
+    kFastThrNom[s], kFastPos[k-1]   nominal sorted thresholds (2^32 fixed point) / sorted position of threshold k
+
+Arithmetic of the body: the int8 samples are never unpacked.  Each re-aligned 32-bit word of
 four samples is AND-masked to the bytes that belong to a segment and fed to IDP.2A
 (dp2a: two int16 carrier values x two int8 samples, int32 accumulate), once for the real and once
 for the imaginary carrier table, straight into the accumulator of that segment's class:
@@ -21,18 +35,13 @@ Usage: python gen_fast_wb.py [fs_hz fc_hz d] > bds_track_fast_gen.inc
 """
 from __future__ import annotations
 
-import os
 import sys
 from fractions import Fraction as F
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from gen_fast_common import emit_body  # noqa: E402
+RANK_BINS = 512
 
 
-def main():
-    fs = F(sys.argv[1]) if len(sys.argv) > 1 else F(99375000)
-    fc = F(sys.argv[2]) if len(sys.argv) > 2 else F(1023000)
-    d = F(sys.argv[3]) if len(sys.argv) > 3 else F(6, 100)
+def geometry(fs, fc, d):
     S = fs / (12 * fc)                 # samples per sub-chip
     delta = 12 * d
     assert F(1, 2) < delta < 1, "generator assumes 0.5 < 12*d < 1"
@@ -42,8 +51,92 @@ def main():
     beta.append(F(12))                 # 37 boundaries, beta[0] = chip start, beta[36] = chip end
     R = [int(b * S // 1) for b in beta]
     assert all(R[k + 1] - R[k] >= 1 for k in range(36)), "segments shorter than one sample"
+    theta = [b * S - r for b, r in zip(beta, R)]        # exact fractions, theta[k] in [0, 1)
+    return S, beta, R, theta
+
+
+def rank_tables(R, theta):
+    """sorted thresholds, positions, rank -> decision bits, prefix masks, rank lower bounds"""
+    order = sorted(range(1, 37), key=lambda k: (theta[k], k))        # boundary numbers by ascending threshold
+    pos = [0] * 36
+    for s, k in enumerate(order):
+        pos[k - 1] = s
+    thr_nom = [int(theta[k] * (1 << 32)) for k in order]
+    gaps = [b - a for a, b in zip(thr_nom, thr_nom[1:])]
+    w = (1 << 32) // RANK_BINS
+    assert min(gaps) > 3 * w, "nominal thresholds too close for the one-compare rank search"
+    assert thr_nom[0] > 2 * w and thr_nom[-1] < (1 << 32) - 2 * w, "a threshold too close to the chip edge decision"
+    masks = []
+    for j in range(37):                # j = number of thresholds < Psi
+        # bit k-1: Theta_k >= Psi, i.e. the jitter sample R_k still belongs to segment k-1
+        masks.append(sum(1 << (k - 1) for k in range(1, 37) if pos[k - 1] >= j))
+    rank_lo = []
+    for b in range(RANK_BINS):
+        lo = (b - 1) * w
+        rank_lo.append(sum(1 for t in thr_nom if t < lo))
+    return order, pos, thr_nom, masks, rank_lo
+
+
+def emit_body(R, acc_name):
+    """straight-line per-word code with one prefix mask per boundary (FAST_PSEL(k, lo, hi), k = 1..36)"""
+    nseg = 36
+    nwords = (R[nseg] + 1 + 3) // 4
+    lines = []
+    e = lines.append
+    loaded = set()
+
+    def pfx(k):                        # P_k = (jitter sample old) ? bytes 0..b : bytes 0..b-1, b = R_k & 3
+        if k not in loaded:
+            loaded.add(k)
+            b = R[k] & 3
+            lo = (1 << (8 * b)) - 1
+            hi = (lo | (0xFF << (8 * b))) & 0xFFFFFFFF
+            e("const unsigned P%d = FAST_PSEL(%d, 0x%08xu, 0x%08xu);" % (k, k, lo, hi))
+        return "P%d" % k
+
+    for i in range(nwords):
+        body = []
+        for k in range(nseg):
+            lo_s = R[k] if k >= 1 else 0                         # first sample that can belong to segment k
+            hi_s = R[k + 1]                                      # last sample that can belong to it
+            pot = 0
+            for s in range(lo_s, hi_s + 1):
+                if s >> 2 == i:
+                    pot |= 0xFF << (8 * (s & 3))
+            if pot == 0:
+                continue
+            lb = k if (k >= 1 and R[k] >> 2 == i) else None       # boundary k (start of the segment) inside this word
+            ub = k + 1 if R[k + 1] >> 2 == i else None            # boundary k+1 (its end) inside this word
+            if lb is None and ub is None:
+                expr = "X"
+            elif lb is None:
+                expr = "X & %s" % pfx(ub)
+            elif ub is None:
+                expr = "X & ~%s" % pfx(lb)
+            else:
+                expr = "X & ~%s & %s" % (pfx(lb), pfx(ub))
+            n = acc_name(k)
+            s_ = "{ const unsigned M = %s; " % expr
+            if pot & 0x0000FFFF:
+                s_ += "%sr = FAST_DP_LO(T.x, M, %sr); %si = FAST_DP_LO(T.z, M, %si); " % (n, n, n, n)
+            if pot & 0xFFFF0000:
+                s_ += "%sr = FAST_DP_HI(T.y, M, %sr); %si = FAST_DP_HI(T.w, M, %si); " % (n, n, n, n)
+            s_ += "}"
+            body.append(s_)
+        e("{ const unsigned X = FAST_FSH(FAST_RAW(%d), FAST_RAW(%d)); const int4 T = FAST_WTAB(%d);" % (i, i + 1, i))
+        for b in body:
+            e(b)
+        e("}")
+    return lines, nwords
+
+
+def main():
+    fs = F(sys.argv[1]) if len(sys.argv) > 1 else F(99375000)
+    fc = F(sys.argv[2]) if len(sys.argv) > 2 else F(1023000)
+    d = F(sys.argv[3]) if len(sys.argv) > 3 else F(6, 100)
+    S, beta, R, theta = geometry(fs, fc, d)
+    order, pos, thr_nom, masks, rank_lo = rank_tables(R, theta)
     nsamp = R[36] + 1                  # samples 0..R36 (the last one is the end-boundary jitter sample)
-    nwords = (nsamp + 3) // 4
     out = []
     w = out.append
     w("// GENERATED by gen_fast_wb.py — do not edit.  fs=%s Hz, fc=%s Hz, d=%s" % (fs, fc, float(d)))
@@ -51,12 +144,18 @@ def main():
     w("#define FAST_FC_HZ %.1f" % float(fc))
     w("#define FAST_D %.17g" % float(d))
     w("#define FAST_NSAMP %d" % nsamp)
-    w("#define FAST_NWORDS %d" % nwords)
+    w("#define FAST_NWORDS %d" % ((nsamp + 3) // 4))
     w("#define FAST_RLAST %d" % R[36])
-    w("static __constant__ int kFastR[37] = {%s};" % ", ".join(map(str, R)))
-    w("static __constant__ double kFastBeta[37] = {%s};" % ", ".join("%.17g" % float(b) for b in beta))
-    frac = [float(b * S - r) for b, r in zip(beta, R)]
-    w("// nominal frac(beta_k * S): %s" % " ".join("%.3f" % f for f in frac[1:]))
+    w("#define FAST_RANK_BINS %d" % RANK_BINS)
+    w("#define FAST_POS_LAST %d   /* sorted position of the chip-end threshold (boundary 36) */" % pos[35])
+    w("#define FAST_SAMPLES_PER_CHIP %.17g" % float(12 * S))
+    w("FAST_CONST int kFastR[37] = {%s};" % ", ".join(map(str, R)))
+    w("FAST_CONST double kFastBeta[37] = {%s};" % ", ".join("%.17g" % float(b) for b in beta))
+    w("// nominal frac(beta_k * S): %s" % " ".join("%.3f" % float(t) for t in theta[1:]))
+    w("FAST_CONST unsigned kFastThrNom[36] = {%s};" % ", ".join("0x%08xu" % t for t in thr_nom))
+    w("FAST_CONST unsigned char kFastPos[36] = {%s};" % ", ".join(map(str, pos)))
+    w("FAST_CONST unsigned char kFastRankLo[%d] = {%s};" % (RANK_BINS, ", ".join(map(str, rank_lo))))
+    w("FAST_CONST unsigned long long kFastMask[37] = {%s};" % ", ".join("0x%010xull" % m for m in masks))
 
     special = {(1, 0): "A1", (1, 1): "B1", (7, 0): "A7", (7, 1): "B7", (6, 1): "B6", (6, 2): "C6", (12, 1): "B12",
                (12, 2): "C12"}
@@ -74,9 +173,9 @@ def main():
             names.append(n)
     w("#define FAST_DECL_ACCS int " + ", ".join("%sr = 0, %si = 0" % (n, n) for n in names) + ";")
 
-    # ---- body: per word, per overlapping segment (gen_fast_common.emit_body)
+    body, nwords = emit_body(R, acc_name)
     w("#define FAST_CHIP_BODY \\")
-    for ln in emit_body(R, 36, nwords, acc_name, "FAST"):
+    for ln in body:
         w("    " + ln + " \\")
     w("    /* end */")
 

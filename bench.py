@@ -380,10 +380,6 @@ def run_b200(args):
     wall = time.perf_counter() - t0
     s1 = sampler.mark()
     launches = B.launch_count() - launches0
-    if os.environ.get('BDS_TRK_TIMING'):
-        sess.counters()
-    if os.environ.get('BDS_TRK_TRACE'):
-        L.check(L.lib().bds_track_dump_trace(sess.h, os.path.join(ROOT, 'gpurun_out', 'trace.bin').encode()))
     clocks = sampler.stop(s0, s1) if rank == 0 else None
     # ---- untimed: the run that was just timed proves its own correctness (every rank, its own channels)
     check = self_check(sess, st_local, mine, n_epochs, x_dev, n_samples)

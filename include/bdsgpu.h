@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BDS_ABI_VERSION 1
+#define BDS_ABI_VERSION 2
 
 /* error codes */
 #define BDS_OK 0
@@ -132,7 +132,15 @@ typedef struct bds_trk_cfg {
     double wbFactor;             /* WB only */
     int32_t kernel;              /* BDS_KERNEL_* */
     int32_t reserved;            /* 0; bit 0 = test hook: widen the fast kernel's exact-path guard band */
+    /* Tuning and diagnostics of the chip-synchronous kernel.  All 0 = library defaults.  The library never reads the
+     * caller's environment: everything that changes its behaviour is in this struct. */
+    int32_t fwPassesPerTask;     /* passes of 512 chips per queued (channel, epoch, slice) task, 1..8 */
+    int32_t fwPrefetch;          /* tasks a CTA may stage ahead of its compute warps, plus one (1 = none) */
+    int32_t debug;               /* BDS_DBG_* bits */
+    int32_t traceTickets;        /* BDS_DBG_TRACE: number of queue tickets to record (bds_track_dump_trace) */
 } bds_trk_cfg;
+#define BDS_DBG_TIMING 1 /* per-stage cycle counters of the tracking kernel, printed by bds_track_counters */
+#define BDS_DBG_TRACE 2  /* per-ticket timestamps */
 
 typedef struct bds_channel {
     int32_t PRN;         /* 0 = unused channel (WB_tracking.m:165) */
@@ -204,7 +212,7 @@ int bds_track_stats(bds_trk* h, long long* channel_samples, int* epochs_run, flo
  * per-sample path, slices run by the general kernel, 0}.  h == NULL: counters of the last
  * bds_track_correlate_open_loop call (out4[3] = device microseconds of its correlator kernel). */
 int bds_track_counters(bds_trk* h, long long* out4);
-/* developer tracing (env BDS_TRK_TRACE=<n tickets>): dump per-work-item timestamps */
+/* developer tracing (cfg.debug & BDS_DBG_TRACE, cfg.traceTickets): dump per-work-item timestamps */
 int bds_track_dump_trace(bds_trk* h, const char* path);
 /* reset loop state to the initial channel state (re-run the same record) */
 int bds_track_reset(bds_trk* h);

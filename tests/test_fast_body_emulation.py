@@ -47,6 +47,11 @@ def dp2a(lo, a, b, c):
     return _s32(c + _s16(a) * _s8(b >> sh) + _s16(a >> 16) * _s8(b >> (sh + 8)))
 
 
+class _Row:
+    def __init__(self, v):
+        self.x, self.y, self.z, self.w = v
+
+
 class Gen:
     def __init__(self, inc=INC, prefix="FAST", tab="kFast"):
         text = open(inc).read()
@@ -62,7 +67,7 @@ class Gen:
     @staticmethod
     def _to_python(c):
         c = re.sub(r"/\*.*?\*/", "", c)
-        c = re.sub(r"\bconst (unsigned|int4|int)\b", "", c)
+        c = re.sub(r"\bconst (unsigned|uint4|int4|int)\b", "", c)
         c = re.sub(r"0x([0-9a-fA-F]+)u", r"0x\1", c)
         c = c.replace("{", "\n").replace("}", "\n").replace(";", "\n")
         for f, i in (("x", 0), ("y", 1), ("z", 2), ("w", 3)):
@@ -79,6 +84,10 @@ class Gen:
                 out.append(ln)
         return "\n".join(out)
 
+    def _prefix(self, k, mk):
+        b = self.R[k] & 3
+        return (((1 << (8 * b)) - 1) | ((0xFF << (8 * b)) if (mk >> (k - 1)) & 1 else 0)) & 0xFFFFFFFF
+
     def run(self, raw_words, table, sh, mk, extra=None):
         """one chip: raw_words = 32-bit words starting at the aligned word of the first sample, sh = 8 * (offset & 3),
         table[i] = (wr01, wr23, wi01, wi23) packed int16 pairs, mk = jitter mask (bit k-1: boundary k)"""
@@ -90,7 +99,9 @@ class Gen:
             p + "_WTAB": lambda i: table[i],
             p + "_DP_LO": lambda a, b, c: dp2a(True, a, b, c),
             p + "_DP_HI": lambda a, b, c: dp2a(False, a, b, c),
-            p + "_SELU": lambda k, v: v if (mk >> (k - 1)) & 1 else 0})
+            p + "_SELU": lambda k, v: v if (mk >> (k - 1)) & 1 else 0,
+            # B1C body: prefix byte mask of boundary k from its bit of the decision mask
+            p + "_PSEL": lambda k, lo, hi: hi if (mk >> (k - 1)) & 1 else lo})
         env.update(extra or {})
         exec(self.body, env)
         exec(self.combine, env)
@@ -194,6 +205,30 @@ def test_basis_sums_and_chip_signs_reproduce_the_nine_replicas():
                ("p61", "L"): cp * (SA - SB - SC) + (cp - cpn) * W2b}
         for key in got:
             assert got[key] == want[key], (key, psi, off)
+
+
+def test_generated_rank_tables_follow_from_the_geometry():
+    """kFastMask / kFastThrNom / kFastPos / kFastRankLo of the generated file against their definitions, and the
+    (lo, hi) constants of every FAST_PSEL against the prefix-mask definition"""
+    text = open(INC).read()
+    arr = lambda name: [int(v.strip().rstrip("ul"), 0) for v in re.search(name + r"\[\d+\] = \{(.*?)\}", text, flags=re.S).group(1).split(",")]
+    thr_nom, pos, rank_lo = arr("kFastThrNom"), arr("kFastPos"), arr("kFastRankLo")
+    S = 99.375e6 / (12 * 1.023e6)
+    theta = [GEN.beta[k] * S - GEN.R[k] for k in range(37)]
+    order = sorted(range(1, 37), key=lambda k: theta[k])
+    assert [pos[k - 1] for k in order] == list(range(36))
+    assert all(abs(thr_nom[s] - theta[k] * 2 ** 32) < 64 for s, k in enumerate(order))
+    bins = len(rank_lo)
+    w = (1 << 32) // bins
+    assert all(rank_lo[b] == sum(t < (b - 1) * w for t in thr_nom) for b in range(bins))
+    assert min(b - a for a, b in zip(thr_nom, thr_nom[1:])) > 3 * w        # one threshold per three-bin window
+    masks = arr("kFastMask")
+    assert masks == [sum(1 << (k - 1) for k in range(1, 37) if pos[k - 1] >= j) for j in range(37)]   # old <=> threshold k not below Psi
+    sel = {int(k): (int(lo, 16), int(hi, 16)) for k, lo, hi in re.findall(r"FAST_PSEL\((\d+), 0x([0-9a-f]+)u, 0x([0-9a-f]+)u\)", text)}
+    assert sorted(sel) == list(range(1, 37))
+    for k, (lo, hi) in sel.items():
+        assert lo == GEN._prefix(k, 0) and hi == GEN._prefix(k, 1 << (k - 1))
+    assert int(re.search(r"#define FAST_POS_LAST (\d+)", text).group(1)) == pos[35]
 
 
 # ---- B2a: ten chips per thread, 20 half-chip segments (gen_fast_b2a.py; not wired into a kernel yet) ------------

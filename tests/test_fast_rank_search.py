@@ -1,9 +1,5 @@
-"""The two rank searches of fast_chip (csrc/bds_track_fast.cuh) pick the same jitter mask.
-
-Default build: bin start + four dependent refinement steps + distances to the neighbouring thresholds.
--DBDS_FAST_BINREC=1: one 8-byte record per pair of bins (the at most two thresholds inside) + a guard band at the pair's
-edges.  Restated here in Python for the nominal B1C geometry under Doppler: the rank j must be identical for every
-sub-sample phase Psi, and every Psi the default sends to the exact path must go there in the record variant too."""
+"""fast_chip's per-chip bookkeeping (csrc/bds_track_fast.cuh) restated in Python for the nominal B1C geometry: the
+one-compare rank search over the generated tables, and the chips' sample ranges tiling an epoch's block."""
 import re
 import os
 
@@ -16,65 +12,28 @@ R = [int(v) for v in re.search(r"kFastR\[37\] = \{(.*?)\}", TEXT).group(1).split
 BETA = [float(v) for v in re.search(r"kFastBeta\[37\] = \{(.*?)\}", TEXT).group(1).split(",")]
 
 
+RANK_LO = [int(v) for v in re.search(r"kFastRankLo\[\d+\] = \{(.*?)\}", TEXT, flags=re.S).group(1).split(",")]
+POS_LAST = int(re.search(r"#define FAST_POS_LAST (\d+)", TEXT).group(1))
+
+
 def tables(code_freq):
+    """sorted thresholds of an epoch (fast_build_tab_lane)"""
     S = 1.0 / (12.0 * code_freq / 99.375e6)
     thr = []
     for k in range(1, 37):
         th = BETA[k] * S - R[k]
         assert 1e-6 < th < 1 - 1e-6
         thr.append(int(min(th * 4294967296.0, 4294967295.0)))
-    srt = sorted(thr) + [0xFFFFFFFF] * 4
-    bins = [sum((v >> 25) < t for v in thr) for t in range(129)]
-    assert all(sum((v >> 25) == t for v in thr) <= 4 for t in range(129))
-    rec = []
-    for b in range(64):
-        s0, s1 = bins[2 * b], bins[2 * b + 2]
-        assert s1 - s0 <= 2
-        rec.append((srt[s0] if s0 < s1 else 0xFFFFFFFF, srt[s0 + 1] if s0 + 1 < s1 else 0xFFFFFFFF))
-    return srt, bins, rec
+    return sorted(thr) + [0xFFFFFFFF] * 4
 
 
-def search_default(srt, bins, Psi, guard):
-    j = bins[Psi >> 25]
-    for _ in range(4):
-        j += srt[j] < Psi
-    below = Psi - srt[j - 1] if j > 0 else Psi
-    above = srt[j] - Psi if j < 36 else 0xFFFFFFFF - Psi
-    return j, below <= guard or above <= guard or Psi >= 0xFFFFFFFF - guard
-
-
-def search_record(bins, rec, Psi, guard):
-    u32 = lambda v: v & 0xFFFFFFFF
-    rx, ry = rec[Psi >> 26]
-    j = bins[(Psi >> 26) * 2] + (rx < Psi) + (ry < Psi)
-    eg, low = min(guard, 4096), Psi & 0x3FFFFFF
-    exact = (u32(rx - Psi + guard) <= 2 * guard or u32(ry - Psi + guard) <= 2 * guard or low <= eg
-             or low >= 0x3FFFFFF - eg or Psi >= 0xFFFFFFFF - guard)
-    return j, exact
-
-
-def test_record_search_equals_refinement_search():
-    rng = np.random.default_rng(11)
-    for code_freq in (1.023e6, 1.023e6 - 3.2, 1.023e6 + 3.3, 1.023e6 + 0.017):
-        srt, bins, rec = tables(code_freq)
-        probes = [int(v) for v in rng.integers(0, 1 << 32, size=4000)]
-        for t in srt[:36]:                                     # around every threshold and every bin edge
-            probes += [max(0, min(0xFFFFFFFF, t + dlt)) for dlt in (-4097, -17, -16, -1, 0, 1, 16, 17, 4097)]
-        for b in range(1, 128):
-            probes += [(b << 25) + dlt for dlt in (-17, -1, 0, 1, 17)]
-        probes += [0, 1, 15, 16, 17, 0xFFFFFFFF, 0xFFFFFFFF - 16, 0xFFFFFFFF - 17]
-        for guard in (16, 1 << 24):
-            n_def = n_rec = 0
-            for Psi in probes:
-                jd, ed = search_default(srt, bins, Psi, guard)
-                jr, er = search_record(bins, rec, Psi, guard)
-                assert jd == jr, (code_freq, hex(Psi))
-                if guard <= 4096:                              # the wide guard band is a test hook: any subset will do
-                    assert er or not ed, (code_freq, hex(Psi), guard)
-                n_def += ed
-                n_rec += er
-            if guard == 16:
-                assert n_rec <= n_def + 5 * 127 + 8          # extra exact chips only at the 127 bin edges probed
+def search(srt, Psi, guard):
+    """fast_chip: rank = rankLo[bin] + (thr[rankLo[bin]] < Psi); near = within the guard band of that threshold or of 0 / 1"""
+    jlo = RANK_LO[Psi >> 23]
+    t = srt[jlo]
+    j = jlo + (t < Psi)
+    near = ((t - Psi + guard) & 0xFFFFFFFF) <= 2 * guard or Psi <= guard or Psi >= 0xFFFFFFFF - guard
+    return j, near
 
 
 def test_b1c_chip_bookkeeping_tiles_the_block():
@@ -87,7 +46,7 @@ def test_b1c_chip_bookkeeping_tiles_the_block():
     for rem, code_freq in ((0.0, 1.023e6), (0.0093, 1.023e6 - 2.9), (0.0007, 1.023e6 + 3.1)):
         step = code_freq / fs
         blk = int(math.ceil((L - rem) / step))
-        srt, bins, rec = tables(code_freq)
+        srt = tables(code_freq)
         pos = {v: i for i, v in enumerate(srt[:36])}
         S = 1.0 / (12.0 * step)
         thr_of_k = [int(min((BETA[k] * S - R[k]) * 4294967296.0, 4294967295.0)) for k in range(1, 37)]
@@ -99,9 +58,11 @@ def test_b1c_chip_bookkeeping_tiles_the_block():
             nc = int(math.floor(q)) + 1
             psi = nc - q
             Psi = int(min(psi * 4294967296.0, 4294967295.0))
-            j, near = search_default(srt, bins, Psi, 16)
+            j, near = search(srt, Psi, 16)
+            assert j == sum(v < Psi for v in srt[:36])
             mk = masks[j]
-            ln = R[36] + ((mk >> 35) & 1)
+            ln = R[36] + (j <= POS_LAST)
+            assert (j <= POS_LAST) == bool((mk >> 35) & 1)
             if near or nc < 0 or nc + ln > blk:
                 n_exact += 1
                 continue

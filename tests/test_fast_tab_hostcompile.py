@@ -1,12 +1,11 @@
-"""The warp-cooperative per-epoch table builders (fast_build_tab_warp, fastb_build_tab_warp) run on the host.
+"""The warp-cooperative per-epoch table builder of the B2a kernel (fastb_build_tab_warp) run on the host.
 
 A warp is emulated by 32 OS threads: threadIdx.x is thread-local, __syncwarp() is a 32-party barrier and __all_sync() a
 barrier-protected vote, so the code keeps exactly the synchronisation it has on the GPU (a missing __syncwarp shows up
 as a data race here too).  The tables built by the device source are compared with the Python restatement the other
 host-compiled tests use, and a whole epoch is correlated through a table built this way:
-  * B2a: thresholds, rank masks, bins, scalars; epoch sums against the oracle;
-  * B1C: default and -DBDS_FAST_BINREC=1 (per-bin records), fresh build and the reuse path (same sort order as the
-    previous epoch's table: only thresholds, records, rotation table and scalars are rewritten)."""
+thresholds, rank masks, bins, scalars; epoch sums against the oracle.  (The B1C builder has no cross-lane dependency
+any more - tests/test_fast_b1c_hostcompile.py runs its 32 lanes in turn.)"""
 import ctypes as C
 import os
 import subprocess
@@ -15,7 +14,6 @@ import numpy as np
 import pytest
 
 import bds_oracle as O
-import test_fast_b1c_hostcompile as B1
 import test_fast_b2a_hostcompile as B2
 from test_fast_b2a_model import Settings, build_tab, make_epoch
 
@@ -51,15 +49,6 @@ extern "C" void build_tab_host(FastbTab* tab, const EpochParams* p, double fs) {
     run_warp([=] { fastb_build_tab_warp(tab, *p, fs, scratch); });
 }
 """
-
-B1C_DRIVER = r"""
-extern "C" void build_tab_host(FastTab* tab, const EpochParams* p, double fs, const unsigned char* prev) {
-    static unsigned scratch[128];
-    run_warp([=] { fast_build_tab_warp(tab, *p, fs, scratch, prev); });
-}
-extern "C" int offsetof_posbin() { return (int)offsetof(FastTab, posbin); }
-"""
-
 
 def _compile(tmp, name, text, flags=()):
     src = tmp / (name + ".cpp")
@@ -127,54 +116,3 @@ def test_b2a_table_builder_on_host(b2a_lib):
         for k, v in ref.items():
             scale = max(abs(ref[f"{k[0]}_I_P"]), abs(ref[f"{k[0]}_Q_P"]))
             assert abs(got[k] - v) <= 1e-4 * scale, (k, got[k], v)
-
-
-@pytest.mark.parametrize("binrec", [0, 1])
-def test_b1c_table_builder_on_host(binrec, tmp_path):
-    trk = open(os.path.join(CSRC, "bds_track.cuh")).read()
-    fast = open(os.path.join(CSRC, "bds_track_fast.cuh")).read()
-    inc = open(os.path.join(CSRC, "bds_track_fast_gen.inc")).read().replace("static __constant__", "static const")
-    for pat in B1.GPU_ONLY[1:]:                               # keep fast_build_tab_warp
-        fast = B1._cut(fast, pat)
-    fast = fast.replace("#pragma once", "").replace('#include "bds_track.cuh"', "").replace('#include "bds_track_fast_gen.inc"', inc)
-    fast = fast.replace("typedef unsigned long long f2_t;", "").replace("namespace bds {", "", 1)
-    fast = fast[:fast.rindex("}  // namespace bds")]
-    parts = [B2.SHIM.replace("#define BDS_TRK_B2A 2", ""), "#include <cstddef>\n", B1.F2_SHIM, WARP_SHIM,
-             "constexpr int kNSum = 18;\nconstexpr int kPackedWordsDev = 320;\n",
-             B2._block(trk, r"__host__ __device__ constexpr int sum_idx"), "enum { EPL_E = 0, EPL_P = 1, EPL_L = 2 };\n",
-             B2._block(trk, r"struct EpochParams \{"), fast, B1.DRIVER, B1C_DRIVER]
-    lib = _compile(tmp_path, "b1c_tab", "\n".join(parts), ["-DBDS_FAST_BINREC=%d" % binrec])
-    size, off_u0, off_pb = lib.sizeof_tab(), lib.offsetof_u0(), lib.offsetof_posbin()
-
-    def build(rem, step, fc_, rc, prev=None):
-        buf = (C.c_uint8 * size)()
-        if prev is not None:                                   # the table is rewritten in place on the GPU
-            C.memmove(buf, prev[0], size)
-        p = B2.EpochParams(pos=0, blksize=993750, pad=0, rem=rem, step=step, carrFreq=fc_, remCarr=rc)
-        pb = (C.c_uint8 * 80).from_buffer_copy(bytes(prev[0])[off_pb:off_pb + 80]) if prev is not None else None
-        lib.build_tab_host(buf, C.byref(p), C.c_double(99.375e6), pb)
-        return buf, bytes(buf)
-
-    def check(raw, rem, step, fc_, rc):
-        want = B1.build_tab_bytes(lib, rem, step, fc_, rc, bool(binrec))
-        w_end = 26 * 16
-        got_w, want_w = np.frombuffer(raw[:w_end], dtype=np.int16), np.frombuffer(want[:w_end], dtype=np.int16)
-        assert np.max(np.abs(got_w.astype(int) - want_w.astype(int))) <= 1
-        thr_end = w_end + 160
-        assert raw[w_end:thr_end] == want[w_end:thr_end]                       # sorted thresholds
-        got_m = np.frombuffer(raw[thr_end:thr_end + 320], dtype=np.uint64)[:37]
-        want_m = np.frombuffer(want[thr_end:thr_end + 320], dtype=np.uint64)[:37]
-        assert np.array_equal(got_m, want_m)                                   # rank masks
-        assert raw[thr_end + 320:thr_end + 320 + 129] == want[thr_end + 320:thr_end + 320 + 129]   # bins
-        if binrec:
-            assert raw[off_pb + 80:off_u0] == want[off_pb + 80:off_u0]         # per-bin records
-        assert raw[off_u0:off_u0 + 44] == want[off_u0:off_u0 + 44]             # u0, sigma, S, dphi, phi0, valid
-
-    fs = 99.375e6
-    a = ((0.0061, (1.023e6 + 1.9) / fs, 14.58e6 - 3920.0, 4.2), (0.0033, (1.023e6 + 1.9003) / fs, 14.58e6 - 3919.2, 1.7))
-    first = build(*a[0])
-    check(first[1], *a[0])
-    again = build(*a[1], prev=first)                           # same order, same bins: the reuse path
-    check(again[1], *a[1])
-    other = build(0.004, (1.023e6 - 3.0) / fs, 14.58e6 + 10.0, 0.3, prev=again)   # thresholds move across bins: full rebuild
-    check(other[1], 0.004, (1.023e6 - 3.0) / fs, 14.58e6 + 10.0, 0.3)

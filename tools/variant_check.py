@@ -27,7 +27,20 @@ import bds3_b200 as B  # noqa: E402
 from bds3_b200 import _lib as L, _track, synth  # noqa: E402
 
 FS = 99.375e6
-NCH = 60
+NCH = int(os.environ.get("BDS_NCH", 60))
+
+
+def tuning():
+    """developer knobs of these tools (the library itself never reads the environment): BDS_TRK_PASSES, BDS_TRK_AHEAD,
+    BDS_TRK_TIMING -> bds_trk_cfg.fwPassesPerTask / fwPrefetch / debug"""
+    t = {}
+    if "BDS_TRK_PASSES" in os.environ:
+        t["fwPassesPerTask"] = int(os.environ["BDS_TRK_PASSES"])
+    if "BDS_TRK_AHEAD" in os.environ:
+        t["fwPrefetch"] = int(os.environ["BDS_TRK_AHEAD"]) + 1
+    if os.environ.get("BDS_TRK_TIMING"):
+        t["debug"] = L.DBG_TIMING
+    return t
 
 
 def render(seconds):
@@ -59,7 +72,7 @@ def main():
         synth.synth_device("B2a", st, sats, n, out_ptr=p.value)
         L.check(L.lib().bds_dev_sync())
         ne = max(1, int(n // 99376) - 2)
-        s = _track.TrackSession("B2a", st, ch, device_ptr=p.value, n_samples=n)
+        s = _track.TrackSession("B2a", st, ch, device_ptr=p.value, n_samples=n, tuning=tuning())
         ms = []
         for _ in range(3):
             s.reset()
@@ -77,7 +90,7 @@ def main():
         seconds = float(sys.argv[3]) if len(sys.argv) > 3 else 5.0
         st, ch, n, xp = render(seconds)
         ne = max(1, int((n - 993750) // 993760) - 1)
-        s = _track.TrackSession("WB", st, ch, device_ptr=xp, n_samples=n)
+        s = _track.TrackSession("WB", st, ch, device_ptr=xp, n_samples=n, tuning=tuning())
         ms = []
         for _ in range(4):
             s.reset()
