@@ -250,23 +250,22 @@ __device__ bool next_params(const TrkDev& g, const ChanState& st, EpochParams& n
     return off >= 0 && off + np.blksize <= g.winLen && np.blksize > 0;
 }
 
-// Loop-closure arithmetic of one epoch (no memory traffic): discriminators, loop filters, state update.
+// Loop-closure arithmetic of one epoch (no memory traffic), in two phases so that a latency-critical caller can publish
+// the next epoch's NCO before it formats this epoch's outputs:
+//   close_nco  discriminators, loop filters, state update (everything the next epoch depends on);
+//   close_out  the value of every trackResults plane for this epoch (plus the raw sums).
 //   s[18]  correlator sums;  p  the epoch's NCO parameters;  st  channel state (updated in place);
-//   outv[kNFields]  receives the value of every trackResults plane for this epoch (plus the raw sums);
 //   pre (optional, WB with pilot only) = {atan(Q_P/I_P)/2pi, atan(pQ_P/pI_P)/2pi, dll(data), dll(pilot), fmod(trig,2pi)}
 //   already evaluated with the expressions below by other lanes of a closing warp.
-__device__ void close_core(const TrkDev& g, const double* s, const EpochParams& p, double chCodeFreq, ChanState& st,
-                           double* outv, const double* pre = nullptr) {
+struct CloseAux {
+    double carrError, codeError, carrNco, codeNco, carrFreqOld, codeFreqOld;
+    double pI[3], pQ[3];   // stored pilot values (E, P, L): WB composite, NB / B2a the pilot prompt itself in [EPL_P]
+};
+
+__device__ void close_nco(const TrkDev& g, const double* s, const EpochParams& p, double chCodeFreq, ChanState& st,
+                          CloseAux& a, const double* pre = nullptr) {
     const double twopi = 6.283185307179586476925286766559;
     const bool b1c = g.mode != BDS_TRK_B2A;
-#pragma unroll
-    for (int i = 0; i < kNFields; ++i) outv[i] = 0.0;
-    outv[F_ABS] = (double)p.pos;           // WB:254
-    outv[F_REMCODE] = p.rem;               // WB:287
-    outv[F_REMCARR] = p.remCarr;           // WB:332
-#pragma unroll
-    for (int i = 0; i < kNSum; ++i) outv[F_RAW0 + i] = s[i];
-
     // remCodePhase / remCarrPhase updates (WB:327,335-337; B2a:295,303-305)
     double base = (double)(p.blksize - 1) * p.step + p.rem;
     st.remCodePhase = base + p.step - g.L;
@@ -284,24 +283,19 @@ __device__ void close_core(const TrkDev& g, const double* s, const EpochParams& 
     double carrError = pre ? pre[0] : atan(Q_P / I_P) / twopi;
     double codeError = pre ? pre[2] : dll_disc(I_E, Q_E, I_L, Q_L);
     if (b1c) codeError = codeError * (1.0 - g.d);
+#pragma unroll
+    for (int o = 0; o < 3; ++o) a.pI[o] = a.pQ[o] = 0.0;
     if (g.mode == BDS_TRK_B1C_WB && g.hasPilot) {
         const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
-        double pI[3], pQ[3];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {  // WB:375-380
-            pI[o] = -ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)];
-            pQ[o] = -ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)];
+            a.pI[o] = -ka * s[sum_idx(2, o, 0)] + kb * s[sum_idx(1, o, 1)];
+            a.pQ[o] = -ka * s[sum_idx(2, o, 1)] - kb * s[sum_idx(1, o, 0)];
         }
-        double pe = pre ? pre[1] : atan(pQ[EPL_P] / pI[EPL_P]) / twopi;
+        double pe = pre ? pre[1] : atan(a.pQ[EPL_P] / a.pI[EPL_P]) / twopi;
         carrError = (carrError * 1 + pe * 3) / 4;
-        double pc = (pre ? pre[3] : dll_disc(pI[EPL_E], pQ[EPL_E], pI[EPL_L], pQ[EPL_L])) * (1.0 - g.d);
+        double pc = (pre ? pre[3] : dll_disc(a.pI[EPL_E], a.pQ[EPL_E], a.pI[EPL_L], a.pQ[EPL_L])) * (1.0 - g.d);
         codeError = codeError * g.factor + pc * (1.0 - g.factor);
-        outv[F_PI_P] = pI[EPL_P];
-        outv[F_PI_E] = pI[EPL_E];
-        outv[F_PI_L] = pI[EPL_L];
-        outv[F_PQ_P] = pQ[EPL_P];
-        outv[F_PQ_E] = pQ[EPL_E];
-        outv[F_PQ_L] = pQ[EPL_L];
     } else if (g.hasPilot) {
         double pIP = s[sum_idx(1, EPL_P, 0)], pQP = s[sum_idx(1, EPL_P, 1)];
         double pc = dll_disc(s[sum_idx(1, EPL_E, 0)], s[sum_idx(1, EPL_E, 1)], s[sum_idx(1, EPL_L, 0)],
@@ -318,31 +312,60 @@ __device__ void close_core(const TrkDev& g, const double* s, const EpochParams& 
             carrError = (carrError + pe) / 2;
             codeError = (codeError + pc) / 2;
         }
-        outv[F_PI_P] = pIP;
-        outv[F_PQ_P] = pQP;
+        a.pI[EPL_P] = pIP;
+        a.pQ[EPL_P] = pQP;
     }
     // PLL filter WB:399-406
     st.d2CarrError = st.d2CarrError + carrError * g.pf3;
     st.dCarrError = st.d2CarrError + carrError * g.pf2 + st.dCarrError;
     double carrNco = st.dCarrError + carrError * g.pf1;
-    outv[F_CARRFREQ] = st.carrFreq;
+    a.carrFreqOld = st.carrFreq;
     st.carrFreq = st.carrFreqBasis + carrNco;
     // DLL filter WB:422-430
     double codeNco = st.oldCodeNco + g.tau2over1 * (codeError - st.oldCodeError) + codeError * g.PDIoverTau1;  // (tau2/tau1), (PDI/tau1)
     st.oldCodeNco = codeNco;
     st.oldCodeError = codeError;
-    outv[F_CODEFREQ] = st.codeFreq;
+    a.codeFreqOld = st.codeFreq;
     st.codeFreq = chCodeFreq - codeNco;
-    outv[F_DLL] = codeError;
-    outv[F_DLLF] = codeNco;
-    outv[F_PLL] = carrError;
-    outv[F_PLLF] = carrNco;
-    outv[F_I_E] = I_E;
-    outv[F_I_P] = I_P;
-    outv[F_I_L] = I_L;
-    outv[F_Q_E] = Q_E;
-    outv[F_Q_P] = Q_P;
-    outv[F_Q_L] = Q_L;
+    a.carrError = carrError;
+    a.codeError = codeError;
+    a.carrNco = carrNco;
+    a.codeNco = codeNco;
+}
+
+__device__ void close_out(const TrkDev& g, const double* s, const EpochParams& p, const CloseAux& a, double* outv) {
+#pragma unroll
+    for (int i = 0; i < kNFields; ++i) outv[i] = 0.0;
+    outv[F_ABS] = (double)p.pos;           // WB:254
+    outv[F_REMCODE] = p.rem;               // WB:287
+    outv[F_REMCARR] = p.remCarr;           // WB:332
+#pragma unroll
+    for (int i = 0; i < kNSum; ++i) outv[F_RAW0 + i] = s[i];
+    outv[F_PI_P] = a.pI[EPL_P];
+    outv[F_PI_E] = a.pI[EPL_E];
+    outv[F_PI_L] = a.pI[EPL_L];
+    outv[F_PQ_P] = a.pQ[EPL_P];
+    outv[F_PQ_E] = a.pQ[EPL_E];
+    outv[F_PQ_L] = a.pQ[EPL_L];
+    outv[F_CARRFREQ] = a.carrFreqOld;
+    outv[F_CODEFREQ] = a.codeFreqOld;
+    outv[F_DLL] = a.codeError;
+    outv[F_DLLF] = a.codeNco;
+    outv[F_PLL] = a.carrError;
+    outv[F_PLLF] = a.carrNco;
+    outv[F_I_E] = s[sum_idx(0, EPL_E, 0)];
+    outv[F_I_P] = s[sum_idx(0, EPL_P, 0)];
+    outv[F_I_L] = s[sum_idx(0, EPL_L, 0)];
+    outv[F_Q_E] = s[sum_idx(0, EPL_E, 1)];
+    outv[F_Q_P] = s[sum_idx(0, EPL_P, 1)];
+    outv[F_Q_L] = s[sum_idx(0, EPL_L, 1)];
+}
+
+__device__ void close_core(const TrkDev& g, const double* s, const EpochParams& p, double chCodeFreq, ChanState& st,
+                           double* outv, const double* pre = nullptr) {
+    CloseAux a;
+    close_nco(g, s, p, chCodeFreq, st, a, pre);
+    close_out(g, s, p, a, outv);
 }
 
 // planes a mode does not produce keep their preallocation values (NB / B2a have no E/L pilot planes, data-only
@@ -866,16 +889,19 @@ int plan_grid(bds_trk* h) {
         h->gridBlocks = g_num_sms;
         // a few CTAs only close loops: one warp per channel (16 warps per CTA)
         int nCloser = (h->nAct + (kFwThreads / 32) - 1) / (kFwThreads / 32);
+        nCloser = std::min(nCloser, std::max(1, h->gridBlocks / 16));   // many channels: several channels per closer warp
+        if ((long long)nCloser * (kFwThreads / 32) * 8 < h->nAct)
+            return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: too many channels for the closer warps");
         h->nCompute = std::max(1, h->gridBlocks - nCloser);
         // slices of kFwChips*k chips (one chip per compute thread and pass); >= ~4 work items per CTA and round
         int k = 4;
         while (k > 1 && (long long)h->nAct * ((10230 + kFwChips * k - 1) / (kFwChips * k)) < 4LL * h->gridBlocks) --k;
         if (h->cfg.fwPassesPerTask > 0) k = std::max(1, std::min(8, (int)h->cfg.fwPassesPerTask));  // caller's tuning
         h->S = (10230 + kFwChips * k - 1) / (kFwChips * k);
-        // queue payload: 7 bits of channel, 6 bits of slice, 19 bits of epoch (fw_payload)
-        if (h->nCh > 127 || h->S > 63)
-            return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: at most 127 channels per session (got %d); "
-                                                  "open several sessions or use BDS_KERNEL_GENERAL", h->nCh);
+        // queue entry: 10 bits of channel, 6 bits of slice, 19 bits of epoch (fw_put); a closer warp owns up to 8 channels
+        if (h->nCh > kFwMaxChannels || h->S > 63)
+            return set_error(BDS_ERR_UNSUPPORTED, "chip-synchronous kernel: at most %d channels per session (got %d); "
+                                                  "open several sessions or use BDS_KERNEL_GENERAL", kFwMaxChannels, h->nCh);
     } else {
         BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_persistent_kernel, kTrkThreads, h->smemBytes));
         if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
@@ -905,7 +931,7 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
         delete h;
         return rc;
     }
-    if (h->fast && cfg->kernel == BDS_KERNEL_AUTO && n_ch > 127) h->fast = false;   // queue payload holds 7 bits of channel
+    if (h->fast && cfg->kernel == BDS_KERNEL_AUTO && n_ch > kFwMaxChannels) h->fast = false;   // queue entries hold 10 bits of channel
     h->b2aUnit = !h->fast && b2a_unit_enabled(mode, cfg);
     auto fail = [&](int code) {
         bds_track_close(h);
@@ -948,7 +974,7 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
         unsigned need = (unsigned)(2 * n_ch * h->S + 2 * h->gridBlocks + 64);
         h->qSize = 1024;
         while (h->qSize < need) h->qSize <<= 1;
-        TRY(cudaMalloc(&h->dQueue, sizeof(unsigned long long) * 2 * h->qSize));   // 16-byte entries
+        TRY(cudaMalloc(&h->dQueue, sizeof(unsigned long long) * kFwQueueWords * h->qSize));   // 64-byte entries
         TRY(cudaMalloc(&h->dQctl, sizeof(unsigned) * kQWords));
         if ((cfg->debug & BDS_DBG_TRACE) && cfg->traceTickets > 0) {
             h->traceCap = (unsigned)cfg->traceTickets;
@@ -1058,7 +1084,7 @@ static int launch_run(bds_trk* h, int maxEpochs, int epochLimit) {
         return BDS_OK;
     }
     if (h->fast) {
-        BDS_CUDA(cudaMemsetAsync(h->dQueue, 0, sizeof(unsigned long long) * 2 * h->qSize, h->stream));
+        BDS_CUDA(cudaMemsetAsync(h->dQueue, 0, sizeof(unsigned long long) * kFwQueueWords * h->qSize, h->stream));
         fw_prepare_kernel<<<1, 1024, 0, h->stream>>>(g, h->nCompute);
     } else trk_prepare_kernel<<<h->nCh, kTrkThreads, sizeof(TrkSmem), h->stream>>>(g);
     count_launch();

@@ -65,8 +65,6 @@ struct __align__(128) FwSmem {
     unsigned long long full[kFwStages], empty[kFwStages], pfull[kFwStages], resFull[2], resEmpty[2];
     int res[2][kFwCompute][kNSum];
     int resTask[2][4];
-    unsigned nUnits;              // number of passes the producer issued (0xffffffff while it is still issuing)
-    unsigned pad_[3];
     FastStatic fsx;
     FwStage st[kFwStages];
 };
@@ -106,12 +104,19 @@ __device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned phas
         : "memory");
     return ok != 0;
 }
-// service-warp wait: lane 0 polls with a short sleep, then every lane observes the completed phase itself
-__device__ __forceinline__ void mbar_wait_warp(unsigned long long* bar, unsigned phase, unsigned ns) {
-    if ((threadIdx.x & 31) == 0)
-        while (!mbar_test(bar, phase)) __nanosleep(ns);
-    __syncwarp();
-    mbar_wait(bar, phase);
+// service-warp wait: the hardware suspends the warp until the phase completes or the hint (ns) runs out - no
+// instructions are issued while it waits (a polling loop on the highest warp ids would take issue slots from the
+// compute warps of its sub-partition)
+__device__ __forceinline__ void mbar_wait_hint(unsigned long long* bar, unsigned phase, unsigned hint_ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITH_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@!p bra WAITH_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase), "r"(hint_ns)
+        : "memory");
 }
 
 __host__ __device__ inline int fw_chips_per_slice(int S) {
@@ -120,51 +125,75 @@ __host__ __device__ inline int fw_chips_per_slice(int S) {
 }
 
 // ---- ready-task queue -----------------------------------------------------------------------------
-// Ring of 16-byte entries {tag, info}: tag = (ticket + 1) << 32 | payload, info = lap << 48 | block start (absolute
-// sample index, 48 bits).  payload: channel (7 bits) | slice (6 bits) << 7 | epoch (19 bits) << 13; 0xffffffff =
-// terminate, 0xfffffffe = skip.  A consumer reads an entry with ONE 16-byte load and accepts it when the tag carries
-// its ticket and info carries the ring lap of that ticket (so a torn read can never be mistaken for a valid entry);
-// everything it needs to start the TMA copies is in the entry, so popping a task costs one L2 round trip.
-__device__ __forceinline__ unsigned fw_payload(int c, int sl, int e) { return (unsigned)c | ((unsigned)sl << 7) | ((unsigned)e << 13); }
+// Ring of 64-byte entries, four 16-byte pieces {data64, tag32 << 32 | data32}, tag = ticket + 1 in EVERY piece: a
+// consumer polls the slot of its ticket with four independent 16-byte loads and accepts the entry when all four
+// pieces carry its tag, so a torn read can never be mistaken for a valid entry and no fence is needed on either
+// side.  The entry holds everything a pass needs to start - the epoch's whole NCO (48 bytes of EpochParams) besides
+// (channel, slice, epoch) - so the loop closure publishes by writing the entries and nothing else, and popping a
+// task costs one L2 round trip.
+//   piece 0: pos                | payload = slice (6 bits) | epoch (19 bits) << 6; 0xffffffff terminate, 0xfffffffe skip
+//   piece 1: remCodePhase       | step, low word
+//   piece 2: carrFreq           | step, high word
+//   piece 3: remCarrPhase       | blksize (22 bits) | channel (10 bits) << 22
+constexpr int kFwQueueWords = 8;            // 64-bit words per entry
+constexpr int kFwMaxChannels = 1023;
+__device__ __forceinline__ unsigned fw_payload(int sl, int e) { return (unsigned)sl | ((unsigned)e << 6); }
 constexpr unsigned kFwSkip = 0xfffffffeu;   // reserved-but-unused queue slot: consumers pop the next ticket
 constexpr unsigned kFwTerminate = 0xffffffffu;
-__device__ __forceinline__ unsigned fw_lap(const TrkDev& g, unsigned ticket) { return (ticket >> __popc(g.qMask)) & 0xffffu; }
-__device__ __forceinline__ void fw_put(const TrkDev& g, unsigned ticket, unsigned payload, long long pos) {
-    const unsigned long long tag = ((unsigned long long)(ticket + 1u) << 32) | payload;
-    const unsigned long long info = ((unsigned long long)fw_lap(g, ticket) << 48) | ((unsigned long long)pos & 0xffffffffffffull);
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(g.queue + 2 * (size_t)(ticket & g.qMask)), "l"(tag), "l"(info)
-                 : "memory");
+__device__ __forceinline__ void fw_put(const TrkDev& g, unsigned ticket, unsigned payload, int c, const EpochParams& p) {
+    unsigned long long* q = g.queue + (size_t)kFwQueueWords * (ticket & g.qMask);
+    const unsigned long long tag = (unsigned long long)(ticket + 1u) << 32;
+    const unsigned long long stp = (unsigned long long)__double_as_longlong(p.step);
+    const unsigned long long d0 = (unsigned long long)p.pos, d1 = (unsigned long long)__double_as_longlong(p.rem),
+                             d2 = (unsigned long long)__double_as_longlong(p.carrFreq),
+                             d3 = (unsigned long long)__double_as_longlong(p.remCarr);
+    const unsigned long long h0 = tag | payload, h1 = tag | (stp & 0xffffffffull), h2 = tag | (stp >> 32),
+                             h3 = tag | ((unsigned)p.blksize & 0x3fffffu) | ((unsigned long long)(unsigned)c << 22);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(q), "l"(d0), "l"(h0) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(q + 2), "l"(d1), "l"(h1) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(q + 4), "l"(d2), "l"(h2) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(q + 6), "l"(d3), "l"(h3) : "memory");
 }
-// one poll of the slot of `ticket`; true when the entry is there
-__device__ __forceinline__ bool fw_peek(const TrkDev& g, unsigned ticket, unsigned& payload, long long& pos) {
-    unsigned long long tag, info;
-    asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];"
-                 : "=l"(tag), "=l"(info)
-                 : "l"(g.queue + 2 * (size_t)(ticket & g.qMask))
-                 : "memory");
-    payload = (unsigned)tag;
-    pos = (long long)(info & 0xffffffffffffull);
-    return (tag >> 32) == (unsigned long long)ticket + 1ull && (unsigned)(info >> 48) == fw_lap(g, ticket);
+// one poll of the slot of `ticket`; true when the whole entry is there
+__device__ __forceinline__ bool fw_peek(const TrkDev& g, unsigned ticket, unsigned& payload, int& c, EpochParams& p) {
+    const unsigned long long* q = g.queue + (size_t)kFwQueueWords * (ticket & g.qMask);
+    unsigned long long d0, d1, d2, d3, h0, h1, h2, h3;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(d0), "=l"(h0) : "l"(q) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(d1), "=l"(h1) : "l"(q + 2) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(d2), "=l"(h2) : "l"(q + 4) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(d3), "=l"(h3) : "l"(q + 6) : "memory");
+    const unsigned want = ticket + 1u;
+    if ((unsigned)(h0 >> 32) != want || (unsigned)(h1 >> 32) != want || (unsigned)(h2 >> 32) != want ||
+        (unsigned)(h3 >> 32) != want)
+        return false;
+    payload = (unsigned)h0;
+    p.pos = (long long)d0;
+    p.rem = __longlong_as_double((long long)d1);
+    p.step = __longlong_as_double((long long)((h1 & 0xffffffffull) | (h2 << 32)));
+    p.carrFreq = __longlong_as_double((long long)d2);
+    p.remCarr = __longlong_as_double((long long)d3);
+    p.blksize = (int)((unsigned)h3 & 0x3fffffu);
+    p.pad = 0;
+    c = (int)((unsigned)h3 >> 22);
+    return true;
 }
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-// Writers issue a gpu-scope release fence after the last write the consumers will read, then fw_put; fw_peek is an
-// acquire load.
-// push the S slices of (c, e) at freshly reserved tickets
-__device__ void fw_push_slices(const TrkDev& g, int c, int e, long long pos, int lane) {
+// push the S slices of epoch e of channel c at freshly reserved tickets
+__device__ void fw_push_slices(const TrkDev& g, int c, int e, const EpochParams& p, int lane) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(g.qctl + kQTail, (unsigned)g.S);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (int s = lane; s < g.S; s += 32) fw_put(g, base + s, fw_payload(c, s, e), pos);
+    for (int s = lane; s < g.S; s += 32) fw_put(g, base + s, fw_payload(s, e), c, p);
 }
 // fill S slots reserved earlier at `base` (atomicAdd on the tail) with the slices of (c, e), or with skip entries
-__device__ void fw_fill_slices(const TrkDev& g, unsigned base, int c, int e, long long pos, int lane, bool skip) {
-    for (int s = lane; s < g.S; s += 32) fw_put(g, base + s, skip ? kFwSkip : fw_payload(c, s, e), pos);
+__device__ void fw_fill_slices(const TrkDev& g, unsigned base, int c, int e, const EpochParams& p, int lane, bool skip) {
+    for (int s = lane; s < g.S; s += 32) fw_put(g, base + s, skip ? kFwSkip : fw_payload(s, e), c, p);
 }
 __device__ void fw_push_terminate(const TrkDev& g, int n, int lane) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(g.qctl + kQTail, (unsigned)n);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (int s = lane; s < n; s += 32) fw_put(g, base + s, kFwTerminate, 0);
+    EpochParams z{};
+    for (int s = lane; s < n; s += 32) fw_put(g, base + s, kFwTerminate, 0, z);
 }
 // a channel has no further epoch in this launch: the last one to end shuts the grid down
 __device__ void fw_channel_done(const TrkDev& g, int lane, int nCtas) {
@@ -221,10 +250,12 @@ __device__ void cno_pld_warp(const double* ip, const double* qp, int n, double T
 
 // ---- closure by one warp ----------------------------------------------------------------------
 // All S slices of (c, e) have arrived.  Critical path (everything the next epoch's slices wait for):
-//   one L2 round trip (the S slice slots summed in a fixed order, state, params; the next epoch's queue slots are
-//   reserved in the same round trip) -> discriminator pieces in parallel lanes -> sequential loop filters on lane 0
-//   -> 48 bytes of next-epoch parameters -> fence -> publish.  Output planes, C/N0 and the state write-back follow
-//   after the publication.  Returns true if another epoch of the channel was published.
+//   one L2 round trip (all S slice slots in flight at once, summed in a fixed order; state, params; the next epoch's
+//   queue slots are reserved in the same round trip) -> discriminator pieces in parallel lanes -> loop filters and the
+//   next epoch's NCO on lane 0 (close_nco, next_params) -> the queue entries, which carry that NCO.  No fence: the
+//   entries validate themselves, the slice slots were read before they can be rewritten, the arrival counter only grows.
+//   Output planes, C/N0, parameters and state write-back follow after the publication.
+//   Returns true if another epoch of the channel was published.
 __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, int e0 /* first epoch of this launch */) {
     const int lane = threadIdx.x & 31;
     const unsigned long long tIn = g.pubTime ? gtimer_ns() : 0ull;
@@ -238,8 +269,13 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     if (lane < kNSum) {      // slice sums are integer multiples of 2^-8 below 2^45: the fp64 sum is exact, any order
         const double* part = g.partial + (size_t)c * g.S * kNSum + lane;
         double a = 0.0;
-#pragma unroll 4
-        for (int s = 0; s < g.S; ++s) a += __ldcg(part + (size_t)s * kNSum);
+        for (int s0 = 0; s0 < g.S; s0 += 16) {   // sixteen loads in flight, then their sum
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = s0 + k < g.S ? __ldcg(part + (size_t)(s0 + k) * kNSum) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a += v[k];
+        }
         sm.sums[lane] = a;
     } else if (lane < kNSum + 8)
         reinterpret_cast<uint4*>(&sm.st)[lane - kNSum] = __ldcg(reinterpret_cast<const uint4*>(g.st + c) + (lane - kNSum));
@@ -248,7 +284,7 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     else if (lane == 29) sm.chCodeFreq = g.cc[c].chCodeFreq;
     __syncwarp();
     const long long tc0 = clock64();
-    // ---- discriminator pieces, one per lane, uniform control flow (same expressions as close_core) ----
+    // ---- discriminator pieces, one per lane, uniform control flow (same expressions as close_nco) ----
     {
         const double* s = sm.sums;
         const double ka = sqrt(4.0 / 33.0), kb = sqrt(29.0 / 33.0);
@@ -289,8 +325,9 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     }
     __syncwarp();
     int ok = 0;
+    CloseAux aux;   // lane 0
     if (lane == 0) {
-        close_core(g, sm.sums, sm.p, sm.chCodeFreq, sm.st, sm.outv, sm.pre);
+        close_nco(g, sm.sums, sm.p, sm.chCodeFreq, sm.st, aux, sm.pre);
         sm.st.epoch = e + 1;
         ok = next_params(g, sm.st, sm.np) && e + 1 < g.epochLimit;
     }
@@ -298,19 +335,20 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     __syncwarp();
     const long long tc1 = clock64();
     const bool more = ok && (e + 1 - e0) < g.maxEpochs;  // another epoch of this channel in this launch?
+    const long long tc2 = clock64();
+    qbase = __shfl_sync(0xffffffffu, qbase, 31);
+    fw_fill_slices(g, qbase, c, e + 1, sm.np, lane, !more);
+    const long long tc3 = clock64();
+    // ---- off the critical path: parameters (read by the channel's next closure), output planes, C/N0 + lock
+    //      detector, state write-back ----
     if (more && lane < 3)
         __stcg(reinterpret_cast<uint4*>(g.params + c * 2 + ((e + 1) & 1)) + lane, reinterpret_cast<const uint4*>(&sm.np)[lane]);
-    const long long tc2 = clock64();
-    __syncwarp();
-    fence_acq_rel_gpu();
-    qbase = __shfl_sync(0xffffffffu, qbase, 31);
-    fw_fill_slices(g, qbase, c, e + 1, sm.np.pos, lane, !more);
-    if (lane == 0) {   // bookkeeping for the next launch's prepare kernel
-        if (ok) g.ready[c] = e + 1;
+    if (lane == 0) {
+        close_out(g, sm.sums, sm.p, aux, sm.outv);
+        if (ok) g.ready[c] = e + 1;   // bookkeeping for the next launch's prepare kernel
         else g.stop[c] = e + 1;
     }
-    const long long tc3 = clock64();
-    // ---- off the critical path: output planes, C/N0 + lock detector, state write-back ----
+    __syncwarp();
     {
         const int cap = g.capacity;
         double* out = g.out + (size_t)c * kNFields * cap;
@@ -372,13 +410,12 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
             for (int s = 0; s < kFwStages; ++s) {
                 mbar_init(&sm.full[s], 2);       // producer (tile + codes, with byte count) + builder (table)
                 mbar_init(&sm.empty[s], kFwCompute);
-                mbar_init(&sm.pfull[s], 1);      // producer (parameters, with byte count)
+                mbar_init(&sm.pfull[s], 1);      // producer (parameters written)
             }
             for (int r = 0; r < 2; ++r) {
                 mbar_init(&sm.resFull[r], kFwCompute);
                 mbar_init(&sm.resEmpty[r], 1);
             }
-            sm.nUnits = 0xffffffffu;
         }
         fast_load_static(&sm.fsx, threadIdx.x, kFwThreads);
     }
@@ -412,10 +449,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 int v = 0;
                 if (lane == 0) v = ld_acquire(g.count + chan[i]);
                 v = __shfl_sync(0xffffffffu, v, 0);
-                if (v != g.S) continue;
+                if (v != g.S * (ep[i] - ep0[i] + 1)) continue;   // the counter only grows: S arrivals per epoch of this launch
                 fired = true;
-                if (lane == 0) g.count[chan[i]] = 0;
-                __syncwarp();
                 const bool more = fw_closure(g, *cs, chan[i], ep[i], ep0[i]);
                 if (more) {
                     ++ep[i];
@@ -431,7 +466,13 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         }
         return;
     }
+#ifdef BDS_FW_SERVICE_LO   // developer A/B: service warps on the lowest warp ids
+    const int svc = warp < kFwService ? warp : -1;
+    const int cwIdx = warp - kFwService;
+#else
     const int svc = warp - kFwCompute;    // 0..3 for the service warps (highest warp ids), < 0 for compute warps
+    const int cwIdx = warp;
+#endif
     if (svc >= 0) {
 #ifdef BDS_FW_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
@@ -445,7 +486,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         unsigned curTicket = 0;
         for (long long t = blockIdx.x;; t += gridDim.x) {
             int c, e, sl, ce = 0;
-            const EpochParams* gp;
+            EpochParams P;                // the epoch's NCO: from the queue entry (closed loop) / the caller's array (open loop)
             long long B0;
             bool nominal = true;          // tile bounds from the nominal chip rate (no dependence on the epoch's NCO)
             double u0 = 0, Ss = 0;
@@ -455,11 +496,10 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 sl = (int)(t - (long long)ce * g.S);
                 c = ce / g.olEpochs;
                 e = ce - c * g.olEpochs;
-                gp = g.olParams + ce;
-                const EpochParams p = load_cg(gp);
-                u0 = 12.0 * p.rem;
-                Ss = 1.0 / (12.0 * p.step);   // == tab.u0, tab.S (same expressions)
-                B0 = p.pos - g.winFirst;
+                P = load_cg(g.olParams + ce);
+                u0 = 12.0 * P.rem;
+                Ss = 1.0 / (12.0 * P.step);   // == tab.u0, tab.S (same expressions)
+                B0 = P.pos - g.winFirst;
                 nominal = false;
             } else {
                 // take work only when a stage is free for it (tasks are scarce while channels sit in loop
@@ -476,8 +516,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 const unsigned ticket = atomicAdd(g.qctl + kQHead, 1u);
                 tTicket += clock64() - t0;
                 unsigned pl;
-                long long pos;
-                while (!fw_peek(g, ticket, pl, pos)) __nanosleep(32);
+                while (!fw_peek(g, ticket, pl, c, P)) __nanosleep(32);
                 tQueue += clock64() - t0;
                 curTicket = ticket;
                 if (g.trace && ticket < g.traceCap) {
@@ -486,18 +525,9 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 }
                 if (pl == kFwTerminate) break;
                 if (pl == kFwSkip) continue;
-                // params were written with generic-proxy stores by a closer warp (made visible by its release
-                // fence + the acquire load above) and are read below through the async proxy (TMA)
-                {
-                    long long tf = clock64();
-                    asm volatile("fence.proxy.async.global;" ::: "memory");
-                    tFence += clock64() - tf;
-                }
-                c = (int)(pl & 127u);
-                sl = (int)((pl >> 7) & 63u);
-                e = (int)(pl >> 13);
-                gp = g.params + c * 2 + (e & 1);
-                B0 = pos - g.winFirst;
+                sl = (int)(pl & 63u);
+                e = (int)(pl >> 6);
+                B0 = P.pos - g.winFirst;
             }
             const int cLo = sl * cps, cHi = min(10230, cLo + cps);  // host guarantees S = ceil(10230 / cps): never empty
             const long long gMax = (g.winLen + 16) & ~15LL;         // every IF buffer has >= 16 bytes of slack past winLen
@@ -539,9 +569,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 d.tileBytes = (int)bytes; d.pad_ = 0;
                 d.tileBase = gA; d.B0 = B0;
                 st.u = d;
-                // the parameters first, on their own barrier: the builder warp starts while the tile is in flight
-                mbar_expect_tx(&sm.pfull[stage], (unsigned)sizeof(EpochParams));
-                tma_bulk(&st.p, gp, (unsigned)sizeof(EpochParams), &sm.pfull[stage]);
+                st.p = P;
+                mbar_arrive(&sm.pfull[stage]);   // the builder warp starts on the table while the tile is in flight
                 mbar_expect_tx(&sm.full[stage], bytes + kFwBitsBytes);
                 if (bytes) tma_bulk(st.tile, g.x + gA, bytes, &sm.full[stage]);
                 tma_bulk(st.bits, g.codeBits + (size_t)c * 2 * kPackedWordsDev, kFwBitsBytes, &sm.full[stage]);
@@ -552,15 +581,19 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
             } while (c0 < cHi);
             ++seq;
         }
-        // terminate: the builders stop at unit nUnits; the compute warps get a stage with c = -1 (the producer stands in
-        // for the builder's arrival)
-        *reinterpret_cast<volatile unsigned*>(&sm.nUnits) = u;
-        const int stage = u % nst;
-        mbar_wait(&sm.empty[stage], ((u / nst) & 1) ^ 1);
-        sm.st[stage].u.c = -1;
-        sm.st[stage].u.seq = seq;
-        mbar_arrive(&sm.full[stage]);
-        mbar_arrive(&sm.full[stage]);
+        // terminate: one unit with c = -1 for each builder warp (units u and u + 1); the compute warps leave at the
+        // first one, for which the producer stands in for the builder's arrival on the stage barrier
+        for (int k = 0; k < 2; ++k, ++u) {
+            const int stage = u % nst;
+            mbar_wait(&sm.empty[stage], ((u / nst) & 1) ^ 1);
+            sm.st[stage].u.c = -1;
+            sm.st[stage].u.seq = seq;
+            mbar_arrive(&sm.pfull[stage]);
+            if (k == 0) {
+                mbar_arrive(&sm.full[stage]);
+                mbar_arrive(&sm.full[stage]);
+            }
+        }
         if (g.counters) {
             atomicAdd(g.counters + 4, (unsigned long long)tQueue);
             atomicAdd(g.counters + 5, (unsigned long long)tEmpty);
@@ -575,19 +608,9 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         static_assert(kFwStages % 2 == 0, "the two builder warps own the even / odd stages");
         for (unsigned u = (unsigned)(svc - 2);; u += 2) {
             const int stage = u % nst;
-            int quit = 0;
-            if (lane == 0)
-                for (unsigned n = 0; !mbar_test(&sm.pfull[stage], (u / nst) & 1); ++n) {
-                    if ((n & 15u) == 15u && u >= *reinterpret_cast<volatile unsigned*>(&sm.nUnits)) {
-                        quit = 1;
-                        break;
-                    }
-                    __nanosleep(40);
-                }
-            quit = __shfl_sync(0xffffffffu, quit, 0);
-            if (quit) break;
-            mbar_wait(&sm.pfull[stage], (u / nst) & 1);   // every lane observes the completed phase itself
+            mbar_wait_hint(&sm.pfull[stage], (u / nst) & 1, 20000u);
             FwStage& st = sm.st[stage];
+            if (st.u.c < 0) break;   // terminate unit (the producer posts one for each builder)
             fast_build_tab_warp(&st.tab, sm.fsx, st.p, g.fs);
             if (lane == 0) mbar_arrive(&sm.full[stage]);
         }
@@ -597,7 +620,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
         int nClose = 0;
         for (int k = 0;; ++k) {
             const int rs = k & 1;
-            mbar_wait_warp(&sm.resFull[rs], (k >> 1) & 1, 32);
+            mbar_wait_hint(&sm.resFull[rs], (k >> 1) & 1, 20000u);
             long long t0 = clock64();
             const int c = sm.resTask[rs][0], sl = sm.resTask[rs][2], ce = sm.resTask[rs][3];
             double v = 0;
@@ -637,7 +660,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
 #ifdef BDS_FW_SETMAXNREG
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BDS_FW_SETMAXNREG));
 #endif
-        const int cw = warp;
+        const int cw = cwIdx;
         fast_acc_t acc[kFastAccN];
         fast_acc_zero(acc);
         const unsigned guard = g.pad ? (1u << 24) : kFastGuard;  // g.pad: test hook, widens the guard band
@@ -772,7 +795,7 @@ __global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
             if (lane == 0) store_cg(g.params + c * 2 + (e & 1), nps[w]);
             __threadfence();
             __syncwarp();
-            fw_push_slices(g, c, e, nps[w].pos, lane);
+            fw_push_slices(g, c, e, nps[w], lane);
         } else {
             fw_channel_done(g, lane, nCtas);
         }

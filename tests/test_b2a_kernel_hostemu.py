@@ -140,7 +140,9 @@ def emu(tmp_path_factory):
              blk(fast, r"struct ExactCtx \{"), blk(fast, r"__device__ __forceinline__ double colon_elem_f"),
              blk(fast, r"__device__ __forceinline__ int bit_of"),
              blk(trk_cu, r"__device__ __forceinline__ double dll_disc"), blk(trk_cu, r"__device__ void cno_pld"),
-             blk(trk_cu, r"__device__ bool next_params"), blk(trk_cu, r"__device__ void close_core"),
+             blk(trk_cu, r"__device__ bool next_params"), blk(trk_cu, r"struct CloseAux \{"),
+             blk(trk_cu, r"__device__ void close_nco"), blk(trk_cu, r"__device__ void close_out"),
+             blk(trk_cu, r"__device__ void close_core"),
              blk(trk_cu, r"__device__ __forceinline__ bool field_written"), blk(trk_cu, r"__device__ void close_cno"),
              b2a, DRIVER]
     d = tmp_path_factory.mktemp("b2a_emu")

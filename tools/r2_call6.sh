@@ -13,4 +13,4 @@ echo "== open" >> $LOG
 timeout 30 python tools/variant_check.py open gpurun_out/r2/closed6.npz gpurun_out/r2/open6 2>&1 | grep -E "^\{" | cut -c1-300 >> $LOG
 for n in 8 30; do run BDS_NCH=$n; done
 cat $LOG
-bash tools/r2_ncu.sh open 2>&1 | tail -2
+
