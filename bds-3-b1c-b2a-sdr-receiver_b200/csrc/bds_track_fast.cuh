@@ -6,7 +6,7 @@
 //   * inside a chip all nine replicas are constant on 36 segments (gen_fast_wb.py); a re-aligned word of four
 //     int8 samples is AND-masked to a segment (one LOP3 with the prefix masks of the segment's boundaries, each a
 //     SEL between two constants on a bit of the rank's decision mask) and multiplied with the Q15 carrier by IDP.2A into the segment's class accumulator; class sums are
-//     folded into nine complex "basis" sums (SA,SB,SC,H1,H2,W1a,W1b,W2a,W2b) from which E/P/L of data, BOC(1,1)
+//     folded into eight complex "basis" sums (X = H2 - H1, SA, SB, SC, W1a, W1b, W2a, W2b) from which E/P/L of data, BOC(1,1)
 //     pilot and BOC(6,1) pilot follow by +-1 combinations with the chip signs;
 //   * the carrier is exp(-i theta(n_c)) * exp(-i 2 pi r dphi): a per-epoch table of the
 //     second factor (r = 0..103, Q15) is broadcast from shared memory, the first factor is
@@ -336,7 +336,7 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
 #define FAST_DP_HI(a, b, c) __dp2a_hi((int)(a), (int)(b), (c))
 #if BDS_ABL & 4   // developer ablation (wrong results): no per-sample body, one word of the tile per chip
         const int v0 = (int)__funnelshift_r(raw[0], raw[1], sh) + wt[0].x + (int)mk.x;
-        const int SAr = v0, SAi = v0, SBr = v0, SBi = v0, SCr = v0, SCi = v0, H1r = v0, H1i = v0, H2r = v0, H2i = v0,
+        const int SAr = v0, SAi = v0, SBr = v0, SBi = v0, SCr = v0, SCi = v0, Xr = v0, Xi = v0,
                   W1ar = v0, W1ai = v0, W1br = v0, W1bi = v0, W2ar = v0, W2ai = v0, W2br = v0, W2bi = v0;
 #else
         FAST_CHIP_BODY
@@ -351,7 +351,7 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
 #if BDS_ABL & 1   // developer ablation (wrong results): no rotation, no chip-sign combination
         {
             float tmp[kNSum] = {(float)SAr, (float)SAi, (float)SBr, (float)SBi, (float)SCr, (float)SCi,
-                                (float)H1r, (float)H1i, (float)H2r, (float)H2i, (float)W1ar, (float)W1ai,
+                                (float)Xr, (float)Xi, (float)Xr, (float)Xi, (float)W1ar, (float)W1ai,
                                 (float)W1br, (float)W1bi, (float)W2ar, (float)W2ai, (float)W2br, (float)W2bi};
             fast_acc_add(acc, tmp);
         }
@@ -363,14 +363,13 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
         const float rr = cs * (1.0f / 32767.0f), ri = -sn * (1.0f / 32767.0f);
         const f2_t rotA = f2_pk(rr, ri), rotB = f2_pk(-ri, rr);
 #define ROT(N) const f2_t N##p = f2_sfma((float)N##i, rotB, f2_mul(f2_pk((float)N##r, (float)N##r), rotA));
-        ROT(SA) ROT(SB) ROT(SC) ROT(H1) ROT(H2) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
+        ROT(SA) ROT(SB) ROT(SC) ROT(X) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
 #undef ROT
         const int cp_ = c == 0 ? 10229 : c - 1, cn_ = c == 10229 ? 0 : c + 1;
         const float cd = bit_of(bitsData, c) ? -1.f : 1.f, cdp = bit_of(bitsData, cp_) ? -1.f : 1.f,
                     cdn = bit_of(bitsData, cn_) ? -1.f : 1.f;
         const float cp = bit_of(bitsPilot, c) ? -1.f : 1.f, cpp = bit_of(bitsPilot, cp_) ? -1.f : 1.f,
                     cpn = bit_of(bitsPilot, cn_) ? -1.f : 1.f;
-        const f2_t Xp = f2_sub(H2p, H1p);
         const f2_t XEp = f2_sfma(-2.f, W1bp, f2_add(Xp, W1ap));
         const f2_t XLp = f2_sfma(2.f, W2ap, f2_sub(Xp, W2bp));
         const f2_t sAB = f2_add(SAp, SBp), sBC = f2_add(SBp, SCp);

@@ -29,7 +29,7 @@ four samples is AND-masked to the bytes that belong to a segment and fed to IDP.
 for the imaginary carrier table, straight into the accumulator of that segment's class:
     {E,O}{1,2}{A,B,C}  - even/odd sub-chip, first/second half chip, segment class A/B/C
     A1,B1,A7,B7,B6,C6,B12,C12 - the eight segments that also form the BOC(1,1) early/late windows
-from which SA,SB,SC,H1,H2,W1a,W1b,W2a,W2b follow by additions at the end of the chip.
+from which X = H2 - H1, SA, SB, SC, W1a, W1b, W2a, W2b follow by additions at the end of the chip.
 
 Usage: python gen_fast_wb.py [fs_hz fc_hz d] > bds_track_fast_gen.inc
 """
@@ -179,23 +179,36 @@ def main():
         w("    " + ln + " \\")
     w("    /* end */")
 
-    # ---- chip-end combination into the nine basis sums
+    # ---- chip-end combination into the eight basis sums, as chains of three-input adds (IADD3)
+    #   X  = H2 - H1 (second minus first half chip), SA/SB/SC = even minus odd sub-chips per segment class,
+    #   W1a = A1+B1, W1b = A7+B7 (windows after the two BOC(1,1) edges), W2a = B6+C6, W2b = B12+C12 (before them)
     comb = []
     c = comb.append
+
+    def chain(name, comp, terms):
+        """name = sum of signed terms, three inputs per statement"""
+        terms = [(sg, t if t.startswith("W") else t) for sg, t in terms]
+        cur, k, n = None, 0, 0
+        while k < len(terms):
+            take = terms[k:k + (3 if cur is None else 2)]
+            k += len(take)
+            expr = (cur or "")
+            for sg, t in take:
+                v = t + comp
+                expr += (" %s %s" % (sg, v)) if expr else (v if sg == "+" else "-" + v)
+            last = k >= len(terms)
+            dst = name + comp if last else "u%s%s%d" % (name, comp, n)
+            c("const int %s = %s;" % (dst, expr))
+            cur, n = dst, n + 1
+
+    P, M = "+", "-"
     for comp in ("r", "i"):
-        def v(n):
-            return n + comp
-        c("const int tO1A%s = %s + %s, tO1B%s = %s + %s, tO2A%s = %s + %s, tO2B%s = %s + %s;" % (
-            comp, v("O1A"), v("A1"), comp, v("O1B"), v("B1"), comp, v("O2A"), v("A7"), comp, v("O2B"), v("B7")))
-        c("const int tE1B%s = %s + %s, tE1C%s = %s + %s, tE2B%s = %s + %s, tE2C%s = %s + %s;" % (
-            comp, v("E1B"), v("B6"), comp, v("E1C"), v("C6"), comp, v("E2B"), v("B12"), comp, v("E2C"), v("C12")))
-        c("const int SA%s = (%s + %s) - (tO1A%s + tO2A%s);" % (comp, v("E1A"), v("E2A"), comp, comp))
-        c("const int SB%s = (tE1B%s + tE2B%s) - (tO1B%s + tO2B%s);" % (comp, comp, comp, comp, comp))
-        c("const int SC%s = (tE1C%s + tE2C%s) - (%s + %s);" % (comp, comp, comp, v("O1C"), v("O2C")))
-        c("const int H1%s = (%s + tO1A%s) + (tE1B%s + tO1B%s) + (tE1C%s + %s);" % (comp, v("E1A"), comp, comp, comp, comp, v("O1C")))
-        c("const int H2%s = (%s + tO2A%s) + (tE2B%s + tO2B%s) + (tE2C%s + %s);" % (comp, v("E2A"), comp, comp, comp, comp, v("O2C")))
-        c("const int W1a%s = %s + %s, W1b%s = %s + %s, W2a%s = %s + %s, W2b%s = %s + %s;" % (
-            comp, v("A1"), v("B1"), comp, v("A7"), v("B7"), comp, v("B6"), v("C6"), comp, v("B12"), v("C12")))
+        c("const int W1a%s = A1%s + B1%s, W1b%s = A7%s + B7%s, W2a%s = B6%s + C6%s, W2b%s = B12%s + C12%s;" % ((comp,) * 12))
+        chain("X", comp, [(P, "E2A"), (P, "O2A"), (P, "E2B"), (P, "O2B"), (P, "E2C"), (P, "O2C"), (P, "W1b"), (P, "W2b"),
+                          (M, "E1A"), (M, "O1A"), (M, "E1B"), (M, "O1B"), (M, "E1C"), (M, "O1C"), (M, "W1a"), (M, "W2a")])
+        chain("SA", comp, [(P, "E1A"), (P, "E2A"), (M, "O1A"), (M, "O2A"), (M, "A1"), (M, "A7")])
+        chain("SB", comp, [(P, "E1B"), (P, "E2B"), (M, "O1B"), (M, "O2B"), (P, "B6"), (P, "B12"), (M, "B1"), (M, "B7")])
+        chain("SC", comp, [(P, "E1C"), (P, "E2C"), (M, "O1C"), (M, "O2C"), (P, "C6"), (P, "C12")])
     w("#define FAST_COMBINE \\")
     for ln in comb:
         w("    " + ln + " \\")

@@ -194,9 +194,8 @@ def test_basis_sums_and_chip_signs_reproduce_the_nine_replicas():
                 if fam == "p":
                     want[("p61", name)] = acc61
         g = lambda nm: complex(env[nm + "r"], env[nm + "i"])
-        SA, SB, SC, H1, H2 = g("SA"), g("SB"), g("SC"), g("H1"), g("H2")
+        SA, SB, SC, X = g("SA"), g("SB"), g("SC"), g("X")
         W1a, W1b, W2a, W2b = g("W1a"), g("W1b"), g("W2a"), g("W2b")
-        X = H2 - H1
         XE = X + W1a - 2 * W1b
         XL = X + 2 * W2a - W2b
         got = {("d", "P"): cd * X, ("d", "E"): cd * XE + cdp * W1a, ("d", "L"): cd * XL - cdn * W2b,
