@@ -255,7 +255,7 @@ __device__ bool next_params(const TrkDev& g, const ChanState& st, EpochParams& n
 //   close_nco  discriminators, loop filters, state update (everything the next epoch depends on);
 //   close_out  the value of every trackResults plane for this epoch (plus the raw sums).
 //   s[18]  correlator sums;  p  the epoch's NCO parameters;  st  channel state (updated in place);
-//   pre (optional, WB with pilot only) = {atan(Q_P/I_P)/2pi, atan(pQ_P/pI_P)/2pi, dll(data), dll(pilot), fmod(trig,2pi)}
+//   pre (optional; modes with a pilot) = {atan(Q_P/I_P)/2pi, atan(pQ_P/pI_P)/2pi, dll(data), dll(pilot), fmod(trig,2pi)}
 //   already evaluated with the expressions below by other lanes of a closing warp.
 struct CloseAux {
     double carrError, codeError, carrNco, codeNco, carrFreqOld, codeFreqOld;
@@ -308,7 +308,7 @@ __device__ void close_nco(const TrkDev& g, const double* s, const EpochParams& p
         } else {
             const double cr = 6.123233995736766e-17;  // cos(pi/2) in double, B2a:345
             double re = pIP * cr + pQP, im = pQP * cr - pIP;
-            double pe = atan(im / re) / twopi;
+            double pe = pre ? pre[1] : atan(im / re) / twopi;
             carrError = (carrError + pe) / 2;
             codeError = (codeError + pc) / 2;
         }
@@ -1333,7 +1333,10 @@ int bds_track_counters(bds_trk* h, long long* out4) {
     unsigned long long v[24];
     BDS_CUDA(cudaMemcpy(v, h->dCounters, 192, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 4; ++i) out4[i] = (long long)v[i];
-    if (h->cfg.debug & BDS_DBG_TIMING)  // developer breakdown (SM cycles summed over CTAs)
+    if ((h->cfg.debug & BDS_DBG_TIMING) && h->b2aUnit && v[8])   // developer build (-DBDS_FW_DEV): cycles per epoch of thread 0
+        fprintf(stderr, "[bds timing] b2a per epoch (cycles): tile wait %.0f, correlate %.0f, loop closure %.0f, table + outputs %.0f\n",
+                (double)v[4] / v[8], (double)v[5] / v[8], (double)v[6] / v[8], (double)v[7] / v[8]);
+    if ((h->cfg.debug & BDS_DBG_TIMING) && !h->b2aUnit)  // developer breakdown (SM cycles summed over CTAs)
         fprintf(stderr, "[bds timing] producer: queue %llu empty %llu total %llu | compute(w2): full-wait %llu res-wait %llu | closer: closure %llu epilogue %llu closures %llu\n",
                 v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
     if (h->cfg.debug & BDS_DBG_TIMING)

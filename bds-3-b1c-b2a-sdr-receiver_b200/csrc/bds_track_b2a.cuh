@@ -4,13 +4,15 @@
 // closes its loops 1000 times per second of signal: the latency of one closure bounds the speed, not the arithmetic.
 // The multi-CTA scheduler of the B1C kernel (slices of an epoch on many SMs, a closer CTA, three L2 round trips per
 // closure) is the wrong shape for that; here a channel owns one SM:
-//   * the epoch's samples (99 KB) are staged into shared memory with one TMA bulk copy, issued for epoch e+1 as soon
-//     as the correlator has finished reading epoch e (the start of the next block is known before the loops close);
+//   * the epoch's samples (99 KB) are staged into shared memory with one TMA bulk copy into one of two buffers, issued
+//     for epoch e+1 when the correlation of epoch e starts (the start of the next block is pos + blksize, whatever the
+//     loops decide), so the copy is never waited for;
 //   * 512 threads integrate the 1 023 ten-chip units of the epoch (two per thread) with the generated IDP.2A body
 //     of gen_fast_b2a.py: 20 half-chip segments per unit, the chip signs applied by integer adds at the end of the
 //     unit, one fp32 rotation per unit and replica;
-//   * warp sums in Q8 fixed point (REDUX) -> warp 0 -> thread 0 runs the same close_core / close_cno as the general
-//     kernel, writes the trackResults planes and the next epoch's NCO parameters; warp 0 rebuilds the per-epoch table.
+//   * warp sums in Q8 fixed point (REDUX) -> warp 0: discriminators in parallel lanes, loop filters and the next NCO on
+//     lane 0 (close_nco, the general kernel's arithmetic) -> the next table by five warps while another warp writes
+//     the trackResults planes (close_out / close_cno).
 // Segment-edge decisions use the same fixed-point thresholds + guard band as the B1C body; units that come within
 // the guard band of a decision, or that touch the ends of the block, are evaluated sample by sample with the float64
 // expressions of the general kernel (tracking.m:262-296 incl. the two-ended colon), so chip lookups are the oracle's.
@@ -46,7 +48,24 @@ inline bool fastb_supported(int mode, double fs, double fc, int codeLength, doub
 }
 
 // ---- per-epoch table (one warp; tab and scratch (>= 64 words) in shared memory) ------------------------------
-__device__ void fastb_build_tab_warp(FastbTab* tab, const EpochParams& np, double fs, unsigned* scratch) {
+// carrier rotation entries t = first, first + stride, ... of the table (any group of threads)
+__device__ inline void fastb_build_rot(FastbTab* tab, unsigned long long dphi, int first, int stride) {
+    short* w = reinterpret_cast<short*>(tab->w);   // word i: [wr(4i..4i+3) | wi(4i..4i+3)] as int16
+    for (int t = first; t < 4 * (FASTB_NWORDS + 1); t += stride) {
+        unsigned long long ph = (unsigned long long)t * dphi;
+        float sn, cs;
+        sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
+        w[(t >> 2) * 8 + (t & 3)] = (short)__float2int_rn(cs * 32767.0f);
+        w[(t >> 2) * 8 + 4 + (t & 3)] = (short)__float2int_rn(-sn * 32767.0f);
+    }
+}
+__device__ inline unsigned long long fastb_dphi(const EpochParams& np, double fs) {
+    double r = np.carrFreq / fs;
+    r -= floor(r);
+    return __double2ull_rn(r * 18446744073709551616.0);
+}
+
+__device__ void fastb_build_tab_warp(FastbTab* tab, const EpochParams& np, double fs, unsigned* scratch, bool withRotation = true) {
     const int lane = threadIdx.x & 31;
     const double sigma = 2.0 * np.step, S = 1.0 / sigma;
     double r = np.carrFreq / fs;
@@ -55,14 +74,7 @@ __device__ void fastb_build_tab_warp(FastbTab* tab, const EpochParams& np, doubl
     double r0 = np.remCarr / 6.283185307179586476925286766559;
     r0 -= floor(r0);
     const unsigned long long phi0 = __double2ull_rn(r0 * 18446744073709551616.0);
-    short* w = reinterpret_cast<short*>(tab->w);   // word i: [wr(4i..4i+3) | wi(4i..4i+3)] as int16
-    for (int t = lane; t < 4 * (FASTB_NWORDS + 1); t += 32) {
-        unsigned long long ph = (unsigned long long)t * dphi;
-        float sn, cs;
-        sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
-        w[(t >> 2) * 8 + (t & 3)] = (short)__float2int_rn(cs * 32767.0f);
-        w[(t >> 2) * 8 + 4 + (t & 3)] = (short)__float2int_rn(-sn * 32767.0f);
-    }
+    if (withRotation) fastb_build_rot(tab, dphi, lane, 32);
     unsigned* thr = scratch;        // [20] unsorted thresholds
     unsigned* pos = scratch + 32;   // [20] sorted position of threshold k-1
     int ok = 1;
@@ -245,18 +257,25 @@ __device__ __forceinline__ bool fastb_unit(const FastbTab& tab, const EpochParam
 
 // ---- shared memory of the per-channel CTA ------------------------------------------------------------------------
 struct __align__(128) B2aSmem {
-    unsigned char tile[kB2aTileBytes];
+    unsigned char tile[2][kB2aTileBytes];   // epoch e in tile[e & 1]: the next block is staged while this one is correlated
     FastbTab tab;
     uint32_t bits[2][kPackedWordsDev];  // packed primaries: data, pilot (bit k of word w = chip 32 w + k)
     uint32_t ext[2][kPackedWordsDev];   // the same rotated by one chip (fastb_code12)
     int res[kB2aThreads / 32][12];      // warp sums, Q8 fixed point
     double sums[kNSum];
-    EpochParams p;
+    double v[12];                       // loop closure: {data, pilot} x {E, L, P} x {I, Q} as the discriminators take them
+    double pre[8];                      // discriminator pieces evaluated by parallel lanes (close_nco)
+    EpochParams p;                      // the epoch being correlated / about to be correlated
+    EpochParams pDone;                  // the epoch whose loops were just closed (output phase)
+    ChanState st;                       // channel state (thread 0 closes the loops on it)
+    CloseAux aux;
     unsigned scratch[64];
-    unsigned long long full;            // mbarrier: the staged block has arrived
-    long long tileBase;                 // window byte offset of tile[0]
-    int tileBytes;
+    unsigned long long full[2];         // mbarriers: the staged block has arrived
+    long long tileBase[2];              // window byte offset of tile[b][0]
+    int tileBytes[2];
     int run;
+    int eDone;                          // index of the epoch in pDone
+    int pad_;
 };
 
 // whole CTA (no barrier inside): the channel's code bits and their rotated copy
@@ -274,28 +293,28 @@ __device__ __forceinline__ void b2a_load_bits(const TrkDev& g, B2aSmem& sm, int 
     }
 }
 
-// thread 0: stage the block that starts at absolute sample `pos` (whatever of it the window holds); returns the bytes
-// requested (0: nothing to load, the barrier is not armed)
-__device__ __forceinline__ int b2a_issue_tile(const TrkDev& g, B2aSmem& sm, long long pos) {
+// thread 0: stage the block that starts at absolute sample `pos` (whatever of it the window holds) into buffer b;
+// returns the bytes requested (0: nothing to load, the barrier is not armed)
+__device__ __forceinline__ int b2a_issue_tile(const TrkDev& g, B2aSmem& sm, long long pos, int b) {
     const long long off = pos - g.winFirst;
     const long long base = off & ~15LL;
     const long long lim = (g.winLen + 16) & ~15LL;     // staged tiles may extend 16 bytes past winLen (set_window)
     long long bytes = lim - base;
     if (bytes > kB2aTileBytes) bytes = kB2aTileBytes;
-    sm.tileBase = base;
+    sm.tileBase[b] = base;
     if (off < 0 || bytes <= 0) {
-        sm.tileBytes = 0;
+        sm.tileBytes[b] = 0;
         return 0;
     }
-    sm.tileBytes = (int)bytes;
+    sm.tileBytes[b] = (int)bytes;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile was last read through the generic proxy
-    tma_load_1d(sm.tile, g.x + base, (unsigned)bytes, &sm.full);
+    tma_load_1d(sm.tile[b], g.x + base, (unsigned)bytes, &sm.full[b]);
     return (int)bytes;
 }
 
 // the correlator part of one epoch, whole CTA: per-warp Q8 sums -> sm.res
 __device__ __forceinline__ void b2a_correlate(const TrkDev& g, B2aSmem& sm, const EpochParams& p, unsigned guard,
-                                              unsigned& nFast, unsigned& nExact) {
+                                              unsigned& nFast, unsigned& nExact, int b) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long B0 = p.pos - g.winFirst;
     float acc[kNSum];
@@ -308,8 +327,8 @@ __device__ __forceinline__ void b2a_correlate(const TrkDev& g, B2aSmem& sm, cons
         fastb_exact_range(ex, g.x + B0, sm.bits[0], sm.bits[1], 0, 0, -100, 0, acc);
     }
     for (int u = tid; u < kB2aUnits; u += kB2aThreads) {
-        const bool ex = fastb_unit(sm.tab, p, sm.bits[0], sm.bits[1], sm.ext[0], sm.ext[1], sm.tile, sm.tileBase,
-                                   sm.tileBytes, B0, g.x + B0, g.d, g.fs, u, guard, acc);
+        const bool ex = fastb_unit(sm.tab, p, sm.bits[0], sm.bits[1], sm.ext[0], sm.ext[1], sm.tile[b], sm.tileBase[b],
+                                   sm.tileBytes[b], B0, g.x + B0, g.d, g.fs, u, guard, acc);
         nFast += !ex;
         nExact += ex;
     }
@@ -337,9 +356,55 @@ __device__ __forceinline__ void b2a_collect(const TrkDev& g, B2aSmem& sm) {
     __syncwarp();
 }
 
+// exact fmod(x, y) for 0 <= x, 0 < y, x/y < 2^52 (one fma; libdevice fmod iterates ~20 times here)
+__device__ __forceinline__ double b2a_fmod_pos(double x, double y) {
+    if (!(x >= 0.0)) return fmod(x, y);
+    const double n = floor(x / y);
+    double r = fma(-n, y, x);
+    if (r < 0.0) r += y;
+    if (r >= y) r -= y;
+    return r;
+}
+
+// warp 0: the discriminator pieces of tracking.m:337-377 in parallel lanes with uniform control flow (the same
+// expressions as close_nco evaluates when it gets no `pre`): square roots, arctangents and the exact fmod of the
+// carrier phase are what makes a one-thread loop closure slow.
+__device__ __forceinline__ void b2a_discriminators(const TrkDev& g, B2aSmem& sm, const EpochParams& p) {
+    const int lane = threadIdx.x & 31;
+    const double* s = sm.sums;
+    if (lane < 6) {            // data E, L, P as (I, Q)
+        const int o = lane >> 1 == 0 ? EPL_E : (lane >> 1 == 1 ? EPL_L : EPL_P);
+        sm.v[lane] = s[sum_idx(0, o, lane & 1)];
+    } else if (lane < 10) {    // pilot E, L as (I, Q)
+        const int k = lane - 6;
+        sm.v[lane] = s[sum_idx(1, k >> 1 == 0 ? EPL_E : EPL_L, k & 1)];
+    } else if (lane < 12) {    // pilot prompt rotated by exp(-i pi/2) (tracking.m:345): (re, im)
+        const double cr = 6.123233995736766e-17;  // cos(pi/2) in double
+        const double pIP = s[sum_idx(1, EPL_P, 0)], pQP = s[sum_idx(1, EPL_P, 1)];
+        sm.v[lane] = lane == 10 ? pIP * cr + pQP : pQP * cr - pIP;
+    }
+    __syncwarp();
+    const int l6 = lane < 6 ? lane : 0;   // lanes 0..5: data E, data L, data P, pilot E, pilot L, pilot P'
+    const double A = sm.v[2 * l6], B = sm.v[2 * l6 + 1];
+    const double mag = sqrt(A * A + B * B);
+    const double ang = atan(B / A) / 6.283185307179586476925286766559;
+    const double magN = __shfl_down_sync(0xffffffffu, mag, 1);
+    const double disc = (mag - magN) / (mag + magN);
+    const double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
+    const double fm = b2a_fmod_pos(trig, 6.283185307179586476925286766559);   // tracking.m:305 (trig >= 0)
+    if (lane == 2) sm.pre[0] = ang;
+    if (lane == 5) sm.pre[1] = ang;
+    if (lane == 0) sm.pre[2] = disc;
+    if (lane == 3) sm.pre[3] = disc;
+    if (lane == 6) sm.pre[4] = fm;
+    __syncwarp();
+}
+
 // Closed loop: grid = active channels.  Every launch runs each channel for up to g.maxEpochs epochs from its device-side
 // state, never past epoch index g.epochLimit, as far as the resident window allows (a short read stops the channel
-// exactly like tracking.m:246-251).
+// exactly like tracking.m:246-251).  Per epoch: correlate (all warps) | barrier | warp 0: sums, discriminators in
+// parallel lanes, loop filters + next NCO on lane 0 | barrier | next epoch's table (warp 0: thresholds, warps 1-4:
+// carrier rotation) while warp 15 formats and stores this epoch's outputs | barrier.
 __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     B2aSmem& sm = *reinterpret_cast<B2aSmem*>(dyn_smem);
@@ -347,62 +412,106 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
     const int c = g.act[blockIdx.x];
     if (!g.cc[c].active) return;
     b2a_load_bits(g, sm, c);
-    ChanState st;            // thread 0
-    int done = 0, pendingTile = 0;
+    int done = 0, pending[2] = {0, 0};   // thread 0: a bulk copy into tile[b] is in flight
     double* const out = g.out + (size_t)c * kNFields * g.capacity;
     const int cap = g.capacity;
     const unsigned guard = g.pad ? (1u << 24) : kFastGuard;   // g.pad: test hook, widens the guard band
     unsigned nFast = 0, nExact = 0;
-    unsigned phase = 0;
+    unsigned phase[2] = {0, 0};
+    int buf = 0;
     if (tid == 0) {
-        mbar_init(&sm.full, 1);
-        st = g.st[c];
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        sm.tileBytes[0] = sm.tileBytes[1] = 0;
+        sm.st = g.st[c];
         EpochParams np;
-        const bool okp = next_params(g, st, np), lim = st.epoch < g.epochLimit;
-        if (!okp && lim) out[(size_t)F_ABS * cap + st.epoch] = (double)st.pos;   // tracking.m:228 precedes the failed read
+        const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
+        if (!okp && lim) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;   // tracking.m:228 precedes the failed read
         sm.run = okp && lim && g.maxEpochs > 0;
+        sm.eDone = -1;
         if (sm.run) {
             sm.p = np;
-            pendingTile = b2a_issue_tile(g, sm, np.pos);
+            pending[0] = b2a_issue_tile(g, sm, np.pos, 0);
         }
     }
     __syncthreads();
     if (warp == 0 && sm.run) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
     __syncthreads();
+#ifdef BDS_FW_DEV
+    long long tW = 0, tC = 0, tL = 0, tT = 0, t0_ = 0;
+#define B2A_T(acc) { const long long t1_ = clock64(); acc += t1_ - t0_; t0_ = t1_; }
+    t0_ = clock64();
+#else
+#define B2A_T(acc)
+#endif
     while (sm.run) {
         const EpochParams p = sm.p;
-        if (sm.tileBytes > 0) mbar_wait(&sm.full, phase), phase ^= 1;
-        b2a_correlate(g, sm, p, guard, nFast, nExact);
+        // the next block starts at pos + blksize whatever the loops decide: stage it now, under this epoch's correlation
+        // (the other buffer was last read before the barrier that ended the previous iteration)
+        if (tid == 0) pending[buf ^ 1] = b2a_issue_tile(g, sm, p.pos + p.blksize, buf ^ 1);
+        if (sm.tileBytes[buf] > 0) {
+            mbar_wait(&sm.full[buf], phase[buf]);
+            phase[buf] ^= 1;
+            if (tid == 0) pending[buf] = 0;
+        }
+        B2A_T(tW)
+        b2a_correlate(g, sm, p, guard, nFast, nExact, buf);
         __syncthreads();   // every warp is done with the tile and the table; warp sums are visible
+        B2A_T(tC)
         if (warp == 0) {
             b2a_collect(g, sm);
+            b2a_discriminators(g, sm, p);
             if (lane == 0) {
-                pendingTile = b2a_issue_tile(g, sm, p.pos + p.blksize);   // the next block, while the loops close
-                const int e = st.epoch;
-                double outv[kNFields];
-                close_core(g, sm.sums, p, g.cc[c].chCodeFreq, st, outv);
-#pragma unroll
-                for (int f = 0; f < kNFields; ++f)
-                    if (field_written(g, f)) out[(size_t)f * cap + e] = outv[f];
-                __threadfence();
-                close_cno(g, c, e, st);
-                st.epoch = e + 1;
+                close_nco(g, sm.sums, p, g.cc[c].chCodeFreq, sm.st, sm.aux, sm.pre);
+                sm.pDone = p;
+                sm.eDone = sm.st.epoch;
+                sm.st.epoch += 1;
                 ++done;
                 EpochParams np;
-                const bool okp = next_params(g, st, np), lim = st.epoch < g.epochLimit;
-                if (!okp && lim) out[(size_t)F_ABS * cap + st.epoch] = (double)st.pos;
+                const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
+                if (!okp && lim) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;
                 const int run = okp && lim && done < g.maxEpochs;
                 if (run) sm.p = np;
                 sm.run = run;
             }
+        }
+        __syncthreads();   // the next epoch's NCO (sm.p), sm.run and the closure's by-products are visible
+        B2A_T(tL)
+        if (sm.run) {
+            if (warp == 0) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch, false);
+            else if (warp <= 4) fastb_build_rot(&sm.tab, fastb_dphi(sm.p, g.fs), tid - 32, 128);
+        }
+        if (warp == kB2aThreads / 32 - 1) {   // this epoch's outputs, off the critical path
+            __shared__ double outv[kNFields];
+            const int e = sm.eDone;
+            if (lane == 0) close_out(g, sm.sums, sm.pDone, sm.aux, outv);
             __syncwarp();
-            if (sm.run) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
+            for (int f = lane; f < kNFields; f += 32)
+                if (field_written(g, f)) out[(size_t)f * cap + e] = outv[f];
+            if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) close_cno(g, c, e, sm.st);   // touches cnoPrev only; thread 0 is past its use of sm.st
+            }
         }
         __syncthreads();
+        B2A_T(tT)
+        buf ^= 1;
     }
+#ifdef BDS_FW_DEV
+    if (tid == 0 && g.counters) {
+        atomicAdd(g.counters + 4, (unsigned long long)tW);
+        atomicAdd(g.counters + 5, (unsigned long long)tC);
+        atomicAdd(g.counters + 6, (unsigned long long)tL);
+        atomicAdd(g.counters + 7, (unsigned long long)tT);
+        atomicAdd(g.counters + 8, (unsigned long long)done);
+    }
+#endif
+#undef B2A_T
     if (tid == 0) {
-        if (pendingTile) mbar_wait(&sm.full, phase);   // never leave with a bulk copy in flight
-        g.st[c] = st;
+        for (int b = 0; b < 2; ++b)
+            if (pending[b]) mbar_wait(&sm.full[b], phase[b]);   // never leave with a bulk copy in flight
+        g.st[c] = sm.st;
     }
     __syncwarp();
     if (g.counters) {
@@ -423,17 +532,17 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_open_kernel(TrkDe
     const int ce = blockIdx.x, c = ce / nEpochs;
     b2a_load_bits(g, sm, c);
     if (tid == 0) {
-        mbar_init(&sm.full, 1);
+        mbar_init(&sm.full[0], 1);
         sm.p = params[ce];
-        b2a_issue_tile(g, sm, sm.p.pos);
+        b2a_issue_tile(g, sm, sm.p.pos, 0);
     }
     __syncthreads();
     if (warp == 0) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
     __syncthreads();
     const EpochParams p = sm.p;
-    if (sm.tileBytes > 0) mbar_wait(&sm.full, 0);
+    if (sm.tileBytes[0] > 0) mbar_wait(&sm.full[0], 0);
     unsigned nFast = 0, nExact = 0;
-    b2a_correlate(g, sm, p, g.pad ? (1u << 24) : kFastGuard, nFast, nExact);
+    b2a_correlate(g, sm, p, g.pad ? (1u << 24) : kFastGuard, nFast, nExact, 0);
     __syncthreads();
     if (warp == 0) {
         b2a_collect(g, sm);

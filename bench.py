@@ -32,6 +32,23 @@ N_CHANNELS = 60
 METRIC = "IF Msamples/s through 60-ch B1C tracking"
 UNIT = "Msamples/s"
 
+# tracking workloads: signal, reference function mirrored, samples per epoch, closed-loop Doppler range of the synthetic
+# scenario (B2a gets no code-Doppler aiding: SURVEY 8(d)), self spectral separation coefficient (dB/Hz) for the expected
+# C/N0 with the record's other satellites as noise, dominant kernel, CPU-baseline epochs per step
+TRACK = {
+    "track": dict(sig="B1C", mode="WB", spc=993750, max_doppler=4500.0, kappa_db=-64.8, kernel="trk_fw_kernel", cpu_epochs=2,
+                  cn0_total=45.0,   # synth: data 11/44 + pilot 33/44 of the 45 dB-Hz carrier
+                  what="WB tracking (data + QMBOC pilot)"),
+    "track_b2a": dict(sig="B2a", mode="B2a", spc=99375, max_doppler=100.0, kappa_db=-71.9, kernel="trk_b2a_unit_kernel",
+                      cpu_epochs=20, what="tracking (data + pilot)",
+                      cn0_total=48.01),   # synth: data and pilot at 45 dB-Hz EACH (equal amplitudes), B2a_CNo is their sum
+}
+
+
+def metric_name(args):
+    w = TRACK[args.workload]
+    return METRIC if args.workload == "track" else f"IF Msamples/s through {args.channels}-ch {w['sig']} tracking"
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -43,9 +60,11 @@ def parse():
                     help="length of the synthetic IF record (BASELINE config 4: 30 s)")
     ap.add_argument("--channels", type=int, default=N_CHANNELS)
     ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast"])
-    ap.add_argument("--workload", default="track", choices=["track", "acq_b2a", "acq_b1c"],
-                    help="track = the headline metric (BASELINE config 4); acq_b2a = secondary line, BASELINE config 2 "
-                         "(B2a 63-PRN x +-5 kHz acquisition grid)")
+    ap.add_argument("--workload", default="track", choices=["track", "track_b2a", "acq_b2a", "acq_b1c"],
+                    help="track = the headline metric (BASELINE config 4; --channels 12 = config 3); track_b2a = 60-channel "
+                         "B2a tracking; acq_b2a = BASELINE config 2 (B2a 63-PRN x +-5 kHz acquisition grid); acq_b1c")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --channels in total, sharded over the GPUs (BASELINE config 4); weak: --channels per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -55,6 +74,13 @@ def settings_b1c(n_ch, seconds):
     import bds3_b200 as B
     return B.b1c.initSettings(samplingFreq=FS, numberOfChannels=n_ch, pilotTRKflag=2,
                               msToProcess=int(round(seconds * 1000)))
+
+
+def settings_for(workload, n_ch, seconds):
+    import bds3_b200 as B
+    if TRACK[workload]["sig"] == "B1C":
+        return settings_b1c(n_ch, seconds)
+    return B.b2a.initSettings(numberOfChannels=n_ch, msToProcess=int(round(seconds * 1000)))
 
 
 def measured_traffic(kernel, channels, seconds, world):
@@ -126,7 +152,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement (C correlator + python loop closure), all host threads
 # ----------------------------------------------------------------------------------------------
-def cpu_track_sample(x, st, ch, n_epochs, threads):
+def cpu_track_sample(x, st, ch, n_epochs, threads, mode="WB"):
     """Tracks every channel of ``ch`` for n_epochs with the oracle on ``threads`` host threads.
     Returns wall seconds."""
     from concurrent.futures import ThreadPoolExecutor
@@ -135,10 +161,11 @@ def cpu_track_sample(x, st, ch, n_epochs, threads):
     c_oracle.lib()
     so = O.Settings(dict(st))
     so.numberOfChannels = 1
-    O.CalcWeighingFactor(so)  # warm scipy import outside the timed region
+    if mode == "WB":
+        O.CalcWeighingFactor(so)  # warm scipy import outside the timed region
 
     def one(c):
-        O.tracking("WB", x, [O.Settings(dict(c))], so, n_epochs=n_epochs, correlator=c_oracle.correlate_epoch)
+        O.tracking(mode, x, [O.Settings(dict(c))], so, n_epochs=n_epochs, correlator=c_oracle.correlate_epoch)
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
@@ -146,19 +173,20 @@ def cpu_track_sample(x, st, ch, n_epochs, threads):
     return time.perf_counter() - t0
 
 
-def workload_string(channels, seconds):
+def workload_string(channels, seconds, workload="track"):
     """config.workload shared by both arms (the reference arm times a bounded sample of it, see config.sample)"""
-    return (f"B1C {channels}-channel WB tracking (data + QMBOC pilot), fs=99.375 MHz int8 IF, {seconds:g} s record")
+    w = TRACK[workload]
+    return (f"{w['sig']} {channels}-channel {w['what']}, fs=99.375 MHz int8 IF, {seconds:g} s record")
 
 
-def host_record_numpy(st, sats, n):
+def host_record_numpy(st, sats, n, sig="B1C"):
     """Host record for the reference arm, rendered with numpy and the ORACLE's code generators: nothing of the product
     (libbdsgpu.so) is loaded in a `--impl reference` process.  Cached under /tmp (rendering 60 satellites takes a while)."""
     import hashlib
     import numpy as np
     import bds_oracle as O
     from bds3_b200 import synth          # pure-python scenario / signal model; does not load the CUDA library
-    key = hashlib.sha1(repr((n, [(s_.PRN, s_.doppler, s_.codeDelay, s_.carrPhase, s_.amplitude) for s_ in sats])).encode()).hexdigest()[:16]
+    key = hashlib.sha1(repr((sig, n, [(s_.PRN, s_.doppler, s_.codeDelay, s_.carrPhase, s_.amplitude) for s_ in sats])).encode()).hexdigest()[:16]
     path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"bds_ref_record_{key}.npy")
     if os.path.exists(path):
         try:
@@ -168,13 +196,16 @@ def host_record_numpy(st, sats, n):
         except Exception:
             pass
     from concurrent.futures import ThreadPoolExecutor
-    codes = {s_.PRN: (O.b1c_data_primary(s_.PRN), O.b1c_pilot_primary(s_.PRN)) for s_ in sats}
+    if sig == "B1C":
+        codes = {s_.PRN: (O.b1c_data_primary(s_.PRN), O.b1c_pilot_primary(s_.PRN)) for s_ in sats}
+    else:
+        codes = {s_.PRN: (O.generateB2aDataCode(s_.PRN), O.generateB2aPilotCode(s_.PRN)) for s_ in sats}
     # numpy releases the GIL in its kernels: render blocks of the record on all host threads
     nthr = os.cpu_count() or 1
     blk = max(1 << 16, (n + nthr - 1) // nthr)
     parts = [(o, min(blk, n - o)) for o in range(0, n, blk)]
     with ThreadPoolExecutor(max_workers=nthr) as ex:
-        xs = list(ex.map(lambda a: synth.synth_numpy("B1C", st, sats, a[1], first_sample=a[0], chunk=1 << 18,
+        xs = list(ex.map(lambda a: synth.synth_numpy(sig, st, sats, a[1], first_sample=a[0], chunk=1 << 18,
                                                      noise_seed=7919 + a[0], primary_codes=lambda prn: codes[prn]), parts))
     x = np.concatenate(xs)
     try:
@@ -195,29 +226,37 @@ def run_reference(args):
     from bds3_b200.settings import Settings
     import bds_oracle as O
     threads = os.cpu_count() or 1
-    n_ep = 2
-    st = Settings(dict(O.initSettings_B1C(samplingFreq=FS, numberOfChannels=args.channels, pilotTRKflag=2,
-                                          msToProcess=int(round(args.seconds * 1000)))))
-    sats = synth.make_sats(args.channels, st, "B1C")
-    n = int((n_ep + 1.2) * 993750)
-    x = host_record_numpy(st, sats, n)
-    ch = synth.channels_from_sats(sats, st, "B1C", freq_error=2.0)
+    if args.workload not in TRACK:
+        print(json.dumps({"impl": "reference", "unavailable": f"no reference arm for workload {args.workload}"}))
+        return
+    w = TRACK[args.workload]
+    n_ep, spc, mode = w["cpu_epochs"], w["spc"], w["mode"]
+    ms = int(round(args.seconds * 1000))
+    if w["sig"] == "B1C":
+        st = Settings(dict(O.initSettings_B1C(samplingFreq=FS, numberOfChannels=args.channels, pilotTRKflag=2, msToProcess=ms)))
+    else:
+        st = Settings(dict(O.initSettings_B2a(numberOfChannels=args.channels, msToProcess=ms)))
+    sats = synth.make_sats(args.channels, st, w["sig"], max_doppler=w["max_doppler"])
+    n = int((n_ep + 1.2) * spc) + spc
+    x = host_record_numpy(st, sats, n, w["sig"])
+    ch = synth.channels_from_sats(sats, st, w["sig"], freq_error=2.0)
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_track_sample(x, st, ch[:threads], 1, threads)
+        cpu_track_sample(x, st, ch[:threads], 1, threads, mode)
     times = []
     for _ in range(args.steps):
-        times.append(cpu_track_sample(x, st, ch, n_ep, threads))
+        times.append(cpu_track_sample(x, st, ch, n_ep, threads, mode))
     t = sum(times) / len(times)
-    val = n_ep * 993750 / t / 1e6
-    sample = (f"{args.channels} channels x {n_ep} epochs (10 ms each) per step; Msamples/s = IF samples the channels "
-              "advanced through / wall time, the same normalisation as the GPU arm (which runs every epoch of the record)")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+    val = n_ep * spc / t / 1e6
+    sample = (f"{args.channels} channels x {n_ep} epochs ({spc / FS * 1e3:g} ms each) per step; Msamples/s = IF samples the "
+              "channels advanced through / wall time, the same normalisation as the GPU arm (which runs every epoch of the record)")
+    line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_string(args.channels, args.seconds), "sample": sample},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_string(args.channels, args.seconds, args.workload), "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{args.channels} ch x {n_ep} epochs per step; float64 oracle restatement "
-                                       "of WB_tracking.m (C correlator + python loop closure); MATLAB unavailable"},
+                                       f"of {'WB_tracking.m' if mode == 'WB' else 'B2a tracking.m'} (C correlator + python loop "
+                                       "closure); MATLAB unavailable"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "native_so_loaded": repo_native_libraries()}
     print(json.dumps(line))
@@ -238,7 +277,7 @@ def repo_native_libraries():
 
 # ----------------------------------------------------------------------------------------------
 def self_check(sess, st, chans, n_epochs, x_dev, n_samples, mode="WB", injected_cn0=45.0, n_sampled_channels=3,
-               n_sampled_epochs=20):
+               n_sampled_epochs=20, kappa_db=-64.8):
     """Untimed checks on the result of the timed run (VERDICT r1 'make the headline run prove its own correctness'):
       * every channel completed every epoch;
       * the loop bookkeeping of EVERY epoch of EVERY channel follows from the device's own discriminators through the
@@ -262,11 +301,12 @@ def self_check(sess, st, chans, n_epochs, x_dev, n_samples, mode="WB", injected_
     assert len(act) == len(chans)
     mem = util.replay_loop_chain(mode, so, act, planes, N)                      # [N, 4, nch]
     lock = util.lock_report(mode, so, planes, N, seconds_tail=10.0)
-    # effective C/N0 with K-1 equal-power interferers: C / (N0 + (K-1) C kappa), kappa = BOC(1,1) self spectral
-    # separation coefficient (-64.8 dB/Hz); the estimator itself scatters by about +-1 dB over a 0.5 s interval
+    # effective C/N0 with K-1 equal-power interferers: C / (N0 + (K-1) C kappa), kappa = the signal's self spectral
+    # separation coefficient (BOC(1,1): -64.8 dB/Hz, BPSK(10): -71.9 dB/Hz); the estimator itself scatters by about
+    # +-1 dB over an interval
     K = int(st.numberOfChannels_total) if "numberOfChannels_total" in st else len(act)
     cn = 10 ** (injected_cn0 / 10)
-    eff = 10 * math.log10(1.0 / (1.0 / cn + max(0, K - 1) * 10 ** (-6.48)))
+    eff = 10 * math.log10(1.0 / (1.0 / cn + max(0, K - 1) * 10 ** (kappa_db / 10)))
     lo, hi = eff - 1.5, injected_cn0 + 1.0
     locked = (lock["data_pld_min"] > 0.9) & (lock["pilot_pld_min"] > 0.9) & (lock["cno_median"] > lo) & (lock["cno_median"] < hi)
     assert bool(locked.all()), ("channels out of lock", np.nonzero(~locked)[0].tolist(), lock["cno_median"].round(2).tolist(),
@@ -314,21 +354,27 @@ def run_b200(args):
     L.init(local)
     kern = {"auto": L.KERNEL_AUTO, "general": L.KERNEL_GENERAL, "fast": L.KERNEL_FAST}[args.kernel]
 
-    st = settings_b1c(args.channels, args.seconds)
-    sats = synth.make_sats(args.channels, st, "B1C")
-    chans = synth.channels_from_sats(sats, st, "B1C", freq_error=2.0)
+    w = TRACK[args.workload]
+    sig, mode, spc = w["sig"], w["mode"], w["spc"]
+    # strong scaling (BASELINE config 4): --channels in total over the ranks; weak: --channels on every rank
+    total_channels = args.channels * (world if args.scaling == "weak" else 1)
+    if total_channels > 63:
+        raise SystemExit("the synthetic scenario has one satellite per PRN: at most 63 channels in total")
+    st = settings_for(args.workload, total_channels, args.seconds)
+    sats = synth.make_sats(total_channels, st, sig, max_doppler=w["max_doppler"])
+    chans = synth.channels_from_sats(sats, st, sig, freq_error=2.0)
     n_samples = int(round(args.seconds * FS))
-    n_epochs = max(1, int(math.floor((n_samples - 993750) / 993760.0)) - 1)
+    n_epochs = max(1, int(math.floor((n_samples - spc) / (spc * (1 + 1e-5)))) - 1)
     # ---- synthetic IF, generated straight into HBM (identical on every rank: replicated record)
     x_dev = torch.empty(n_samples + 64, dtype=torch.int8, device="cuda")
-    synth.synth_device("B1C", st, sats, n_samples, out_ptr=x_dev.data_ptr())
+    synth.synth_device(sig, st, sats, n_samples, out_ptr=x_dev.data_ptr())
     torch.cuda.synchronize()
     # ---- channel shard of this rank (round robin)
     mine = _shard.shard_list(chans, rank, world)
     st_local = st.copy()
     st_local.numberOfChannels = len(mine)
-    st_local.numberOfChannels_total = args.channels   # satellites in the record (self_check: multiple-access noise)
-    sess = _track.TrackSession("WB", st_local, mine, kernel=kern, device_ptr=x_dev.data_ptr(), n_samples=n_samples)
+    st_local.numberOfChannels_total = total_channels   # satellites in the record (self_check: multiple-access noise)
+    sess = _track.TrackSession(mode, st_local, mine, kernel=kern, device_ptr=x_dev.data_ptr(), n_samples=n_samples)
 
     def barrier():
         torch.cuda.synchronize()
@@ -382,7 +428,8 @@ def run_b200(args):
     launches = B.launch_count() - launches0
     clocks = sampler.stop(s0, s1) if rank == 0 else None
     # ---- untimed: the run that was just timed proves its own correctness (every rank, its own channels)
-    check = self_check(sess, st_local, mine, n_epochs, x_dev, n_samples)
+    check = self_check(sess, st_local, mine, n_epochs, x_dev, n_samples, mode=mode, kappa_db=w["kappa_db"],
+                       injected_cn0=w["cn0_total"])
     if dist is not None:
         agg = torch.tensor([check["locked_channels"], check["channels"], check["fast_chips"], check["exact_chips"],
                             check["parity_epochs"]], device="cuda", dtype=torch.float64)
@@ -403,7 +450,7 @@ def run_b200(args):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms_max, step_ms_max = float(tmax[0]), float(tmax[1])
     total_ch_samples = float(tot[0])
-    if_samples = n_epochs * 993750.0  # IF samples the channels advanced through (nominal epoch length)
+    if_samples = n_epochs * float(spc)  # IF samples the channels advanced through (nominal epoch length)
     value = if_samples / (step_ms_max * 1e-3) / 1e6
 
     # ---- e2e: the public host-buffer call: pinned host IF -> (chunked H2D overlapped with tracking) -> D2H of the
@@ -413,7 +460,7 @@ def run_b200(args):
         x_host = torch.empty(n_samples, dtype=torch.int8).pin_memory()
         x_host.copy_(x_dev[:n_samples])
         torch.cuda.synchronize()
-        sess2 = _track.TrackSession("WB", st_local, mine, kernel=kern)     # no resident record: fed from the host
+        sess2 = _track.TrackSession(mode, st_local, mine, kernel=kern)     # no resident record: fed from the host
         # caller-owned result planes, pinned like the input (the MEX gateway would hand mxArrays here)
         res = {name: torch.empty((len(mine), n_epochs), dtype=torch.float64).pin_memory().numpy() for name in L.TRK_PLANES}
         times, parts = [], []
@@ -491,13 +538,13 @@ def run_b200(args):
         # algorithmic bytes: 1 byte per channel-sample; dominant kernel = trk_fw_kernel
         per_launch_bytes = total_ch_samples / world  # per-GPU launch
         achieved = per_launch_bytes / (dev_ms_max * 1e-3) / 1e9
-        kname = "trk_fw_kernel" if args.kernel != "general" else "trk_persistent_kernel"
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "strong",
+        kname = w["kernel"] if args.kernel != "general" else "trk_persistent_kernel"
+        line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32 accumulate / f64 loop closure (int8 IF)", "data": "synthetic",
-                "config": {"workload": workload_string(args.channels, args.seconds),
+                "config": {"workload": workload_string(total_channels, args.seconds, args.workload),
                            "epochs_per_channel": n_epochs,
-                           "parallelism": f"channels round-robin over {world} GPU(s), IF replicated",
+                           "parallelism": f"{total_channels} channels round-robin over {world} GPU(s), IF replicated",
                            "l2": f"input {n_samples / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
                            "kernel": args.kernel, "x_realtime": value / (FS / 1e6)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -513,12 +560,12 @@ def run_b200(args):
                 "exact_chip_frac": check["exact_chip_frac"], "self_check": check}
         if not args.no_cpu_baseline and world >= 1:
             threads = os.cpu_count() or 1
-            n_ep = 2
-            nh = int((n_ep + 1.2) * 993750)
+            n_ep = w["cpu_epochs"]
+            nh = int((n_ep + 1.2) * spc) + spc
             xh = x_dev[:nh].cpu().numpy()
-            t = cpu_track_sample(xh, st, chans, n_ep, threads)
-            line["cpu_baseline"] = {"value": n_ep * 993750 / t / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{args.channels} ch x {n_ep} epochs, float64 oracle restatement "
+            t = cpu_track_sample(xh, st, chans, n_ep, threads, mode)
+            line["cpu_baseline"] = {"value": n_ep * spc / t / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{total_channels} ch x {n_ep} epochs, float64 oracle restatement "
                                               "(C correlator), all host threads; MATLAB unavailable"}
         print(json.dumps(line))
     sess.close()

@@ -62,6 +62,19 @@ template <typename T> static inline T __reduce_add_sync(unsigned, T v) {
     g_warp_bar[w]->arrive_and_wait();
     return (T)r;
 }
+static inline double __shfl_down_sync(unsigned, double v, int d) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    long long b;
+    std::memcpy(&b, &v, 8);
+    g_warp_val[w][l] = b;
+    g_warp_bar[w]->arrive_and_wait();
+    b = g_warp_val[w][l + d < 32 ? l + d : l];
+    g_warp_bar[w]->arrive_and_wait();
+    double r;
+    std::memcpy(&r, &b, 8);
+    return r;
+}
+#define __shared__ static
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }

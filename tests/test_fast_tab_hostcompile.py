@@ -73,7 +73,8 @@ def b2a_lib(tmp_path_factory):
              blk(trk, r"struct EpochParams \{"), blk(fast, r"struct ExactCtx \{"),
              blk(fast, r"__device__ __forceinline__ double colon_elem_f"), blk(fast, r"__device__ __forceinline__ int bit_of"),
              inc, "constexpr int kB2aUnits = 10230 / FASTB_CHIPS;\n",
-             blk(b2a, r"struct __align__\(16\) FastbTab \{"), blk(b2a, r"__device__ void fastb_build_tab_warp"),
+             blk(b2a, r"struct __align__\(16\) FastbTab \{"), blk(b2a, r"__device__ inline void fastb_build_rot"),
+             blk(b2a, r"__device__ void fastb_build_tab_warp"),
              blk(b2a, r"__device__ inline void make_exact_ctx_b2a"), blk(b2a, r"__device__ __noinline__ void fastb_exact_range"),
              blk(b2a, r"__device__ __forceinline__ unsigned fastb_code12"), blk(b2a, r"__device__ __forceinline__ bool fastb_unit"),
              B2.DRIVER, B2A_DRIVER]

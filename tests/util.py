@@ -137,14 +137,22 @@ def replay_loop_chain(mode, s, chans, planes, n_epochs):
     for e in range(n_epochs):
         mem[e] = (d2, d1, old_nco, old_err)
         ce = g["pllDiscr"][:, e]
+        d1_prev = d1
         d2 = d2 + ce * pf3
         d1 = d2 + ce * pf2 + d1
         nco = d1 + ce * pf1
         np.testing.assert_allclose(g["pllDiscrFilt"][:, e], nco, rtol=1e-12, atol=1e-13)
+        # continue from the DEVICE's filter memories (recovered from its outputs), so that every epoch is checked as one
+        # step and the rounding differences of 30 000 accumulations (fma on the device, two roundings here) do not add up
+        nco = g["pllDiscrFilt"][:, e]
+        d1_dev = nco - ce * pf1
+        d2 = d1_dev - ce * pf2 - d1_prev
+        d1 = d1_dev
         de = g["dllDiscr"][:, e]
         cn = old_nco + (tau2 / tau1) * (de - old_err) + de * (PDI / tau1)
-        old_nco, old_err = cn, de
         np.testing.assert_allclose(g["dllDiscrFilt"][:, e], cn, rtol=1e-12, atol=1e-13)
+        cn = g["dllDiscrFilt"][:, e]
+        old_nco, old_err = cn, de
         step = g["codeFreq"][:, e] / fs
         rem = g["remCodePhase"][:, e]
         blk = np.ceil((L - rem) / step)
