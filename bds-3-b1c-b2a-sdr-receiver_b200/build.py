@@ -34,7 +34,8 @@ def _newer(src: str, dst: str) -> bool:
     if not os.path.exists(dst):
         return True
     t = os.path.getmtime(dst)
-    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    # headers, the generated chip bodies and their generators (a regenerated .inc must rebuild the objects)
+    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc")) or f.startswith("gen_fast_")]
     deps.append(os.path.join(HERE, "..", "include", "bdsgpu.h"))
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps)

@@ -679,7 +679,6 @@ struct bds_trk {
     // mmap'd file
     void* map = nullptr;
     size_t mapLen = 0;
-    bool mapUploaded = false;
 };
 
 namespace {
@@ -714,6 +713,7 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.x = h->dX;
     g.winFirst = h->winFirst;
     g.winLen = h->winLen;
+    g.winStage = h->ownX ? ((h->winLen + 16) & ~15LL) : (h->winLen & ~15LL);
     g.mode = h->mode;
     mode_flags(h->mode, h->cfg.pilotTRKflag, g.hasPilot, g.hasP61);
     g.nCh = h->nCh;
@@ -996,9 +996,7 @@ int set_window(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long first
         if (h->ownX && h->dX) cudaFree(h->dX);
         h->dX = const_cast<int8_t*>(x);
         h->ownX = false;
-        h->xCap = n;
-        // kernels read whole 16-byte chunks / TMA tiles: keep the last 32 bytes of a caller-owned buffer as slack
-        n = n > 32 ? n - 32 : 0;
+        h->xCap = n;   // used in place, all n samples: nothing is read past x[n-1] (TrkDev::winStage)
     } else {
         if (!h->ownX || h->xCap < n + 64) {
             if (h->ownX && h->dX) cudaFree(h->dX);
@@ -1070,6 +1068,7 @@ int bds_track_feed(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long f
 }
 
 int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs);
+static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs, long long first);
 
 // One launch of the persistent kernel on the session's stream: up to maxEpochs more epochs per channel,
 // no epoch index >= epochLimit, over the currently resident window.
@@ -1101,9 +1100,26 @@ static int launch_run(bds_trk* h, int maxEpochs, int epochLimit) {
 
 int bds_track_run_async(bds_trk* h, int n_epochs) {
     if (!h || n_epochs <= 0) return set_error(BDS_ERR_ARG, "bds_track_run: bad arguments");
-    if (h->map && !h->mapUploaded) {  // file-backed session: first run streams the mapping to the device
-        h->mapUploaded = true;
-        return bds_track_run_streamed(h, (const int8_t*)h->map, h->mapLen, 0, n_epochs);
+    if (h->map) {
+        // file-backed session (the reference's fid): like the reference's one fread per epoch, only the part of the file
+        // the requested epochs can touch is brought in - from the earliest channel position to the latest one plus
+        // n_epochs + 1 code periods at the slowest plausible code rate - streamed under the tracking kernel
+        int rc = bds_track_sync(h);
+        if (rc) return rc;
+        long long lo = LLONG_MAX, hi = 0;
+        const double spc = h->cfg.samplingFreq / (h->cfg.codeFreqBasis / (double)h->cfg.codeLength);
+        const long long span = (long long)std::ceil(spc * (1.0 + 1e-4) * (n_epochs + 1)) + 64;
+        for (int c = 0; c < h->nCh; ++c) {
+            if (h->ch[c].PRN == 0) continue;
+            lo = std::min(lo, h->hSt[c].pos);
+            hi = std::max(hi, h->hSt[c].pos + span);
+        }
+        if (lo == LLONG_MAX) lo = hi = 0;
+        if (lo >= (long long)h->mapLen) lo = (long long)h->mapLen - 1;   // past the end of the file: the run reports the short read
+        lo = std::max(0LL, lo) & ~4095LL;                       // page aligned in the mapping, 16-byte aligned on the device
+        hi = std::min(hi, (long long)h->mapLen);
+        if (hi <= lo) hi = std::min((long long)h->mapLen, lo + 1);   // nothing left: the run reports the short read
+        return run_streamed_from(h, (const int8_t*)h->map + lo, (size_t)(hi - lo), 0, n_epochs, lo);
     }
     int rc = BDS_OK;
     if (h->pending) {  // the output block may be re-allocated below: finish the previous run first
@@ -1127,6 +1143,11 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
 // runs out of samples stops exactly like a short read and is resumed from its device-side state by the
 // next launch).  Loop state never leaves the device between launches.
 int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs) {
+    return run_streamed_from(h, x, n, chunk_bytes, n_epochs, 0);
+}
+
+// x[n] holds samples [first, first + n) of the record
+static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs, long long first) {
     if (!h || !x || n == 0 || n_epochs <= 0) return set_error(BDS_ERR_ARG, "bds_track_run_streamed: bad arguments");
     int rc = BDS_OK;
     if (h->pending) {
@@ -1167,7 +1188,7 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
         BDS_CUDA(cudaEventRecord(h->chunkEv[i], h->copyStream));
         return BDS_OK;
     };
-    h->winFirst = 0;
+    h->winFirst = first;
     BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
     rc = copy_chunk(0);
     if (rc) return rc;
@@ -1212,7 +1233,7 @@ int bds_track_run_window(bds_trk* h, const int8_t* x_dev, size_t n_avail, int ep
     h->ownX = false;
     h->xCap = n_avail;
     h->winFirst = 0;
-    h->winLen = n_avail > 32 ? (long long)n_avail - 32 : 0;   // kernels read whole 16-byte chunks / TMA tiles
+    h->winLen = (long long)n_avail;   // nothing is read past x_dev[n_avail-1] (TrkDev::winStage)
     if (!h->pending) BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
     rc = launch_run(h, epoch_limit, epoch_limit);
     if (rc) return rc;
@@ -1470,9 +1491,10 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     std::memset(&g, 0, sizeof(g));
     g.x = dX;
     g.winFirst = 0;
-    // staged tiles may extend 16 bytes past winLen: a host record was copied with 64 bytes of slack, a caller-owned
-    // device buffer has none
-    g.winLen = x_loc == BDS_LOC_HOST ? (long long)n : (long long)n - 16;
+    // staged tiles may extend 16 bytes past winLen only where the buffer has slack: a host record was copied with 64
+    // bytes of it, a caller-owned device buffer has none
+    g.winLen = (long long)n;
+    g.winStage = x_loc == BDS_LOC_HOST ? (((long long)n + 16) & ~15LL) : ((long long)n & ~15LL);
     g.mode = mode;
     g.hasPilot = hp;
     g.hasP61 = h6;

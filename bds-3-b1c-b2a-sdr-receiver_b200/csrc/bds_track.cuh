@@ -58,6 +58,9 @@ struct TrkDev {
     const int8_t* x;      // resident IF window
     long long winFirst;   // absolute index of x[0]
     long long winLen;
+    long long winStage;   // bytes of the window a TMA tile may cover: winLen rounded up to 16 when the buffer has slack past
+                          // winLen (session-owned records), rounded DOWN for caller-owned device records (no over-read;
+                          // the last partial 16 bytes are then read per sample by the exact path)
     int mode, hasPilot, hasP61, nCh;
     int S, nAct, maxEpochs, capacity;
     int cnoCap, cnoInterval, kernelKind, pad;

@@ -298,7 +298,7 @@ __device__ __forceinline__ void b2a_load_bits(const TrkDev& g, B2aSmem& sm, int 
 __device__ __forceinline__ int b2a_issue_tile(const TrkDev& g, B2aSmem& sm, long long pos, int b) {
     const long long off = pos - g.winFirst;
     const long long base = off & ~15LL;
-    const long long lim = (g.winLen + 16) & ~15LL;     // staged tiles may extend 16 bytes past winLen (set_window)
+    const long long lim = g.winStage;                  // what a staged tile may cover (see TrkDev)
     long long bytes = lim - base;
     if (bytes > kB2aTileBytes) bytes = kB2aTileBytes;
     sm.tileBase[b] = base;

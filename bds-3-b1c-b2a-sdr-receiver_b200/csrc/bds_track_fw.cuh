@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
                 B0 = P.pos - g.winFirst;
             }
             const int cLo = sl * cps, cHi = min(10230, cLo + cps);  // host guarantees S = ceil(10230 / cps): never empty
-            const long long gMax = (g.winLen + 16) & ~15LL;         // every IF buffer has >= 16 bytes of slack past winLen
+            const long long gMax = g.winStage;                      // what a staged tile may cover (see TrkDev)
             int c0 = cLo;
             do {
                 const int cEnd = min(c0 + kFwChips, cHi);

@@ -172,7 +172,8 @@ typedef struct bds_trk_out {
 typedef struct bds_trk bds_trk;
 
 /* Open a tracking session on the IF record x[n] (real int8).  With BDS_LOC_HOST the
- * record is copied to the device; with BDS_LOC_DEVICE it is used in place.
+ * record is copied to the device; with BDS_LOC_DEVICE it is used in place (16-byte aligned; all n samples
+ * are usable and nothing is read past x[n-1], so an epoch may end on the record's last sample).
  * skipNumberOfBytes is settings.skipNumberOfBytes; channel blocks start at
  * skip + codePhase - 1 (WB_tracking.m:174-176). */
 int bds_track_open(int mode, const bds_trk_cfg* cfg, const int8_t* x, size_t n, int x_loc,
@@ -200,7 +201,7 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
 /* Device-record variant for a record that is still arriving on the device (multi-GPU: every rank uploads 1/N of
  * each chunk and the ranks all-gather it over NVLink): one asynchronous launch over the first n_avail samples of
  * x_dev (valid and device-synchronised by the caller); channels stop at the end of the data or at epoch index
- * epoch_limit and are resumed by the next call with a larger n_avail.  x_dev needs 32 bytes of slack. */
+ * epoch_limit and are resumed by the next call with a larger n_avail.  Nothing is read past x_dev[n_avail-1]. */
 int bds_track_run_window(bds_trk* h, const int8_t* x_dev, size_t n_avail, int epoch_limit);
 int bds_track_sync(bds_trk* h);
 int bds_track_fetch(bds_trk* h, const bds_trk_out* out, int out_stride);

@@ -321,3 +321,65 @@ def test_run_window_on_an_arriving_device_record():
     assert list(got["epochsDone"]) == [N, N]
     for k in want:
         np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+
+
+@pytest.mark.parametrize("mode,kernel", [("WB", "fast"), ("WB", "general"), ("B2a", "fast")])
+def test_device_record_that_ends_on_the_last_sample_of_an_epoch(mode, kernel):
+    """A caller-owned device record is used in place, all n samples of it: the epoch whose block ends on the record's
+    last sample completes (WB_tracking.m:265-283 reads exactly blksize samples), nothing is read past it, and the next
+    epoch is the short read."""
+    s, sats, x, ch = util.record(mode, 2, 0.13 if mode == "WB" else 0.02)
+    ps = util.product_settings(s)
+    kern = L.KERNEL_GENERAL if kernel == "general" else L.KERNEL_FAST
+    N = 6
+    ref, _ = _track.run_tracking(mode, x, ch[:1], ps, n_epochs=N + 1, kernel=kern, raw=True)
+    # the first channel's block of epoch N-1 ends at absoluteSample[N] (start of the following block)
+    n_exact = int(ref[0].absoluteSample[N])
+    p = C.c_void_p()
+    L.check(L.lib().bds_dev_alloc(C.byref(p), n_exact))          # no slack on purpose
+    try:
+        L.check(L.lib().bds_memcpy_h2d(p, L.ptr(x), n_exact))
+        st1 = ps.copy()
+        st1.numberOfChannels = 1
+        with _track.TrackSession(mode, st1, ch[:1], kernel=kern, device_ptr=p.value, n_samples=n_exact) as ses:
+            ses.run_async(N + 1)
+            got = ses.fetch(N + 1, raw=True)
+        assert int(got["epochsDone"][0]) == N
+        for k in ("absoluteSample", "carrFreq", "codeFreq", "remCodePhase"):
+            np.testing.assert_array_equal(got[k][0, :N], ref[0][k][:N], err_msg=k)
+        np.testing.assert_array_equal(got["raw"][0, :N - 1], ref[0].raw[:N - 1])
+        # the last epoch: with no slack behind the record the chip-synchronous kernels stage whole 16-byte pieces only and
+        # take the final chips through their exact per-sample path (a few Q8 units of different rounding); the general
+        # kernel is bit-identical
+        sc = util.family_scale(ref[0].raw[N - 1][None, :])[0]
+        err = np.abs(got["raw"][0, N - 1] - ref[0].raw[N - 1]) / sc
+        assert np.max(err[np.isfinite(err)]) <= (0.0 if kernel == "general" else 1e-6)
+    finally:
+        L.lib().bds_dev_free(p)
+
+
+def test_file_backed_session_reads_only_what_the_epochs_need(tmp_path):
+    """bds_track_open_file behind a large skipNumberOfBytes and a long (sparse) tail: the requested epochs are tracked
+    from the part of the file they touch (the reference reads one block per epoch), a second run resumes where the
+    first stopped, and the result equals the resident-record run."""
+    s, sats, x, ch = util.record("WB", 2, 0.13)
+    ps = util.product_settings(s)
+    skip = 3 * 4096 + 123
+    ps_skip = ps.copy()
+    ps_skip.skipNumberOfBytes = skip
+    path = tmp_path / "if_skip.bin"
+    with open(path, "wb") as f:
+        f.write(bytes(skip))
+        f.write(x.tobytes())
+        f.truncate(skip + x.size + (6 << 30))       # 6 GiB of sparse zeros after the record
+    want, _ = _track.run_tracking("WB", x, ch, ps, n_epochs=9, raw=True)
+    with _track.TrackSession("WB", ps_skip, ch, source=str(path)) as ses:
+        ses.run_async(4)
+        ses.sync()
+        ses.run_async(5)
+        got = ses.fetch(9, raw=True)
+    assert list(got["epochsDone"]) == [9, 9]
+    for c in range(2):
+        np.testing.assert_array_equal(got["absoluteSample"][c], want[c].absoluteSample + skip)
+        for k in ("carrFreq", "codeFreq", "I_P", "Q_P"):
+            np.testing.assert_array_equal(got[k][c], want[c][k], err_msg=k)
