@@ -29,7 +29,8 @@ class bds_trk_cfg(C.Structure):
                 ("CNoInterval", C.c_int32), ("tau1code", C.c_double), ("tau2code", C.c_double),
                 ("pf3", C.c_double), ("pf2", C.c_double), ("pf1", C.c_double), ("wbFactor", C.c_double),
                 ("kernel", C.c_int32), ("reserved", C.c_int32), ("fwPassesPerTask", C.c_int32),
-                ("fwPrefetch", C.c_int32), ("debug", C.c_int32), ("traceTickets", C.c_int32)]
+                ("fwPrefetch", C.c_int32), ("debug", C.c_int32), ("traceTickets", C.c_int32),
+                ("lockLossPLD", C.c_double), ("lockLossIntervals", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class bds_channel(C.Structure):
@@ -46,7 +47,7 @@ CNO_PLANES = ["DataCNo", "DataPLD", "PilotCNo", "PilotPLD", "TotalCNo"]
 
 class bds_trk_out(C.Structure):
     _fields_ = ([(n, _PD) for n in TRK_PLANES] + [(n, _PD) for n in CNO_PLANES] +
-                [("raw", _PD), ("epochsDone", C.POINTER(C.c_int32))])
+                [("raw", _PD), ("epochsDone", C.POINTER(C.c_int32)), ("lockLostEpoch", C.POINTER(C.c_int32))])
 
 
 class bds_sat(C.Structure):
@@ -70,7 +71,7 @@ EXPORTS = ["bds_abi_version", "bds_init", "bds_shutdown", "bds_last_error", "bds
            "bds_gen_code", "bds_make_code_table", "bds_acquire", "bds_track_open", "bds_track_open_file",
            "bds_track_feed", "bds_track_run", "bds_track_run_async", "bds_track_run_streamed", "bds_track_run_window", "bds_track_sync", "bds_track_fetch",
            "bds_track_device_block", "bds_track_stats", "bds_track_counters", "bds_track_dump_trace", "bds_track_reset", "bds_track_close",
-           "bds_track_correlate_open_loop", "bds_synth_if", "bds_dev_alloc", "bds_dev_free",
+           "bds_track_correlate_open_loop", "bds_secondary_code", "bds_frame_sync", "bds_synth_if", "bds_dev_alloc", "bds_dev_free",
            "bds_host_alloc_pinned", "bds_host_free_pinned", "bds_memcpy_h2d", "bds_memcpy_d2h", "bds_dev_sync"]
 
 _lib = None
@@ -117,6 +118,8 @@ def lib():
     L.bds_track_close.restype = None
     L.bds_track_correlate_open_loop.argtypes = [C.c_int, C.POINTER(bds_trk_cfg), vp, C.c_size_t, C.c_int, vp,
                                                 C.c_int, C.c_int, vp, vp]
+    L.bds_secondary_code.argtypes = [C.c_int, vp]
+    L.bds_frame_sync.argtypes = [C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]
     L.bds_synth_if.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(bds_sat), C.c_int,
                                C.c_double, C.c_uint64, C.c_longlong, C.c_size_t, vp, C.c_int]
     L.bds_dev_alloc.argtypes = [C.POINTER(vp), C.c_size_t]

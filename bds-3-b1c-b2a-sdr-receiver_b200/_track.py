@@ -38,6 +38,10 @@ def make_cfg(mode, settings, kernel=L.KERNEL_AUTO, tuning=None) -> L.bds_trk_cfg
                         intTime=settings.intTime, pilotTRKflag=int(settings.pilotTRKflag),
                         CNoInterval=int(settings.CNoInterval), tau1code=tau1, tau2code=tau2, pf3=pf3, pf2=pf2,
                         pf1=pf1, wbFactor=factor, kernel=int(kernel), reserved=0)
+    # lock-loss status / early channel drop: an extension of the reference, off unless the settings carry it
+    if settings.get("lockLossPLD", 0):
+        cfg.lockLossPLD = float(settings.lockLossPLD)
+        cfg.lockLossIntervals = int(settings.get("lockLossIntervals", 1))
     for k, v in (tuning or {}).items():
         setattr(cfg, k, int(v))
     return cfg
@@ -191,6 +195,9 @@ class TrackSession:
         done = np.zeros(self.nch, dtype=np.int32)
         out.epochsDone = done.ctypes.data_as(C.POINTER(C.c_int32))
         planes["epochsDone"] = done
+        lost = np.zeros(self.nch, dtype=np.int32)
+        out.lockLostEpoch = lost.ctypes.data_as(C.POINTER(C.c_int32))
+        planes["lockLostEpoch"] = lost
         L.check(L.lib().bds_track_fetch(self.h, C.byref(out), N))
         return planes
 
@@ -225,9 +232,12 @@ def assemble(mode, settings, channel, planes, N):
                 tr.PilotPLD[:ncd] = planes["PilotPLD"][c, :ncd]
                 tr[cno_name][:ncd] = planes["TotalCNo"][c, :ncd]
             tr.PRN = int(ch.PRN)                                        # WB_tracking.m:167
+            lost = int(planes["lockLostEpoch"][c]) if "lockLostEpoch" in planes else 0
             if done >= N:
                 tr.status = ch.status                                    # WB_tracking.m:485-488
-            else:
+            elif lost:
+                tr.lockLostEpoch = lost      # extension (settings.lockLossPLD): dropped for loss of lock, status stays '-',
+            else:                            # the following channels are tracked (not the reference's bare return)
                 stopped = True
             if "raw" in planes:
                 tr.raw = planes["raw"][c].copy()
@@ -245,3 +255,17 @@ def run_tracking(mode, source, channel, settings, n_epochs=None, kernel=L.KERNEL
         planes = s.fetch(N, raw=raw)
         run_tracking.last_counters = s.counters()
     return assemble(mode, settings, channel, planes, N), channel
+
+
+def frame_sync(signal, prompt, prn=0, want_xcorr=True, index_cap=4096):
+    """(XcorrResult for lags >= 0, index (1-based, ascending)) of bds_frame_sync: the correlation that opens the
+    reference's nav decoding (BCNAV1decoding.m:66-91 / BCNAV2decoding.m:69-97), on the device."""
+    v = np.ascontiguousarray(prompt, dtype=np.float64).reshape(-1)
+    x = np.zeros(v.size) if want_xcorr else None
+    idx = np.zeros(index_cap, dtype=np.int32)
+    n = C.c_int32(0)
+    L.check(L.lib().bds_frame_sync(int(signal), int(prn), L.ptr(v), v.size, L.LOC_HOST, L.ptr(x) if want_xcorr else None,
+                                   L.ptr(idx), index_cap, C.byref(n)))
+    if n.value > index_cap:
+        return frame_sync(signal, prompt, prn, want_xcorr, n.value)
+    return x, idx[:n.value].astype(np.int64)

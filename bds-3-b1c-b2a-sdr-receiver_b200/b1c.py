@@ -47,6 +47,21 @@ def NB_tracking(fid, channel, settings, **kw):
     return _track.run_tracking("NB", fid, channel, settings, **kw)
 
 
+def generate2ndCode(PRN):
+    """Secondary = generate2ndCode(PRN)   (BDS-3_B1C/include/generate2ndCode.m:1): 1800 chips, +-1"""
+    import ctypes as C
+    out = np.zeros(1800, dtype=np.int8)
+    L.check(L.lib().bds_secondary_code(int(PRN), out.ctypes.data_as(C.c_void_p)))
+    return out.astype(np.float64)
+
+
+def frameSync(trackResult, settings):
+    """The frame-synchronisation correlation of BCNAV1decoding.m:66-91 on the device: (XcorrResult for lags >= 0,
+    index) with index = find(abs(XcorrResult) >= 1799.5) (1-based epoch numbers where a secondary-code period starts)."""
+    bits = trackResult.Pilot_I_P if settings.pilotTRKflag == 2 else trackResult.Pilot_Q_P
+    return _track.frame_sync(L.SIG_B1C, bits, trackResult.PRN)
+
+
 def postProcessing(settings, acqResults=None):
     """Acquisition -> preRun -> tracking part of BDS-3_B1C/postProcessing.m:61-149 (navigation and
     plots stay in MATLAB).  Returns (acqResults, channel, trackResults)."""

@@ -37,6 +37,12 @@ def tracking(fid, channel, settings, **kw):
     return _track.run_tracking("B2a", fid, channel, settings, **kw)
 
 
+def frameSync(I_P_InputBits):
+    """The preamble correlation of BCNAV2decoding.m:69-97 on the device: (tlmXcorrResult for lags >= 0, index) with
+    index = find(abs(.) > 115)."""
+    return _track.frame_sync(L.SIG_B2A, I_P_InputBits)
+
+
 def postProcessing(settings, acqResults=None):
     """BDS-3_B2a/postProcessing.m:57-129 up to tracking."""
     with open(settings.fileName, "rb") as fid:

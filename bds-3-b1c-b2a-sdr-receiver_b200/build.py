@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, os.environ.get("BDS_LIB_NAME", "libbdsgpu.so"))
 OBJ = OBJ + os.environ.get("BDS_OBJ_SUFFIX", "")
-SOURCES = ["bds_api.cu", "bds_codes.cpp", "bds_track.cu", "bds_acq.cu", "bds_synth.cu"]
+SOURCES = ["bds_api.cu", "bds_codes.cpp", "bds_track.cu", "bds_acq.cu", "bds_synth.cu", "bds_nav.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v", "-DBDS_BUILDING"]

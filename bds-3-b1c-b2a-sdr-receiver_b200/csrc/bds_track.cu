@@ -247,7 +247,7 @@ __device__ bool next_params(const TrkDev& g, const ChanState& st, EpochParams& n
     np.remCarr = st.remCarrPhase;
     np.pad = 0;
     long long off = np.pos - g.winFirst;
-    return off >= 0 && off + np.blksize <= g.winLen && np.blksize > 0;
+    return off >= 0 && off + np.blksize <= g.winLen && np.blksize > 0 && st.lockLost == 0;
 }
 
 // Loop-closure arithmetic of one epoch (no memory traffic), in two phases so that a latency-critical caller can publish
@@ -378,6 +378,17 @@ __device__ __forceinline__ bool field_written(const TrkDev& g, int f) {
     return true;
 }
 
+// Lock-loss status and early channel drop (an extension: the reference copies channel.status
+// unconditionally, WB_tracking.m:485-488).  Off unless cfg.lockLossPLD > 0.  Evaluated at the end of every C/N0
+// interval on the lock detector of Calc_CNo_PLD.m:70-73 (the pilot's when the mode tracks a pilot, else the data
+// component's): lockLossIntervals consecutive values below lockLossPLD drop the channel - it runs no further epoch.
+__device__ __forceinline__ void lock_update(const TrkDev& g, ChanState& st, double pldData, double pldPilot, int e) {
+    if (!(g.lockPLD > 0.0)) return;
+    const double pld = g.hasPilot ? pldPilot : pldData;
+    st.lowLock = pld < g.lockPLD ? st.lowLock + 1 : 0;    // NaN (0/0: no signal at all) counts as locked, like a comparison in MATLAB
+    if (st.lowLock >= g.lockIntervals && st.lockLost == 0) st.lockLost = e + 1;
+}
+
 // C/N0 + lock detector every CNoInterval epochs (WB:459-481), single thread
 __device__ void close_cno(const TrkDev& g, int c, int e, ChanState& st) {
     if (!(g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0)) return;
@@ -408,6 +419,7 @@ __device__ void close_cno(const TrkDev& g, int c, int e, ChanState& st) {
     st.cnoPrev[0] = c0;
     st.cnoPrev[1] = c1;
     st.cnoPrev[2] = c2;
+    lock_update(g, st, dp, pp, e);
 }
 
 // Single-thread closure used by the general kernel: loads state, closes the loops, stores outputs + state and
@@ -430,7 +442,7 @@ __device__ void close_epoch(const TrkDev& g, int c, int e, const double* s /*18 
     // stage the next epoch's params; the CTA publishes them (publish_next)
     EpochParams np;
     bool ok = next_params(g, st, np) && e + 1 < g.epochLimit;
-    if (!ok && e + 1 < g.epochLimit) out[F_ABS * cap + e + 1] = (double)st.pos;  // WB_tracking.m:254 precedes the failed read
+    if (!ok && e + 1 < g.epochLimit && st.lockLost == 0) out[F_ABS * cap + e + 1] = (double)st.pos;  // WB_tracking.m:254 precedes the failed read
     npOut = np;
     npOk = ok;
 }
@@ -584,7 +596,7 @@ __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
         ChanState st = g.st[c];
         g.cc[c].pad = st.epoch;
         sm.npOk = next_params(g, st, sm.np) && st.epoch < g.epochLimit;
-        if (!sm.npOk && st.epoch < g.epochLimit)
+        if (!sm.npOk && st.epoch < g.epochLimit && st.lockLost == 0)
             g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
         g.ready[c] = st.epoch - 1;
         g.stop[c] = INT_MAX;
@@ -751,6 +763,8 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.tau2 = h->cfg.tau2code;
     g.tau2over1 = h->cfg.tau2code / h->cfg.tau1code;   // same IEEE divisions as WB_tracking.m:422-424, hoisted
     g.PDIoverTau1 = h->cfg.intTime / h->cfg.tau1code;
+    g.lockPLD = h->cfg.lockLossPLD;
+    g.lockIntervals = std::max(1, (int)h->cfg.lockLossIntervals);
     g.pf1 = h->cfg.pf1;
     g.pf2 = h->cfg.pf2;
     g.pf3 = h->cfg.pf3;
@@ -1300,6 +1314,8 @@ int bds_track_fetch(bds_trk* h, const bds_trk_out* o, int stride) {
                     o->raw[((size_t)c * stride + e) * kNSum + k] = raw[((size_t)c * kNSum + k) * nE + e];
     if (o->epochsDone)
         for (int c = 0; c < h->nCh; ++c) o->epochsDone[c] = h->hSt[c].epoch;
+    if (o->lockLostEpoch)
+        for (int c = 0; c < h->nCh; ++c) o->lockLostEpoch[c] = (int32_t)h->hSt[c].lockLost;
     if (!cn.empty()) {
         double* cp[kNCno] = {o->DataCNo, o->DataPLD, o->PilotCNo, o->PilotPLD, o->TotalCNo};
         const int n = std::min(nC, h->cnoCap);

@@ -38,8 +38,8 @@ struct ChanState {
     long long pos;        // absolute sample index of the next block
     long long samples;    // samples consumed so far
     int epoch;            // epochs completed
-    int pad;
-    long long pad2;       // keep sizeof a multiple of 16 (cache-global vector copies)
+    int lowLock;          // consecutive C/N0 intervals with the lock detector below cfg.lockLossPLD
+    long long lockLost;   // 0, or the number of epochs completed when the channel was dropped for loss of lock
 };
 static_assert(sizeof(ChanState) % 16 == 0, "ChanState must be a 16-byte multiple");
 
@@ -66,6 +66,8 @@ struct TrkDev {
     int cnoCap, cnoInterval, kernelKind, pad;
     double fs, L, d, PDI, tau1, tau2, pf1, pf2, pf3, factor;
     double tau2over1, PDIoverTau1;   // tau2/tau1 and PDI/tau1 (loop invariant)
+    double lockPLD;                  // > 0: drop a channel whose lock detector stays below this (cfg.lockLossPLD)
+    int lockIntervals, padLock;      // ... for this many consecutive C/N0 intervals
     const uint32_t* codeBits;  // [nCh][3][320] packed primaries: data, pilot, (unused)
     ChanConst* cc;
     ChanState* st;

@@ -275,7 +275,8 @@ struct __align__(128) B2aSmem {
     int tileBytes[2];
     int run;
     int eDone;                          // index of the epoch in pDone
-    int pad_;
+    int outDone;                        // the outputs of epoch eDone were already written (lock-loss handling, interval end)
+    double outv[kNFields];
 };
 
 // whole CTA (no barrier inside): the channel's code bits and their rotated copy
@@ -426,9 +427,10 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
         sm.st = g.st[c];
         EpochParams np;
         const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
-        if (!okp && lim) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;   // tracking.m:228 precedes the failed read
+        if (!okp && lim && sm.st.lockLost == 0) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;   // tracking.m:228 precedes the failed read
         sm.run = okp && lim && g.maxEpochs > 0;
         sm.eDone = -1;
+        sm.outDone = 0;
         if (sm.run) {
             sm.p = np;
             pending[0] = b2a_issue_tile(g, sm, np.pos, 0);
@@ -464,12 +466,23 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
             if (lane == 0) {
                 close_nco(g, sm.sums, p, g.cc[c].chCodeFreq, sm.st, sm.aux, sm.pre);
                 sm.pDone = p;
-                sm.eDone = sm.st.epoch;
+                const int e = sm.eDone = sm.st.epoch;
                 sm.st.epoch += 1;
                 ++done;
+                sm.outDone = 0;
+                if (g.lockPLD > 0.0 && g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
+                    // lock-loss handling on and a C/N0 interval ends here: the lock detector decides whether there is a
+                    // next epoch, so this epoch's outputs and the interval's C/N0 come first
+                    close_out(g, sm.sums, p, sm.aux, sm.outv);
+                    for (int f = 0; f < kNFields; ++f)
+                        if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
+                    __threadfence();
+                    close_cno(g, c, e, sm.st);
+                    sm.outDone = 1;
+                }
                 EpochParams np;
                 const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
-                if (!okp && lim) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;
+                if (!okp && lim && sm.st.lockLost == 0) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;
                 const int run = okp && lim && done < g.maxEpochs;
                 if (run) sm.p = np;
                 sm.run = run;
@@ -481,13 +494,12 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
             if (warp == 0) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch, false);
             else if (warp <= 4) fastb_build_rot(&sm.tab, fastb_dphi(sm.p, g.fs), tid - 32, 128);
         }
-        if (warp == kB2aThreads / 32 - 1) {   // this epoch's outputs, off the critical path
-            __shared__ double outv[kNFields];
+        if (warp == kB2aThreads / 32 - 1 && !sm.outDone) {   // this epoch's outputs, off the critical path
             const int e = sm.eDone;
-            if (lane == 0) close_out(g, sm.sums, sm.pDone, sm.aux, outv);
+            if (lane == 0) close_out(g, sm.sums, sm.pDone, sm.aux, sm.outv);
             __syncwarp();
             for (int f = lane; f < kNFields; f += 32)
-                if (field_written(g, f)) out[(size_t)f * cap + e] = outv[f];
+                if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
             if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
                 __threadfence();
                 __syncwarp();

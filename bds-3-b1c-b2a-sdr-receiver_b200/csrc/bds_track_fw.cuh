@@ -248,6 +248,42 @@ __device__ void cno_pld_warp(const double* ip, const double* qp, int n, double T
     pld = (aa - qq) / (aa + qq);
 }
 
+// This epoch's output planes and, at the end of a C/N0 interval, C/N0 + lock detector (+ the lock-loss decision) -
+// off the critical path, except when lock-loss handling is on and the interval ends here: then it runs before the
+// next epoch is decided.
+__device__ void fw_outputs(const TrkDev& g, FwCloseScratch& sm, int c, int e, const CloseAux& aux) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) close_out(g, sm.sums, sm.p, aux, sm.outv);
+    __syncwarp();
+    const int cap = g.capacity;
+    double* out = g.out + (size_t)c * kNFields * cap;
+    for (int f = lane; f < kNFields; f += 32)
+        if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
+    if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0 && (e + 1) / g.cnoInterval - 1 < g.cnoCap) {
+        __threadfence();   // the prompts of this interval were stored by different lanes of this warp
+        __syncwarp();
+        const int ci = (e + 1) / g.cnoInterval - 1, n = g.cnoInterval, e0 = e + 1 - n;
+        double* cn = g.cno + (size_t)c * kNCno * g.cnoCap;
+        double d, dp, pv, pp;   // pilot (I, Q) as stored for wide band, swapped for narrow band (Calc_CNo_PLD.m:80-88)
+        cno_pld_warp(out + (size_t)F_I_P * cap + e0, out + (size_t)F_Q_P * cap + e0, n, g.PDI, d, dp);
+        const int fpi = g.mode == BDS_TRK_B1C_WB ? F_PI_P : F_PQ_P, fpq = g.mode == BDS_TRK_B1C_WB ? F_PQ_P : F_PI_P;
+        cno_pld_warp(out + (size_t)fpi * cap + e0, out + (size_t)fpq * cap + e0, n, g.PDI, pv, pp);
+        if (lane == 0) {
+            const double c0 = 10.0 * log10(d), c1 = 10.0 * log10(pv), c2 = 10.0 * log10(d + pv);
+            cn[0 * g.cnoCap + ci] = c0 * 0.5 + sm.st.cnoPrev[0] * 0.5;
+            cn[1 * g.cnoCap + ci] = dp;
+            cn[2 * g.cnoCap + ci] = c1 * 0.5 + sm.st.cnoPrev[1] * 0.5;
+            cn[3 * g.cnoCap + ci] = pp;
+            cn[4 * g.cnoCap + ci] = c2 * 0.5 + sm.st.cnoPrev[2] * 0.5;
+            sm.st.cnoPrev[0] = c0;
+            sm.st.cnoPrev[1] = c1;
+            sm.st.cnoPrev[2] = c2;
+            lock_update(g, sm.st, dp, pp, e);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- closure by one warp ----------------------------------------------------------------------
 // All S slices of (c, e) have arrived.  Critical path (everything the next epoch's slices wait for):
 //   one L2 round trip (all S slice slots in flight at once, summed in a fixed order; state, params; the next epoch's
@@ -326,11 +362,17 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     __syncwarp();
     int ok = 0;
     CloseAux aux;   // lane 0
+    // lock-loss handling on and a C/N0 interval ends with this epoch: the lock detector decides whether there is a next one
+    const bool early = g.lockPLD > 0.0 && g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0;
     if (lane == 0) {
         close_nco(g, sm.sums, sm.p, sm.chCodeFreq, sm.st, aux, sm.pre);
         sm.st.epoch = e + 1;
-        ok = next_params(g, sm.st, sm.np) && e + 1 < g.epochLimit;
     }
+    if (early) {
+        __syncwarp();
+        fw_outputs(g, sm, c, e, aux);
+    }
+    if (lane == 0) ok = next_params(g, sm.st, sm.np) && e + 1 < g.epochLimit;
     ok = __shfl_sync(0xffffffffu, ok, 0);
     __syncwarp();
     const long long tc1 = clock64();
@@ -343,42 +385,15 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     //      detector, state write-back ----
     if (more && lane < 3)
         __stcg(reinterpret_cast<uint4*>(g.params + c * 2 + ((e + 1) & 1)) + lane, reinterpret_cast<const uint4*>(&sm.np)[lane]);
+    if (!early) fw_outputs(g, sm, c, e, aux);
     if (lane == 0) {
-        close_out(g, sm.sums, sm.p, aux, sm.outv);
         if (ok) g.ready[c] = e + 1;   // bookkeeping for the next launch's prepare kernel
         else g.stop[c] = e + 1;
+        if (!ok && e + 1 < g.epochLimit && sm.st.lockLost == 0)
+            g.out[((size_t)c * kNFields + F_ABS) * g.capacity + e + 1] = (double)sm.st.pos;  // WB_tracking.m:254
     }
     __syncwarp();
-    {
-        const int cap = g.capacity;
-        double* out = g.out + (size_t)c * kNFields * cap;
-        for (int f = lane; f < kNFields; f += 32)
-            if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
-        if (lane == 0 && !ok && e + 1 < g.epochLimit) out[(size_t)F_ABS * cap + e + 1] = (double)sm.st.pos;  // WB_tracking.m:254
-        if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0 && (e + 1) / g.cnoInterval - 1 < g.cnoCap) {
-            __threadfence();   // the prompts of this interval were stored by different lanes of this warp
-            __syncwarp();
-            const int ci = (e + 1) / g.cnoInterval - 1, n = g.cnoInterval, e0 = e + 1 - n;
-            double* cn = g.cno + (size_t)c * kNCno * g.cnoCap;
-            double d, dp, pv, pp;   // pilot (I, Q) as stored for wide band, swapped for narrow band (Calc_CNo_PLD.m:80-88)
-            cno_pld_warp(out + (size_t)F_I_P * cap + e0, out + (size_t)F_Q_P * cap + e0, n, g.PDI, d, dp);
-            const int fpi = g.mode == BDS_TRK_B1C_WB ? F_PI_P : F_PQ_P, fpq = g.mode == BDS_TRK_B1C_WB ? F_PQ_P : F_PI_P;
-            cno_pld_warp(out + (size_t)fpi * cap + e0, out + (size_t)fpq * cap + e0, n, g.PDI, pv, pp);
-            if (lane == 0) {
-                const double c0 = 10.0 * log10(d), c1 = 10.0 * log10(pv), c2 = 10.0 * log10(d + pv);
-                cn[0 * g.cnoCap + ci] = c0 * 0.5 + sm.st.cnoPrev[0] * 0.5;
-                cn[1 * g.cnoCap + ci] = dp;
-                cn[2 * g.cnoCap + ci] = c1 * 0.5 + sm.st.cnoPrev[1] * 0.5;
-                cn[3 * g.cnoCap + ci] = pp;
-                cn[4 * g.cnoCap + ci] = c2 * 0.5 + sm.st.cnoPrev[2] * 0.5;
-                sm.st.cnoPrev[0] = c0;
-                sm.st.cnoPrev[1] = c1;
-                sm.st.cnoPrev[2] = c2;
-            }
-            __syncwarp();
-        }
-        if (lane < 8) __stcg(reinterpret_cast<uint4*>(g.st + c) + lane, reinterpret_cast<const uint4*>(&sm.st)[lane]);
-    }
+    if (lane < 8) __stcg(reinterpret_cast<uint4*>(g.st + c) + lane, reinterpret_cast<const uint4*>(&sm.st)[lane]);
     if (lane == 0 && g.pubTime) {   // developer timing
         atomicAdd(g.counters + 14, (unsigned long long)(tc0 - tcIn));
         atomicAdd(g.counters + 15, (unsigned long long)(tc1 - tc0));
@@ -794,7 +809,7 @@ __global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
                 g.cc[c].pad = st.epoch;
                 e = st.epoch;
                 ok = next_params(g, st, nps[w]) && st.epoch < g.epochLimit && g.maxEpochs > 0;
-                if (!ok && st.epoch < g.epochLimit)
+                if (!ok && st.epoch < g.epochLimit && st.lockLost == 0)
                     g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
                 g.ready[c] = ok ? e : e - 1;
                 g.stop[c] = ok ? INT_MAX : e;

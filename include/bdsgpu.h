@@ -138,6 +138,14 @@ typedef struct bds_trk_cfg {
     int32_t fwPrefetch;          /* tasks a CTA may stage ahead of its compute warps, plus one (1 = none) */
     int32_t debug;               /* BDS_DBG_* bits */
     int32_t traceTickets;        /* BDS_DBG_TRACE: number of queue tickets to record (bds_track_dump_trace) */
+    /* Lock-loss status and early channel drop.  An EXTENSION, off by default (0): the reference
+     * copies channel.status unconditionally (WB_tracking.m:485-488).  With lockLossPLD > 0 a channel whose lock
+     * detector (Calc_CNo_PLD.m:70-73; the pilot's when a pilot is tracked, else the data component's) stays below
+     * lockLossPLD for lockLossIntervals consecutive C/N0 intervals runs no further epoch; bds_trk_out.lockLostEpoch
+     * reports the number of epochs it completed. */
+    double lockLossPLD;
+    int32_t lockLossIntervals;   /* >= 1 */
+    int32_t reserved2;
 } bds_trk_cfg;
 #define BDS_DBG_TIMING 1 /* per-stage cycle counters of the tracking kernel, printed by bds_track_counters */
 #define BDS_DBG_TRACE 2  /* per-ticket timestamps */
@@ -167,6 +175,9 @@ typedef struct bds_trk_out {
     /* [n_ch] number of epochs completed per channel (short input stops a channel
      * like WB_tracking.m:279-283) */
     int32_t* epochsDone;
+    /* [n_ch] optional: 0, or the number of epochs completed when the channel was dropped for loss of lock
+     * (cfg.lockLossPLD > 0 only) */
+    int32_t* lockLostEpoch;
 } bds_trk_out;
 
 typedef struct bds_trk bds_trk;
@@ -226,6 +237,19 @@ void bds_track_close(bds_trk* h);
 int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t* x, size_t n, int x_loc,
                                   const int32_t* prn, int n_ch, int n_epochs, const double* nco,
                                   double* sums);
+
+/* ---- frame synchronisation on the device ------------ */
+/* The PRN's 1800-chip B1C pilot secondary code as +1/-1 (generate2ndCode.m:44-84). */
+int bds_secondary_code(int prn, int8_t* out1800);
+/* The correlation that starts the reference's nav decoding, on the prompt plane the tracker produced:
+ *   BDS_SIG_B1C  BCNAV1decoding.m:66-91: bits = sign(prompt) (caller passes Pilot_I_P for pilotTRKflag 2, else
+ *                Pilot_Q_P), XcorrResult = xcorr(bits, Secondary(prn)) for lags >= 0, index = find(abs(.) >= 1799.5)
+ *   BDS_SIG_B2A  BCNAV2decoding.m:69-97: bits = sign(I_P), pattern = kron(preamble_bits, secondCode),
+ *                index = find(abs(.) > 115); prn is ignored
+ * prompt[n]: host or device doubles (loc).  xcorr (optional, host): [n] correlation values for lags 0..n-1 (integers).
+ * index (host): up to index_cap 1-based lags in ascending order, *n_index = how many the record holds. */
+int bds_frame_sync(int signal, int prn, const double* prompt, int n, int loc, double* xcorr, int32_t* index,
+                   int index_cap, int32_t* n_index);
 
 /* ---- synthetic IF (bench / tests; the reference has no generator) ---------- */
 typedef struct bds_sat {

@@ -800,6 +800,7 @@ def tracking(mode: str, data: np.ndarray, channel, settings, n_epochs: int | Non
                        pos=int(settings.skipNumberOfBytes + ch.codePhase - 1))
         CNoValue = np.zeros(3)
         tempCNo = np.zeros(3)
+        low_lock, lost = 0, False
         if record_nco:
             tr.nco = np.zeros((N, 6))
         for k in range(N):
@@ -828,8 +829,20 @@ def tracking(mode: str, data: np.ndarray, channel, settings, n_epochs: int | Non
                     tr.PilotCNo[c] = CNoValue[1] * 0.5 + tempCNo[1] * 0.5
                     tr["B1C_CNo" if mode != "B2a" else "B2a_CNo"][c] = CNoValue[2] * 0.5 + tempCNo[2] * 0.5
                     tr.PilotPLD[c] = PLD[1]
+                # EXTENSION (not in the reference, which copies channel.status unconditionally, WB_tracking.m:485-488):
+                # settings.lockLossPLD > 0 drops a channel whose lock detector stays below it for lockLossIntervals
+                # consecutive C/N0 intervals; the channel keeps status '-' and the following channels are still tracked
+                if settings.get("lockLossPLD", 0) > 0:
+                    pld = PLD[1] if "PilotCNo" in tr else PLD[0]
+                    low_lock = low_lock + 1 if pld < settings.lockLossPLD else 0
+                    if low_lock >= max(1, int(settings.get("lockLossIntervals", 1))):
+                        tr.lockLostEpoch = k + 1
+                        lost = True
             tempCNo = CNoValue
-        tr.status = ch.status
+            if lost:
+                break
+        if not lost:
+            tr.status = ch.status
     return results, channel
 
 
@@ -843,3 +856,56 @@ def NB_tracking(data, channel, settings, **kw):
 
 def B2a_tracking(data, channel, settings, **kw):
     return tracking("B2a", data, channel, settings, **kw)
+
+
+# ----------------------------------------------------------------------------
+# 8(f) rank 3  frame synchronisation (first consumer of the tracking output)
+# ----------------------------------------------------------------------------
+# generate2ndCode.m:44-56: pilot secondary code (w, p) per PRN (ICD constants)
+B1C_2ND_WP = [(269, 1889), (1448, 1268), (1028, 1593), (1324, 1186), (822, 1239), (5, 1930), (155, 176), (458, 1696),
+              (310, 26), (959, 1344), (1238, 1271), (1180, 1182), (1288, 1381), (334, 1604), (885, 1333), (1362, 1185),
+              (181, 31), (1648, 704), (838, 1190), (313, 1646), (750, 1385), (225, 113), (1477, 860), (309, 1656),
+              (108, 1921), (1457, 1173), (149, 1928), (322, 57), (271, 150), (576, 1214), (1103, 1148), (450, 1458),
+              (399, 1519), (241, 1635), (1045, 1257), (164, 1687), (513, 1382), (687, 1514), (422, 1), (303, 1583),
+              (324, 1806), (495, 1664), (725, 1338), (780, 1111), (367, 1706), (882, 1543), (631, 1813), (37, 228),
+              (647, 2871), (1043, 2884), (24, 1823), (120, 75), (134, 11), (136, 63), (158, 1937), (214, 22), (335, 1768),
+              (340, 1526), (661, 1402), (889, 1445), (929, 1680), (1002, 1290), (1149, 1245)]
+
+
+def generate2ndCode(PRN: int) -> np.ndarray:
+    """B1C pilot secondary code, 1800 chips, +-1 (B1C/include/generate2ndCode.m:58-84): Weil code of the Legendre
+    sequence of length 3607, chip ind = L(k) xor L((k + w) mod N), k = (ind + p - 1) mod N, bipolar 1 - 2*chip."""
+    N = 3607
+    leg = np.zeros(N, dtype=np.int64)
+    for ind in range(1, N):
+        leg[ind] = 1 if pow(ind, (N - 1) // 2, N) == 1 else 0      # JacobiSymbol(ind, N) == 1 for prime N; -1 -> 0
+    w, p = B1C_2ND_WP[PRN - 1]
+    ind = np.arange(1800)
+    k = (ind + p - 1) % N
+    return (1 - 2 * (leg[k] ^ leg[(k + w) % N])).astype(np.float64)
+
+
+def _xcorr_nonneg_lags(bits: np.ndarray, pattern: np.ndarray) -> np.ndarray:
+    """MATLAB xcorr(bits, pattern) for lags 0 .. numel(bits)-1 (the shorter input is zero padded):
+    X(lag + 1) = sum_n bits(n + lag) * pattern(n)."""
+    n, K = bits.size, pattern.size
+    padded = np.concatenate([bits, np.zeros(K)])
+    return np.array([float(np.dot(padded[lag:lag + K], pattern)) for lag in range(n)])
+
+
+def frame_sync_B1C(trackResult, settings):
+    """BCNAV1decoding.m:66-91 -> (XcorrResult for lags >= 0, index (1-based))."""
+    bits = np.array(trackResult.Pilot_I_P if settings.pilotTRKflag == 2 else trackResult.Pilot_Q_P, dtype=np.float64)
+    bits = np.where(bits > 0, 1.0, -1.0)
+    X = _xcorr_nonneg_lags(bits, generate2ndCode(trackResult.PRN))
+    return X, np.flatnonzero(np.abs(X) >= 1799.5) + 1
+
+
+def frame_sync_B2a(I_P_InputBits):
+    """BCNAV2decoding.m:69-97 -> (tlmXcorrResult for lags >= 0, index (1-based))."""
+    secondCode = np.array([1, 1, 1, -1, 1], dtype=np.float64)
+    preamble_bits = np.array([-1, -1, -1, 1, 1, 1, -1, 1, 1, -1, 1, 1, -1, -1, 1, -1, -1, -1, -1, 1, -1, 1, 1, 1], dtype=np.float64)
+    preamble_ms = np.kron(preamble_bits, secondCode)
+    bits = np.where(np.asarray(I_P_InputBits, dtype=np.float64) > 0, 1.0, -1.0)
+    X = _xcorr_nonneg_lags(bits, preamble_ms)
+    return X, np.flatnonzero(np.abs(X) > 115) + 1

@@ -383,3 +383,81 @@ def test_file_backed_session_reads_only_what_the_epochs_need(tmp_path):
         np.testing.assert_array_equal(got["absoluteSample"][c], want[c].absoluteSample + skip)
         for k in ("carrFreq", "codeFreq", "I_P", "Q_P"):
             np.testing.assert_array_equal(got[k][c], want[c][k], err_msg=k)
+
+
+def test_frame_sync_on_device_equals_oracle():
+    """bds_frame_sync against BCNAV1decoding.m:66-91 / BCNAV2decoding.m:69-97 as restated by the
+    oracle: the whole correlation vector and the index list, bit for bit; both polarities, a pattern cut off by the end
+    of the record, values that are exactly zero (which the reference maps to -1)."""
+    import bds_oracle as O
+    import bds3_b200 as B
+    rng = np.random.default_rng(9)
+    s = O.initSettings_B1C(pilotTRKflag=2)
+    for prn in (1, 19, 63):
+        assert np.array_equal(B.b1c.generate2ndCode(prn), O.generate2ndCode(prn))
+        n = 5000 + prn
+        v = rng.standard_normal(n) * 100.0
+        sec = O.generate2ndCode(prn)
+        v[300:2100] = sec * (1.0 + np.abs(v[300:2100]))
+        v[2100:3900] = -sec * (1.0 + np.abs(v[2100:3900]))
+        v[n - 900:] = sec[:900] * 7.0                      # truncated period at the end of the record
+        v[rng.integers(0, n, 40)] = 0.0
+        tr = O.Settings(PRN=prn, Pilot_I_P=v, Pilot_Q_P=-v)
+        X, idx = O.frame_sync_B1C(tr, s)
+        gX, gidx = B.b1c.frameSync(B.settings.Struct(PRN=prn, Pilot_I_P=v, Pilot_Q_P=-v), util.product_settings(s))
+        np.testing.assert_array_equal(gX, X)
+        np.testing.assert_array_equal(gidx, idx)
+    ip = rng.standard_normal(30000)
+    pre = np.kron([-1, -1, -1, 1, 1, 1, -1, 1, 1, -1, 1, 1, -1, -1, 1, -1, -1, -1, -1, 1, -1, 1, 1, 1], [1, 1, 1, -1, 1])
+    for o in (17, 3017, 6017, 29950):
+        ip[o:o + 120] = (pre * (1 if o % 2 else -1))[:30000 - o]
+    X, idx = O.frame_sync_B2a(ip)
+    gX, gidx = B.b2a.frameSync(ip)
+    np.testing.assert_array_equal(gX, X)
+    np.testing.assert_array_equal(gidx, idx)
+    assert {18, 3018, 6018} <= set(gidx.tolist())
+
+
+@pytest.mark.parametrize("mode,kernel", [("WB", "fast"), ("NB", "fast"), ("WB", "general"), ("B2a", "fast")])
+def test_lock_loss_status_and_early_channel_drop(mode, kernel):
+    """settings.lockLossPLD (an extension that is off by default): a channel whose signal vanishes
+    is dropped at the end of the C/N0 interval in which its lock detector has been low for lockLossIntervals
+    intervals - by the rule applied to the device's own lock-detector plane -, it keeps status '-', its later epochs
+    keep the preallocation values, and the other channel's results are bit-identical to a run without the option."""
+    from bds3_b200 import synth
+    sig = "B2a" if mode == "B2a" else "B1C"
+    s = util.settings_for(mode, numberOfChannels=2)
+    s.CNoInterval = 5 if sig == "B1C" else 20
+    ep = 0.01 if sig == "B1C" else 0.001
+    sats = synth.make_sats(2, s, sig, seed=11, cn0=50.0, max_doppler=100.0 if sig == "B2a" else 4500.0)
+    n_on, n_off, N = int(30 * ep * util.FS), int(66 * ep * util.FS), 90
+    if sig == "B2a":
+        n_on, n_off, N = int(300 * ep * util.FS), int(660 * ep * util.FS), 900
+    ps0 = util.product_settings(s)
+    x = np.concatenate([synth.synth_device(sig, ps0, sats, n_on, seed=11),      # rendered on the device (fast); any record will do
+                        synth.synth_device(sig, ps0, [sats[1]], n_off, seed=12, first_sample=n_on)])   # PRN 1 vanishes
+    ch = synth.channels_from_sats(sats, s, sig, freq_error=0.0)
+    kern = L.KERNEL_GENERAL if kernel == "general" else L.KERNEL_FAST
+    ps = util.product_settings(s)
+    base, _ = _track.run_tracking(mode, x, ch, ps, n_epochs=N, kernel=kern)
+    ps2 = ps.copy()
+    ps2.lockLossPLD, ps2.lockLossIntervals = 0.95, 3     # three intervals: the two of the pull-in do not drop the channel
+    got, _ = _track.run_tracking(mode, x, ch, ps2, n_epochs=N, kernel=kern)
+    assert base[0].status == "T" and base[1].status == "T" and "lockLostEpoch" not in base[0]
+    ci = int(s.CNoInterval)
+    pld = base[0].PilotPLD
+    low, want = 0, None
+    for c, v in enumerate(pld):
+        low = low + 1 if v < 0.95 else 0
+        if low >= 3:
+            want = (c + 1) * ci
+            break
+    assert want is not None and want > n_on / (ep * util.FS), pld
+    assert got[0].status == "-" and got[0].lockLostEpoch == want and got[0].epochsDone == want
+    for f in ("I_P", "carrFreq", "absoluteSample", "PilotPLD"):
+        k = want if f != "PilotPLD" else want // ci
+        np.testing.assert_array_equal(got[0][f][:k], base[0][f][:k], err_msg=f)
+    assert np.all(got[0].I_P[want:] == 0) and np.all(np.isinf(got[0].carrFreq[want:])) and np.all(got[0].absoluteSample[want:] == 0)
+    assert got[1].status == "T"
+    for f in ("I_P", "Q_P", "carrFreq", "codeFreq", "PilotPLD"):
+        np.testing.assert_array_equal(got[1][f], base[1][f], err_msg=f)

@@ -313,3 +313,62 @@ def test_golden_fixtures():
                                     nco[4], nco[5])
     got = np.array([out.get(k, 0.0) for k in util.RAW_NAMES])
     np.testing.assert_allclose(got, g["trk_sums_B2a"], rtol=0, atol=1e-6)
+
+
+def test_secondary_code_and_frame_sync_restatement():
+    """generate2ndCode.m / BCNAV1decoding.m:66-91 / BCNAV2decoding.m:69-97 as restated by the oracle: the secondary
+    codes are 1800 +-1 chips, distinct per PRN, with the Weil structure; a prompt sequence that carries the pattern
+    (either polarity) at a known epoch is found there and nowhere else."""
+    codes = [O.generate2ndCode(p) for p in (1, 2, 19, 63)]
+    for c in codes:
+        assert c.size == 1800 and set(np.unique(c)) == {-1.0, 1.0} and abs(c.sum()) < 120
+    assert all(abs(np.dot(codes[0], c)) < 200 for c in codes[1:])
+    # Weil structure: chip = L(k) xor L(k + w), against a Legendre sequence built from the squares
+    N = 3607
+    leg = np.zeros(N, dtype=int)
+    leg[(np.arange(1, N) ** 2) % N] = 1
+    w, p = O.B1C_2ND_WP[18]
+    k = (np.arange(1800) + p - 1) % N
+    assert np.array_equal(O.generate2ndCode(19), 1 - 2 * (leg[k] ^ leg[(k + w) % N]))
+    rng = np.random.default_rng(4)
+    tr = O.Settings(PRN=19, Pilot_I_P=rng.standard_normal(4000) * 3.0)
+    tr.Pilot_I_P[700:2500] = -O.generate2ndCode(19) * np.abs(tr.Pilot_I_P[700:2500] + 5.0)     # inverted polarity
+    s = O.initSettings_B1C(pilotTRKflag=2)
+    X, idx = O.frame_sync_B1C(tr, s)
+    assert list(idx) == [701] and X[700] == -1800.0 and X.size == 4000
+    ip = rng.standard_normal(3000)
+    pre = np.kron([-1, -1, -1, 1, 1, 1, -1, 1, 1, -1, 1, 1, -1, -1, 1, -1, -1, -1, -1, 1, -1, 1, 1, 1], [1, 1, 1, -1, 1])
+    ip[1234:1354] = pre * 2.0
+    X, idx = O.frame_sync_B2a(ip)
+    assert 1235 in idx and X[1234] == 120.0
+
+
+def test_lock_loss_extension_is_off_by_default_and_drops_a_dead_channel():
+    """settings.lockLossPLD (extension): without it the trajectory is the reference's; with it a channel whose signal
+    disappears is dropped at the end of the C/N0 interval in which its lock detector has stayed low for
+    lockLossIntervals intervals, and the next channel is still tracked."""
+    FS = util.FS
+    s = O.initSettings_B1C(samplingFreq=FS, pilotTRKflag=1, numberOfChannels=2, CNoInterval=5)
+    sats = synth.make_sats(2, s, "B1C", seed=11, cn0=50.0)
+    n1 = int(0.3 * FS)
+    x = np.concatenate([synth.synth_numpy("B1C", s, sats, n1, seed=11),
+                        synth.synth_numpy("B1C", s, [sats[1]], int(0.35 * FS), seed=12, first_sample=n1)])   # PRN 1 vanishes
+    ch = [O.Settings(dict(c)) for c in synth.channels_from_sats(sats, s, "B1C", freq_error=0.0)]
+    N = 60
+    base, _ = O.tracking("NB", x, ch, s, n_epochs=N, correlator=c_oracle.correlate_epoch)
+    s2 = s.copy()
+    s2.lockLossPLD, s2.lockLossIntervals = 0.9, 3
+    got, _ = O.tracking("NB", x, ch, s2, n_epochs=N, correlator=c_oracle.correlate_epoch)
+    assert base[0].status == "T" and "lockLostEpoch" not in base[0]
+    lost = got[0].lockLostEpoch
+    assert got[0].status == "-" and 30 < lost < N and lost % 5 == 0
+    # the rule, from the channel's own lock detector values
+    low = 0
+    for c, v in enumerate(base[0].PilotPLD):
+        low = low + 1 if v < 0.9 else 0
+        if low >= 3:
+            assert lost == (c + 1) * 5
+            break
+    np.testing.assert_array_equal(got[0].I_P[:lost], base[0].I_P[:lost])
+    assert np.all(got[0].I_P[lost:] == 0) and np.all(np.isinf(got[0].carrFreq[lost:]))
+    assert got[1].status == "T" and np.array_equal(got[1].I_P, base[1].I_P)       # the other channel is untouched
