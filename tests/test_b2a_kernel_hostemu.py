@@ -132,7 +132,7 @@ class ChanState(C.Structure):
     _fields_ = [("codeFreq", C.c_double), ("remCodePhase", C.c_double), ("carrFreq", C.c_double), ("carrFreqBasis", C.c_double),
                 ("remCarrPhase", C.c_double), ("oldCodeNco", C.c_double), ("oldCodeError", C.c_double),
                 ("d2CarrError", C.c_double), ("dCarrError", C.c_double), ("cnoPrev", C.c_double * 3), ("pos", C.c_longlong),
-                ("samples", C.c_longlong), ("epoch", C.c_int), ("pad", C.c_int), ("pad2", C.c_longlong)]
+                ("samples", C.c_longlong), ("epoch", C.c_int), ("lowLock", C.c_int), ("lockLost", C.c_longlong)]
 
 
 @pytest.fixture(scope="module")
@@ -156,7 +156,8 @@ def emu(tmp_path_factory):
              blk(trk_cu, r"__device__ bool next_params"), blk(trk_cu, r"struct CloseAux \{"),
              blk(trk_cu, r"__device__ void close_nco"), blk(trk_cu, r"__device__ void close_out"),
              blk(trk_cu, r"__device__ void close_core"),
-             blk(trk_cu, r"__device__ __forceinline__ bool field_written"), blk(trk_cu, r"__device__ void close_cno"),
+             blk(trk_cu, r"__device__ __forceinline__ bool field_written"),
+             blk(trk_cu, r"__device__ __forceinline__ void lock_update"), blk(trk_cu, r"__device__ void close_cno"),
              b2a, DRIVER]
     d = tmp_path_factory.mktemp("b2a_emu")
     src = d / "b2a_emu.cpp"
