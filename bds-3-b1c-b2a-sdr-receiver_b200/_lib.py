@@ -30,7 +30,7 @@ class bds_trk_cfg(C.Structure):
                 ("pf3", C.c_double), ("pf2", C.c_double), ("pf1", C.c_double), ("wbFactor", C.c_double),
                 ("kernel", C.c_int32), ("reserved", C.c_int32), ("fwPassesPerTask", C.c_int32),
                 ("fwPrefetch", C.c_int32), ("debug", C.c_int32), ("traceTickets", C.c_int32),
-                ("lockLossPLD", C.c_double), ("lockLossIntervals", C.c_int32), ("reserved2", C.c_int32)]
+                ("lockLossPLD", C.c_double), ("lockLossIntervals", C.c_int32), ("fwMaxCtas", C.c_int32)]
 
 
 class bds_channel(C.Structure):

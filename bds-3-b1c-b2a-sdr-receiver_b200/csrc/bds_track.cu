@@ -901,6 +901,7 @@ int plan_grid(bds_trk* h) {
         BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_fw_kernel, kFwThreads, h->smemBytes));
         if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
         h->gridBlocks = g_num_sms;
+        if (h->cfg.fwMaxCtas > 0) h->gridBlocks = std::max(2, std::min(g_num_sms, (int)h->cfg.fwMaxCtas));
         // a few CTAs only close loops: one warp per channel (16 warps per CTA)
         int nCloser = (h->nAct + (kFwThreads / 32) - 1) / (kFwThreads / 32);
         nCloser = std::min(nCloser, std::max(1, h->gridBlocks / 16));   // many channels: several channels per closer warp

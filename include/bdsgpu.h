@@ -145,7 +145,8 @@ typedef struct bds_trk_cfg {
      * reports the number of epochs it completed. */
     double lockLossPLD;
     int32_t lockLossIntervals;   /* >= 1 */
-    int32_t reserved2;
+    int32_t fwMaxCtas;           /* 0 = one CTA per SM; else the chip-synchronous kernel's persistent grid is limited to this
+                                  * many CTAs, leaving SMs to kernels on other streams (a second session, NCCL) */
 } bds_trk_cfg;
 #define BDS_DBG_TIMING 1 /* per-stage cycle counters of the tracking kernel, printed by bds_track_counters */
 #define BDS_DBG_TRACE 2  /* per-ticket timestamps */
