@@ -83,13 +83,13 @@ def settings_for(workload, n_ch, seconds):
     return B.b2a.initSettings(numberOfChannels=n_ch, msToProcess=int(round(seconds * 1000)))
 
 
-def measured_traffic(kernel, channels, seconds, world):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
-    exact configuration (profiles/traffic.json), else None."""
+def measured_traffic(kernel, channels, seconds, world, key="dram_bytes_per_launch"):
+    """DRAM bytes per launch of the dominant kernel (or, key="issue", its issue-slot figures) from the committed
+    `ncu --set full` capture of this exact configuration (profiles/traffic.json), else None."""
     try:
         for e in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))):
             if (e["kernel"], e["channels"], e["seconds"], e["n_gpus"]) == (kernel, channels, seconds, world):
-                return e["dram_bytes_per_launch"]
+                return e.get(key)
     except Exception:
         pass
     return None
@@ -553,7 +553,11 @@ def run_b200(args):
                              "peak_source": peak_src,
                              "kernel": kname,
                              "kernel_ms_per_launch": dev_ms_max,
-                             "algorithmic_bytes_per_launch": per_launch_bytes},
+                             "algorithmic_bytes_per_launch": per_launch_bytes,
+                             # what ncu shows as the limiter: instruction issue (L2 serves 98 % of the bytes, DRAM is < 2 %
+                             # busy); figures of the committed capture of this configuration, None for other configurations
+                             "measured_limiter": "instruction issue",
+                             "issue": measured_traffic(kname, args.channels, args.seconds, world, key="issue")},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 # correctness of the timed run itself (untimed checks after the timed region, see self_check)
                 "parity_max_rel": check["parity_max_rel"], "locked_channels": check["locked_channels"],
