@@ -9,7 +9,7 @@ from . import _lib as L
 from .settings import Struct
 
 
-def acquire(signal, longSignal, settings, prn_range=None, device_ptr=None, n_samples=None, return_debug=False):
+def acquire(signal, longSignal, settings, prn_range=None, device_ptr=None, n_samples=None, return_debug=False, iq=None):
     """Replaces BDS-3_B1C/acquisition.m / GPU_acquisition.m and BDS-3_B2a/acquisition.m.
 
     Returns acqResults with .carrFreq/.codePhase/.peakMetric, each 1 x max(acqSatelliteList),
@@ -24,6 +24,10 @@ def acquire(signal, longSignal, settings, prn_range=None, device_ptr=None, n_sam
                         acqStep=settings.acqStep, acqThreshold=settings.acqThreshold,
                         acqCohT=int(settings.get("acqCohT", 0)), pilotACQflag=int(settings.get("pilotACQflag", 0)),
                         fineNoncoh=int(settings.get("fineNoncoh", 0)))
+    # a complex longSignal is the reference's fileType-2 record (postProcessing.m:96-99); a device record says so itself
+    if iq is None:
+        iq = longSignal is not None and np.iscomplexobj(longSignal)
+    cfg.fileType = 2 if iq else 1
     prn = np.asarray(sats, dtype=np.int32)
     lo, hi = (0, prn.size) if prn_range is None else prn_range
     carr, cph, pm = np.zeros(maxprn), np.zeros(maxprn), np.zeros(maxprn)
@@ -32,7 +36,7 @@ def acquire(signal, longSignal, settings, prn_range=None, device_ptr=None, n_sam
         xp, n, loc, keep = C.c_void_p(device_ptr), int(n_samples), L.LOC_DEVICE, None
     else:
         keep = L.as_int8(longSignal)
-        xp, n, loc = L.ptr(keep), keep.size, L.LOC_HOST
+        xp, n, loc = L.ptr(keep), keep.size // (2 if iq else 1), L.LOC_HOST
     L.check(L.lib().bds_acquire(signal, xp, n, loc, C.byref(cfg), L.ptr(prn), prn.size, int(lo), int(hi), L.ptr(carr),
                                 L.ptr(cph), L.ptr(pm), maxprn, L.ptr(dbg)))
     acq = Struct(carrFreq=carr, codePhase=cph, peakMetric=pm)

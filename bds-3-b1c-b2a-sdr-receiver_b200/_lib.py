@@ -20,7 +20,7 @@ class bds_acq_cfg(C.Structure):
     _fields_ = [("samplingFreq", C.c_double), ("IF", C.c_double), ("codeFreqBasis", C.c_double),
                 ("codeLength", C.c_int32), ("acqSearchBand", C.c_double), ("acqStep", C.c_double),
                 ("acqThreshold", C.c_double), ("acqCohT", C.c_int32), ("pilotACQflag", C.c_int32),
-                ("fineNoncoh", C.c_int32)]
+                ("fineNoncoh", C.c_int32), ("fileType", C.c_int32)]
 
 
 class bds_trk_cfg(C.Structure):
@@ -30,7 +30,8 @@ class bds_trk_cfg(C.Structure):
                 ("pf3", C.c_double), ("pf2", C.c_double), ("pf1", C.c_double), ("wbFactor", C.c_double),
                 ("kernel", C.c_int32), ("reserved", C.c_int32), ("fwPassesPerTask", C.c_int32),
                 ("fwPrefetch", C.c_int32), ("debug", C.c_int32), ("traceTickets", C.c_int32),
-                ("lockLossPLD", C.c_double), ("lockLossIntervals", C.c_int32), ("fwMaxCtas", C.c_int32)]
+                ("lockLossPLD", C.c_double), ("lockLossIntervals", C.c_int32), ("fwMaxCtas", C.c_int32),
+                ("fileType", C.c_int32), ("reserved3", C.c_int32)]
 
 
 class bds_channel(C.Structure):
@@ -63,7 +64,7 @@ CODE_B1C_PILOT_BOC61, CODE_B2A_DATA, CODE_B2A_PILOT = 5, 6, 7
 LOC_HOST, LOC_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERAL, KERNEL_FAST = 0, 1, 2
 DBG_TIMING, DBG_TRACE = 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 ERR_NO_DEVICE = -2
 
 # every symbol include/bdsgpu.h declares (tests check that the .so exports all of them)
@@ -154,14 +155,22 @@ def ptr(a: np.ndarray):
 
 
 def as_int8(x) -> np.ndarray:
-    """IF samples as a contiguous int8 vector (the reference reads 'schar' into double;
-    the values are integers by construction, postProcessing.m:94)."""
+    """IF samples as a contiguous int8 vector (the reference reads 'schar' into double; the values are integers by
+    construction, postProcessing.m:94).  A complex vector (fileType 2: longSignal = I + 1i*Q, postProcessing.m:96-99)
+    becomes the interleaved I, Q byte pairs of the file it was read from; ``is_iq`` tells the two apart."""
     a = np.asarray(x)
+    if np.iscomplexobj(a):
+        a = np.ascontiguousarray(a.reshape(-1), dtype=np.complex128).view(np.float64)   # I0, Q0, I1, Q1, ...
     if a.dtype != np.int8:
-        if np.iscomplexobj(a):
-            raise BdsError(-6, "complex (fileType 2) IF input is not supported yet")
         r = np.rint(a)
         if np.any(r != a) or np.any(np.abs(r) > 127):
             raise BdsError(-1, "IF samples must be integers in [-127,127] (schar file contents)")
         a = r.astype(np.int8)
     return np.ascontiguousarray(a.reshape(-1))
+
+
+def is_iq(x, settings=None) -> bool:
+    """True if the samples are I/Q pairs: a complex array, or a raw byte record / file with settings.fileType == 2."""
+    if isinstance(x, np.ndarray) and np.iscomplexobj(x):
+        return True
+    return settings is not None and int(settings.get("fileType", 1)) == 2

@@ -37,7 +37,8 @@ def make_cfg(mode, settings, kernel=L.KERNEL_AUTO, tuning=None) -> L.bds_trk_cfg
                         codeLength=int(settings.codeLength), dllCorrelatorSpacing=settings.dllCorrelatorSpacing,
                         intTime=settings.intTime, pilotTRKflag=int(settings.pilotTRKflag),
                         CNoInterval=int(settings.CNoInterval), tau1code=tau1, tau2code=tau2, pf3=pf3, pf2=pf2,
-                        pf1=pf1, wbFactor=factor, kernel=int(kernel), reserved=0)
+                        pf1=pf1, wbFactor=factor, kernel=int(kernel), reserved=0,
+                        fileType=int(settings.get("fileType", 1)))
     # lock-loss status / early channel drop: an extension of the reference, off unless the settings carry it
     if settings.get("lockLossPLD", 0):
         cfg.lockLossPLD = float(settings.lockLossPLD)
@@ -94,6 +95,9 @@ class TrackSession:
         self.mode, self.settings = mode, settings
         self.nch = len(channel)
         self.cfg = make_cfg(mode, settings, kernel, tuning)
+        if isinstance(source, np.ndarray) and np.iscomplexobj(source):
+            self.cfg.fileType = 2     # rawSignal = I + 1i*Q (WB_tracking.m:270-274): uploaded as the file's I, Q byte pairs
+        self.bps = 2 if self.cfg.fileType == 2 else 1   # bytes per sample
         self.chs = make_channels(channel)
         self.h = C.c_void_p()
         lib = L.lib()
@@ -136,12 +140,12 @@ class TrackSession:
             x = L.as_int8(x)
             self._keep = x
             self._host = None
-            L.check(L.lib().bds_track_feed(self.h, L.ptr(x), x.size, L.LOC_HOST, int(first_sample)))
+            L.check(L.lib().bds_track_feed(self.h, L.ptr(x), x.size // self.bps, L.LOC_HOST, int(first_sample)))
 
     def run_async(self, n_epochs):
         if self._host is not None:      # host record not uploaded yet: stream it under the kernel
             x, self._host, self._keep = self._host, None, self._host
-            L.check(L.lib().bds_track_run_streamed(self.h, L.ptr(x), x.size, 0, int(n_epochs)))
+            L.check(L.lib().bds_track_run_streamed(self.h, L.ptr(x), x.size // self.bps, 0, int(n_epochs)))
         else:
             L.check(L.lib().bds_track_run_async(self.h, int(n_epochs)))
 

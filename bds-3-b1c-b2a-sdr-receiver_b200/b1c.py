@@ -68,9 +68,10 @@ def postProcessing(settings, acqResults=None):
     with open(settings.fileName, "rb") as fid:
         if settings.skipAcquisition == 0 or acqResults is None:
             spc = samples_per_code(settings)
-            fid.seek(int(settings.skipNumberOfBytes))
-            data = np.frombuffer(fid.read(20 * spc), dtype=np.int8)        # postProcessing.m:94
-            acqResults = acquisition(data, settings)
+            k = 2 if int(settings.get("fileType", 1)) == 2 else 1          # dataAdaptCoeff, postProcessing.m:67-71
+            fid.seek(k * int(settings.skipNumberOfBytes))                  # :79
+            data = np.frombuffer(fid.read(k * 20 * spc), dtype=np.int8)    # :94; fileType 2: I, Q byte pairs (:96-99)
+            acqResults = acquisition(data, settings, iq=(k == 2))
         if not np.any(acqResults.carrFreq):
             return acqResults, None, []
         channel = preRun(acqResults, settings)

@@ -48,9 +48,10 @@ def postProcessing(settings, acqResults=None):
     with open(settings.fileName, "rb") as fid:
         if settings.skipAcquisition == 0 or acqResults is None:
             spc = samples_per_code(settings)
-            fid.seek(int(settings.skipNumberOfBytes))
-            data = np.frombuffer(fid.read(spc * (int(settings.fineNoncoh) + 2)), dtype=np.int8)   # :89-90
-            acqResults = acquisition(data, settings)
+            k = 2 if int(settings.get("fileType", 1)) == 2 else 1          # dataAdaptCoeff, postProcessing.m:63-67
+            fid.seek(k * int(settings.skipNumberOfBytes))
+            data = np.frombuffer(fid.read(k * spc * (int(settings.fineNoncoh) + 2)), dtype=np.int8)   # :89-90; I, Q pairs (:92-96)
+            acqResults = acquisition(data, settings, iq=(k == 2))
         if not np.any(acqResults.carrFreq):
             return acqResults, None, []
         channel = preRun(acqResults, settings)

@@ -179,9 +179,19 @@ __device__ void smem_fft(float2* buf, int lg, int lgBatch, int seqStride, const 
 //                 (acquisition.m:194-205; periodic extension see file header)
 // kind 1: code    y[n] = table[n] for n < M else 0   (acquisition.m:176-180)
 // grid = (P2/kColTile, batch); batch index selects the Doppler bin / code table.
+// sample m of the record as (I, Q): real int8 samples, or interleaved I/Q int8 pairs (settings.fileType == 2:
+// longSignal = I + 1i*Q, postProcessing.m:96-99)
+__device__ __forceinline__ float2 acq_sample(const int8_t* x, size_t m, int iq) {
+    if (iq) {
+        const char2 v = reinterpret_cast<const char2*>(x)[m];
+        return make_float2((float)v.x, (float)v.y);
+    }
+    return make_float2((float)x[m], 0.f);
+}
+
 __global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_col_kernel(AcqPlan pl, int kind, const int8_t* src,
                                                                   size_t srcStride, const unsigned long long* dphi,
-                                                                  float2* spec) {
+                                                                  float2* spec, int iq) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
     const int col0 = blockIdx.x * kColTile;
@@ -196,11 +206,11 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_col_kernel(AcqPlan pl,
         if (kind == 0) {
             if (n < (unsigned)pl.Next) {
                 unsigned m = n >= (unsigned)pl.N ? n - pl.N : n;
-                float xs = (float)x[m];
+                const float2 xs = acq_sample(x, m, iq);
                 unsigned long long ph = (unsigned long long)m * dp;
                 float sn, cs;
                 sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
-                v = make_float2(xs * cs, xs * sn);
+                v = make_float2(xs.x * cs - xs.y * sn, xs.x * sn + xs.y * cs);   // sigCarr .* sig, acquisition.m:198-205
             }
         } else if (n < (unsigned)pl.M) {
             v.x = (float)x[n];
@@ -385,20 +395,24 @@ __global__ void acq_peak_reduce_kernel(const AcqPeak* peaks, int groups, AcqPeak
 }
 
 // ---- integer power sums for sigPower (acquisition.m:150) ------------------------------------
-__global__ void acq_power_kernel(const int8_t* x, int n, long long* sums /*[2]*/) {
-    long long s1 = 0, s2 = 0;
+// sums = {sum I, sum (I^2 + Q^2), sum Q, -}: mean and var() of a real or complex record in exact integers
+__global__ void acq_power_kernel(const int8_t* x, int n, long long* sums /*[4]*/, int iq) {
+    long long s1 = 0, s2 = 0, s3 = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int v = x[i];
+        const int v = iq ? x[2 * (size_t)i] : x[i], w = iq ? x[2 * (size_t)i + 1] : 0;
         s1 += v;
-        s2 += v * v;
+        s2 += v * v + w * w;
+        s3 += w;
     }
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd((unsigned long long*)&sums[0], (unsigned long long)s1);
         atomicAdd((unsigned long long*)&sums[1], (unsigned long long)s2);
+        if (iq) atomicAdd((unsigned long long*)&sums[2], (unsigned long long)s3);
     }
 }
 
@@ -407,7 +421,7 @@ __global__ void acq_power_kernel(const int8_t* x, int n, long long* sums /*[2]*/
 //   A = sum_n x[n] T[n] e^{i phi_j n},  B = sum_n T[n] e^{i phi_j n}   (DC removal applied on host: A - mean*B)
 // out[(j*ncodes+dp)*4 + {0..3}] = {Re A, Im A, Re B, Im B}; grid = (slices, nfine, ncodes)
 __global__ void acq_fine_b1c_kernel(const int8_t* x, const int8_t* tables, int spc, const unsigned long long* dphi,
-                                    int ncodes, double* out) {
+                                    int ncodes, double* out, int iq) {
     const int j = blockIdx.y, dp = blockIdx.z;
     const int8_t* T = tables + (size_t)dp * spc;
     const unsigned long long d = dphi[j];
@@ -416,9 +430,11 @@ __global__ void acq_fine_b1c_kernel(const int8_t* x, const int8_t* tables, int s
         unsigned long long ph = (unsigned long long)n * d;
         float sn, cs;
         sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
-        float t = (float)T[n], xs = (float)x[n] * t;
-        ar += xs * cs;
-        ai += xs * sn;
+        const float t = (float)T[n];
+        const float2 xv = acq_sample(x, n, iq);
+        const float xs = xv.x * t, xq = xv.y * t;
+        ar += xs * cs - xq * sn;
+        ai += xs * sn + xq * cs;
         br += t * cs;
         bi += t * sn;
     }
@@ -433,7 +449,7 @@ __global__ void acq_fine_b1c_kernel(const int8_t* x, const int8_t* tables, int s
 // B2a (acquisition.m:279-320): K = fineNoncoh*spc samples; code index floor((ts*n)/tc), n = 1..K,
 // rem(.,10230); per-ms coherent sums.  out[((j*2+dp)*nseg + seg)*2 + {re,im}]; grid = (slices, nfine, nseg)
 __global__ void acq_fine_b2a_kernel(const int8_t* x, const uint32_t* bits /*[2][320]*/, int spc, double ts,
-                                    double tc, const unsigned long long* dphi, int nseg, double* out) {
+                                    double tc, const unsigned long long* dphi, int nseg, double* out, int iq) {
     const int j = blockIdx.y, seg = blockIdx.z;
     const unsigned long long d = dphi[j];
     float dr = 0, di = 0, pr = 0, pi = 0;
@@ -446,11 +462,12 @@ __global__ void acq_fine_b2a_kernel(const int8_t* x, const uint32_t* bits /*[2][
         unsigned long long ph = (unsigned long long)n0 * d;
         float sn, cs;
         sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);
-        float xs = (float)x[n0];
-        dr += cd * xs * cs;
-        di += cd * xs * sn;
-        pr += cp * xs * cs;
-        pi += cp * xs * sn;
+        const float2 xv = acq_sample(x, (size_t)n0, iq);
+        const float mr = xv.x * cs - xv.y * sn, mi = xv.x * sn + xv.y * cs;
+        dr += cd * mr;
+        di += cd * mi;
+        pr += cp * mr;
+        pi += cp * mi;
     }
     double v[4] = {warp_sum((double)dr), warp_sum((double)di), warp_sum((double)pr), warp_sum((double)pi)};
     if ((threadIdx.x & 31) == 0) {
@@ -560,6 +577,9 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     prn_hi = std::min(prn_hi, n_prn);
 
     const bool b1c = signal == BDS_SIG_B1C;
+    if (cfg->fileType != 0 && cfg->fileType != 1 && cfg->fileType != 2)
+        return set_error(BDS_ERR_ARG, "fileType must be 1 (real) or 2 (I/Q), got %d", cfg->fileType);
+    const int iq = cfg->fileType == 2;   // x holds n I/Q pairs = 2n bytes
     const double fs = cfg->samplingFreq;
     const long spc = mround(fs / (cfg->codeFreqBasis / cfg->codeLength));
     long M, N;
@@ -624,8 +644,8 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     // ---- IF record on the device
     const int8_t* dx = x;
     if (x_loc == BDS_LOC_HOST) {
-        TRYA(dX.alloc(n));
-        TRYA(cudaMemcpy(dX.p, x, n, cudaMemcpyHostToDevice));
+        TRYA(dX.alloc(n << iq));
+        TRYA(cudaMemcpy(dX.p, x, n << iq, cudaMemcpyHostToDevice));
         dx = dX.as<int8_t>();
     }
 
@@ -655,7 +675,7 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     const int thrRow = std::min(kAcqThreads, std::max(128, (pl.P2 >> 4) * rowTile));
     const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
     acq_fwd_col_kernel<<<dim3(colGroups, nbins), thrCol, smemCol>>>(pl, 0, dx, 0, dDphi.as<unsigned long long>(),
-                                                                       dSig.as<float2>());
+                                                                       dSig.as<float2>(), iq);
     acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, nbins), thrRow, smemRow>>>(pl, dSig.as<float2>(), 0.f);
     count_launch(2);
     TRYA(cudaGetLastError());
@@ -663,14 +683,14 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     // ---- signal power (B1C metric normaliser)  acquisition.m:150
     double sigPower = 0;
     if (b1c) {
-        TRYA(dSums.alloc(16));
-        TRYA(cudaMemset(dSums.p, 0, 16));
-        acq_power_kernel<<<g_num_sms * 4, 256>>>(dx, (int)M, dSums.as<long long>());
+        TRYA(dSums.alloc(32));
+        TRYA(cudaMemset(dSums.p, 0, 32));
+        acq_power_kernel<<<g_num_sms * 4, 256>>>(dx, (int)M, dSums.as<long long>(), iq);
         count_launch();
-        long long hs[2];
-        TRYA(cudaMemcpy(hs, dSums.p, 16, cudaMemcpyDeviceToHost));
-        double mean = (double)hs[0] / (double)M;
-        double var = ((double)hs[1] - (double)hs[0] * mean) / (double)(M - 1);
+        long long hs[4];
+        TRYA(cudaMemcpy(hs, dSums.p, 32, cudaMemcpyDeviceToHost));
+        // var() of a real or complex vector: (sum |x|^2 - |sum x|^2 / M) / (M - 1)
+        double var = ((double)hs[1] - ((double)hs[0] * (double)hs[0] + (double)hs[2] * (double)hs[2]) / (double)M) / (double)(M - 1);
         sigPower = std::sqrt(var * (double)M);
     }
 
@@ -731,7 +751,7 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
         count_launch();
         TRYA(dCode.alloc(specBytes * ncodes * nSel));
         acq_fwd_col_kernel<<<dim3(colGroups, ncodes * nSel), thrCol, smemCol>>>(pl, 1, dTab.as<int8_t>(), (size_t)spc, nullptr,
-                                                                                   dCode.as<float2>());
+                                                                                   dCode.as<float2>(), 0);
         acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, ncodes * nSel), thrRow, smemRow>>>(pl, dCode.as<float2>(), 1.0f / (float)pl.P);
         count_launch(2);
         // ---- phase 1: coarse PRN x Doppler grid; per (PRN, bin) peak and first lag
@@ -840,7 +860,7 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
                 j.nfine = (int)mround(cfg->acqStep / 25) * 2 + 1;             // acquisition.m:266-267
                 for (int q = 0; q < j.nfine; ++q) j.ff.push_back(frq[cd.bestBin] - cfg->acqStep + 25.0 * q);
                 j.off = fineDoubles;
-                fineDoubles += (size_t)j.nfine * ncodes * 4 + 2;              // + 2 slots for the power sums (as long long)
+                fineDoubles += (size_t)j.nfine * ncodes * 4 + 4;              // + 4 slots for the power sums (as long long)
             } else {
                 if (nseg <= 0 || (size_t)(cd.cp - 1 + (long)nseg * spc) > n) continue;
                 j.nfine = (int)mround(cfg->acqStep / 25) + 1;                 // B2a acquisition.m:265
@@ -881,13 +901,13 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
                 const unsigned long long* dph = dFineDphi.as<unsigned long long>() + dphiOff;
                 if (b1c) {   // acquisition.m:253-307
                     long long* pw = reinterpret_cast<long long*>(out + (size_t)j.nfine * ncodes * 4);
-                    acq_power_kernel<<<g_num_sms * 4, 256>>>(dx + (j.cp - 1), (int)spc, pw);
+                    acq_power_kernel<<<g_num_sms * 4, 256>>>(dx + ((size_t)(j.cp - 1) << iq), (int)spc, pw, iq);
                     acq_fine_b1c_kernel<<<dim3(g_num_sms, j.nfine, ncodes), 256>>>(
-                        dx + (j.cp - 1), dTab.as<int8_t>() + (size_t)j.i * ncodes * spc, (int)spc, dph, ncodes, out);
+                        dx + ((size_t)(j.cp - 1) << iq), dTab.as<int8_t>() + (size_t)j.i * ncodes * spc, (int)spc, dph, ncodes, out, iq);
                     count_launch(2);
                 } else {     // B2a acquisition.m:256-335
-                    acq_fine_b2a_kernel<<<dim3(32, j.nfine, nseg), 256>>>(dx + (j.cp - 1), dBits.as<uint32_t>() + q * 2 * kPackedWords,
-                                                                         (int)spc, 1.0 / fs, 1.0 / cfg->codeFreqBasis, dph, nseg, out);
+                    acq_fine_b2a_kernel<<<dim3(32, j.nfine, nseg), 256>>>(dx + ((size_t)(j.cp - 1) << iq), dBits.as<uint32_t>() + q * 2 * kPackedWords,
+                                                                         (int)spc, 1.0 / fs, 1.0 / cfg->codeFreqBasis, dph, nseg, out, iq);
                     count_launch();
                 }
                 dphiOff += j.nfine;
@@ -901,14 +921,14 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
                 int best = 0;
                 double bestV = -1;
                 if (b1c) {
-                    long long hs[2];
-                    std::memcpy(hs, o0 + (size_t)j.nfine * ncodes * 4, 16);
-                    const double mean = (double)hs[0] / (double)spc;
+                    long long hs[4];
+                    std::memcpy(hs, o0 + (size_t)j.nfine * ncodes * 4, 32);
+                    const double mr = (double)hs[0] / (double)spc, mi = (double)hs[2] / (double)spc;   // mean(signal), complex for I/Q
                     for (int q = 0; q < j.nfine; ++q) {
                         double v[2] = {0, 0};
                         for (int dp = 0; dp < ncodes; ++dp) {
-                            const double* o = o0 + ((size_t)q * ncodes + dp) * 4;
-                            v[dp] = std::hypot(o[0] - mean * o[2], o[1] - mean * o[3]);
+                            const double* o = o0 + ((size_t)q * ncodes + dp) * 4;   // sum (x - mean) T e = A - mean * B
+                            v[dp] = std::hypot(o[0] - (mr * o[2] - mi * o[3]), o[1] - (mr * o[3] + mi * o[2]));
                         }
                         const double r = ncodes == 2 ? (v[0] * 11 + v[1] * 29) / 40 : v[0];
                         if (r > bestV) {

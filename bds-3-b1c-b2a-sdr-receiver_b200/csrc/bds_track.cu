@@ -39,6 +39,7 @@ struct SliceCtx {
     EpochParams p;
     int mode, hasPilot, hasP61;
     double L, d, fs;
+    int iq;                 // 1: interleaved I/Q int8 pairs (settings.fileType == 2, WB_tracking.m:155-159,270-274)
 };
 
 template <typename T>
@@ -99,7 +100,9 @@ __device__ __forceinline__ float plain_sign(const uint32_t* w, int idx, int L) {
 __device__ void correlate_general(const SliceCtx& c, const uint32_t* bitsData, const uint32_t* bitsPilot,
                                   long long q0, long long q1, float* acc) {
     const EpochParams& p = c.p;
-    const long long B0 = p.pos - c.winFirst;  // byte offset of the block in the window
+    const long long B0 = p.pos - c.winFirst;  // sample offset of the block in the window
+    const int iq = c.iq;                      // bytes per sample = 1 << iq
+    const long long winBytes = c.winLen << iq;
     const int n = p.blksize - 1;              // colon steps
     const bool b1c = c.mode != BDS_TRK_B2A;
     const double mul = b1c ? 2.0 : 1.0;
@@ -125,28 +128,30 @@ __device__ void correlate_general(const SliceCtx& c, const uint32_t* bitsData, c
     for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
         const int8_t* src = c.x + q * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if ((q + 1) * 16 <= c.winLen) {
+        if ((q + 1) * 16 <= winBytes) {
             v = ldg_nc_v4(src);
         } else {  // last, partial chunk of a caller-owned buffer: byte loads only
             int8_t* vb = reinterpret_cast<int8_t*>(&v);
-            for (int j = 0; j < 16 && q * 16 + j < c.winLen; ++j) vb[j] = src[j];
+            for (int j = 0; j < 16 && q * 16 + j < winBytes; ++j) vb[j] = src[j];
         }
         const int8_t* b = reinterpret_cast<const int8_t*>(&v);
+        const int per = 16 >> iq;   // samples in the chunk
 #pragma unroll 1
-        for (int j = 0; j < 16; ++j) {
-            long long k = q * 16 + j - B0;
+        for (int j = 0; j < per; ++j) {
+            long long k = ((q * 16) >> iq) + j - B0;
             if (k < 0 || k > n) continue;
-            float xs = (float)b[j];
+            const float xs = (float)b[j << iq];
+            const float xi = iq ? (float)b[(j << 1) + 1] : 0.f;   // rawSignal = I + 1i*Q, WB_tracking.m:270-274
             unsigned long long ph = phi0 + (unsigned long long)k * dphi;
             float sn, cs;
             sincospif((float)(int)(ph >> 32) * 4.656612873077392578125e-10f, &sn, &cs);  // 2^-31 -> angle/pi
             float iB, qB;
-            if (b1c) {  // carrsig = exp(-i*theta): WB_tracking.m:341-346
-                iB = xs * cs;
-                qB = -xs * sn;
+            if (b1c) {  // carrsig = exp(-i*theta), i = real(carrsig .* x), q = imag(.): WB_tracking.m:341-346
+                iB = xs * cs + xi * sn;
+                qB = xi * cs - xs * sn;
             } else {    // exp(+i*theta), I = imag, Q = real: B2a tracking.m:309-314
-                qB = xs * cs;
-                iB = xs * sn;
+                qB = xs * cs - xi * sn;
+                iB = xs * sn + xi * cs;
             }
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
@@ -173,10 +178,10 @@ __device__ void correlate_general(const SliceCtx& c, const uint32_t* bitsData, c
 }
 
 // chunk range of slice sl of S for the epoch block
-__device__ __forceinline__ void slice_chunks(const EpochParams& p, long long winFirst, int sl, int S, long long& q0,
+__device__ __forceinline__ void slice_chunks(const EpochParams& p, long long winFirst, int iq, int sl, int S, long long& q0,
                                              long long& q1) {
-    long long B0 = p.pos - winFirst;
-    long long B1 = B0 + p.blksize;
+    long long B0 = (p.pos - winFirst) << iq;            // byte range of the block in the window
+    long long B1 = B0 + ((long long)p.blksize << iq);
     long long qa = B0 >> 4, qb = (B1 + 15) >> 4;
     long long nq = qb - qa;
     q0 = qa + nq * sl / S;
@@ -497,9 +502,9 @@ __device__ void reduce_partials(const TrkDev& g, TrkSmem& sm, int c) {
 __device__ __forceinline__ void correlate_slice(const TrkDev& g, TrkSmem& sm, const EpochParams& p, int sl, int S,
                                                 float* acc) {
     if (g.counters && threadIdx.x == 0) atomicAdd(g.counters + 2, 1ull);
-    SliceCtx ctx{g.x, g.winFirst, g.winLen, p, g.mode, g.hasPilot, g.hasP61, g.L, g.d, g.fs};
+    SliceCtx ctx{g.x, g.winFirst, g.winLen, p, g.mode, g.hasPilot, g.hasP61, g.L, g.d, g.fs, g.iq};
     long long q0, q1;
-    slice_chunks(p, g.winFirst, sl, S, q0, q1);
+    slice_chunks(p, g.winFirst, g.iq, sl, S, q0, q1);
     correlate_general(ctx, sm.bits[0], sm.bits[1], q0, q1, acc);
 }
 
@@ -680,6 +685,7 @@ struct bds_trk {
     unsigned traceCap = 0;
     bool fast = false;
     bool b2aUnit = false;   // B2a on the per-channel chip-synchronous kernel
+    int iq = 0;             // 1: the record holds interleaved I/Q int8 pairs (cfg.fileType == 2); window quantities are samples
     size_t smemBytes = 0;
     int epochsRun = 0;  // max over channels, as seen by the host
     cudaStream_t stream = nullptr, copyStream = nullptr;
@@ -765,6 +771,7 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.PDIoverTau1 = h->cfg.intTime / h->cfg.tau1code;
     g.lockPLD = h->cfg.lockLossPLD;
     g.lockIntervals = std::max(1, (int)h->cfg.lockLossIntervals);
+    g.iq = h->iq;
     g.pf1 = h->cfg.pf1;
     g.pf2 = h->cfg.pf2;
     g.pf3 = h->cfg.pf3;
@@ -785,10 +792,13 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
 int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
     int hasPilot, hasP61;
     mode_flags(mode, cfg->pilotTRKflag, hasPilot, hasP61);
-    bool can = fast_wb_supported(mode, hasPilot, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
-                                 cfg->dllCorrelatorSpacing);
+    if (cfg->fileType != 0 && cfg->fileType != 1 && cfg->fileType != 2)
+        return set_error(BDS_ERR_ARG, "fileType must be 1 (real) or 2 (I/Q), got %d", cfg->fileType);
+    const bool iq = cfg->fileType == 2;   // the chip-synchronous bodies pack real samples: I/Q records take the general kernel
+    bool can = !iq && fast_wb_supported(mode, hasPilot, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
+                                        cfg->dllCorrelatorSpacing);
     if (cfg->kernel == BDS_KERNEL_FAST && !can &&
-        !fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing))
+        (iq || !fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing)))
         return set_error(BDS_ERR_UNSUPPORTED, "fast tracking kernel does not support this configuration");
     fast = can && cfg->kernel != BDS_KERNEL_GENERAL;   // B1C chip-synchronous kernel; B2a: see b2a_unit_enabled
     return BDS_OK;
@@ -797,7 +807,7 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
 // B2a at the supported configuration runs on the per-channel chip-synchronous kernel (validated on hardware against the
 // oracle: tests/test_gpu_b2a_unit.py); BDS_KERNEL_GENERAL selects the exact general kernel.
 bool b2a_unit_enabled(int mode, const bds_trk_cfg* cfg) {
-    return cfg->kernel != BDS_KERNEL_GENERAL &&
+    return cfg->kernel != BDS_KERNEL_GENERAL && cfg->fileType != 2 &&
            fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing);
 }
 
@@ -946,6 +956,7 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
         delete h;
         return rc;
     }
+    h->iq = cfg->fileType == 2;
     if (h->fast && cfg->kernel == BDS_KERNEL_AUTO && n_ch > kFwMaxChannels) h->fast = false;   // queue entries hold 10 bits of channel
     h->b2aUnit = !h->fast && b2a_unit_enabled(mode, cfg);
     auto fail = [&](int code) {
@@ -1011,17 +1022,18 @@ int set_window(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long first
         if (h->ownX && h->dX) cudaFree(h->dX);
         h->dX = const_cast<int8_t*>(x);
         h->ownX = false;
-        h->xCap = n;   // used in place, all n samples: nothing is read past x[n-1] (TrkDev::winStage)
+        h->xCap = n << h->iq;   // used in place, all n samples: nothing is read past the last one (TrkDev::winStage)
     } else {
-        if (!h->ownX || h->xCap < n + 64) {
+        const size_t nb = n << h->iq;   // bytes
+        if (!h->ownX || h->xCap < nb + 64) {
             if (h->ownX && h->dX) cudaFree(h->dX);
             h->dX = nullptr;
             h->ownX = true;
-            h->xCap = n + 64;
+            h->xCap = nb + 64;
             BDS_CUDA(cudaMalloc(&h->dX, h->xCap));
         }
-        BDS_CUDA(cudaMemcpyAsync(h->dX, x, n, cudaMemcpyHostToDevice, h->stream));
-        BDS_CUDA(cudaMemsetAsync(h->dX + n, 0, 64, h->stream));
+        BDS_CUDA(cudaMemcpyAsync(h->dX, x, nb, cudaMemcpyHostToDevice, h->stream));
+        BDS_CUDA(cudaMemsetAsync(h->dX + nb, 0, 64, h->stream));
     }
     h->winFirst = first;
     h->winLen = (long long)n;
@@ -1057,7 +1069,9 @@ int bds_track_open_file(int mode, const bds_trk_cfg* cfg, const char* path, long
         return set_error(BDS_ERR_IO, "cannot stat %s", path);
     }
     size_t len = (size_t)sb.st_size;
-    if (max_samples > 0 && (size_t)max_samples < len) len = (size_t)max_samples;
+    const int iq = cfg && cfg->fileType == 2;   // fileType 2: two bytes per sample (postProcessing.m:67-71)
+    if (max_samples > 0 && ((size_t)max_samples << iq) < len) len = (size_t)max_samples << iq;
+    len &= ~(size_t)iq;
     void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
     ::close(fd);
     if (m == MAP_FAILED) return set_error(BDS_ERR_IO, "mmap of %s failed", path);
@@ -1129,12 +1143,13 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
             lo = std::min(lo, h->hSt[c].pos);
             hi = std::max(hi, h->hSt[c].pos + span);
         }
+        const long long mapSamples = (long long)(h->mapLen >> h->iq);
         if (lo == LLONG_MAX) lo = hi = 0;
-        if (lo >= (long long)h->mapLen) lo = (long long)h->mapLen - 1;   // past the end of the file: the run reports the short read
+        if (lo >= mapSamples) lo = mapSamples - 1;   // past the end of the file: the run reports the short read
         lo = std::max(0LL, lo) & ~4095LL;                       // page aligned in the mapping, 16-byte aligned on the device
-        hi = std::min(hi, (long long)h->mapLen);
-        if (hi <= lo) hi = std::min((long long)h->mapLen, lo + 1);   // nothing left: the run reports the short read
-        return run_streamed_from(h, (const int8_t*)h->map + lo, (size_t)(hi - lo), 0, n_epochs, lo);
+        hi = std::min(hi, mapSamples);
+        if (hi <= lo) hi = std::min(mapSamples, lo + 1);   // nothing left: the run reports the short read
+        return run_streamed_from(h, (const int8_t*)h->map + (lo << h->iq), (size_t)(hi - lo), 0, n_epochs, lo);
     }
     int rc = BDS_OK;
     if (h->pending) {  // the output block may be re-allocated below: finish the previous run first
@@ -1175,6 +1190,7 @@ static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk
     if (rc) return rc;
     if (chunk_bytes == 0) chunk_bytes = (size_t)128 << 20;
     chunk_bytes = (chunk_bytes + 4095) & ~(size_t)4095;
+    n <<= h->iq;   // from here on n, the chunk ends and the copies are in BYTES; the window the kernels see is in samples
     if (!h->ownX || h->xCap < n + 64) {
         if (h->ownX && h->dX) cudaFree(h->dX);
         h->dX = nullptr;
@@ -1213,7 +1229,7 @@ static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk
             if (rc) return rc;
         }
         BDS_CUDA(cudaStreamWaitEvent(h->stream, h->chunkEv[i], 0));
-        h->winLen = (long long)ends[i];
+        h->winLen = (long long)(ends[i] >> h->iq);
         rc = launch_run(h, n_epochs, limit);
         if (rc) return rc;
     }
@@ -1246,7 +1262,7 @@ int bds_track_run_window(bds_trk* h, const int8_t* x_dev, size_t n_avail, int ep
     }
     h->dX = const_cast<int8_t*>(x_dev);
     h->ownX = false;
-    h->xCap = n_avail;
+    h->xCap = n_avail << h->iq;
     h->winFirst = 0;
     h->winLen = (long long)n_avail;   // nothing is read past x_dev[n_avail-1] (TrkDev::winStage)
     if (!h->pending) BDS_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -1469,6 +1485,8 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         if (p.pos < 0 || p.blksize <= 0 || (size_t)(p.pos + p.blksize) > n)
             return set_error(BDS_ERR_ARG, "open loop: block %d outside the record", i);
     }
+    const int iq = cfg->fileType == 2;
+    const size_t nb = n << iq;   // bytes of the record
     std::vector<uint32_t> bits;
     rc = build_code_bits(mode, prn, n_ch, bits);
     if (rc) return rc;
@@ -1492,9 +1510,9 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         return set_error(BDS_ERR_CUDA, "open loop: %s failed", #x_);   \
     }
     if (x_loc == BDS_LOC_HOST) {
-        TRYC(cudaMalloc(&dX, n + 64));
-        TRYC(cudaMemcpy(dX, x, n, cudaMemcpyHostToDevice));
-        TRYC(cudaMemset(dX + n, 0, 64));
+        TRYC(cudaMalloc(&dX, nb + 64));
+        TRYC(cudaMemcpy(dX, x, nb, cudaMemcpyHostToDevice));
+        TRYC(cudaMemset(dX + nb, 0, 64));
     } else {
         dX = const_cast<int8_t*>(x);
     }
@@ -1522,6 +1540,7 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     g.codeBits = dBits;
     g.S = S;
     g.pad = cfg->reserved & 1;
+    g.iq = iq;
     TRYC(cudaMalloc(&dCnt, 128));
     TRYC(cudaMemset(dCnt, 0, 128));
     g.counters = dCnt;

@@ -67,7 +67,8 @@ struct TrkDev {
     double fs, L, d, PDI, tau1, tau2, pf1, pf2, pf3, factor;
     double tau2over1, PDIoverTau1;   // tau2/tau1 and PDI/tau1 (loop invariant)
     double lockPLD;                  // > 0: drop a channel whose lock detector stays below this (cfg.lockLossPLD)
-    int lockIntervals, padLock;      // ... for this many consecutive C/N0 intervals
+    int lockIntervals;               // ... for this many consecutive C/N0 intervals
+    int iq;                          // 1: x holds interleaved I/Q int8 pairs (fileType 2); window quantities stay in samples
     const uint32_t* codeBits;  // [nCh][3][320] packed primaries: data, pilot, (unused)
     ChanConst* cc;
     ChanState* st;

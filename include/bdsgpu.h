@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BDS_ABI_VERSION 2
+#define BDS_ABI_VERSION 3
 
 /* error codes */
 #define BDS_OK 0
@@ -100,11 +100,14 @@ typedef struct bds_acq_cfg {
     int32_t acqCohT;      /* B1C: settings.acqCohT [ms]; ignored for B2a */
     int32_t pilotACQflag; /* B1C: settings.pilotACQflag; ignored for B2a */
     int32_t fineNoncoh;   /* B2a: settings.fineNoncoh [ms]; ignored for B1C */
+    int32_t fileType;     /* settings.fileType: 0/1 = real samples, 2 = interleaved I/Q pairs, longSignal = I + 1i*Q
+                           * (postProcessing.m:94-99); x then holds 2*n int8 values for n samples */
 } bds_acq_cfg;
 
 /* Replaces acquisition(longSignal, settings):
  *   B1C: BDS-3_B1C/acquisition.m:129-338   B2a: BDS-3_B2a/acquisition.m:130-365
- * x: n real int8 IF samples (host or device per x_loc).  prn[n_prn] = acqSatelliteList.
+ * x: n int8 IF samples (host or device per x_loc; real, or n interleaved I/Q pairs = 2n bytes with cfg.fileType 2).
+ * prn[n_prn] = acqSatelliteList.
  * carrFreq/codePhase/peakMetric: caller-allocated [max_prn] doubles, indexed PRN-1,
  * zero-filled by the callee, 0 = not found (acquisition.m:161-165).
  * prn_lo/prn_hi shard the list for multi-GPU: only list entries with index in
@@ -147,6 +150,12 @@ typedef struct bds_trk_cfg {
     int32_t lockLossIntervals;   /* >= 1 */
     int32_t fwMaxCtas;           /* 0 = one CTA per SM; else the chip-synchronous kernel's persistent grid is limited to this
                                   * many CTAs, leaving SMs to kernels on other streams (a second session, NCCL) */
+    int32_t fileType;            /* settings.fileType: 0/1 = real int8 samples; 2 = interleaved I/Q int8 pairs,
+                                  * rawSignal = I + 1i*Q (WB_tracking.m:155-159,270-274; B2a tracking.m:143-147,241-244).
+                                  * Every sample count, offset and absoluteSample of this API stays in SAMPLES (the reference's
+                                  * ftell/dataAdaptCoeff); buffers and files hold 2 bytes per sample.  I/Q records run on
+                                  * the general kernel (BDS_KERNEL_FAST is refused). */
+    int32_t reserved3;           /* 0 */
 } bds_trk_cfg;
 #define BDS_DBG_TIMING 1 /* per-stage cycle counters of the tracking kernel, printed by bds_track_counters */
 #define BDS_DBG_TRACE 2  /* per-ticket timestamps */
@@ -183,14 +192,15 @@ typedef struct bds_trk_out {
 
 typedef struct bds_trk bds_trk;
 
-/* Open a tracking session on the IF record x[n] (real int8).  With BDS_LOC_HOST the
+/* Open a tracking session on the IF record x[n] (int8; n samples = n bytes, or 2n bytes of I/Q pairs with cfg.fileType 2).  With BDS_LOC_HOST the
  * record is copied to the device; with BDS_LOC_DEVICE it is used in place (16-byte aligned; all n samples
  * are usable and nothing is read past x[n-1], so an epoch may end on the record's last sample).
  * skipNumberOfBytes is settings.skipNumberOfBytes; channel blocks start at
  * skip + codePhase - 1 (WB_tracking.m:174-176). */
 int bds_track_open(int mode, const bds_trk_cfg* cfg, const int8_t* x, size_t n, int x_loc,
                    long long skipNumberOfBytes, const bds_channel* ch, int n_ch, bds_trk** out);
-/* Same, reading the record from a file (the reference's `fid`): fileType 1, schar. */
+/* Same, reading the record from a file (the reference's `fid`): schar, fileType 1 or 2 (cfg.fileType); max_samples
+ * (0 = whole file) and skipNumberOfBytes count samples, as the reference's dataAdaptCoeff*(skip + codePhase - 1) does. */
 int bds_track_open_file(int mode, const bds_trk_cfg* cfg, const char* path, long long skipNumberOfBytes,
                         long long max_samples, const bds_channel* ch, int n_ch, bds_trk** out);
 /* Replace the resident IF window: the session keeps loop state; x[n] holds samples

@@ -11,6 +11,8 @@
  *   [carrFreq, codePhase, peakMetric] = bds_mex('acquire', signal, int8(longSignal), acqCfg, prnList)
  *        replaces acquisition(longSignal, settings)
  *        BDS-3_B1C/postProcessing.m:105-111, BDS-3_B2a/postProcessing.m:100
+ *        a complex int8 longSignal (settings.fileType == 2, postProcessing.m:96-99) is passed as its interleaved I, Q
+ *        pairs with cfg.fileType = 2
  *   [planes, cno, epochsDone] = bds_mex('track', mode, fileName, skipNumberOfBytes, trkCfg, channelMatrix, nEpochs)
  *        replaces {WB_,NB_,}tracking(fid, channel, settings)
  *        BDS-3_B1C/postProcessing.m:137-143, BDS-3_B2a/postProcessing.m:123
@@ -49,6 +51,7 @@ static void do_acquire(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[
     const int signal = (int)mxGetScalar(prhs[1]);
     const double* c = mxGetDoubles(prhs[3]);
     bds_acq_cfg cfg;
+    memset(&cfg, 0, sizeof cfg);
     cfg.samplingFreq = c[0]; cfg.IF = c[1]; cfg.codeFreqBasis = c[2]; cfg.codeLength = (int32_t)c[3];
     cfg.acqSearchBand = c[4]; cfg.acqStep = c[5]; cfg.acqThreshold = c[6]; cfg.acqCohT = (int32_t)c[7];
     cfg.pilotACQflag = (int32_t)c[8]; cfg.fineNoncoh = (int32_t)c[9];
@@ -62,7 +65,11 @@ static void do_acquire(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[
         if (prn[i] > maxprn) maxprn = prn[i];
     }
     for (int k = 0; k < 3; ++k) plhs[k] = mxCreateDoubleMatrix(1, maxprn, mxREAL); /* MATLAB owns the outputs */
-    check(bds_acquire(signal, (const int8_t*)mxGetInt8s(prhs[2]), mxGetNumberOfElements(prhs[2]), BDS_LOC_HOST, &cfg,
+    /* interleaved complex API (-R2018a): a complex int8 array is stored as I0, Q0, I1, Q1, ... = the fileType-2 file layout */
+    const int iq = mxIsComplex(prhs[2]) ? 1 : 0;
+    cfg.fileType = iq ? 2 : 1;
+    const int8_t* xs = iq ? (const int8_t*)mxGetComplexInt8s(prhs[2]) : (const int8_t*)mxGetInt8s(prhs[2]);
+    check(bds_acquire(signal, xs, mxGetNumberOfElements(prhs[2]), BDS_LOC_HOST, &cfg,
                       prn, (int)nprn, 0, (int)nprn, mxGetDoubles(plhs[0]), mxGetDoubles(plhs[1]),
                       mxGetDoubles(plhs[2]), maxprn, NULL));
     (void)nlhs;
@@ -81,6 +88,7 @@ static void do_track(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     cfg.dllCorrelatorSpacing = c[3]; cfg.intTime = c[4]; cfg.pilotTRKflag = (int32_t)c[5];
     cfg.CNoInterval = (int32_t)c[6]; cfg.tau1code = c[7]; cfg.tau2code = c[8];
     cfg.pf3 = c[9]; cfg.pf2 = c[10]; cfg.pf1 = c[11]; cfg.wbFactor = c[12]; cfg.kernel = BDS_KERNEL_AUTO;
+    cfg.fileType = mxGetNumberOfElements(prhs[4]) > 13 ? (int32_t)c[13] : 1; /* settings.fileType (WB_tracking.m:155-159) */
     const mwSize nch = mxGetM(prhs[5]);
     const double* cm = mxGetDoubles(prhs[5]); /* column major [nCh x 5] */
     bds_channel* ch = (bds_channel*)mxCalloc(nch, sizeof(bds_channel));

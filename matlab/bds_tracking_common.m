@@ -37,7 +37,8 @@ trackResults = repmat(t, 1, settings.numberOfChannels);
 factor = 0;
 if mode == 1, factor = CalcWeighingFactor(settings); end          % WB_tracking.m:138
 cfg = [settings.samplingFreq, settings.codeFreqBasis, settings.codeLength, settings.dllCorrelatorSpacing, ...
-       settings.intTime, settings.pilotTRKflag, settings.CNoInterval, tau1, tau2, pf3, pf2, pf1, factor];
+       settings.intTime, settings.pilotTRKflag, settings.CNoInterval, tau1, tau2, pf3, pf2, pf1, factor, ...
+       settings.fileType];                                        % 2 = I/Q pairs (WB_tracking.m:155-159)
 cm = zeros(settings.numberOfChannels, 5);
 for c = 1:settings.numberOfChannels
     cm(c, :) = [channel(c).PRN, double(channel(c).status), channel(c).acquiredFreq, ...

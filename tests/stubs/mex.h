@@ -15,6 +15,8 @@ int mxIsInt8(const mxArray*);
 double mxGetScalar(const mxArray*);
 double* mxGetDoubles(const mxArray*);
 int8_t* mxGetInt8s(const mxArray*);
+int mxIsComplex(const mxArray*);
+void* mxGetComplexInt8s(const mxArray*);
 void* mxGetData(const mxArray*);
 size_t mxGetNumberOfElements(const mxArray*);
 size_t mxGetM(const mxArray*);

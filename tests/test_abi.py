@@ -28,7 +28,7 @@ def test_header_symbols_all_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in bdsgpu.h but not exported by libbdsgpu.so"
     assert sorted(L.EXPORTS) == names, "ctypes binding table out of sync with the header"
-    assert lib.bds_abi_version() == L.ABI_VERSION == 2
+    assert lib.bds_abi_version() == L.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():

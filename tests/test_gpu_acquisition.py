@@ -80,3 +80,42 @@ def test_acquisition_then_tracking_pipeline():
     och = O.preRun(want, s, "B1C")
     for a, b in zip(ch, och):
         assert (a.PRN, a.codePhase, a.acquiredFreq, a.codeFreq) == (b.PRN, b.codePhase, b.acquiredFreq, b.codeFreq)
+
+
+def _iq(signal, s, sats, n, seed):
+    """I/Q sampling of the scenario (settings.fileType == 2, postProcessing.m:96-99).  Both acquisitions mix with
+    exp(+1i*f*t) (acquisition.m:198), so a complex record is found at +f when it rotates as exp(-i theta): the
+    quadrature rail is a quarter cycle AHEAD (for real records the sign does not matter)."""
+    quad = [B.Settings(dict(st, carrPhase=st.carrPhase - np.pi / 2)) for st in sats]
+    xr = synth.synth_numpy(signal, s, sats, n, seed=seed)
+    xq = synth.synth_numpy(signal, s, quad, n, seed=seed, noise_seed=seed + 104729)
+    return xr.astype(np.float64) - 1j * xq.astype(np.float64)
+
+
+def test_b1c_acquisition_parity_iq_record():
+    s = O.initSettings_B1C(samplingFreq=util.FS, acqSearchBand=150, acqSatelliteList=[1, 2], fileType=2)
+    sats = synth.make_sats(1, s, "B1C", seed=5, max_doppler=90.0, cn0=47.0)
+    x = _iq("B1C", s, sats, int(0.0305 * s.samplingFreq), 5)
+    want, wd = O.acquisition_B1C(x, s, return_debug=True)
+    got, gd = B.b1c.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for prn in (1, 2):
+        assert gd[prn - 1, 0] == wd[prn]["bin"] and gd[prn - 1, 1] == wd[prn]["codePhase"]
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+    assert want.carrFreq[0] != 0 and want.carrFreq[1] == 0
+    assert abs(got.carrFreq[0] - (s.IF + sats[0].doppler)) <= 25
+
+
+def test_b2a_acquisition_parity_iq_record():
+    s = O.initSettings_B2a(acqSatelliteList=[4, 9], fileType=2)
+    sats = synth.make_sats(1, s, "B2a", seed=3, prns=[4], cn0=47.0)
+    x = _iq("B2a", s, sats, 17 * 99375, 3)
+    want, wd = O.acquisition_B2a(x, s, return_debug=True)
+    got, gd = B.b2a.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for prn in (4, 9):
+        assert gd[prn - 1, 0] == wd[prn]["bin"] and gd[prn - 1, 1] == wd[prn]["codePhase"]
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+    assert want.carrFreq[3] != 0 and want.carrFreq[8] == 0

@@ -461,3 +461,58 @@ def test_lock_loss_status_and_early_channel_drop(mode, kernel):
     assert got[1].status == "T"
     for f in ("I_P", "Q_P", "carrFreq", "codeFreq", "PilotPLD"):
         np.testing.assert_array_equal(got[1][f], base[1][f], err_msg=f)
+
+
+# ---- fileType 2: interleaved I/Q records (WB_tracking.m:155-159,270-274; B2a tracking.m) -------------------------
+@pytest.mark.parametrize("mode,seconds,epochs", [("WB", 0.05, 2), ("NB", 0.05, 2), ("B2a", 0.012, 8)])
+def test_open_loop_parity_iq_record(mode, seconds, epochs):
+    """complex rawSignal = I + 1i*Q: the 18 sums against the float64 (numpy) oracle, teacher forced"""
+    s, sats, x, ch = util.record_iq(mode, 2, seconds)
+    tr, raw = util.oracle_track(mode, s, x, ch, epochs)
+    nco = np.ascontiguousarray(np.stack([t.nco for t in tr]))
+    cfg = _track.make_cfg(mode, util.product_settings(s), L.KERNEL_AUTO)
+    assert cfg.fileType == 2
+    xi = L.as_int8(x)                       # I0, Q0, I1, Q1, ... as the file holds them
+    assert xi.size == 2 * x.size
+    sums = np.zeros((2, epochs, 18))
+    prn = np.asarray([c.PRN for c in ch], dtype=np.int32)
+    L.check(L.lib().bds_track_correlate_open_loop(MODES[mode], C.byref(cfg), L.ptr(xi), x.size, L.LOC_HOST, L.ptr(prn),
+                                                  2, epochs, L.ptr(nco), L.ptr(sums)))
+    err = np.abs(sums - raw) / util.family_scale(raw)
+    assert np.nanmax(err[np.isfinite(err)]) <= 1e-4, np.nanmax(err[np.isfinite(err)])
+    assert _track.counters(None)[2] > 0     # I/Q records run on the general kernel
+    cfg.kernel = L.KERNEL_FAST              # ... and the chip-synchronous kernels refuse them
+    rc = L.lib().bds_track_correlate_open_loop(MODES[mode], C.byref(cfg), L.ptr(xi), x.size, L.LOC_HOST, L.ptr(prn), 2,
+                                               epochs, L.ptr(nco), L.ptr(sums))
+    assert rc == -6
+
+
+@pytest.mark.parametrize("mode,seconds,epochs", [("WB", 0.075, 5), ("B2a", 0.02, 15)])
+def test_closed_loop_iq_record_array_and_file(mode, seconds, epochs, tmp_path):
+    """closed loop on an I/Q record: complex array == the fileType-2 file it came from (skip counted in samples,
+    dataAdaptCoeff*(skipNumberOfBytes + codePhase - 1)), both against the oracle trajectory"""
+    s, sats, x, ch = util.record_iq(mode, 2, seconds)
+    tr, raw = util.oracle_track(mode, s, x, ch, epochs)
+    ps = util.product_settings(s)
+    got, _ = _track.run_tracking(mode, x, ch, ps, n_epochs=epochs, raw=True)
+    skip = 4096 + 3
+    path = tmp_path / "iq.bin"
+    pad = np.zeros(2 * skip, dtype=np.int8)
+    np.concatenate([pad, L.as_int8(x)]).tofile(path)
+    pf = util.product_settings(s)
+    pf.skipNumberOfBytes = skip
+    with open(path, "rb") as fid:
+        gotf, _ = _track.run_tracking(mode, fid, ch, pf, n_epochs=epochs, raw=True)
+    for c in range(len(ch)):
+        g, o, f = got[c], tr[c], gotf[c]
+        assert g.status == "T" and f.status == "T"
+        np.testing.assert_array_equal(g.absoluteSample, o.absoluteSample)
+        np.testing.assert_array_equal(f.absoluteSample, o.absoluteSample + skip)     # ftell/dataAdaptCoeff
+        # the file's samples sit at another 16-byte phase (skip): same arithmetic, another fp32 summation grouping
+        assert np.max(np.abs(f.raw - g.raw) / util.family_scale(g.raw)) <= 1e-5
+        sc = util.family_scale(raw[c])
+        err = np.abs(g.raw - raw[c]) / sc
+        assert np.max(err) <= 1e-3, np.max(err)
+        assert np.mean(err <= 1e-4) >= 0.99
+        for k in ("carrFreq", "codeFreq"):
+            np.testing.assert_allclose(g[k], o[k], rtol=1e-9)

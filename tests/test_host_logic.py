@@ -82,8 +82,12 @@ def test_as_int8_validation():
     np.testing.assert_array_equal(L.as_int8(np.array([1.0, -127.0, 0.0])), np.array([1, -127, 0], dtype=np.int8))
     with pytest.raises(L.BdsError):
         L.as_int8(np.array([0.5]))
+    # fileType 2: a complex vector becomes the file's interleaved I, Q byte pairs (postProcessing.m:96-99)
+    np.testing.assert_array_equal(L.as_int8(np.array([1 + 2j, -3 - 127j])), np.array([1, 2, -3, -127], dtype=np.int8))
     with pytest.raises(L.BdsError):
-        L.as_int8(np.array([1 + 2j]))
+        L.as_int8(np.array([1 + 2.5j]))
+    assert L.is_iq(np.zeros(2, dtype=complex)) and not L.is_iq(np.zeros(2))
+    assert L.is_iq(np.zeros(2, dtype=np.int8), B.Settings(fileType=2))
 
 
 def test_resampling_branch_is_refused():

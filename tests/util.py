@@ -39,6 +39,21 @@ def record(mode, n_sats, seconds, seed=11, sigma=25.0, max_doppler=None):
     return s, sats, x, ch
 
 
+@functools.lru_cache(maxsize=4)
+def record_iq(mode, n_sats, seconds, seed=11, sigma=25.0):
+    """The same scenario as ``record`` sampled as I/Q (settings.fileType == 2): complex x = I + 1i*Q, the quadrature
+    rail being the same satellites a quarter cycle behind (Re / Im of the analytic signal) with independent noise."""
+    s, sats, xr, ch = record(mode, n_sats, seconds, seed=seed, sigma=sigma)
+    sig = "B2a" if mode == "B2a" else "B1C"
+    quad = [B.Settings(dict(st, carrPhase=st.carrPhase - np.pi / 2)) for st in sats]
+    xq = synth.synth_numpy(sig, s, quad, xr.size, sigma=sigma, seed=seed, noise_seed=seed + 104729)
+    s = O.Settings(dict(s, fileType=2))
+    x = xr.astype(np.float64) + 1j * xq.astype(np.float64)
+    # the trackers wipe the carrier off with exp(-i theta) for B1C (WB_tracking.m:341) and exp(+i theta) for B2a
+    # (tracking.m:309): a B1C tracker locks to exp(+i theta), the B2a tracker to its conjugate
+    return s, sats, (np.conj(x) if mode == "B2a" else x), ch
+
+
 def ochannels(ch):
     return [O.Settings(dict(c)) for c in ch]
 
@@ -51,7 +66,9 @@ def oracle_track(mode, s, x, ch, n_epochs, record_nco=True):
     raws = []
 
     def corr(mode_, st_, raw, codes, rem, step, cf, rc):
-        out = c_oracle.correlate_epoch(mode_, st_, raw, codes, rem, step, cf, rc)
+        # the C restatement takes real int8 blocks; complex (fileType 2) blocks go through the numpy oracle
+        fn = O.correlate_epoch if np.iscomplexobj(raw) else c_oracle.correlate_epoch
+        out = fn(mode_, st_, raw, codes, rem, step, cf, rc)
         raws.append(np.array([out[0].get(k, 0.0) for k in RAW_NAMES]))
         return out
 
