@@ -14,16 +14,15 @@ def acquire(signal, longSignal, settings, prn_range=None, device_ptr=None, n_sam
 
     Returns acqResults with .carrFreq/.codePhase/.peakMetric, each 1 x max(acqSatelliteList),
     indexed by PRN, zero = not found (acquisition.m:161-165)."""
-    if int(settings.get("resamplingflag", 0)) == 1 and settings.samplingFreq > settings.resamplingThreshold:
-        raise L.BdsError(-6, "the resampling pre-conditioner (acquisition.m:56-123) is out of scope; "
-                             "set resamplingflag = 0")
     sats = [int(p) for p in np.atleast_1d(settings.acqSatelliteList)]
     maxprn = max(sats)
     cfg = L.bds_acq_cfg(samplingFreq=settings.samplingFreq, IF=settings.IF, codeFreqBasis=settings.codeFreqBasis,
                         codeLength=int(settings.codeLength), acqSearchBand=settings.acqSearchBand,
                         acqStep=settings.acqStep, acqThreshold=settings.acqThreshold,
                         acqCohT=int(settings.get("acqCohT", 0)), pilotACQflag=int(settings.get("pilotACQflag", 0)),
-                        fineNoncoh=int(settings.get("fineNoncoh", 0)))
+                        fineNoncoh=int(settings.get("fineNoncoh", 0)),
+                        resamplingThreshold=float(settings.get("resamplingThreshold", 0.0)),
+                        resamplingflag=int(settings.get("resamplingflag", 0)))
     # a complex longSignal is the reference's fileType-2 record (postProcessing.m:96-99); a device record says so itself
     if iq is None:
         iq = longSignal is not None and np.iscomplexobj(longSignal)

@@ -179,15 +179,19 @@ __device__ void smem_fft(float2* buf, int lg, int lgBatch, int seqStride, const 
 //                 (acquisition.m:194-205; periodic extension see file header)
 // kind 1: code    y[n] = table[n] for n < M else 0   (acquisition.m:176-180)
 // grid = (P2/kColTile, batch); batch index selects the Doppler bin / code table.
-// sample m of the record as (I, Q): real int8 samples, or interleaved I/Q int8 pairs (settings.fileType == 2:
-// longSignal = I + 1i*Q, postProcessing.m:96-99)
-__device__ __forceinline__ float2 acq_sample(const int8_t* x, size_t m, int iq) {
-    if (iq) {
+// sample m of the record as (I, Q).  fmt bit 0: interleaved I/Q pairs (settings.fileType == 2: longSignal = I + 1i*Q,
+// postProcessing.m:96-99); fmt bit 1: float samples (the output of the resampling pre-conditioner) instead of int8
+enum { kFmtI8 = 0, kFmtI8IQ = 1, kFmtF32 = 2, kFmtF32IQ = 3 };
+__device__ __forceinline__ float2 acq_sample(const int8_t* x, size_t m, int fmt) {
+    if (fmt == kFmtI8) return make_float2((float)x[m], 0.f);
+    if (fmt == kFmtI8IQ) {
         const char2 v = reinterpret_cast<const char2*>(x)[m];
         return make_float2((float)v.x, (float)v.y);
     }
-    return make_float2((float)x[m], 0.f);
+    if (fmt == kFmtF32) return make_float2(reinterpret_cast<const float*>(x)[m], 0.f);
+    return reinterpret_cast<const float2*>(x)[m];
 }
+__host__ __device__ inline size_t acq_sample_bytes(int fmt) { return (fmt & 2 ? 4 : 1) << (fmt & 1); }
 
 __global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_col_kernel(AcqPlan pl, int kind, const int8_t* src,
                                                                   size_t srcStride, const unsigned long long* dphi,
@@ -416,6 +420,79 @@ __global__ void acq_power_kernel(const int8_t* x, int n, long long* sums /*[4]*/
     }
 }
 
+// the same for float samples (resampled records): sums = {sum I, sum (I^2 + Q^2), sum Q, -} as doubles
+__global__ void acq_power_f32_kernel(const int8_t* x, int n, double* sums /*[4]*/, int fmt) {
+    double s1 = 0, s2 = 0, s3 = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 v = acq_sample(x, (size_t)i, fmt);
+        s1 += (double)v.x;
+        s2 += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+        s3 += (double)v.y;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    s3 = warp_sum(s3);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sums[0], s1);
+        atomicAdd(&sums[1], s2);
+        atomicAdd(&sums[2], s3);
+    }
+}
+
+// ---- resampling pre-conditioner (acquisition.m:56-123) --------------------------------------------------------------
+// longSignal = filtfilt(b, 1, longSignal); longSignal = longSignal(index), index = ceil((0:len-1)/fsNew*fsOld), index(1) = 1.
+// For an FIR b the zero-phase result on the original samples is exactly the correlation of the record, extended by
+// filtfilt's odd reflection (nfact = 3*(numel(b)-1) >= 2*(numel(b)-1) samples at both ends), with g = b (*) flip(b): the
+// start-up states filtfilt adds only shape the reflected margins it strips again.  Only the samples the index vector
+// picks are evaluated (float64 accumulation; the acquisition continues on float samples).  grid-stride, one output each.
+constexpr int kResampleThreads = 256;
+__global__ void __launch_bounds__(kResampleThreads) acq_resample_kernel(const int8_t* x, int iq, long long n, const double* g,
+                                                                       int half /* numel(b) - 1 */, double fsNew, double fsOld,
+                                                                       long long outLen, float* out) {
+    extern __shared__ double gs[];
+    for (int i = threadIdx.x; i < 2 * half + 1; i += blockDim.x) gs[i] = g[i];
+    __syncthreads();
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < outLen; k += (long long)gridDim.x * blockDim.x) {
+        long long idx = (long long)ceil(__dmul_rn(__ddiv_rn((double)k, fsNew), fsOld)) - 1;   // 0-based sample
+        if (k == 0) idx = 0;
+        double ar = 0.0, ai = 0.0;
+        if (idx - half >= 0 && idx + half < n) {   // interior: plain correlation
+            if (iq) {
+                const char2* p = reinterpret_cast<const char2*>(x) + (idx - half);
+                for (int j = 0; j <= 2 * half; ++j) {
+                    const char2 v = p[j];
+                    ar = fma(gs[j], (double)v.x, ar);
+                    ai = fma(gs[j], (double)v.y, ai);
+                }
+            } else {
+                const int8_t* p = x + (idx - half);
+                for (int j = 0; j <= 2 * half; ++j) ar = fma(gs[j], (double)p[j], ar);
+            }
+        } else {                                   // margins: odd reflection about the first / last sample
+            for (int j = 0; j <= 2 * half; ++j) {
+                long long m = idx - half + j;
+                double sr, si = 0.0;
+                if (m < 0) {
+                    const long long r = -m;
+                    sr = 2.0 * (double)x[0] - (double)(iq ? x[2 * r] : x[r]);
+                    if (iq) si = 2.0 * (double)x[1] - (double)x[2 * r + 1];
+                } else if (m >= n) {
+                    const long long r = 2 * (n - 1) - m;
+                    sr = 2.0 * (double)(iq ? x[2 * (n - 1)] : x[n - 1]) - (double)(iq ? x[2 * r] : x[r]);
+                    if (iq) si = 2.0 * (double)x[2 * (n - 1) + 1] - (double)x[2 * r + 1];
+                } else {
+                    sr = (double)(iq ? x[2 * m] : x[m]);
+                    if (iq) si = (double)x[2 * m + 1];
+                }
+                ar = fma(gs[j], sr, ar);
+                ai = fma(gs[j], si, ai);
+            }
+        }
+        if (iq) reinterpret_cast<float2*>(out)[k] = make_float2((float)ar, (float)ai);
+        else out[k] = (float)ar;
+    }
+}
+
 // ---- fine search ---------------------------------------------------------------------------
 // B1C (acquisition.m:253-300): for fine bin j, component dp:
 //   A = sum_n x[n] T[n] e^{i phi_j n},  B = sum_n T[n] e^{i phi_j n}   (DC removal applied on host: A - mean*B)
@@ -555,31 +632,13 @@ const std::vector<int8_t>* cached_component(int component, int prn) {
     return &cache.emplace(std::make_pair(component, prn), std::move(v)).first->second;
 }
 
-}  // namespace
-
-extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, const bds_acq_cfg* cfg,
-                           const int32_t* prn, int n_prn, int prn_lo, int prn_hi, double* carrFreq,
-                           double* codePhase, double* peakMetric, int max_prn, double* dbg) {
-    if (!x || !cfg || !prn || !carrFreq || !codePhase || !peakMetric || n_prn <= 0)
-        return set_error(BDS_ERR_ARG, "bds_acquire: null/empty argument");
-    if (signal != BDS_SIG_B1C && signal != BDS_SIG_B2A) return set_error(BDS_ERR_ARG, "unknown signal %d", signal);
-    if (cfg->codeLength != kCodeLen) return set_error(BDS_ERR_UNSUPPORTED, "codeLength must be 10230");
-    for (int i = 0; i < n_prn; ++i)
-        if (prn[i] < 1 || prn[i] > 63 || prn[i] > max_prn)
-            return set_error(BDS_ERR_ARG, "PRN %d out of range (max_prn %d)", prn[i], max_prn);
-    int rc = require_device();
-    if (rc) return rc;
-    std::memset(carrFreq, 0, sizeof(double) * max_prn);
-    std::memset(codePhase, 0, sizeof(double) * max_prn);
-    std::memset(peakMetric, 0, sizeof(double) * max_prn);
-    if (dbg) std::memset(dbg, 0, sizeof(double) * max_prn * 4);
-    prn_lo = std::max(prn_lo, 0);
-    prn_hi = std::min(prn_hi, n_prn);
-
+// The search proper (acquisition.m:129-338 / B2a acquisition.m:130-365) on a DEVICE record dx of n samples in format fmt
+// (kFmt*: int8 or float, real or I/Q).  Outputs are zero-filled by the caller.
+int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_cfg* cfg, const int32_t* prn, int n_prn,
+                 int prn_lo, int prn_hi, double* carrFreq, double* codePhase, double* peakMetric, int max_prn, double* dbg) {
     const bool b1c = signal == BDS_SIG_B1C;
-    if (cfg->fileType != 0 && cfg->fileType != 1 && cfg->fileType != 2)
-        return set_error(BDS_ERR_ARG, "fileType must be 1 (real) or 2 (I/Q), got %d", cfg->fileType);
-    const int iq = cfg->fileType == 2;   // x holds n I/Q pairs = 2n bytes
+    const int iq = fmt;   // the kernels' sample-format argument
+    const size_t sampleBytes = acq_sample_bytes(fmt);
     const double fs = cfg->samplingFreq;
     const long spc = mround(fs / (cfg->codeFreqBasis / cfg->codeLength));
     long M, N;
@@ -641,14 +700,6 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     pl.twHi = dTwHi.as<float2>();
     pl.twLo = dTwLo.as<float2>();
 
-    // ---- IF record on the device
-    const int8_t* dx = x;
-    if (x_loc == BDS_LOC_HOST) {
-        TRYA(dX.alloc(n << iq));
-        TRYA(cudaMemcpy(dX.p, x, n << iq, cudaMemcpyHostToDevice));
-        dx = dX.as<int8_t>();
-    }
-
     // ---- Doppler bins: frqBins = IF - band + step*(k-1)   acquisition.m:194-195
     std::vector<double> frq(nbins);
     std::vector<unsigned long long> dphi(nbins);
@@ -685,12 +736,19 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
     if (b1c) {
         TRYA(dSums.alloc(32));
         TRYA(cudaMemset(dSums.p, 0, 32));
-        acq_power_kernel<<<g_num_sms * 4, 256>>>(dx, (int)M, dSums.as<long long>(), iq);
+        double ps[4];   // sum I, sum |x|^2, sum Q
+        if (fmt & 2) {
+            acq_power_f32_kernel<<<g_num_sms * 4, 256>>>(dx, (int)M, dSums.as<double>(), fmt);
+            TRYA(cudaMemcpy(ps, dSums.p, 32, cudaMemcpyDeviceToHost));
+        } else {
+            acq_power_kernel<<<g_num_sms * 4, 256>>>(dx, (int)M, dSums.as<long long>(), iq);
+            long long hs[4];
+            TRYA(cudaMemcpy(hs, dSums.p, 32, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < 4; ++k) ps[k] = (double)hs[k];
+        }
         count_launch();
-        long long hs[4];
-        TRYA(cudaMemcpy(hs, dSums.p, 32, cudaMemcpyDeviceToHost));
         // var() of a real or complex vector: (sum |x|^2 - |sum x|^2 / M) / (M - 1)
-        double var = ((double)hs[1] - ((double)hs[0] * (double)hs[0] + (double)hs[2] * (double)hs[2]) / (double)M) / (double)(M - 1);
+        double var = (ps[1] - (ps[0] * ps[0] + ps[2] * ps[2]) / (double)M) / (double)(M - 1);
         sigPower = std::sqrt(var * (double)M);
     }
 
@@ -900,13 +958,15 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
                 double* out = dFine.as<double>() + j.off;
                 const unsigned long long* dph = dFineDphi.as<unsigned long long>() + dphiOff;
                 if (b1c) {   // acquisition.m:253-307
-                    long long* pw = reinterpret_cast<long long*>(out + (size_t)j.nfine * ncodes * 4);
-                    acq_power_kernel<<<g_num_sms * 4, 256>>>(dx + ((size_t)(j.cp - 1) << iq), (int)spc, pw, iq);
+                    double* pw = out + (size_t)j.nfine * ncodes * 4;   // power sums: long long (int8 records) or double
+                    const int8_t* xs = dx + (size_t)(j.cp - 1) * sampleBytes;
+                    if (fmt & 2) acq_power_f32_kernel<<<g_num_sms * 4, 256>>>(xs, (int)spc, pw, fmt);
+                    else acq_power_kernel<<<g_num_sms * 4, 256>>>(xs, (int)spc, reinterpret_cast<long long*>(pw), iq);
                     acq_fine_b1c_kernel<<<dim3(g_num_sms, j.nfine, ncodes), 256>>>(
-                        dx + ((size_t)(j.cp - 1) << iq), dTab.as<int8_t>() + (size_t)j.i * ncodes * spc, (int)spc, dph, ncodes, out, iq);
+                        xs, dTab.as<int8_t>() + (size_t)j.i * ncodes * spc, (int)spc, dph, ncodes, out, iq);
                     count_launch(2);
                 } else {     // B2a acquisition.m:256-335
-                    acq_fine_b2a_kernel<<<dim3(32, j.nfine, nseg), 256>>>(dx + ((size_t)(j.cp - 1) << iq), dBits.as<uint32_t>() + q * 2 * kPackedWords,
+                    acq_fine_b2a_kernel<<<dim3(32, j.nfine, nseg), 256>>>(dx + (size_t)(j.cp - 1) * sampleBytes, dBits.as<uint32_t>() + q * 2 * kPackedWords,
                                                                          (int)spc, 1.0 / fs, 1.0 / cfg->codeFreqBasis, dph, nseg, out, iq);
                     count_launch();
                 }
@@ -921,9 +981,14 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
                 int best = 0;
                 double bestV = -1;
                 if (b1c) {
-                    long long hs[4];
-                    std::memcpy(hs, o0 + (size_t)j.nfine * ncodes * 4, 32);
-                    const double mr = (double)hs[0] / (double)spc, mi = (double)hs[2] / (double)spc;   // mean(signal), complex for I/Q
+                    double ps[4];
+                    if (fmt & 2) std::memcpy(ps, o0 + (size_t)j.nfine * ncodes * 4, 32);
+                    else {
+                        long long hs[4];
+                        std::memcpy(hs, o0 + (size_t)j.nfine * ncodes * 4, 32);
+                        for (int k = 0; k < 4; ++k) ps[k] = (double)hs[k];
+                    }
+                    const double mr = ps[0] / (double)spc, mi = ps[2] / (double)spc;   // mean(signal), complex for I/Q
                     for (int q = 0; q < j.nfine; ++q) {
                         double v[2] = {0, 0};
                         for (int dp = 0; dp < ncodes; ++dp) {
@@ -957,6 +1022,113 @@ extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, con
         }
     }
     TRYA(cudaDeviceSynchronize());
+    return BDS_OK;
+}
+
+// b = fir1(order, [w1 w2]) (band-pass, Hamming window, scaled to unit gain at the centre of the pass band) and
+// g = b (*) flip(b), the zero-phase kernel filtfilt(b, 1, .) applies (acquisition.m:70-74)
+void fir1_bandpass_autocorr(int order, double w1, double w2, std::vector<double>& g) {
+    const int L = order + 1;
+    const double pi = 3.14159265358979323846;
+    std::vector<double> b(L);
+    auto sinc = [&](double x) { return x == 0.0 ? 1.0 : std::sin(pi * x) / (pi * x); };
+    for (int i = 0; i < L; ++i) {
+        const double m = (double)i - 0.5 * order;
+        const double ideal = w2 * sinc(w2 * m) - w1 * sinc(w1 * m);           // least-squares fit of the ideal band
+        const double win = 0.54 - 0.46 * std::cos(2.0 * pi * (double)i / (double)order);   // hamming(L)
+        b[i] = ideal * win;
+    }
+    const double f0 = 0.5 * (w1 + w2);   // b = b / abs(exp(-j*2*pi*(0:L-1)*(f0/2)) * b.')
+    double re = 0, im = 0;
+    for (int i = 0; i < L; ++i) {
+        re += b[i] * std::cos(pi * f0 * i);
+        im -= b[i] * std::sin(pi * f0 * i);
+    }
+    const double sc = std::hypot(re, im);
+    for (auto& v : b) v /= sc;
+    g.assign(2 * order + 1, 0.0);
+    for (int k = -order; k <= order; ++k) {
+        double a = 0;
+        for (int i = std::max(0, -k); i < L && i + k < L; ++i) a += b[i] * b[i + k];
+        g[k + order] = a;
+    }
+}
+
+}  // namespace
+
+extern "C" int bds_acquire(int signal, const int8_t* x, size_t n, int x_loc, const bds_acq_cfg* cfg,
+                           const int32_t* prn, int n_prn, int prn_lo, int prn_hi, double* carrFreq,
+                           double* codePhase, double* peakMetric, int max_prn, double* dbg) {
+    if (!x || !cfg || !prn || !carrFreq || !codePhase || !peakMetric || n_prn <= 0)
+        return set_error(BDS_ERR_ARG, "bds_acquire: null/empty argument");
+    if (signal != BDS_SIG_B1C && signal != BDS_SIG_B2A) return set_error(BDS_ERR_ARG, "unknown signal %d", signal);
+    if (cfg->codeLength != kCodeLen) return set_error(BDS_ERR_UNSUPPORTED, "codeLength must be 10230");
+    for (int i = 0; i < n_prn; ++i)
+        if (prn[i] < 1 || prn[i] > 63 || prn[i] > max_prn)
+            return set_error(BDS_ERR_ARG, "PRN %d out of range (max_prn %d)", prn[i], max_prn);
+    if (cfg->fileType != 0 && cfg->fileType != 1 && cfg->fileType != 2)
+        return set_error(BDS_ERR_ARG, "fileType must be 1 (real) or 2 (I/Q), got %d", cfg->fileType);
+    int rc = require_device();
+    if (rc) return rc;
+    std::memset(carrFreq, 0, sizeof(double) * max_prn);
+    std::memset(codePhase, 0, sizeof(double) * max_prn);
+    std::memset(peakMetric, 0, sizeof(double) * max_prn);
+    if (dbg) std::memset(dbg, 0, sizeof(double) * max_prn * 4);
+    prn_lo = std::max(prn_lo, 0);
+    prn_hi = std::min(prn_hi, n_prn);
+    const int iq = cfg->fileType == 2;   // x holds n I/Q pairs = 2n bytes
+
+    // ---- IF record on the device
+    DevBuf dX, dRes, dG;
+    const int8_t* dx = x;
+    if (x_loc == BDS_LOC_HOST) {
+        TRYA(dX.alloc(n << iq));
+        TRYA(cudaMemcpy(dX.p, x, n << iq, cudaMemcpyHostToDevice));
+        dx = dX.as<int8_t>();
+    }
+    if (!(cfg->resamplingflag == 1 && cfg->samplingFreq > cfg->resamplingThreshold))
+        return acquire_core(signal, dx, iq, n, cfg, prn, n_prn, prn_lo, prn_hi, carrFreq, codePhase, peakMetric, max_prn, dbg);
+
+    // ---- resampling pre-conditioner (acquisition.m:56-123 / B2a acquisition.m:56-124): zero-phase band-pass around the IF,
+    //      then the search runs at a band-pass sampling rate on every index-th sample
+    const double fsOld = cfg->samplingFreq, IF = cfg->IF;
+    const double BW = signal == BDS_SIG_B1C ? 9e6 : cfg->codeFreqBasis * 2 + 0.5e6;     // :63 / B2a :64
+    const double w1 = IF - BW / 2, w2 = IF + BW / 2;
+    const double wp1 = w1 * 2 / fsOld - 0.002, wp2 = w2 * 2 / fsOld + 0.002;            // :67
+    if (!(wp1 > 0.0 && wp2 < 1.0)) return set_error(BDS_ERR_ARG, "resampling: pass band [%g, %g] outside (0, 1)", wp1, wp2);
+    const int order = 700;                                                              // fir1(700, wp), :69
+    if (n <= (size_t)3 * order) return set_error(BDS_ERR_ARG, "resampling: filtfilt needs more than %d samples", 3 * order);
+    std::vector<double> g;
+    fir1_bandpass_autocorr(order, wp1, wp2, g);
+    const double fu = IF + BW / 2, fl = IF - BW / 2;                                    // :79-95
+    double nn = std::floor(fu / BW);
+    if (nn < 1) nn = 1;
+    const double lowerFreq = 2 * fu / nn;
+    const double upperFreq = nn > 1 ? 2 * fl / (nn - 1) : lowerFreq;
+    const double fsNew = std::ceil((lowerFreq + upperFreq) / 2);                        // :105
+    const long long outLen = (long long)std::floor((double)(n - 1) / fsOld * fsNew);    // :109
+    if (outLen <= 0) return set_error(BDS_ERR_ARG, "resampling: empty record");
+    TRYA(dG.alloc(sizeof(double) * g.size()));
+    TRYA(cudaMemcpy(dG.p, g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice));
+    TRYA(dRes.alloc(sizeof(float) * ((size_t)outLen << iq)));
+    acq_resample_kernel<<<g_num_sms * 8, kResampleThreads, sizeof(double) * g.size()>>>(
+        dx, iq, (long long)n, dG.as<double>(), order, fsNew, fsOld, outLen, dRes.as<float>());
+    count_launch();
+    TRYA(cudaGetLastError());
+    bds_acq_cfg c2 = *cfg;
+    c2.samplingFreq = fsNew;
+    c2.IF = std::fmod(IF, fsNew);                                                       // :122
+    c2.resamplingflag = 0;
+    rc = acquire_core(signal, dRes.as<int8_t>(), kFmtF32 | iq, (size_t)outLen, &c2, prn, n_prn, prn_lo, prn_hi, carrFreq,
+                      codePhase, peakMetric, max_prn, dbg);
+    if (rc) return rc;
+    // ---- results back at the original sampling rate (acquisition.m:321-338)
+    for (int p = 0; p < max_prn; ++p) {
+        if (carrFreq[p] == 0) continue;   // not detected
+        codePhase[p] = std::floor((codePhase[p] - 1) / fsNew * fsOld) + 1;
+        const double doppler = c2.IF >= fsNew / 2 ? (fsNew - c2.IF) - carrFreq[p] : carrFreq[p] - c2.IF;
+        carrFreq[p] = doppler + IF;
+    }
 #undef TRYA
     return BDS_OK;
 }

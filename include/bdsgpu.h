@@ -102,6 +102,12 @@ typedef struct bds_acq_cfg {
     int32_t fineNoncoh;   /* B2a: settings.fineNoncoh [ms]; ignored for B1C */
     int32_t fileType;     /* settings.fileType: 0/1 = real samples, 2 = interleaved I/Q pairs, longSignal = I + 1i*Q
                            * (postProcessing.m:94-99); x then holds 2*n int8 values for n samples */
+    /* resampling pre-conditioner (acquisition.m:56-123, B2a acquisition.m:56-124): with resamplingflag == 1 and
+     * samplingFreq > resamplingThreshold the record is band-pass filtered around the IF (fir1(700) + filtfilt), the search
+     * runs at a band-pass sampling rate on every index-th sample and codePhase / carrFreq are mapped back (:321-338) */
+    double resamplingThreshold; /* settings.resamplingThreshold [Hz] */
+    int32_t resamplingflag;     /* settings.resamplingflag */
+    int32_t reserved;           /* 0 */
 } bds_acq_cfg;
 
 /* Replaces acquisition(longSignal, settings):

@@ -5,11 +5,10 @@ function acqResults = acquisition(longSignal, settings)
 % libbdsgpu (bds_acquire); the struct layout is the reference's (acquisition.m:161-165):
 % carrFreq, codePhase, peakMetric, each 1 x max(acqSatelliteList), zero = not found.
 isB2a = settings.codeFreqBasis > 5e6;            % B2a: 10.23 Mcps, B1C: 1.023 Mcps
-if settings.resamplingflag == 1 && settings.samplingFreq > settings.resamplingThreshold
-    error('bds:unsupported', 'resampling pre-conditioner is not part of the GPU path; set resamplingflag = 0');
-end
+% the resampling pre-conditioner (acquisition.m:56-123) runs inside the library when settings ask for it
 cfg = [settings.samplingFreq, settings.IF, settings.codeFreqBasis, settings.codeLength, ...
-       settings.acqSearchBand, settings.acqStep, settings.acqThreshold, 0, 0, 0];
+       settings.acqSearchBand, settings.acqStep, settings.acqThreshold, 0, 0, 0, ...
+       settings.resamplingThreshold, settings.resamplingflag];
 if isB2a
     cfg(10) = settings.fineNoncoh;  signal = 2;
 else

@@ -55,6 +55,10 @@ static void do_acquire(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[
     cfg.samplingFreq = c[0]; cfg.IF = c[1]; cfg.codeFreqBasis = c[2]; cfg.codeLength = (int32_t)c[3];
     cfg.acqSearchBand = c[4]; cfg.acqStep = c[5]; cfg.acqThreshold = c[6]; cfg.acqCohT = (int32_t)c[7];
     cfg.pilotACQflag = (int32_t)c[8]; cfg.fineNoncoh = (int32_t)c[9];
+    if (mxGetNumberOfElements(prhs[3]) > 11) { /* resampling pre-conditioner, acquisition.m:56-123 */
+        cfg.resamplingThreshold = c[10];
+        cfg.resamplingflag = (int32_t)c[11];
+    }
     const mwSize nprn = mxGetNumberOfElements(prhs[4]);
     const double* pl = mxGetDoubles(prhs[4]);
     int32_t prn[64];

@@ -254,11 +254,83 @@ def makeB2aPilotTable(PRN, settings):
 
 
 # ----------------------------------------------------------------------------
+# resampling pre-conditioner (B1C/acquisition.m:56-123, B2a/acquisition.m:56-124)
+# ----------------------------------------------------------------------------
+def fir1_bandpass(order: int, wp) -> np.ndarray:
+    """b = fir1(order, [w1 w2]): MATLAB's window-method band-pass (fir1.m): the least-squares fit of the ideal band
+    (firls with contiguous bands = the truncated ideal impulse response), times hamming(order+1), scaled to unit
+    magnitude at the centre of the pass band (b / abs(exp(-j*2*pi*(0:L-1)*(f0/2))*b.')).  Third-party arithmetic
+    (Signal Processing Toolbox), restated from its published algorithm - parity unpinned."""
+    w1, w2 = float(wp[0]), float(wp[1])
+    L = order + 1
+    m = np.arange(L, dtype=np.float64) - order / 2
+    ideal = w2 * np.sinc(w2 * m) - w1 * np.sinc(w1 * m)
+    win = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(L) / order)
+    b = ideal * win
+    f0 = (w1 + w2) / 2
+    return b / abs(np.sum(np.exp(-1j * 2 * np.pi * np.arange(L) * (f0 / 2)) * b))
+
+
+def filtfilt_fir(b: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """y = filtfilt(b, 1, x) as filtfilt.m does it: nfact = 3*(numel(b)-1); odd reflection of nfact samples about both
+    end points; steady-state initial conditions zi scaled by the first sample of each pass; filter forward, reverse,
+    filter again, reverse; strip the reflected margins."""
+    from scipy.signal import lfilter
+    nb = b.size
+    nfact = 3 * (nb - 1)
+    if x.size <= nfact:
+        raise ValueError("filtfilt: data must have length more than 3 times filter order")
+    # zi: filter(b, 1, ones) starts in its steady state.  With a = 1: zi(k) = sum(b(k+1:end))
+    zi = np.cumsum(b[::-1])[::-1][1:]
+    xt = np.concatenate([2 * x[0] - x[nfact:0:-1], x, 2 * x[-1] - x[-2:-nfact - 2:-1]])
+    y, _ = lfilter(b, [1.0], xt, zi=zi * xt[0])
+    y = y[::-1]
+    y, _ = lfilter(b, [1.0], y, zi=zi * y[0])
+    return y[::-1][nfact:-nfact]
+
+
+def resample_for_acquisition(longSignal, settings, BW):
+    """acquisition.m:56-123.  Returns (longSignal, settings', oldFreq, oldIF), or the inputs and None when the branch is off."""
+    if not (settings.samplingFreq > settings.resamplingThreshold and settings.get("resamplingflag", 0) == 1):
+        return longSignal, settings, None, None
+    fs, IF = settings.samplingFreq, settings.IF
+    w1, w2 = IF - BW / 2, IF + BW / 2
+    wp = [w1 * 2 / fs - 0.002, w2 * 2 / fs + 0.002]
+    b = fir1_bandpass(700, wp)
+    x = np.asarray(longSignal)
+    x = x.astype(np.complex128 if np.iscomplexobj(x) else np.float64)
+    x = filtfilt_fir(b, x.real) + 1j * filtfilt_fir(b, x.imag) if np.iscomplexobj(x) else filtfilt_fir(b, x)
+    fu = IF + BW / 2
+    n = max(1, math.floor(fu / BW))
+    lowerFreq = 2 * fu / n
+    fl = IF - BW / 2
+    upperFreq = 2 * fl / (n - 1) if n > 1 else lowerFreq
+    st = Settings(dict(settings))
+    st.samplingFreq = float(math.ceil((lowerFreq + upperFreq) / 2))
+    signalLen = int(math.floor((x.size - 1) / fs * st.samplingFreq))
+    index = np.ceil(np.arange(signalLen, dtype=np.float64) / st.samplingFreq * fs).astype(np.int64)
+    index[0] = 1
+    x = x[index - 1]
+    st.IF = math.fmod(IF, st.samplingFreq)
+    return x, st, fs, IF
+
+
+def _resampling_recovery(acq, PRN, codePhase, st, oldFreq, oldIF):
+    """acquisition.m:321-338: results at the original sampling rate."""
+    acq.codePhase[PRN - 1] = math.floor((codePhase - 1) / st.samplingFreq * oldFreq) + 1
+    if st.IF >= st.samplingFreq / 2:
+        doppler = (st.samplingFreq - st.IF) - acq.carrFreq[PRN - 1]
+    else:
+        doppler = acq.carrFreq[PRN - 1] - st.IF
+    acq.carrFreq[PRN - 1] = doppler + oldIF
+
+
+# ----------------------------------------------------------------------------
 # a1/a2  B1C acquisition
 # ----------------------------------------------------------------------------
 def acquisition_B1C(longSignal: np.ndarray, settings, return_debug: bool = False):
-    """B1C/acquisition.m:129-338 (resampling branch :56-123 not restated:
-    ``resamplingflag = 0`` in every shipped/benchmarked config)."""
+    """B1C/acquisition.m:56-338."""
+    longSignal, settings, oldFreq, oldIF = resample_for_acquisition(longSignal, settings, 9e6)   # :56-123
     longSignal = np.asarray(longSignal)
     if not np.iscomplexobj(longSignal):
         longSignal = longSignal.astype(np.float64)
@@ -327,6 +399,8 @@ def acquisition_B1C(longSignal: np.ndarray, settings, return_debug: bool = False
                 acq.carrFreq[PRN - 1] = 1
             acq.codePhase[PRN - 1] = codePhase
             dbg[PRN]["fine"] = FineRes
+            if oldFreq is not None:
+                _resampling_recovery(acq, PRN, codePhase, settings, oldFreq, oldIF)              # :321-338
     return (acq, dbg) if return_debug else acq
 
 
@@ -334,7 +408,9 @@ def acquisition_B1C(longSignal: np.ndarray, settings, return_debug: bool = False
 # a4/a5  B2a acquisition
 # ----------------------------------------------------------------------------
 def acquisition_B2a(longSignal: np.ndarray, settings, return_debug: bool = False):
-    """B2a/acquisition.m:130-335."""
+    """B2a/acquisition.m:56-365."""
+    longSignal, settings, oldFreq, oldIF = resample_for_acquisition(longSignal, settings,
+                                                                    settings.codeFreqBasis * 2 + 0.5e6)   # :56-124
     longSignal = np.asarray(longSignal)
     if not np.iscomplexobj(longSignal):
         longSignal = longSignal.astype(np.float64)
@@ -401,6 +477,8 @@ def acquisition_B2a(longSignal: np.ndarray, settings, return_debug: bool = False
             acq.codePhase[PRN - 1] = codePhase
             if acq.carrFreq[PRN - 1] == 0:
                 acq.carrFreq[PRN - 1] = 1
+            if oldFreq is not None:
+                _resampling_recovery(acq, PRN, codePhase, settings, oldFreq, oldIF)              # :339-356
             dbg[PRN]["fine"] = FineRes
     return (acq, dbg) if return_debug else acq
 

@@ -119,3 +119,35 @@ def test_b2a_acquisition_parity_iq_record():
     np.testing.assert_array_equal(got.codePhase, want.codePhase)
     np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
     assert want.carrFreq[3] != 0 and want.carrFreq[8] == 0
+
+
+# ---- resampling pre-conditioner (acquisition.m:56-123 / B2a :56-124, results mapped back :321-338) -----------------
+def test_b1c_acquisition_with_resampling_preconditioner():
+    s, sats, x = _b1c_record(1, 0.0305, 5, acqSearchBand=150, acqSatelliteList=[1, 2], resamplingflag=1)
+    assert s.samplingFreq > s.resamplingThreshold
+    want, wd = O.acquisition_B1C(x, s, return_debug=True)
+    got, gd = B.b1c.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for prn in (1, 2):
+        assert gd[prn - 1, 0] == wd[prn]["bin"] and gd[prn - 1, 1] == wd[prn]["codePhase"]     # at the resampled rate
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+    assert want.carrFreq[0] != 0 and want.carrFreq[1] == 0
+    spc = O.samples_per_code(s)
+    d = (got.codePhase[0] - 1 - sats[0].codeDelay) % spc
+    assert min(d, spc - d) <= 6            # one resampled sample = 5.07 original ones
+
+
+def test_b2a_acquisition_with_resampling_preconditioner():
+    s = O.initSettings_B2a(acqSatelliteList=[4, 9], resamplingflag=1)
+    sats = synth.make_sats(1, s, "B2a", seed=3, prns=[4], cn0=47.0)
+    x = synth.synth_numpy("B2a", s, sats, 17 * 99375, seed=3)
+    want, wd = O.acquisition_B2a(x, s, return_debug=True)
+    got, gd = B.b2a.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for prn in (4, 9):
+        assert gd[prn - 1, 0] == wd[prn]["bin"] and gd[prn - 1, 1] == wd[prn]["codePhase"]
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+    assert want.carrFreq[3] != 0 and want.carrFreq[8] == 0
+    assert abs(got.carrFreq[3] - (s.IF + sats[0].doppler)) <= 25

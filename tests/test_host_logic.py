@@ -90,10 +90,14 @@ def test_as_int8_validation():
     assert L.is_iq(np.zeros(2, dtype=np.int8), B.Settings(fileType=2))
 
 
-def test_resampling_branch_is_refused():
+def test_resampling_settings_reach_the_library():
+    """acquisition.m:56-57: the branch is the library's (bds_acq_cfg.resamplingflag / resamplingThreshold)"""
+    assert {"resamplingThreshold", "resamplingflag", "fileType"} <= {f[0] for f in L.bds_acq_cfg._fields_}
     s = B.b1c.initSettings(samplingFreq=99.375e6, resamplingflag=1)
-    with pytest.raises(L.BdsError):
-        _acq.acquire(L.SIG_B1C, np.zeros(16, dtype=np.int8), s)
+    if not L.device_ok():
+        with pytest.raises(L.BdsError) as e:     # no CPU fallback: the call reaches the library and fails on the device check
+            _acq.acquire(L.SIG_B1C, np.zeros(16, dtype=np.int8), s)
+        assert e.value.code == -2
 
 
 def test_shard_helpers():

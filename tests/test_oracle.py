@@ -372,3 +372,38 @@ def test_lock_loss_extension_is_off_by_default_and_drops_a_dead_channel():
     np.testing.assert_array_equal(got[0].I_P[:lost], base[0].I_P[:lost])
     assert np.all(got[0].I_P[lost:] == 0) and np.all(np.isinf(got[0].carrFreq[lost:]))
     assert got[1].status == "T" and np.array_equal(got[1].I_P, base[1].I_P)       # the other channel is untouched
+
+
+# ---- resampling pre-conditioner (acquisition.m:56-123): third-party arithmetic (fir1 / filtfilt), restated ---------
+def test_fir1_and_filtfilt_restatements_against_scipy():
+    """fir1 == scipy.signal.firwin (an independent implementation of the same published window method), filtfilt ==
+    scipy.signal.filtfilt with MATLAB's padding length, and the zero-phase result on the original samples equals the
+    correlation of the odd-extended record with b (*) flip(b) - the form the device kernel evaluates."""
+    from scipy import signal
+    wp = [(14.58e6 - 4.5e6) * 2 / 99.375e6 - 0.002, (14.58e6 + 4.5e6) * 2 / 99.375e6 + 0.002]     # acquisition.m:64-67
+    b = O.fir1_bandpass(700, wp)
+    np.testing.assert_allclose(b, signal.firwin(701, wp, window="hamming", pass_zero=False, scale=True), rtol=0, atol=1e-14)
+    assert abs(abs(np.sum(b * np.exp(-1j * np.pi * np.mean(wp) * np.arange(701)))) - 1) < 1e-12
+    x = np.rint(np.random.default_rng(1).normal(0, 25, 9000))
+    y = O.filtfilt_fir(b, x)
+    np.testing.assert_allclose(y, signal.filtfilt(b, [1.0], x, padlen=2100), rtol=0, atol=1e-11)
+    g = np.correlate(b, b, mode="full")
+    xt = np.concatenate([2 * x[0] - x[2100:0:-1], x, 2 * x[-1] - x[-2:-2102:-1]])
+    np.testing.assert_allclose(y, np.correlate(xt, g, mode="same")[2100:-2100], rtol=0, atol=1e-11)
+    with pytest.raises(ValueError):
+        O.filtfilt_fir(b, x[:2100])
+
+
+def test_resampling_rates_and_index_vector():
+    """acquisition.m:79-122 at the BASELINE sampling rate: B1C 19.62 MHz (IF above fs/2: the mirrored branch of
+    :327-333), B2a 48.06 MHz"""
+    s = O.initSettings_B1C(samplingFreq=99.375e6, resamplingflag=1)
+    x = np.arange(5000, dtype=np.float64)
+    y, st, oldFreq, oldIF = O.resample_for_acquisition(x, s, 9e6)
+    assert st.samplingFreq == 19620000.0 and st.IF == s.IF and st.IF >= st.samplingFreq / 2 and (oldFreq, oldIF) == (99.375e6, s.IF)
+    assert y.size == int(np.floor(4999 / 99.375e6 * 19.62e6))
+    s2 = O.initSettings_B2a(resamplingflag=1)
+    y2, st2, _, _ = O.resample_for_acquisition(x, s2, s2.codeFreqBasis * 2 + 0.5e6)
+    assert st2.samplingFreq == 48060000.0 and st2.IF == s2.IF < st2.samplingFreq / 2
+    same, st3, o3, _ = O.resample_for_acquisition(x, O.initSettings_B1C(samplingFreq=99.375e6), 9e6)
+    assert same is x and o3 is None                                   # resamplingflag = 0: untouched
