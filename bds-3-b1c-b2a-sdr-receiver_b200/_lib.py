@@ -32,7 +32,7 @@ class bds_trk_cfg(C.Structure):
                 ("kernel", C.c_int32), ("reserved", C.c_int32), ("fwPassesPerTask", C.c_int32),
                 ("fwPrefetch", C.c_int32), ("debug", C.c_int32), ("traceTickets", C.c_int32),
                 ("lockLossPLD", C.c_double), ("lockLossIntervals", C.c_int32), ("fwMaxCtas", C.c_int32),
-                ("fileType", C.c_int32), ("reserved3", C.c_int32)]
+                ("fileType", C.c_int32), ("b2aClusterSize", C.c_int32)]
 
 
 class bds_channel(C.Structure):

@@ -685,6 +685,7 @@ struct bds_trk {
     unsigned traceCap = 0;
     bool fast = false;
     bool b2aUnit = false;   // B2a on the per-channel chip-synchronous kernel
+    int b2aCluster = 1;     // ... with this many CTAs (a thread-block cluster) per channel
     int iq = 0;             // 1: the record holds interleaved I/Q int8 pairs (cfg.fileType == 2); window quantities are samples
     size_t smemBytes = 0;
     int epochsRun = 0;  // max over channels, as seen by the host
@@ -902,9 +903,35 @@ int plan_grid(bds_trk* h) {
     if (h->b2aUnit) {
         h->smemBytes = sizeof(B2aSmem);
         BDS_CUDA(cudaFuncSetAttribute(trk_b2a_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_b2a_unit_kernel, kB2aThreads, h->smemBytes));
+        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_b2a_unit_kernel, kB2aThreadsAll, h->smemBytes));
         if (occ < 1) return set_error(BDS_ERR_CUDA, "B2a tracking kernel does not fit on an SM");
-        h->gridBlocks = h->nAct;   // one CTA per channel, no co-residency requirement
+        // CTAs per channel (one thread-block cluster): the loop closure is a serial chain of 1 000 steps per second of
+        // signal, so with few channels per GPU the idle SMs shorten each step - the largest cluster for which every
+        // channel's cluster is resident at once (a cluster of 8 needs 8 free SMs in one GPC)
+        int cs = h->cfg.b2aClusterSize;
+        if (cs != 0 && cs != 1 && cs != 2 && cs != 4 && cs != 8)
+            return set_error(BDS_ERR_ARG, "b2aClusterSize must be 0 (auto), 1, 2, 4 or 8, got %d", cs);
+        const bool autoCs = cs == 0;
+        if (autoCs) cs = kB2aMaxCluster;
+        for (; cs > 1; cs >>= 1) {
+            if ((long long)h->nAct * cs > g_num_sms) continue;
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3(h->nAct * cs);
+            lc.blockDim = dim3(kB2aThreadsAll);
+            lc.dynamicSmemBytes = h->smemBytes;
+            cudaLaunchAttribute at{};
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = cs;
+            at.val.clusterDim.y = at.val.clusterDim.z = 1;
+            lc.attrs = &at;
+            lc.numAttrs = 1;
+            int nClusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nClusters, trk_b2a_unit_kernel, &lc) == cudaSuccess && nClusters >= h->nAct) break;
+            cudaGetLastError();
+            if (!autoCs) return set_error(BDS_ERR_UNSUPPORTED, "b2aClusterSize %d: only %d clusters fit at once, %d channels", cs, nClusters, h->nAct);
+        }
+        h->b2aCluster = std::max(1, cs);
+        h->gridBlocks = h->nAct * h->b2aCluster;   // one cluster per channel, all resident at once
         h->S = 1;
     } else if (h->fast) {
         BDS_CUDA(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
@@ -1105,10 +1132,20 @@ static int launch_run(bds_trk* h, int maxEpochs, int epochLimit) {
     TrkDev g;
     fill_dev(h, g, maxEpochs);
     g.epochLimit = std::min(epochLimit, h->capacity);
-    if (h->b2aUnit) {   // self-contained: every CTA starts from its channel's device-side state
-        trk_b2a_unit_kernel<<<h->nAct, kB2aThreads, h->smemBytes, h->stream>>>(g);
+    if (h->b2aUnit) {   // self-contained: every cluster starts from its channel's device-side state
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(h->nAct * h->b2aCluster);
+        lc.blockDim = dim3(kB2aThreadsAll);
+        lc.dynamicSmemBytes = h->smemBytes;
+        lc.stream = h->stream;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = h->b2aCluster;
+        at.val.clusterDim.y = at.val.clusterDim.z = 1;
+        lc.attrs = &at;
+        lc.numAttrs = 1;
+        BDS_CUDA(cudaLaunchKernelEx(&lc, trk_b2a_unit_kernel, g));
         count_launch();
-        BDS_CUDA(cudaGetLastError());
         return BDS_OK;
     }
     if (h->fast) {

@@ -1,4 +1,5 @@
-// Chip-synchronous B2a tracking (sm_100a): one CTA per channel, epoch and loop closure inside the CTA.
+// Chip-synchronous B2a tracking (sm_100a): one thread-block cluster (1, 2, 4 or 8 CTAs) per channel, epoch and loop
+// closure inside the cluster.
 //
 // BDS-3_B2a/tracking.m integrates 1 ms (10 230 chips, 99 375 samples at 99.375 MHz) per loop update, so a channel
 // closes its loops 1000 times per second of signal: the latency of one closure bounds the speed, not the arithmetic.
@@ -11,8 +12,14 @@
 //     of gen_fast_b2a.py: 20 half-chip segments per unit, the chip signs applied by integer adds at the end of the
 //     unit, one fp32 rotation per unit and replica;
 //   * warp sums in Q8 fixed point (REDUX) -> warp 0: discriminators in parallel lanes, loop filters and the next NCO on
-//     lane 0 (close_nco, the general kernel's arithmetic) -> the next table by five warps while another warp writes
-//     the trackResults planes (close_out / close_cno).
+//     lane 0 (close_nco, the general kernel's arithmetic) -> the next table by five warps;
+//   * a service warp (the 17th) issues the bulk copies and writes the trackResults planes of epoch e-1 (close_out /
+//     close_cno) while the compute warps correlate epoch e: neither is on the closure path;
+//   * with a cluster of CS CTAs per channel (latency mode: few channels per GPU) every CTA stages and integrates 1/CS of
+//     the epoch's units, the CTAs exchange their twelve Q8 integer sums through distributed shared memory (one
+//     st.shared::cluster per value and peer, one cluster barrier) and EVERY CTA closes the loops on the identical
+//     integer totals - bit-identical NCO state in all of them, so nothing has to be sent back; CTA 0 alone writes
+//     outputs and the channel state.
 // Segment-edge decisions use the same fixed-point thresholds + guard band as the B1C body; units that come within
 // the guard band of a decision, or that touch the ends of the block, are evaluated sample by sample with the float64
 // expressions of the general kernel (tracking.m:262-296 incl. the two-ended colon), so chip lookups are the oracle's.
@@ -26,7 +33,9 @@ namespace bds {
 
 #include "bds_track_fast_b2a_gen.inc"
 
-constexpr int kB2aThreads = 512;
+constexpr int kB2aThreads = 512;                  // compute threads
+constexpr int kB2aThreadsAll = kB2aThreads + 32;  // + the service warp (bulk copies, outputs of the previous epoch)
+constexpr int kB2aMaxCluster = 8;
 constexpr int kB2aUnits = 10230 / FASTB_CHIPS;   // thread units per epoch
 constexpr int kB2aTileBytes = 99584;             // one block (<= 99 380 samples) + 16-byte alignment + the word reads of
                                                  // the last unit; a multiple of 128
@@ -255,6 +264,33 @@ __device__ __forceinline__ bool fastb_unit(const FastbTab& tab, const EpochParam
     return exact;
 }
 
+// ---- thread-block cluster primitives (a host emulation defines B2A_CLUSTER_SHIM and its own versions) -------------
+#ifndef B2A_CLUSTER_SHIM
+__device__ __forceinline__ unsigned b2a_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned b2a_cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// every thread of every CTA of the cluster arrives (release: its earlier shared::cluster stores are visible to whoever
+// completes the wait) and waits (acquire)
+__device__ __forceinline__ void b2a_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// v -> the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ void b2a_st_peer(long long* p, unsigned rank, long long v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.s64 [%0], %1;" ::"r"(ra), "l"(v) : "memory");
+}
+#endif
+
 // ---- shared memory of the per-channel CTA ------------------------------------------------------------------------
 struct __align__(128) B2aSmem {
     unsigned char tile[2][kB2aTileBytes];   // epoch e in tile[e & 1]: the next block is staged while this one is correlated
@@ -262,6 +298,8 @@ struct __align__(128) B2aSmem {
     uint32_t bits[2][kPackedWordsDev];  // packed primaries: data, pilot (bit k of word w = chip 32 w + k)
     uint32_t ext[2][kPackedWordsDev];   // the same rotated by one chip (fastb_code12)
     int res[kB2aThreads / 32][12];      // warp sums, Q8 fixed point
+    long long part[2][kB2aMaxCluster][12];   // [epoch parity][cluster rank]: every CTA's Q8 sums, written by the CTAs themselves
+    long long bcast[2];                 // lock-loss handling: CTA 0's {lockLost, lowLock} after a C/N0 interval
     double sums[kNSum];
     double v[12];                       // loop closure: {data, pilot} x {E, L, P} x {I, Q} as the discriminators take them
     double pre[8];                      // discriminator pieces evaluated by parallel lanes (close_nco)
@@ -274,6 +312,8 @@ struct __align__(128) B2aSmem {
     long long tileBase[2];              // window byte offset of tile[b][0]
     int tileBytes[2];
     int run;
+    int u0, u1;                         // this CTA integrates units [u0, u1) of every epoch
+    int tileLo, tileSpan;               // ... which lie in bytes [tileLo, tileLo + tileSpan) of a block (nominal chip rate + margin)
     int eDone;                          // index of the epoch in pDone
     int outDone;                        // the outputs of epoch eDone were already written (lock-loss handling, interval end)
     double outv[kNFields];
@@ -282,7 +322,7 @@ struct __align__(128) B2aSmem {
 // whole CTA (no barrier inside): the channel's code bits and their rotated copy
 __device__ __forceinline__ void b2a_load_bits(const TrkDev& g, B2aSmem& sm, int c) {
     const uint32_t* src = g.codeBits + (size_t)c * 2 * kPackedWordsDev;
-    for (int i = threadIdx.x; i < 2 * kPackedWordsDev; i += kB2aThreads) {
+    for (int i = threadIdx.x; i < 2 * kPackedWordsDev; i += (int)blockDim.x) {
         const int f = i / kPackedWordsDev, k = i - f * kPackedWordsDev;
         const uint32_t* w = src + f * kPackedWordsDev;
         const uint32_t cur = __ldg(w + k);
@@ -294,14 +334,15 @@ __device__ __forceinline__ void b2a_load_bits(const TrkDev& g, B2aSmem& sm, int 
     }
 }
 
-// thread 0: stage the block that starts at absolute sample `pos` (whatever of it the window holds) into buffer b;
-// returns the bytes requested (0: nothing to load, the barrier is not armed)
+// one thread: stage this CTA's part [tileLo, tileLo + tileSpan) of the block that starts at absolute sample `pos`
+// (whatever of it the window holds) into buffer b; returns the bytes requested (0: nothing to load, the barrier is not
+// armed).  Units whose samples fall outside the staged bytes take the exact path from global memory.
 __device__ __forceinline__ int b2a_issue_tile(const TrkDev& g, B2aSmem& sm, long long pos, int b) {
     const long long off = pos - g.winFirst;
-    const long long base = off & ~15LL;
+    const long long base = (off + sm.tileLo) & ~15LL;
     const long long lim = g.winStage;                  // what a staged tile may cover (see TrkDev)
     long long bytes = lim - base;
-    if (bytes > kB2aTileBytes) bytes = kB2aTileBytes;
+    if (bytes > sm.tileSpan) bytes = sm.tileSpan;
     sm.tileBase[b] = base;
     if (off < 0 || bytes <= 0) {
         sm.tileBytes[b] = 0;
@@ -321,13 +362,13 @@ __device__ __forceinline__ void b2a_correlate(const TrkDev& g, B2aSmem& sm, cons
     float acc[kNSum];
 #pragma unroll
     for (int i = 0; i < kNSum; ++i) acc[i] = 0.f;
-    if (tid == 0 && p.rem == 0.0) {
+    if (tid == 0 && sm.u0 == 0 && p.rem == 0.0) {
         // remCodePhase == 0: the t = 0 sample reads the padded table's first entry, the previous period's last chip
         ExactCtx ex;
         make_exact_ctx_b2a(p, g.d, g.fs, ex);
         fastb_exact_range(ex, g.x + B0, sm.bits[0], sm.bits[1], 0, 0, -100, 0, acc);
     }
-    for (int u = tid; u < kB2aUnits; u += kB2aThreads) {
+    for (int u = sm.u0 + tid; u < sm.u1; u += kB2aThreads) {
         const bool ex = fastb_unit(sm.tab, p, sm.bits[0], sm.bits[1], sm.ext[0], sm.ext[1], sm.tile[b], sm.tileBase[b],
                                    sm.tileBytes[b], B0, g.x + B0, g.d, g.fs, u, guard, acc);
         nFast += !ex;
@@ -341,15 +382,24 @@ __device__ __forceinline__ void b2a_correlate(const TrkDev& g, B2aSmem& sm, cons
     }
 }
 
-// warp 0 after the CTA barrier: 12 sums as doubles (the pilot family is zero without a pilot, like the general kernel)
-__device__ __forceinline__ void b2a_collect(const TrkDev& g, B2aSmem& sm) {
+// warp 0 after the CTA barrier: this CTA's 12 Q8 sums (exact integers)
+__device__ __forceinline__ long long b2a_cta_sum(const B2aSmem& sm, int lane) {
+    long long t = 0;
+    if (lane < 12) {
+#pragma unroll
+        for (int w = 0; w < kB2aThreads / 32; ++w) t += sm.res[w][lane];
+    }
+    return t;
+}
+// warp 0: 12 sums as doubles from the Q8 totals of the nParts contributions in part[] (the pilot family is zero without
+// a pilot, like the general kernel).  Integer adds: the total does not depend on the order or the cluster size.
+__device__ __forceinline__ void b2a_collect(const TrkDev& g, B2aSmem& sm, const long long (*part)[12], int nParts) {
     const int lane = threadIdx.x & 31;
     if (lane < kNSum) {
         double v = 0.0;
         if (lane < 6 || (lane < 12 && g.hasPilot)) {
             long long t = 0;
-#pragma unroll
-            for (int w = 0; w < kB2aThreads / 32; ++w) t += sm.res[w][lane];
+            for (int r = 0; r < nParts; ++r) t += part[r][lane];
             v = (double)t * (1.0 / 256.0);
         }
         sm.sums[lane] = v;
@@ -401,42 +451,77 @@ __device__ __forceinline__ void b2a_discriminators(const TrkDev& g, B2aSmem& sm,
     __syncwarp();
 }
 
-// Closed loop: grid = active channels.  Every launch runs each channel for up to g.maxEpochs epochs from its device-side
-// state, never past epoch index g.epochLimit, as far as the resident window allows (a short read stops the channel
-// exactly like tracking.m:246-251).  Per epoch: correlate (all warps) | barrier | warp 0: sums, discriminators in
-// parallel lanes, loop filters + next NCO on lane 0 | barrier | next epoch's table (warp 0: thresholds, warps 1-4:
-// carrier rotation) while warp 15 formats and stores this epoch's outputs | barrier.
-__global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) {
+// this CTA's share of an epoch: units [u0, u1) and the bytes of a block they can touch at any plausible code rate
+__device__ __forceinline__ void b2a_plan_share(const TrkDev& g, B2aSmem& sm, int c, unsigned rk, unsigned CS) {
+    const int U = (kB2aUnits + (int)CS - 1) / (int)CS;
+    sm.u0 = min((int)rk * U, kB2aUnits);
+    sm.u1 = min(sm.u0 + U, kB2aUnits);
+    const double spu = (double)FASTB_CHIPS * g.fs / g.cc[c].chCodeFreq;   // samples per unit at the nominal chip rate
+    const int margin = 96;   // samples: the code phase at the block start (< 1 sample) plus any plausible code Doppler over 1 ms
+    const int lo = rk == 0 ? 0 : max(0, (int)(sm.u0 * spu) - margin);
+    const int hi = rk + 1 == CS ? kB2aTileBytes : min(kB2aTileBytes, (int)(sm.u1 * spu) + margin + 4 * (FASTB_NWORDS + 1) + 32);
+    sm.tileLo = lo;
+    sm.tileSpan = (hi - (lo & ~15) + 15) & ~15;   // the copy starts at a 16-byte boundary at or below lo
+}
+
+// the service warp of CTA 0: trackResults planes (and, at the end of a C/N0 interval, C/N0 + lock detector) of the epoch
+// whose loops were closed last
+__device__ __forceinline__ void b2a_write_outputs(const TrkDev& g, B2aSmem& sm, int c, double* out, int cap) {
+    const int lane = threadIdx.x & 31;
+    const int e = sm.eDone;
+    if (lane == 0) close_out(g, sm.sums, sm.pDone, sm.aux, sm.outv);
+    __syncwarp();
+    for (int f = lane; f < kNFields; f += 32)
+        if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
+    if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) close_cno(g, c, e, sm.st);   // touches cnoPrev / the lock counters only
+    }
+    __syncwarp();
+}
+
+// Closed loop: grid = active channels x cluster size, one cluster per channel.  Every launch runs each channel for up to
+// g.maxEpochs epochs from its device-side state, never past epoch index g.epochLimit, as far as the resident window
+// allows (a short read stops the channel exactly like tracking.m:246-251).  Per epoch:
+//   compute warps: correlate this CTA's units | service warp: stage the next block, write the previous epoch's outputs
+//   CTA barrier | warp 0: Q8 sums of the CTA -> every CTA of the cluster | cluster barrier
+//   warp 0 (every CTA, identical arithmetic): totals, discriminators in parallel lanes, loop filters + next NCO on lane 0
+//   CTA barrier | the next epoch's table (warp 0: thresholds, warps 1-4: carrier rotation) | CTA barrier.
+__global__ void __launch_bounds__(kB2aThreadsAll, 1) trk_b2a_unit_kernel(TrkDev g) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     B2aSmem& sm = *reinterpret_cast<B2aSmem*>(dyn_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = g.act[blockIdx.x];
-    if (!g.cc[c].active) return;
+    const unsigned CS = b2a_cluster_size(), rk = b2a_cluster_rank();
+    const bool lead = rk == 0;                       // writes the channel's outputs and state
+    const bool service = warp == kB2aThreads / 32;   // bulk copies + outputs, off the closure path
+    const int c = g.act[blockIdx.x / CS];
+    if (!g.cc[c].active) return;                     // uniform over the cluster
     b2a_load_bits(g, sm, c);
-    int done = 0, pending[2] = {0, 0};   // thread 0: a bulk copy into tile[b] is in flight
+    int done = 0, pending[2] = {0, 0};   // service lane 0: a bulk copy into tile[b] is in flight
     double* const out = g.out + (size_t)c * kNFields * g.capacity;
     const int cap = g.capacity;
     const unsigned guard = g.pad ? (1u << 24) : kFastGuard;   // g.pad: test hook, widens the guard band
     unsigned nFast = 0, nExact = 0;
     unsigned phase[2] = {0, 0};
-    int buf = 0;
+    int buf = 0, par = 0;
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
         sm.tileBytes[0] = sm.tileBytes[1] = 0;
+        b2a_plan_share(g, sm, c, rk, CS);
         sm.st = g.st[c];
         EpochParams np;
         const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
-        if (!okp && lim && sm.st.lockLost == 0) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;   // tracking.m:228 precedes the failed read
+        if (lead && !okp && lim && sm.st.lockLost == 0) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;   // tracking.m:228 precedes the failed read
         sm.run = okp && lim && g.maxEpochs > 0;
         sm.eDone = -1;
         sm.outDone = 0;
-        if (sm.run) {
-            sm.p = np;
-            pending[0] = b2a_issue_tile(g, sm, np.pos, 0);
-        }
+        if (sm.run) sm.p = np;
     }
     __syncthreads();
+    int eCur = sm.st.epoch;   // index of the epoch about to be correlated (every thread keeps its own copy)
+    if (service && lane == 0 && sm.run) pending[0] = b2a_issue_tile(g, sm, sm.p.pos, 0);
     if (warp == 0 && sm.run) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
     __syncthreads();
 #ifdef BDS_FW_DEV
@@ -448,20 +533,36 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
 #endif
     while (sm.run) {
         const EpochParams p = sm.p;
-        // the next block starts at pos + blksize whatever the loops decide: stage it now, under this epoch's correlation
-        // (the other buffer was last read before the barrier that ended the previous iteration)
-        if (tid == 0) pending[buf ^ 1] = b2a_issue_tile(g, sm, p.pos + p.blksize, buf ^ 1);
-        if (sm.tileBytes[buf] > 0) {
-            mbar_wait(&sm.full[buf], phase[buf]);
-            phase[buf] ^= 1;
-            if (tid == 0) pending[buf] = 0;
+        if (service) {
+            // the next block starts at pos + blksize whatever the loops decide: stage it now, under this epoch's correlation
+            // (the other buffer was last read before the barrier that ended the previous iteration)
+            if (lane == 0) pending[buf ^ 1] = b2a_issue_tile(g, sm, p.pos + p.blksize, buf ^ 1);
+            if (sm.tileBytes[buf] > 0) {   // consumed by the compute warps before the barrier below
+                phase[buf] ^= 1;
+                pending[buf] = 0;
+            }
+            if (lead && sm.eDone >= 0 && !sm.outDone) b2a_write_outputs(g, sm, c, out, cap);   // epoch e-1, under epoch e
+        } else {
+            if (sm.tileBytes[buf] > 0) {
+                mbar_wait(&sm.full[buf], phase[buf]);
+                phase[buf] ^= 1;
+            }
+            B2A_T(tW)
+            b2a_correlate(g, sm, p, guard, nFast, nExact, buf);
         }
-        B2A_T(tW)
-        b2a_correlate(g, sm, p, guard, nFast, nExact, buf);
-        __syncthreads();   // every warp is done with the tile and the table; warp sums are visible
+        __syncthreads();   // every warp is done with the tile and the table; warp sums are visible; epoch e-1 is written out
         B2A_T(tC)
+        if (warp == 0) {   // this CTA's Q8 sums -> slot [rk] of every CTA of the cluster (its own included)
+            const long long t = b2a_cta_sum(sm, lane);
+            if (lane < 12)
+                for (unsigned r = 0; r < CS; ++r) b2a_st_peer(&sm.part[par][rk][lane], r, t);
+        }
+        b2a_cluster_sync();
+        // a C/N0 interval ends with this epoch and lock-loss handling is on: the lock detector decides whether there is
+        // a next epoch, so CTA 0 writes this epoch's outputs and the interval's C/N0 first and tells the others
+        const bool lockStep = g.lockPLD > 0.0 && g.cnoInterval > 0 && (eCur + 1) % g.cnoInterval == 0;
         if (warp == 0) {
-            b2a_collect(g, sm);
+            b2a_collect(g, sm, sm.part[par], (int)CS);
             b2a_discriminators(g, sm, p);
             if (lane == 0) {
                 close_nco(g, sm.sums, p, g.cc[c].chCodeFreq, sm.st, sm.aux, sm.pre);
@@ -470,23 +571,32 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
                 sm.st.epoch += 1;
                 ++done;
                 sm.outDone = 0;
-                if (g.lockPLD > 0.0 && g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
-                    // lock-loss handling on and a C/N0 interval ends here: the lock detector decides whether there is a
-                    // next epoch, so this epoch's outputs and the interval's C/N0 come first
+                if (lockStep && lead) {
                     close_out(g, sm.sums, p, sm.aux, sm.outv);
                     for (int f = 0; f < kNFields; ++f)
                         if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
                     __threadfence();
                     close_cno(g, c, e, sm.st);
-                    sm.outDone = 1;
+                    for (unsigned r = 1; r < CS; ++r) {
+                        b2a_st_peer(&sm.bcast[0], r, sm.st.lockLost);
+                        b2a_st_peer(&sm.bcast[1], r, (long long)sm.st.lowLock);
+                    }
                 }
-                EpochParams np;
-                const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
-                if (!okp && lim && sm.st.lockLost == 0) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;
-                const int run = okp && lim && done < g.maxEpochs;
-                if (run) sm.p = np;
-                sm.run = run;
+                if (lockStep) sm.outDone = 1;
             }
+        }
+        if (lockStep && CS > 1) b2a_cluster_sync();   // uniform over the cluster
+        if (warp == 0 && lane == 0) {
+            if (lockStep && !lead) {
+                sm.st.lockLost = sm.bcast[0];
+                sm.st.lowLock = (int)sm.bcast[1];
+            }
+            EpochParams np;
+            const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
+            if (lead && !okp && lim && sm.st.lockLost == 0) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;
+            const int run = okp && lim && done < g.maxEpochs;
+            if (run) sm.p = np;
+            sm.run = run;
         }
         __syncthreads();   // the next epoch's NCO (sm.p), sm.run and the closure's by-products are visible
         B2A_T(tL)
@@ -494,24 +604,21 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
             if (warp == 0) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch, false);
             else if (warp <= 4) fastb_build_rot(&sm.tab, fastb_dphi(sm.p, g.fs), tid - 32, 128);
         }
-        if (warp == kB2aThreads / 32 - 1 && !sm.outDone) {   // this epoch's outputs, off the critical path
-            const int e = sm.eDone;
-            if (lane == 0) close_out(g, sm.sums, sm.pDone, sm.aux, sm.outv);
-            __syncwarp();
-            for (int f = lane; f < kNFields; f += 32)
-                if (field_written(g, f)) out[(size_t)f * cap + e] = sm.outv[f];
-            if (g.cnoInterval > 0 && (e + 1) % g.cnoInterval == 0) {
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) close_cno(g, c, e, sm.st);   // touches cnoPrev only; thread 0 is past its use of sm.st
-            }
-        }
         __syncthreads();
         B2A_T(tT)
         buf ^= 1;
+        par ^= 1;
+        ++eCur;
     }
+    // the last epoch's outputs (nothing overwrites the closure's by-products any more)
+    if (service && lead && sm.eDone >= 0 && !sm.outDone) b2a_write_outputs(g, sm, c, out, cap);
+    if (service && lane == 0) {
+        for (int b = 0; b < 2; ++b)
+            if (pending[b]) mbar_wait(&sm.full[b], phase[b]);   // never leave with a bulk copy in flight
+    }
+    __syncthreads();   // close_cno of the last interval has updated sm.st
 #ifdef BDS_FW_DEV
-    if (tid == 0 && g.counters) {
+    if (tid == 0 && lead && g.counters) {
         atomicAdd(g.counters + 4, (unsigned long long)tW);
         atomicAdd(g.counters + 5, (unsigned long long)tC);
         atomicAdd(g.counters + 6, (unsigned long long)tL);
@@ -520,13 +627,9 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_kernel(TrkDev g) 
     }
 #endif
 #undef B2A_T
-    if (tid == 0) {
-        for (int b = 0; b < 2; ++b)
-            if (pending[b]) mbar_wait(&sm.full[b], phase[b]);   // never leave with a bulk copy in flight
-        g.st[c] = sm.st;
-    }
+    if (tid == 0 && lead) g.st[c] = sm.st;
     __syncwarp();
-    if (g.counters) {
+    if (g.counters && !service) {
         const unsigned tf = __reduce_add_sync(0xffffffffu, nFast), te = __reduce_add_sync(0xffffffffu, nExact);
         if (lane == 0) {
             if (tf) atomicAdd(g.counters + 0, (unsigned long long)tf);
@@ -545,6 +648,7 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_open_kernel(TrkDe
     b2a_load_bits(g, sm, c);
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
+        b2a_plan_share(g, sm, c, 0, 1);
         sm.p = params[ce];
         b2a_issue_tile(g, sm, sm.p.pos, 0);
     }
@@ -557,7 +661,10 @@ __global__ void __launch_bounds__(kB2aThreads, 1) trk_b2a_unit_open_kernel(TrkDe
     b2a_correlate(g, sm, p, g.pad ? (1u << 24) : kFastGuard, nFast, nExact, 0);
     __syncthreads();
     if (warp == 0) {
-        b2a_collect(g, sm);
+        const long long t = b2a_cta_sum(sm, lane);
+        if (lane < 12) sm.part[0][0][lane] = t;
+        __syncwarp();
+        b2a_collect(g, sm, sm.part[0], 1);
         if (lane < kNSum) sums[(size_t)ce * kNSum + lane] = sm.sums[lane];
     }
     __syncwarp();

@@ -60,9 +60,10 @@ def parse():
                     help="length of the synthetic IF record (BASELINE config 4: 30 s)")
     ap.add_argument("--channels", type=int, default=N_CHANNELS)
     ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast"])
-    ap.add_argument("--workload", default="track", choices=["track", "track_b2a", "acq_b2a", "acq_b1c"],
+    ap.add_argument("--workload", default="track", choices=["track", "track_b2a", "dual", "acq_b2a", "acq_b1c"],
                     help="track = the headline metric (BASELINE config 4; --channels 12 = config 3); track_b2a = 60-channel "
-                         "B2a tracking; acq_b2a = BASELINE config 2 (B2a 63-PRN x +-5 kHz acquisition grid); acq_b1c")
+                         "B2a tracking; dual = BASELINE config 5 (--channels B1C + --channels B2a channels co-scheduled on "
+                         "the same GPUs); acq_b2a = BASELINE config 2 (B2a 63-PRN x +-5 kHz acquisition grid); acq_b1c")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: --channels in total, sharded over the GPUs (BASELINE config 4); weak: --channels per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,6 +227,8 @@ def run_reference(args):
     from bds3_b200.settings import Settings
     import bds_oracle as O
     threads = os.cpu_count() or 1
+    if args.workload == "dual":
+        return run_reference_dual(args)
     if args.workload not in TRACK:
         print(json.dumps({"impl": "reference", "unavailable": f"no reference arm for workload {args.workload}"}))
         return
@@ -260,6 +263,43 @@ def run_reference(args):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "native_so_loaded": repo_native_libraries()}
     print(json.dumps(line))
+
+
+def run_reference_dual(args):
+    """--impl reference --workload dual: the two CPU ports one after the other on 20 ms of each band's record."""
+    from bds3_b200 import synth
+    from bds3_b200.settings import Settings
+    import bds_oracle as O
+    threads = os.cpu_count() or 1
+    ms = int(round(args.seconds * 1000))
+    parts = []
+    for wl in ("track", "track_b2a"):
+        w = TRACK[wl]
+        if w["sig"] == "B1C":
+            st = Settings(dict(O.initSettings_B1C(samplingFreq=FS, numberOfChannels=args.channels, pilotTRKflag=2, msToProcess=ms)))
+        else:
+            st = Settings(dict(O.initSettings_B2a(numberOfChannels=args.channels, msToProcess=ms)))
+        sats = synth.make_sats(args.channels, st, w["sig"], max_doppler=w["max_doppler"])
+        n = int((w["cpu_epochs"] + 1.2) * w["spc"]) + w["spc"]
+        parts.append((w, st, host_record_numpy(st, sats, n, w["sig"]), synth.channels_from_sats(sats, st, w["sig"], freq_error=2.0)))
+    times = []
+    for i in range(max(0, min(args.warmup, 1)) + args.steps):
+        t = sum(cpu_track_sample(x, st, ch, w["cpu_epochs"], threads, w["mode"]) for w, st, x, ch in parts)
+        if i >= max(0, min(args.warmup, 1)):
+            times.append(t)
+    t = sum(times) / len(times)
+    val = sum(w["cpu_epochs"] * w["spc"] for w, _, _, _ in parts) / t / 1e6
+    sample = (f"{args.channels} B1C channels x 2 epochs + {args.channels} B2a channels x 20 epochs (20 ms of each band) per step; "
+              "Msamples/s = IF samples both bands advanced through / wall time, the GPU arm's normalisation")
+    print(json.dumps({"impl": "reference", "metric": f"IF Msamples/s through {2 * args.channels}-ch dual-band ({args.channels} B1C + {args.channels} B2a) tracking",
+                      "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                      "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"BASELINE config 5: {args.channels} B1C WB + {args.channels} B2a channels co-scheduled, two int8 IF "
+                                             f"records at 99.375 MHz, {args.seconds:g} s", "sample": sample},
+                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "native_so_loaded": repo_native_libraries()}))
 
 
 def repo_native_libraries():
@@ -578,6 +618,199 @@ def run_b200(args):
 
 
 # ----------------------------------------------------------------------------------------------
+# BASELINE config 5: dual band.  The reference has no joint B1C/B2a processing - they are two programs sharing Common/
+# (B1C/init.m:42-44, B2a/init.m:38-40; SURVEY 8 mismatch 3) - so this is two independent pipelines co-scheduled on the
+# same GPUs: per rank one B1C wide-band session (chip-synchronous persistent grid, limited to the SMs the B2a channels
+# leave free) and one B2a session (one CTA per channel), each on its own stream over its own IF record.
+# ----------------------------------------------------------------------------------------------
+def run_dual(args):
+    import numpy as np
+    import torch
+    import bds3_b200 as B
+    from bds3_b200 import _lib as L, _shard, _track, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L.init(local)
+    n_sms = torch.cuda.get_device_properties(local).multi_processor_count
+    n_samples = int(round(args.seconds * FS))
+    total = args.channels * (world if args.scaling == "weak" else 1)      # per band
+    if total > 63:
+        raise SystemExit("the synthetic scenario has one satellite per PRN: at most 63 channels per band")
+    bands = []
+    for wl in ("track_b2a", "track"):            # B2a first: its CTA count bounds the B1C grid
+        w = TRACK[wl]
+        st = settings_for(wl, total, args.seconds)
+        sats = synth.make_sats(total, st, w["sig"], max_doppler=w["max_doppler"])
+        chans = synth.channels_from_sats(sats, st, w["sig"], freq_error=2.0)
+        x_dev = torch.empty(n_samples + 64, dtype=torch.int8, device="cuda")
+        synth.synth_device(w["sig"], st, sats, n_samples, out_ptr=x_dev.data_ptr())
+        mine = _shard.shard_list(chans, rank, world)
+        st_local = st.copy()
+        st_local.numberOfChannels = len(mine)
+        st_local.numberOfChannels_total = total
+        n_epochs = max(1, int(math.floor((n_samples - w["spc"]) / (w["spc"] * (1 + 1e-5)))) - 1)
+        tuning = None
+        if wl == "track":   # the B2a kernel holds one SM per channel: the persistent B1C grid takes the others
+            tuning = {"fwMaxCtas": max(16, n_sms - len(bands[0]["mine"]))}
+        bands.append(dict(wl=wl, w=w, st=st, st_local=st_local, chans=chans, mine=mine, x_dev=x_dev, n_epochs=n_epochs,
+                          tuning=tuning,
+                          sess=_track.TrackSession(w["mode"], st_local, mine, device_ptr=x_dev.data_ptr(), n_samples=n_samples,
+                                                   tuning=tuning)))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def _as_tensor(ptr, n):
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
+
+    for b in bands:   # sizing run (allocates the output blocks)
+        b["sess"].run_async(b["n_epochs"])
+    for b in bands:
+        b["sess"].sync()
+        b["max_block"] = _shard.max_block_elems(b["sess"].device_block()[1] // 8, dist)
+
+    def gather(b, s_=None):
+        if dist is None:
+            return
+        p, nbytes, _, _ = (s_ or b["sess"]).device_block()
+        _shard.gather_blocks(_as_tensor(p, nbytes // 8), b["max_block"], dist, dst=0)
+
+    def step():
+        for b in bands:
+            b["sess"].reset()
+        for b in bands:
+            b["sess"].run_async(b["n_epochs"])       # both launches are asynchronous: the two kernels run concurrently
+        for b in bands:
+            b["sess"].sync()
+        for b in bands:
+            gather(b)
+        return [b["sess"].stats() for b in bands]
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    launches0 = B.launch_count()
+    barrier()
+    s0 = sampler.mark()
+    t0 = time.perf_counter()
+    stats = None
+    kms = [[], []]
+    for _ in range(args.steps):
+        stats = step()
+        for i in range(2):
+            kms[i].append(stats[i][2])
+    barrier()
+    wall = time.perf_counter() - t0
+    s1 = sampler.mark()
+    launches = B.launch_count() - launches0
+    clocks = sampler.stop(s0, s1) if rank == 0 else None
+    checks = [self_check(b["sess"], b["st_local"], b["mine"], b["n_epochs"], b["x_dev"], n_samples, mode=b["w"]["mode"],
+                         kappa_db=b["w"]["kappa_db"], injected_cn0=b["w"]["cn0_total"]) for b in bands]
+    agg = torch.tensor([sum(c["locked_channels"] for c in checks), sum(c["channels"] for c in checks),
+                        float(stats[0][0] + stats[1][0])], device="cuda", dtype=torch.float64)
+    mx = torch.tensor([max(c["parity_max_rel"] for c in checks), max(c["exact_chip_frac"] for c in checks),
+                       wall * 1e3 / args.steps, sum(kms[0]) / len(kms[0]), sum(kms[1]) / len(kms[1])],
+                      device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    step_ms = float(mx[2])
+    if_samples = sum(b["n_epochs"] * float(b["w"]["spc"]) for b in bands)    # IF samples advanced through, both bands
+    value = if_samples / (step_ms * 1e-3) / 1e6
+
+    e2e = None
+    if not args.no_e2e and world == 1:
+        # both records from pinned host memory, streamed under the two kernels; result planes of both bands back to the host
+        hosts, sess2, res = [], [], []
+        for b in bands:
+            xh = torch.empty(n_samples, dtype=torch.int8).pin_memory()
+            xh.copy_(b["x_dev"][:n_samples])
+            hosts.append(xh)
+            sess2.append(_track.TrackSession(b["w"]["mode"], b["st_local"], b["mine"], tuning=b["tuning"]))
+            res.append({name: torch.empty((len(b["mine"]), b["n_epochs"]), dtype=torch.float64).pin_memory().numpy()
+                        for name in L.TRK_PLANES})
+        torch.cuda.synchronize()
+        times, d2h = [], 0
+        for i in range(2 + args.steps):
+            barrier()
+            t1 = time.perf_counter()
+            for s_ in sess2:
+                s_.reset()
+            for s_, xh, b in zip(sess2, hosts, bands):
+                s_.run_streamed(xh.data_ptr(), n_samples, b["n_epochs"])
+            d2h = 0
+            for s_, b, r_ in zip(sess2, bands, res):
+                planes = s_.fetch(b["n_epochs"], into=r_)
+                assert int(planes["epochsDone"].min()) == b["n_epochs"], "e2e run did not complete every epoch"
+                d2h += sum(v.nbytes for v in planes.values())
+            barrier()
+            if i >= 2:
+                times.append(time.perf_counter() - t1)
+        for s_ in sess2:
+            s_.close()
+        te = sum(times) / len(times)
+        e2e = {"value": if_samples / te / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * int(n_samples), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": te * 1e3, "path": "bds_track_run_streamed on both sessions (two pinned host records, chunked H2D "
+                                                "on two copy streams under the two kernels) + bds_track_fetch of both"}
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg = float(agg[2]) / world           # channel-samples of both bands per GPU and step
+        line = {"metric": f"IF Msamples/s through {2 * total}-ch dual-band ({total} B1C + {total} B2a) tracking",
+                "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f32 accumulate / f64 loop closure (int8 IF)", "data": "synthetic",
+                "config": {"workload": f"BASELINE config 5: {total} B1C WB + {total} B2a channels co-scheduled, two int8 IF records "
+                                       f"at 99.375 MHz, {args.seconds:g} s",
+                           "epochs_per_channel": {b["w"]["sig"]: b["n_epochs"] for b in bands},
+                           "parallelism": f"channels of both bands round-robin over {world} GPU(s), both IF records replicated; per GPU "
+                                          "two sessions on two streams, the B1C persistent grid limited to the SMs the B2a CTAs leave",
+                           "l2": f"inputs 2 x {n_samples / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+                           "x_realtime": step_ms and args.seconds * 1e3 / step_ms},
+                "roofline": {"bound": "hbm", "achieved": alg / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (step_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "trk_b2a_unit_kernel || trk_fw_kernel (concurrent; the step lasts as long as the slower one)",
+                             "kernel_ms_per_launch": {"trk_b2a_unit_kernel": float(mx[3]), "trk_fw_kernel": float(mx[4])},
+                             "algorithmic_bytes_per_launch": alg, "measured_limiter": "loop-closure latency of the B2a channels"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "parity_max_rel": float(mx[0]), "locked_channels": int(agg[0]), "exact_chip_frac": float(mx[1]),
+                "self_check": {b["w"]["sig"]: c for b, c in zip(bands, checks)}}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            tt, smp = 0.0, 0.0
+            for b in bands:
+                w = b["w"]
+                nh = int((w["cpu_epochs"] + 1.2) * w["spc"]) + w["spc"]
+                tt += cpu_track_sample(b["x_dev"][:nh].cpu().numpy(), b["st"], b["chans"], w["cpu_epochs"], threads, w["mode"])
+                smp += w["cpu_epochs"] * w["spc"]
+            line["cpu_baseline"] = {"value": smp / tt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{total} B1C ch x 2 epochs + {total} B2a ch x 20 epochs (20 ms of each band), float64 "
+                                              "oracle restatement (C correlator), all host threads; MATLAB unavailable"}
+        print(json.dumps(line))
+    for b in bands:
+        b["sess"].close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
 # secondary workload: BASELINE config 2 — B2a full 63-PRN x +-5 kHz acquisition grid (one GPU; PRNs shard across
 # ranks through prn_lo/prn_hi when launched under torchrun)
 # ----------------------------------------------------------------------------------------------
@@ -682,6 +915,8 @@ def main():
         run_reference(args)
     elif args.workload in ("acq_b2a", "acq_b1c"):
         run_acq_b2a(args, b1c=args.workload == "acq_b1c")
+    elif args.workload == "dual":
+        run_dual(args)
     else:
         run_b200(args)
 

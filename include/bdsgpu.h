@@ -161,7 +161,8 @@ typedef struct bds_trk_cfg {
                                   * Every sample count, offset and absoluteSample of this API stays in SAMPLES (the reference's
                                   * ftell/dataAdaptCoeff); buffers and files hold 2 bytes per sample.  I/Q records run on
                                   * the general kernel (BDS_KERNEL_FAST is refused). */
-    int32_t reserved3;           /* 0 */
+    int32_t b2aClusterSize;      /* B2a chip-synchronous kernel: CTAs (one thread-block cluster) per channel: 0 = the largest of
+                                  * 8 / 4 / 2 / 1 for which all channels are resident at once, else 1, 2, 4 or 8 */
 } bds_trk_cfg;
 #define BDS_DBG_TIMING 1 /* per-stage cycle counters of the tracking kernel, printed by bds_track_counters */
 #define BDS_DBG_TRACE 2  /* per-ticket timestamps */

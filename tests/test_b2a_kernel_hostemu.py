@@ -1,6 +1,6 @@
 """The whole per-channel B2a tracking kernel (trk_b2a_unit_kernel, csrc/bds_track_b2a.cuh) emulated on the host.
 
-A CTA is 512 OS threads: threadIdx.x is thread-local, __syncthreads() a 512-party barrier, __syncwarp() /
+A CTA is 544 OS threads (16 compute warps + the service warp), a cluster of one CTA: threadIdx.x is thread-local, __syncthreads() a 512-party barrier, __syncwarp() /
 __all_sync() / __reduce_add_sync() per-warp barriers and votes, the mbarrier a phase counter and the TMA bulk copy a
 memcpy that completes a phase.  Everything else is the device source as it is: prologue, per-epoch loop, early issue
 of the next block, warp sums, loop closure by thread 0 with the general kernel's close_core / close_cno /
@@ -38,7 +38,14 @@ CTA_SHIM = r"""
 struct TidX { unsigned x; };
 static thread_local TidX threadIdx;
 static TidX blockIdx;
-constexpr int kEmuThreads = 512;
+constexpr int kEmuThreads = 544;
+static const TidX blockDim = {kEmuThreads};
+// a cluster of one CTA: rank 0 of 1, the peer store is a local store, the cluster barrier has nobody to wait for
+#define B2A_CLUSTER_SHIM 1
+static inline unsigned b2a_cluster_rank() { return 0u; }
+static inline unsigned b2a_cluster_size() { return 1u; }
+static inline void b2a_cluster_sync() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void b2a_st_peer(long long* p, unsigned, long long v) { *p = v; }
 static std::barrier<> g_cta_bar(kEmuThreads);
 static std::barrier<>* g_warp_bar[kEmuThreads / 32];
 static long long g_warp_val[kEmuThreads / 32][32];
@@ -94,7 +101,7 @@ DRIVER = r"""
 extern "C" int run_b2a_closed(const int8_t* x, long long winLen, const bds_trk_cfg* cfg, int hasPilot, const uint32_t* codeBits,
                               ChanConst* cc, ChanState* st, int nCh, double* out, double* cno, int capacity, int cnoCap,
                               int maxEpochs, int epochLimit, unsigned long long* counters) {
-    static_assert(kB2aThreads == kEmuThreads, "emulated CTA size");
+    static_assert(kB2aThreadsAll == kEmuThreads, "emulated CTA size");
     TrkDev g;
     std::memset(&g, 0, sizeof(g));
     std::vector<int> act(nCh);

@@ -38,6 +38,8 @@ def tuning():
         t["fwPassesPerTask"] = int(os.environ["BDS_TRK_PASSES"])
     if "BDS_TRK_AHEAD" in os.environ:
         t["fwPrefetch"] = int(os.environ["BDS_TRK_AHEAD"]) + 1
+    if "BDS_B2A_CS" in os.environ:
+        t["b2aClusterSize"] = int(os.environ["BDS_B2A_CS"])
     if os.environ.get("BDS_TRK_TIMING"):
         t["debug"] = L.DBG_TIMING
     return t
