@@ -1425,8 +1425,10 @@ int bds_track_counters(bds_trk* h, long long* out4) {
     BDS_CUDA(cudaMemcpy(v, h->dCounters, 192, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 4; ++i) out4[i] = (long long)v[i];
     if ((h->cfg.debug & BDS_DBG_TIMING) && h->b2aUnit && v[8])   // developer build (-DBDS_FW_DEV): cycles per epoch of thread 0
-        fprintf(stderr, "[bds timing] b2a per epoch (cycles): tile wait %.0f, correlate %.0f, loop closure %.0f, table + outputs %.0f\n",
-                (double)v[4] / v[8], (double)v[5] / v[8], (double)v[6] / v[8], (double)v[7] / v[8]);
+        fprintf(stderr, "[bds timing] b2a per epoch (cycles): tile wait %.0f, correlate %.0f, loop closure %.0f (exchange %.0f, sums + discriminators %.0f, "
+                        "filters %.0f, next NCO || table + barrier %.0f) [%.0f]\n",
+                (double)v[4] / v[8], (double)v[5] / v[8], (double)(v[6] + v[9] + v[10] + v[11]) / v[8], (double)v[9] / v[8], (double)v[10] / v[8],
+                (double)v[11] / v[8], (double)v[6] / v[8], (double)v[7] / v[8]);
     if ((h->cfg.debug & BDS_DBG_TIMING) && !h->b2aUnit)  // developer breakdown (SM cycles summed over CTAs)
         fprintf(stderr, "[bds timing] producer: queue %llu empty %llu total %llu | compute(w2): full-wait %llu res-wait %llu | closer: closure %llu epilogue %llu closures %llu\n",
                 v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);

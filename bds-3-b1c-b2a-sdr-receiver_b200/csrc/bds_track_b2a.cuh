@@ -74,7 +74,34 @@ __device__ inline unsigned long long fastb_dphi(const EpochParams& np, double fs
     return __double2ull_rn(r * 18446744073709551616.0);
 }
 
-__device__ void fastb_build_tab_warp(FastbTab* tab, const EpochParams& np, double fs, unsigned* scratch, bool withRotation = true) {
+// the 128-bin rank index: bins [bin0, bin0 + 32) by one warp (entry kFastBins by the warp of bin0 == 0), from thresholds
+// the warp evaluates for itself in its own scratch (>= 32 words) - same expressions as fastb_build_tab_warp
+__device__ __forceinline__ void fastb_build_bins_warp(FastbTab* tab, const EpochParams& np, unsigned* scratch, int bin0) {
+    const int lane = threadIdx.x & 31;
+    const double S = 1.0 / (2.0 * np.step);
+    if (lane < FASTB_NSEG) {
+        double th = kFastbBeta[lane + 1] * S - (double)kFastbR[lane + 1];
+        th = fmin(fmax(th, 0.0), 1.0);
+        scratch[lane] = (unsigned)fmin(th * 4294967296.0, 4294967295.0) >> 25;
+    }
+    __syncwarp();
+    auto put = [&](int t) {
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < FASTB_NSEG; ++j) cnt += scratch[j] < (unsigned)t;
+        tab->binStart[t] = (unsigned char)cnt;
+    };
+    put(bin0 + lane);
+    if (bin0 == 0 && lane == 0) put(kFastBins);
+    __syncwarp();
+}
+
+// reuseOrder (scratch >= 96 words, kept between calls): the thresholds move by ~1e-6 of a sample from one epoch to the
+// next, so their ORDER almost never changes; when the previous build's order still sorts them (one comparison per
+// lane) only the threshold values are refreshed - the rank sort and the decision masks, which depend on the order
+// alone, are skipped.
+__device__ void fastb_build_tab_warp(FastbTab* tab, const EpochParams& np, double fs, unsigned* scratch, bool withRotation = true,
+                                     bool withBins = true, bool reuseOrder = false) {
     const int lane = threadIdx.x & 31;
     const double sigma = 2.0 * np.step, S = 1.0 / sigma;
     double r = np.carrFreq / fs;
@@ -96,32 +123,49 @@ __device__ void fastb_build_tab_warp(FastbTab* tab, const EpochParams& np, doubl
     }
     ok = __all_sync(0xffffffffu, ok);
     __syncwarp();
-    if (lane < FASTB_NSEG) {  // rank sort (ties broken by index)
-        const unsigned v = thr[lane];
-        int rank = 0;
-        for (int j = 0; j < FASTB_NSEG; ++j) rank += (thr[j] < v) || (thr[j] == v && j < lane);
-        tab->thr[rank] = v;
-        pos[lane] = rank;
-    } else if (lane < 24) {
-        tab->thr[lane] = 0xffffffffu;
-    }
-    __syncwarp();
-    if (lane <= FASTB_NSEG) {
-        // mask[j]: bit (k-1) set <=> Theta_k >= Psi <=> sorted position of k >= j (j = number of thresholds < Psi)
-        unsigned m = 0;
-        for (int k = 1; k <= FASTB_NSEG; ++k)
-            if ((int)pos[k - 1] >= lane) m |= 1u << (k - 1);
-        tab->mask[lane] = m;
-    }
-    for (int t = lane; t < kFastBins + 1; t += 32) {
-        int cnt = 0, here = 0;
-        for (int j = 0; j < FASTB_NSEG; ++j) {
-            cnt += (thr[j] >> 25) < (unsigned)t;
-            here += (thr[j] >> 25) == (unsigned)t;
+    int sameOrder = 0;
+    if (reuseOrder) {   // inv[i] = threshold with sorted position i (previous build): still sorted, ties by index?
+        const unsigned* inv = scratch + 64;
+        sameOrder = 1;
+        if (lane + 1 < FASTB_NSEG) {
+            const unsigned a = inv[lane], b = inv[lane + 1];
+            sameOrder = a < (unsigned)FASTB_NSEG && b < (unsigned)FASTB_NSEG && (thr[a] < thr[b] || (thr[a] == thr[b] && a < b));
         }
-        tab->binStart[t] = (unsigned char)cnt;
-        ok &= here <= 4;  // the rank refinement in the correlator does 4 steps
+        sameOrder = __all_sync(0xffffffffu, sameOrder);
     }
+    if (sameOrder) {
+        if (lane < FASTB_NSEG) tab->thr[pos[lane]] = thr[lane];
+        __syncwarp();
+    } else {
+        if (lane < FASTB_NSEG) {  // rank sort (ties broken by index)
+            const unsigned v = thr[lane];
+            int rank = 0;
+            for (int j = 0; j < FASTB_NSEG; ++j) rank += (thr[j] < v) || (thr[j] == v && j < lane);
+            tab->thr[rank] = v;
+            pos[lane] = rank;
+            if (reuseOrder) scratch[64 + rank] = (unsigned)lane;
+        } else if (lane < 24) {
+            tab->thr[lane] = 0xffffffffu;
+        }
+        __syncwarp();
+        if (lane <= FASTB_NSEG) {
+            // mask[j]: bit (k-1) set <=> Theta_k >= Psi <=> sorted position of k >= j (j = number of thresholds < Psi)
+            unsigned m = 0;
+            for (int k = 1; k <= FASTB_NSEG; ++k)
+                if ((int)pos[k - 1] >= lane) m |= 1u << (k - 1);
+            tab->mask[lane] = m;
+        }
+    }
+    if (withBins) {
+        for (int t = lane; t < kFastBins + 1; t += 32) {
+            int cnt = 0;
+            for (int j = 0; j < FASTB_NSEG; ++j) cnt += (thr[j] >> 25) < (unsigned)t;
+            tab->binStart[t] = (unsigned char)cnt;
+        }
+    }
+    // the rank refinement in the correlator does 4 steps: no bin may hold more than 4 thresholds, i.e. sorted
+    // thresholds four places apart lie in different bins
+    if (lane + 4 < FASTB_NSEG) ok &= (tab->thr[lane] >> 25) != (tab->thr[lane + 4] >> 25);
     ok = __all_sync(0xffffffffu, ok);
     if (lane == 0) {
         tab->u0 = 2.0 * np.rem;
@@ -277,10 +321,53 @@ __device__ __forceinline__ unsigned b2a_cluster_size() {
     return r;
 }
 // every thread of every CTA of the cluster arrives (release: its earlier shared::cluster stores are visible to whoever
-// completes the wait) and waits (acquire)
+// completes the wait) and waits (acquire).  Used once at the start (mbarrier initialisation) and once at the end.
 __device__ __forceinline__ void b2a_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// exchange barrier: an mbarrier in every CTA on which the lanes of the PEERS' warp 0 arrive after their stores into
+// this CTA (release at cluster scope); only this CTA's warp 0 waits on it (acquire) - the other 500 threads of the
+// CTA never take part in a cluster-wide barrier
+__device__ __forceinline__ void b2a_xbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void b2a_xbar_arrive_peer(unsigned long long* bar, unsigned rank) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// arm the local exchange barrier for one phase: one arrival (this one) + `bytes` of incoming bulk copies
+__device__ __forceinline__ void b2a_xbar_expect(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bulk copy of `bytes` (a multiple of 16) from this CTA's shared memory into the same-named buffer of CTA `rank`,
+// completing on THAT CTA's barrier (cp.async.bulk, shared::cta -> shared::cluster): one instruction per peer
+__device__ __forceinline__ void b2a_bulk_to_peer(void* dstLocalName, const void* src, unsigned bytes, unsigned long long* barLocalName,
+                                                 unsigned rank) {
+    unsigned rd, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rd) : "r"(smem_u32(dstLocalName)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(barLocalName)), "r"(rank));
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rd),
+                 "r"(smem_u32(src)), "r"(bytes), "r"(rb)
+                 : "memory");
+}
+__device__ __forceinline__ void b2a_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the three loop-closing warps (0..2) meet
+__device__ __forceinline__ void b2a_closers_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+// ... and the ten warps (0..9) that close the loops / build the next epoch's table
+__device__ __forceinline__ void b2a_builders_sync() { asm volatile("bar.sync 2, 320;" ::: "memory"); }
+__device__ __forceinline__ void b2a_xbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "XWAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra XWAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 // v -> the same shared-memory location in CTA `rank` of the cluster
 __device__ __forceinline__ void b2a_st_peer(long long* p, unsigned rank, long long v) {
@@ -298,8 +385,12 @@ struct __align__(128) B2aSmem {
     uint32_t bits[2][kPackedWordsDev];  // packed primaries: data, pilot (bit k of word w = chip 32 w + k)
     uint32_t ext[2][kPackedWordsDev];   // the same rotated by one chip (fastb_code12)
     int res[kB2aThreads / 32][12];      // warp sums, Q8 fixed point
-    long long part[2][kB2aMaxCluster][12];   // [epoch parity][cluster rank]: every CTA's Q8 sums, written by the CTAs themselves
+    __align__(16) long long part[2][kB2aMaxCluster][12];   // [epoch parity][cluster rank]: every CTA's Q8 sums, written by the CTAs themselves
+    __align__(16) long long mine[2][12];     // this CTA's Q8 sums (source of the bulk copies to the peers)
     long long bcast[2];                 // lock-loss handling: CTA 0's {lockLost, lowLock} after a C/N0 interval
+    unsigned long long xbar[2];         // exchange barriers by epoch parity: 96 bytes from every CTA of the cluster
+    unsigned long long bbar;            // followers: CTA 0's bcast has arrived
+    unsigned binScratch[4][32];         // thresholds of the warps that build the rank index
     double sums[kNSum];
     double v[12];                       // loop closure: {data, pilot} x {E, L, P} x {I, Q} as the discriminators take them
     double pre[8];                      // discriminator pieces evaluated by parallel lanes (close_nco)
@@ -307,7 +398,8 @@ struct __align__(128) B2aSmem {
     EpochParams pDone;                  // the epoch whose loops were just closed (output phase)
     ChanState st;                       // channel state (thread 0 closes the loops on it)
     CloseAux aux;
-    unsigned scratch[64];
+    unsigned scratch[96];               // fastb_build_tab_warp: thresholds, sorted positions, inverse order (kept between epochs)
+    EpochParams pNext;                  // the next epoch's NCO as far as the table needs it (step, rem, carrFreq, remCarr)
     unsigned long long full[2];         // mbarriers: the staged block has arrived
     long long tileBase[2];              // window byte offset of tile[b][0]
     int tileBytes[2];
@@ -417,38 +509,45 @@ __device__ __forceinline__ double b2a_fmod_pos(double x, double y) {
     return r;
 }
 
-// warp 0: the discriminator pieces of tracking.m:337-377 in parallel lanes with uniform control flow (the same
-// expressions as close_nco evaluates when it gets no `pre`): square roots, arctangents and the exact fmod of the
-// carrier phase are what makes a one-thread loop closure slow.
-__device__ __forceinline__ void b2a_discriminators(const TrkDev& g, B2aSmem& sm, const EpochParams& p) {
+// one of the 12 sums as a double from the Q8 totals in part[] (zero for the pilot family without a pilot)
+__device__ __forceinline__ double b2a_total(const TrkDev& g, const long long (*part)[12], int nParts, int idx) {
+    if (!(idx < 6 || g.hasPilot)) return 0.0;
+    long long t = 0;
+    for (int r = 0; r < nParts; ++r) t += part[r][idx];
+    return (double)t * (1.0 / 256.0);
+}
+
+// The discriminator pieces of tracking.m:337-377 (the same expressions as close_nco evaluates when it gets no `pre`):
+// square roots, arctangents, divisions and the exact fmod of the carrier phase are long dependent fp64 chains - what
+// makes a one-thread loop closure slow.  They are independent of one another, so three warps evaluate them side by
+// side (a warp's lanes share one instruction stream: inside one warp the chains would run one after the other):
+//   warp 0  |E|, |L| of data and pilot -> the two DLL discriminators        pre[2], pre[3]
+//   warp 1  atan(Q_P / I_P) / 2 pi of data and (rotated) pilot              pre[0], pre[1]
+//   warp 2  rem(trigarg(blksize + 1), 2 pi), the next carrier phase         pre[4]
+__device__ __forceinline__ void b2a_disc_dll(const TrkDev& g, B2aSmem& sm, const long long (*part)[12], int n) {
     const int lane = threadIdx.x & 31;
-    const double* s = sm.sums;
-    if (lane < 6) {            // data E, L, P as (I, Q)
-        const int o = lane >> 1 == 0 ? EPL_E : (lane >> 1 == 1 ? EPL_L : EPL_P);
-        sm.v[lane] = s[sum_idx(0, o, lane & 1)];
-    } else if (lane < 10) {    // pilot E, L as (I, Q)
-        const int k = lane - 6;
-        sm.v[lane] = s[sum_idx(1, k >> 1 == 0 ? EPL_E : EPL_L, k & 1)];
-    } else if (lane < 12) {    // pilot prompt rotated by exp(-i pi/2) (tracking.m:345): (re, im)
-        const double cr = 6.123233995736766e-17;  // cos(pi/2) in double
-        const double pIP = s[sum_idx(1, EPL_P, 0)], pQP = s[sum_idx(1, EPL_P, 1)];
-        sm.v[lane] = lane == 10 ? pIP * cr + pQP : pQP * cr - pIP;
-    }
-    __syncwarp();
-    const int l6 = lane < 6 ? lane : 0;   // lanes 0..5: data E, data L, data P, pilot E, pilot L, pilot P'
-    const double A = sm.v[2 * l6], B = sm.v[2 * l6 + 1];
+    const int l4 = lane & 3;   // 0: data E, 1: data L, 2: pilot E, 3: pilot L
+    const int fam = l4 >> 1, epl = (l4 & 1) ? EPL_L : EPL_E;
+    const double A = b2a_total(g, part, n, sum_idx(fam, epl, 0)), B = b2a_total(g, part, n, sum_idx(fam, epl, 1));
     const double mag = sqrt(A * A + B * B);
-    const double ang = atan(B / A) / 6.283185307179586476925286766559;
     const double magN = __shfl_down_sync(0xffffffffu, mag, 1);
     const double disc = (mag - magN) / (mag + magN);
+    if (lane == 0) sm.pre[2] = disc;
+    if (lane == 2) sm.pre[3] = disc;
+}
+__device__ __forceinline__ void b2a_disc_pll(const TrkDev& g, B2aSmem& sm, const long long (*part)[12], int n) {
+    const int lane = threadIdx.x & 31;
+    const int fam = lane & 1;   // 0: data prompt, 1: pilot prompt rotated by exp(-i pi/2) (tracking.m:345)
+    const double iP = b2a_total(g, part, n, sum_idx(fam, EPL_P, 0)), qP = b2a_total(g, part, n, sum_idx(fam, EPL_P, 1));
+    const double cr = 6.123233995736766e-17;  // cos(pi/2) in double
+    const double A = fam ? iP * cr + qP : iP, B = fam ? qP * cr - iP : qP;
+    const double ang = atan(B / A) / 6.283185307179586476925286766559;
+    if (lane < 2) sm.pre[lane] = ang;
+}
+__device__ __forceinline__ void b2a_disc_carr(const TrkDev& g, B2aSmem& sm, const EpochParams& p) {
     const double trig = ((p.carrFreq * 2.0 * 3.14159265358979323846) * ((double)p.blksize / g.fs)) + p.remCarr;
     const double fm = b2a_fmod_pos(trig, 6.283185307179586476925286766559);   // tracking.m:305 (trig >= 0)
-    if (lane == 2) sm.pre[0] = ang;
-    if (lane == 5) sm.pre[1] = ang;
-    if (lane == 0) sm.pre[2] = disc;
-    if (lane == 3) sm.pre[3] = disc;
-    if (lane == 6) sm.pre[4] = fm;
-    __syncwarp();
+    if ((threadIdx.x & 31) == 0) sm.pre[4] = fm;
 }
 
 // this CTA's share of an epoch: units [u0, u1) and the bytes of a block they can touch at any plausible code rate
@@ -508,7 +607,11 @@ __global__ void __launch_bounds__(kB2aThreadsAll, 1) trk_b2a_unit_kernel(TrkDev 
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
+        b2a_xbar_init(&sm.xbar[0], 1);   // one local arrival (expect_tx) + 96 bytes from every CTA of the cluster per phase
+        b2a_xbar_init(&sm.xbar[1], 1);
+        b2a_xbar_init(&sm.bbar, 1);
         sm.tileBytes[0] = sm.tileBytes[1] = 0;
+        for (int i = 64; i < 96; ++i) sm.scratch[i] = 0xffffffffu;   // no previous threshold order
         b2a_plan_share(g, sm, c, rk, CS);
         sm.st = g.st[c];
         EpochParams np;
@@ -520,12 +623,14 @@ __global__ void __launch_bounds__(kB2aThreadsAll, 1) trk_b2a_unit_kernel(TrkDev 
         if (sm.run) sm.p = np;
     }
     __syncthreads();
+    if (CS > 1) b2a_cluster_sync();   // every CTA's exchange barriers are initialised before anybody arrives on them
     int eCur = sm.st.epoch;   // index of the epoch about to be correlated (every thread keeps its own copy)
+    unsigned xph[2] = {0, 0}, bph = 0;
     if (service && lane == 0 && sm.run) pending[0] = b2a_issue_tile(g, sm, sm.p.pos, 0);
-    if (warp == 0 && sm.run) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch);
+    if (warp == 0 && sm.run) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch, true, true, true);
     __syncthreads();
 #ifdef BDS_FW_DEV
-    long long tW = 0, tC = 0, tL = 0, tT = 0, t0_ = 0;
+    long long tW = 0, tC = 0, tL = 0, tT = 0, tX = 0, tD = 0, tN = 0, t0_ = 0;
 #define B2A_T(acc) { const long long t1_ = clock64(); acc += t1_ - t0_; t0_ = t1_; }
     t0_ = clock64();
 #else
@@ -552,20 +657,57 @@ __global__ void __launch_bounds__(kB2aThreadsAll, 1) trk_b2a_unit_kernel(TrkDev 
         }
         __syncthreads();   // every warp is done with the tile and the table; warp sums are visible; epoch e-1 is written out
         B2A_T(tC)
-        if (warp == 0) {   // this CTA's Q8 sums -> slot [rk] of every CTA of the cluster (its own included)
-            const long long t = b2a_cta_sum(sm, lane);
-            if (lane < 12)
-                for (unsigned r = 0; r < CS; ++r) b2a_st_peer(&sm.part[par][rk][lane], r, t);
-        }
-        b2a_cluster_sync();
         // a C/N0 interval ends with this epoch and lock-loss handling is on: the lock detector decides whether there is
         // a next epoch, so CTA 0 writes this epoch's outputs and the interval's C/N0 first and tells the others
         const bool lockStep = g.lockPLD > 0.0 && g.cnoInterval > 0 && (eCur + 1) % g.cnoInterval == 0;
+        if (warp < 3) {
+            if (warp == 0) {
+                // this CTA's Q8 sums -> slot [rk] of every CTA of the cluster (its own included): one bulk copy through
+                // distributed shared memory per peer, completing on the peer's exchange barrier
+                const long long t = b2a_cta_sum(sm, lane);
+                if (CS > 1) {
+                    if (lane < 12) sm.mine[par][lane] = t;
+                    b2a_fence_async_smem();   // the sums were written through the generic proxy, the copies read them through the async one
+                    __syncwarp();
+                    if (lane == 0) b2a_xbar_expect(&sm.xbar[par], 96u * CS);
+                    if ((unsigned)lane < CS) b2a_bulk_to_peer(sm.part[par][rk], sm.mine[par], 96u, &sm.xbar[par], (unsigned)lane);
+                } else if (lane < 12) {
+                    sm.part[par][0][lane] = t;
+                }
+            }
+            if (CS > 1) {
+                b2a_xbar_wait(&sm.xbar[par], xph[par]);   // everybody's sums have arrived
+                xph[par] ^= 1;
+            } else {
+                b2a_closers_sync();
+            }
+            B2A_T(tX)
+            if (warp == 0) {
+                b2a_collect(g, sm, sm.part[par], (int)CS);
+                b2a_disc_dll(g, sm, sm.part[par], (int)CS);
+            } else if (warp == 1) {
+                b2a_disc_pll(g, sm, sm.part[par], (int)CS);
+            } else {
+                b2a_disc_carr(g, sm, p);
+            }
+            b2a_closers_sync();
+        }
         if (warp == 0) {
-            b2a_collect(g, sm, sm.part[par], (int)CS);
-            b2a_discriminators(g, sm, p);
+            B2A_T(tD)
             if (lane == 0) {
                 close_nco(g, sm.sums, p, g.cc[c].chCodeFreq, sm.st, sm.aux, sm.pre);
+                // what the next table needs of the next NCO, with next_params' own expressions: the builder warps start
+                // on it now, while this thread works out blksize, the window check and whether there is a next epoch
+                sm.pNext.rem = sm.st.remCodePhase;
+                sm.pNext.step = sm.st.codeFreq / g.fs;
+                sm.pNext.carrFreq = sm.st.carrFreq;
+                sm.pNext.remCarr = sm.st.remCarrPhase;
+            }
+        }
+        if (warp <= 9) b2a_builders_sync();   // sm.pNext is visible to the builder warps
+        if (warp == 0) {
+            B2A_T(tN)
+            if (lane == 0) {
                 sm.pDone = p;
                 const int e = sm.eDone = sm.st.epoch;
                 sm.st.epoch += 1;
@@ -580,32 +722,34 @@ __global__ void __launch_bounds__(kB2aThreadsAll, 1) trk_b2a_unit_kernel(TrkDev 
                     for (unsigned r = 1; r < CS; ++r) {
                         b2a_st_peer(&sm.bcast[0], r, sm.st.lockLost);
                         b2a_st_peer(&sm.bcast[1], r, (long long)sm.st.lowLock);
+                        b2a_xbar_arrive_peer(&sm.bbar, r);
                     }
                 }
                 if (lockStep) sm.outDone = 1;
+                if (lockStep && !lead) {
+                    b2a_xbar_wait(&sm.bbar, bph);
+                    sm.st.lockLost = sm.bcast[0];
+                    sm.st.lowLock = (int)sm.bcast[1];
+                }
             }
+            if (lockStep) bph ^= 1;
         }
-        if (lockStep && CS > 1) b2a_cluster_sync();   // uniform over the cluster
         if (warp == 0 && lane == 0) {
-            if (lockStep && !lead) {
-                sm.st.lockLost = sm.bcast[0];
-                sm.st.lowLock = (int)sm.bcast[1];
-            }
             EpochParams np;
             const bool okp = next_params(g, sm.st, np), lim = sm.st.epoch < g.epochLimit;
             if (lead && !okp && lim && sm.st.lockLost == 0) out[(size_t)F_ABS * cap + sm.st.epoch] = (double)sm.st.pos;
             const int run = okp && lim && done < g.maxEpochs;
             if (run) sm.p = np;
             sm.run = run;
+        } else if (warp >= 1 && warp <= 9) {
+            // the next epoch's table from sm.pNext, spread over nine warps, while lane 0 of warp 0 finishes the NCO
+            // (thresholds / order / masks: warp 1; carrier rotation: warps 2-5; rank index: warps 6-9)
+            if (warp == 1) fastb_build_tab_warp(&sm.tab, sm.pNext, g.fs, sm.scratch, false, false, true);
+            else if (warp <= 5) fastb_build_rot(&sm.tab, fastb_dphi(sm.pNext, g.fs), tid - 64, 128);
+            else fastb_build_bins_warp(&sm.tab, sm.pNext, sm.binScratch[warp - 6], 32 * (warp - 6));
         }
-        __syncthreads();   // the next epoch's NCO (sm.p), sm.run and the closure's by-products are visible
+        __syncthreads();   // the next epoch's NCO (sm.p), its table, sm.run and the closure's by-products are visible
         B2A_T(tL)
-        if (sm.run) {
-            if (warp == 0) fastb_build_tab_warp(&sm.tab, sm.p, g.fs, sm.scratch, false);
-            else if (warp <= 4) fastb_build_rot(&sm.tab, fastb_dphi(sm.p, g.fs), tid - 32, 128);
-        }
-        __syncthreads();
-        B2A_T(tT)
         buf ^= 1;
         par ^= 1;
         ++eCur;
@@ -624,9 +768,13 @@ __global__ void __launch_bounds__(kB2aThreadsAll, 1) trk_b2a_unit_kernel(TrkDev 
         atomicAdd(g.counters + 6, (unsigned long long)tL);
         atomicAdd(g.counters + 7, (unsigned long long)tT);
         atomicAdd(g.counters + 8, (unsigned long long)done);
+        atomicAdd(g.counters + 9, (unsigned long long)tX);
+        atomicAdd(g.counters + 10, (unsigned long long)tD);
+        atomicAdd(g.counters + 11, (unsigned long long)tN);
     }
 #endif
 #undef B2A_T
+    if (CS > 1) b2a_cluster_sync();   // nobody leaves while a peer could still store into its shared memory
     if (tid == 0 && lead) g.st[c] = sm.st;
     __syncwarp();
     if (g.counters && !service) {

@@ -66,6 +66,9 @@ def parse():
                          "the same GPUs); acq_b2a = BASELINE config 2 (B2a 63-PRN x +-5 kHz acquisition grid); acq_b1c")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: --channels in total, sharded over the GPUs (BASELINE config 4); weak: --channels per GPU")
+    ap.add_argument("--b2a-cluster", type=int, default=0, choices=[0, 1, 2, 4, 8],
+                    help="B2a kernel: CTAs per channel (0 = library default / for --workload dual the largest cluster that leaves "
+                         "half of the SMs to the B1C grid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -414,7 +417,8 @@ def run_b200(args):
     st_local = st.copy()
     st_local.numberOfChannels = len(mine)
     st_local.numberOfChannels_total = total_channels   # satellites in the record (self_check: multiple-access noise)
-    sess = _track.TrackSession(mode, st_local, mine, kernel=kern, device_ptr=x_dev.data_ptr(), n_samples=n_samples)
+    tuning = {"b2aClusterSize": args.b2a_cluster} if (sig == "B2a" and args.b2a_cluster) else None
+    sess = _track.TrackSession(mode, st_local, mine, kernel=kern, device_ptr=x_dev.data_ptr(), n_samples=n_samples, tuning=tuning)
 
     def barrier():
         torch.cuda.synchronize()
@@ -500,7 +504,7 @@ def run_b200(args):
         x_host = torch.empty(n_samples, dtype=torch.int8).pin_memory()
         x_host.copy_(x_dev[:n_samples])
         torch.cuda.synchronize()
-        sess2 = _track.TrackSession(mode, st_local, mine, kernel=kern)     # no resident record: fed from the host
+        sess2 = _track.TrackSession(mode, st_local, mine, kernel=kern, tuning=tuning)     # no resident record: fed from the host
         # caller-owned result planes, pinned like the input (the MEX gateway would hand mxArrays here)
         res = {name: torch.empty((len(mine), n_epochs), dtype=torch.float64).pin_memory().numpy() for name in L.TRK_PLANES}
         times, parts = [], []
@@ -659,9 +663,16 @@ def run_dual(args):
         st_local.numberOfChannels = len(mine)
         st_local.numberOfChannels_total = total
         n_epochs = max(1, int(math.floor((n_samples - w["spc"]) / (w["spc"] * (1 + 1e-5)))) - 1)
-        tuning = None
-        if wl == "track":   # the B2a kernel holds one SM per channel: the persistent B1C grid takes the others
-            tuning = {"fwMaxCtas": max(16, n_sms - len(bands[0]["mine"]))}
+        if wl == "track_b2a":   # B2a: a cluster of CTAs per channel, on at most half of the SMs
+            cs = args.b2a_cluster
+            if cs == 0:
+                cs = 8
+                while cs > 1 and len(mine) * cs > n_sms // 2:
+                    cs //= 2
+            tuning = {"b2aClusterSize": cs}
+            b2a_ctas = len(mine) * cs
+        else:                   # the persistent B1C grid takes the SMs the B2a clusters leave
+            tuning = {"fwMaxCtas": max(16, n_sms - b2a_ctas)}
         bands.append(dict(wl=wl, w=w, st=st, st_local=st_local, chans=chans, mine=mine, x_dev=x_dev, n_epochs=n_epochs,
                           tuning=tuning,
                           sess=_track.TrackSession(w["mode"], st_local, mine, device_ptr=x_dev.data_ptr(), n_samples=n_samples,
@@ -781,7 +792,9 @@ def run_dual(args):
                                        f"at 99.375 MHz, {args.seconds:g} s",
                            "epochs_per_channel": {b["w"]["sig"]: b["n_epochs"] for b in bands},
                            "parallelism": f"channels of both bands round-robin over {world} GPU(s), both IF records replicated; per GPU "
-                                          "two sessions on two streams, the B1C persistent grid limited to the SMs the B2a CTAs leave",
+                                          "two sessions on two streams, the B1C persistent grid limited to the SMs the B2a clusters leave",
+                           "sm_split": {"b2a_ctas": b2a_ctas, "b2a_cluster": bands[0]["tuning"]["b2aClusterSize"],
+                                        "b1c_ctas": bands[1]["tuning"]["fwMaxCtas"]},
                            "l2": f"inputs 2 x {n_samples / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
                            "x_realtime": step_ms and args.seconds * 1e3 / step_ms},
                 "roofline": {"bound": "hbm", "achieved": alg / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

@@ -46,6 +46,16 @@ static inline unsigned b2a_cluster_rank() { return 0u; }
 static inline unsigned b2a_cluster_size() { return 1u; }
 static inline void b2a_cluster_sync() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void b2a_st_peer(long long* p, unsigned, long long v) { *p = v; }
+static inline void b2a_xbar_init(unsigned long long*, unsigned) {}
+static inline void b2a_xbar_arrive_peer(unsigned long long*, unsigned) {}
+static inline void b2a_xbar_wait(unsigned long long*, unsigned) {}
+static inline void b2a_xbar_expect(unsigned long long*, unsigned) {}
+static inline void b2a_bulk_to_peer(void*, const void*, unsigned, unsigned long long*, unsigned) {}
+static inline void b2a_fence_async_smem() {}
+static std::barrier<> g_closers_bar(96);
+static inline void b2a_closers_sync() { g_closers_bar.arrive_and_wait(); }   // bar.sync 1, 96: warps 0..2
+static std::barrier<> g_builders_bar(320);
+static inline void b2a_builders_sync() { g_builders_bar.arrive_and_wait(); }   // bar.sync 2, 320: warps 0..9
 static std::barrier<> g_cta_bar(kEmuThreads);
 static std::barrier<>* g_warp_bar[kEmuThreads / 32];
 static long long g_warp_val[kEmuThreads / 32][32];
