@@ -69,6 +69,9 @@ def parse():
     ap.add_argument("--b2a-cluster", type=int, default=0, choices=[0, 1, 2, 4, 8],
                     help="B2a kernel: CTAs per channel (0 = library default / for --workload dual the largest cluster that leaves "
                          "half of the SMs to the B1C grid)")
+    ap.add_argument("--gather-every", type=int, default=0,
+                    help="epochs per launch + NCCL gather of the correlator outputs to rank 0 (0 = one gather per step, the "
+                         "default; 1 = the per-epoch gather the north star words, measured for SURVEY 7.7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -445,12 +448,38 @@ def run_b200(args):
     _, nbytes0, _, _ = sess.device_block()
     max_block_elems = _shard.max_block_elems(nbytes0 // 8, dist)
 
+    gather_buf = {}
+
+    def gather_epochs(e0, k):
+        """NCCL gather of epochs [e0, e0 + k) of every output plane (21 trackResults planes + 18 raw sums) to rank 0"""
+        if dist is None:
+            return
+        p, nbytes, nf, cap = sess.device_block()
+        nch = nbytes // 8 // (nf * cap)
+        nmax = max_block_elems // (nf * cap)
+        if k not in gather_buf:
+            gather_buf[k] = (torch.zeros(nmax * nf * k, dtype=torch.float64, device="cuda"),
+                             [torch.empty(nmax * nf * k, dtype=torch.float64, device="cuda") for _ in range(world)] if rank == 0 else None)
+        buf, outs = gather_buf[k]
+        buf[: nch * nf * k].view(nch, nf, k).copy_(_as_tensor(p, nbytes // 8).view(nch, nf, cap)[:, :, e0: e0 + k])
+        dist.gather(buf, outs, dst=0)
+
     def step():
         sess.reset()
-        sess.run_async(n_epochs)
-        sess.sync()
-        gather_block()
-        return sess.stats()
+        if args.gather_every <= 0:
+            sess.run_async(n_epochs)
+            sess.sync()
+            gather_block()
+            return sess.stats()
+        e, ms_total = 0, 0.0
+        while e < n_epochs:     # one launch + one gather per --gather-every epochs
+            k = min(args.gather_every, n_epochs - e)
+            sess.run_async(k)
+            cs, ep, ms = sess.stats()
+            ms_total += ms
+            gather_epochs(e, k)
+            e += k
+        return cs, ep, ms_total
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -504,7 +533,12 @@ def run_b200(args):
         x_host = torch.empty(n_samples, dtype=torch.int8).pin_memory()
         x_host.copy_(x_dev[:n_samples])
         torch.cuda.synchronize()
-        sess2 = _track.TrackSession(mode, st_local, mine, kernel=kern, tuning=tuning)     # no resident record: fed from the host
+        tuning2 = dict(tuning or {})
+        if world > 1 and sig == "B1C" and int(os.environ.get("BDS_BENCH_E2E_FW_CTAS", "0")) > 0:
+            # leave a few SMs to the NCCL all-gather kernels that bring the next chunk in (a persistent grid on every SM
+            # serialises them between its launches)
+            tuning2["fwMaxCtas"] = int(os.environ["BDS_BENCH_E2E_FW_CTAS"])
+        sess2 = _track.TrackSession(mode, st_local, mine, kernel=kern, tuning=tuning2 or None)     # no resident record: fed from the host
         # caller-owned result planes, pinned like the input (the MEX gateway would hand mxArrays here)
         res = {name: torch.empty((len(mine), n_epochs), dtype=torch.float64).pin_memory().numpy() for name in L.TRK_PLANES}
         times, parts = [], []
@@ -521,20 +555,54 @@ def run_b200(args):
             stage = [torch.empty(chunk // world, dtype=torch.int8, device="cuda") for _ in range(2)]
             side = torch.cuda.Stream()
             n_chunks = n_pad // chunk
+            # Exchange of the uploaded slices between the GPUs.  Preferred: copy-engine pushes into the peers' records
+            # (CUDA IPC mappings, device-to-device copies over NVLink) - they need no SM, so they run under the persistent
+            # tracking grid, which occupies every SM and serialises an NCCL all-gather kernel between its launches.
+            # A host-side (gloo) barrier per chunk tells every rank that all pushes of that chunk have landed.
+            peers, cpu_group, e2e_exchange = None, None, "NCCL all-gather"
+            try:
+                # measured on 2 x B200 (profiles/r02/scaling_n2.md): the pushes into IPC-mapped peer memory ran at a fraction of
+                # the NVLink rate (117 ms per step against 46 ms with the all-gather), so NCCL stays the default
+                if os.environ.get("BDS_BENCH_E2E_EXCHANGE", "nccl") == "peer":
+                    import torch.multiprocessing.reductions as red
+                    fn, a = red.reduce_tensor(x_full)
+                    handles = [None] * world
+                    dist.all_gather_object(handles, (fn, a))
+                    peers = [x_full if r == rank else h_[0](*h_[1]) for r, h_ in enumerate(handles)]
+                    cpu_group = dist.new_group(backend="gloo")
+                    probe = torch.full((16,), rank, dtype=torch.int8, device="cuda")
+                    for r in range(world):          # one small push to every peer: fails here rather than in the timed loop
+                        if r != rank:
+                            peers[r][n_pad + 16 * 0: n_pad + 16].copy_(probe, non_blocking=True)
+                    torch.cuda.synchronize()
+                    dist.barrier(group=cpu_group)
+                    e2e_exchange = "copy-engine peer pushes (CUDA IPC) + gloo barrier per chunk"
+            except Exception as ex:   # noqa: BLE001
+                print(f"[bench] peer-copy exchange unavailable ({type(ex).__name__}: {ex}); using the NCCL all-gather", file=sys.stderr)
+                peers, cpu_group = None, None
 
             def e2e_step():
                 evs = []
                 with torch.cuda.stream(side):
                     for k in range(n_chunks):
                         o, sl = k * chunk, chunk // world
-                        st_ = stage[k & 1]
-                        st_.copy_(xh[o + rank * sl: o + (rank + 1) * sl], non_blocking=True)
-                        dist.all_gather_into_tensor(x_full[o: o + chunk], st_)
+                        if peers is not None:
+                            mine_ = x_full[o + rank * sl: o + (rank + 1) * sl]
+                            mine_.copy_(xh[o + rank * sl: o + (rank + 1) * sl], non_blocking=True)
+                            for r in range(1, world):      # staggered so that not everybody pushes to the same GPU at once
+                                q = (rank + r) % world
+                                peers[q][o + rank * sl: o + (rank + 1) * sl].copy_(mine_, non_blocking=True)
+                        else:
+                            st_ = stage[k & 1]
+                            st_.copy_(xh[o + rank * sl: o + (rank + 1) * sl], non_blocking=True)
+                            dist.all_gather_into_tensor(x_full[o: o + chunk], st_)
                         ev = torch.cuda.Event()
                         ev.record(side)
                         evs.append(ev)
                 for k, ev in enumerate(evs):
                     ev.synchronize()
+                    if peers is not None:
+                        dist.barrier(group=cpu_group)   # every rank's pushes of chunk k have completed
                     sess2.run_window(x_full.data_ptr(), min(n_samples, (k + 1) * chunk), n_epochs)
         else:
             def e2e_step():
@@ -572,9 +640,10 @@ def run_b200(args):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt[0]) * 1e3,
                "ms_breakdown": {k: round(1e3 * sum(p_[j] for p_ in parts) / len(parts), 2)
                                 for j, k in enumerate(("reset", "enqueue", "h2d+kernels", "fetch+gather"))},
+               "fw_ctas": tuning2.get("fwMaxCtas", 0),
                "pinned_h2d_GBps_this_box": round(h2d_gbs, 1),
                "path": ("bds_track_run_streamed (128 MiB chunks on a copy stream) + bds_track_fetch" if world == 1 else
-                        f"per 128 MiB chunk: H2D of 1/{world} per rank + NCCL all-gather over NVLink on a side stream, "
+                        f"per 128 MiB chunk: H2D of 1/{world} per rank + {e2e_exchange} over NVLink on a side stream, "
                         "bds_track_run_window per chunk, bds_track_fetch")}
 
     if rank == 0:
@@ -590,7 +659,9 @@ def run_b200(args):
                            "epochs_per_channel": n_epochs,
                            "parallelism": f"{total_channels} channels round-robin over {world} GPU(s), IF replicated",
                            "l2": f"input {n_samples / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
-                           "kernel": args.kernel, "x_realtime": value / (FS / 1e6)},
+                           "kernel": args.kernel, "x_realtime": value / (FS / 1e6),
+                           "gather": ("one NCCL gather of the packed output block per step" if args.gather_every <= 0 else
+                                      f"one launch + one NCCL gather of the outputs every {args.gather_every} epoch(s)")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                              "traffic": measured_traffic(kname, args.channels, args.seconds, world),

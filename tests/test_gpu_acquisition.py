@@ -151,3 +151,26 @@ def test_b2a_acquisition_with_resampling_preconditioner():
     np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
     assert want.carrFreq[3] != 0 and want.carrFreq[8] == 0
     assert abs(got.carrFreq[3] - (s.IF + sats[0].doppler)) <= 25
+
+
+def test_b1c_acquisition_full_reference_grid_against_stored_oracle_results():
+    """The FULL reference grid (+-5 kHz in 50 Hz steps = 201 bins, 10 ms coherent, data + pilot, 2^22-point transforms;
+    acquisition.m:129-307) for three PRNs.  The float64 oracle needs minutes for this, so its results are stored
+    (tests/golden/acq_b1c_full_grid.npz, written by tests/golden/make_golden_acq_full.py); the record is re-rendered
+    from its seed here."""
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_golden_acq_full as G
+    gold = np.load(os.path.join(here, "acq_b1c_full_grid.npz"))
+    s, sats, x = G.scenario()
+    assert int(np.frombuffer(x[:4096].tobytes(), dtype=np.uint8).sum()) == int(gold["record_sha_head"])   # same record
+    got, gd = B.b1c.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for i, prn in enumerate(gold["prns"]):
+        assert gd[prn - 1, 0] == gold["bin"][i] and gd[prn - 1, 1] == gold["coarseCodePhase"][i]
+        np.testing.assert_allclose(gd[prn - 1, 2], gold["peak"][i], rtol=1e-4)
+    np.testing.assert_allclose(got.peakMetric, gold["peakMetric"], rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, gold["codePhase"])
+    np.testing.assert_array_equal(got.carrFreq, gold["carrFreq"])
+    assert got.carrFreq[6] != 0 and got.carrFreq[22] != 0 and got.carrFreq[39] == 0
