@@ -534,10 +534,11 @@ def run_b200(args):
         x_host.copy_(x_dev[:n_samples])
         torch.cuda.synchronize()
         tuning2 = dict(tuning or {})
-        if world > 1 and sig == "B1C" and int(os.environ.get("BDS_BENCH_E2E_FW_CTAS", "0")) > 0:
+        if world > 1 and sig == "B1C" and args.kernel != "general":
             # leave a few SMs to the NCCL all-gather kernels that bring the next chunk in (a persistent grid on every SM
-            # serialises them between its launches)
-            tuning2["fwMaxCtas"] = int(os.environ["BDS_BENCH_E2E_FW_CTAS"])
+            # serialises them between its launches; measured on 8 x B200: 41.2 -> 36.0 ms per step, profiles/r02/scaling.md)
+            n_sms_ = torch.cuda.get_device_properties(local).multi_processor_count
+            tuning2["fwMaxCtas"] = int(os.environ.get("BDS_BENCH_E2E_FW_CTAS", n_sms_ - 12))
         sess2 = _track.TrackSession(mode, st_local, mine, kernel=kern, tuning=tuning2 or None)     # no resident record: fed from the host
         # caller-owned result planes, pinned like the input (the MEX gateway would hand mxArrays here)
         res = {name: torch.empty((len(mine), n_epochs), dtype=torch.float64).pin_memory().numpy() for name in L.TRK_PLANES}
