@@ -174,6 +174,11 @@ __device__ void smem_fft(float2* buf, int lg, int lgBatch, int seqStride, const 
     }
 }
 
+// Global loads of the FFT kernels are issued in batches of kLdBatch per thread before the first one is used: a plain
+// "load, use, next element" loop keeps one or two loads in flight per thread and stalls on every one of them
+// (ncu, round 2: 44 % of the stall samples of the inverse passes sat on the instruction after such a load).
+constexpr int kLdBatch = 8;
+
 // ---- forward column pass -------------------------------------------------------------
 // kind 0: signal  y[n] = x[n mod N] * exp(+i 2 pi f n'/fs), n' = n mod N, n < N+M-1, else 0
 //                 (acquisition.m:194-205; periodic extension see file header)
@@ -224,12 +229,25 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_col_kernel(AcqPlan pl,
     __syncthreads();
     smem_fft<false, true>(buf, pl.log2P1, kLgColTile, 0, pl.tw);
     float2* out = spec + (size_t)bi * pl.P;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        int c = e & (kColTile - 1), r = e >> 3;
-        unsigned k1 = __brev((unsigned)r) >> (32 - pl.log2P1);
-        unsigned n2 = col0 + c;
-        float2 w = twiddleP(pl, k1 * n2);
-        out[(size_t)r * pl.P2 + n2] = cmul(buf[pidx(r) * kColTile + c], w);
+    for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * kLdBatch) {
+        float2 hi[kLdBatch], lo[kLdBatch];
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < total) {
+                const unsigned m = (__brev((unsigned)(e >> 3)) >> (32 - pl.log2P1)) * (unsigned)(col0 + (e & (kColTile - 1)));
+                hi[u] = __ldg(pl.twHi + (m >> 11));
+                lo[u] = __ldg(pl.twLo + (m & 2047));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < total) {
+                const int c = e & (kColTile - 1), r = e >> 3;
+                out[(size_t)r * pl.P2 + col0 + c] = cmul(buf[pidx(r) * kColTile + c], cmul(hi[u], lo[u]));
+            }
+        }
     }
 }
 
@@ -241,7 +259,19 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_row_kernel(AcqPlan pl,
     float2* buf = reinterpret_cast<float2*>(smraw);
     float2* rows = spec + (size_t)blockIdx.y * pl.P + ((size_t)blockIdx.x << pl.lgRowTile) * pl.P2;   // 2^lgRowTile contiguous rows
     const int total = pl.P2 << pl.lgRowTile, rowStride = pl.P2 + (pl.P2 >> 4);
-    for (int i = threadIdx.x; i < total; i += blockDim.x) buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))] = rows[i];
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * kLdBatch) {
+        float2 v[kLdBatch];
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) v[u] = rows[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))] = v[u];
+        }
+    }
     __syncthreads();
     smem_fft<false, false>(buf, pl.log2P2, pl.lgRowTile, rowStride, pl.tw);
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -263,16 +293,42 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_inv_row_kernel(AcqPlan pl,
     const float2* srow = sig + (size_t)bin * pl.P + (size_t)r0 * pl.P2;
     const float2* crow = code + (size_t)dp * pl.P + (size_t)r0 * pl.P2;
     const int total = pl.P2 << pl.lgRowTile, rowStride = pl.P2 + (pl.P2 >> 4);
-    for (int i = threadIdx.x; i < total; i += blockDim.x)
-        buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))] = cmul(srow[i], __ldg(crow + i));
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * kLdBatch) {
+        float2 a[kLdBatch], c[kLdBatch];
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) {
+                a[u] = srow[i];
+                c[u] = __ldg(crow + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))] = cmul(a[u], c[u]);
+        }
+    }
     __syncthreads();
     smem_fft<true, false>(buf, pl.log2P2, pl.lgRowTile, rowStride, pl.tw);
     float2* orow = work + ((size_t)bi * ncodes + dp) * pl.P + (size_t)r0 * pl.P2;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int r = r0 + (i >> pl.log2P2), n2 = i & (pl.P2 - 1);
-        const unsigned k1 = __brev((unsigned)r) >> (32 - pl.log2P1);
-        float2 w = twiddleP(pl, k1 * (unsigned)n2);
-        orow[i] = cmulc(buf[(i >> pl.log2P2) * rowStride + pidx(n2)], w);
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * kLdBatch) {
+        float2 hi[kLdBatch], lo[kLdBatch];
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {     // the two factors of W_P^{k1 n2} (twiddleP), all fetched before the first use
+            const int i = i0 + u * blockDim.x;
+            if (i < total) {
+                const int r = r0 + (i >> pl.log2P2), n2 = i & (pl.P2 - 1);
+                const unsigned m = (__brev((unsigned)r) >> (32 - pl.log2P1)) * (unsigned)n2;
+                hi[u] = __ldg(pl.twHi + (m >> 11));
+                lo[u] = __ldg(pl.twLo + (m & 2047));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kLdBatch; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) orow[i] = cmulc(buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))], cmul(hi[u], lo[u]));
+        }
     }
 }
 
@@ -295,9 +351,18 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_inv_col_kernel(AcqPlan pl,
     const int col0 = blockIdx.x * kColTile, bin = blockIdx.y;
     for (int dp = 0; dp < ncodes; ++dp) {
         const float2* w = work + ((size_t)bin * ncodes + dp) * pl.P;
-        for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            int c = e & (kColTile - 1), r = e >> 3;
-            buf[pidx(r) * kColTile + c] = w[(size_t)r * pl.P2 + col0 + c];
+        for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * kLdBatch) {
+            float2 v[kLdBatch];
+#pragma unroll
+            for (int u = 0; u < kLdBatch; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e < total) v[u] = w[(size_t)(e >> 3) * pl.P2 + col0 + (e & (kColTile - 1))];
+            }
+#pragma unroll
+            for (int u = 0; u < kLdBatch; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e < total) buf[pidx(e >> 3) * kColTile + (e & (kColTile - 1))] = v[u];
+            }
         }
         __syncthreads();
         smem_fft<true, true>(buf, pl.log2P1, kLgColTile, 0, pl.tw);

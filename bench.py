@@ -74,6 +74,9 @@ def parse():
                          "default; 1 = the per-epoch gather the north star words, measured for SURVEY 7.7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-file", action="store_true",
+                    help="skip the file-backed end-to-end leg (N = 1): the record read from a file like the reference's fid, "
+                         "pageable result arrays - the path the MEX drop-in takes")
     return ap.parse_args()
 
 
@@ -633,6 +636,34 @@ def run_b200(args):
         h2d_gbs = n_samples / (time.perf_counter() - t1) / 1e9
         assert int(planes["epochsDone"].min()) == n_epochs, "e2e run did not complete every epoch"
         sess2.close()
+        # ---- the MEX drop-in's path (matlab/bds_mex.c do_track): the record comes from a FILE (bds_track_open_file: mmap,
+        #      pageable, only the range the epochs touch is streamed under the kernel) and the result planes go into
+        #      ordinary pageable arrays.  Per step: open, run, fetch, close.  N = 1 only (a shared file needs no sharding).
+        e2e_file = None
+        if world == 1 and not args.no_e2e_file:
+            import tempfile
+            d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+            path = os.path.join(d, f"bds_bench_if_{os.getpid()}.bin")
+            try:
+                x_host.numpy().tofile(path)
+                tf = []
+                for i in range(1 + min(3, args.steps)):
+                    t1 = time.perf_counter()
+                    with _track.TrackSession(mode, st_local, mine, source=path, kernel=kern, tuning=tuning) as sf:
+                        sf.run_async(n_epochs)
+                        pf = sf.fetch(n_epochs)
+                    if i >= 1:
+                        tf.append(time.perf_counter() - t1)
+                    assert int(pf["epochsDone"].min()) == n_epochs, "file-backed e2e run did not complete every epoch"
+                tfm = sum(tf) / len(tf)
+                e2e_file = {"value": if_samples / tfm / 1e6, "unit": UNIT, "ms_per_step": tfm * 1e3,
+                            "path": "bds_track_open_file (mmap of a page-cache resident file, pageable) + bds_track_run_async + "
+                                    "bds_track_fetch into pageable arrays + bds_track_close, every step"}
+            finally:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
         te = sum(times) / len(times)
         tt = torch.tensor([te], device="cuda", dtype=torch.float64)
         if dist is not None:
@@ -641,7 +672,7 @@ def run_b200(args):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt[0]) * 1e3,
                "ms_breakdown": {k: round(1e3 * sum(p_[j] for p_ in parts) / len(parts), 2)
                                 for j, k in enumerate(("reset", "enqueue", "h2d+kernels", "fetch+gather"))},
-               "fw_ctas": tuning2.get("fwMaxCtas", 0),
+               "fw_ctas": tuning2.get("fwMaxCtas", 0), "file_backed": e2e_file,
                "pinned_h2d_GBps_this_box": round(h2d_gbs, 1),
                "path": ("bds_track_run_streamed (128 MiB chunks on a copy stream) + bds_track_fetch" if world == 1 else
                         f"per 128 MiB chunk: H2D of 1/{world} per rank + {e2e_exchange} over NVLink on a side stream, "
