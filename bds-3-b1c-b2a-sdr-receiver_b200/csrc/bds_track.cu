@@ -10,7 +10,9 @@
 // that channel's next-epoch slices runnable.  CTAs interleave the channels of their
 // group so the loop-closure latency of one channel is hidden behind the others.
 #include <algorithm>
+#include <atomic>
 #include <climits>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -698,6 +700,11 @@ struct bds_trk {
     // mmap'd file
     void* map = nullptr;
     size_t mapLen = 0;
+    int fd = -1;                    // the same file, kept open: its bytes reach the device through pinned staging buffers
+    // pinned staging ring for pageable sources (files): filled by parallel pread()s, drained by the copy engine
+    std::vector<int8_t*> stage;
+    std::vector<cudaEvent_t> stageEv;
+    size_t stageNext = 0;
 };
 
 namespace {
@@ -1100,20 +1107,24 @@ int bds_track_open_file(int mode, const bds_trk_cfg* cfg, const char* path, long
     if (max_samples > 0 && ((size_t)max_samples << iq) < len) len = (size_t)max_samples << iq;
     len &= ~(size_t)iq;
     void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
-    ::close(fd);
-    if (m == MAP_FAILED) return set_error(BDS_ERR_IO, "mmap of %s failed", path);
+    if (m == MAP_FAILED) {
+        ::close(fd);
+        return set_error(BDS_ERR_IO, "mmap of %s failed", path);
+    }
     madvise(m, len, MADV_SEQUENTIAL);
     bds_trk* h = nullptr;
     int rc = open_common(mode, cfg, skip, ch, n_ch, &h);
     if (rc == BDS_OK) rc = set_window(h, nullptr, 0, BDS_LOC_HOST, 0);
     if (rc) {
         munmap(m, len);
+        ::close(fd);
         if (h) bds_track_close(h);
         return rc;
     }
-    // the mapping is uploaded by the first run, streamed chunk by chunk under the tracking kernel
+    // the file is uploaded by the runs, streamed chunk by chunk under the tracking kernel
     h->map = m;
     h->mapLen = len;
+    h->fd = fd;
     *out = h;
     return BDS_OK;
 }
@@ -1124,7 +1135,8 @@ int bds_track_feed(bds_trk* h, const int8_t* x, size_t n, int x_loc, long long f
 }
 
 int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs);
-static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs, long long first);
+static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs, long long first,
+                             long long fileOff = -1);
 
 // One launch of the persistent kernel on the session's stream: up to maxEpochs more epochs per channel,
 // no epoch index >= epochLimit, over the currently resident window.
@@ -1186,7 +1198,7 @@ int bds_track_run_async(bds_trk* h, int n_epochs) {
         lo = std::max(0LL, lo) & ~4095LL;                       // page aligned in the mapping, 16-byte aligned on the device
         hi = std::min(hi, mapSamples);
         if (hi <= lo) hi = std::min(mapSamples, lo + 1);   // nothing left: the run reports the short read
-        return run_streamed_from(h, (const int8_t*)h->map + (lo << h->iq), (size_t)(hi - lo), 0, n_epochs, lo);
+        return run_streamed_from(h, (const int8_t*)h->map + (lo << h->iq), (size_t)(hi - lo), 0, n_epochs, lo, lo << h->iq);
     }
     int rc = BDS_OK;
     if (h->pending) {  // the output block may be re-allocated below: finish the previous run first
@@ -1213,8 +1225,55 @@ int bds_track_run_streamed(bds_trk* h, const int8_t* x, size_t n, size_t chunk_b
     return run_streamed_from(h, x, n, chunk_bytes, n_epochs, 0);
 }
 
-// x[n] holds samples [first, first + n) of the record
-static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs, long long first) {
+// Pageable source (a file): bytes [off, off + len) of h->fd -> dst on the device, through a ring of pinned staging
+// buffers filled by parallel pread()s (the page cache delivers several times what one thread copies) and drained by
+// the copy engine at the pinned rate; cudaMemcpyAsync straight from the pageable mapping runs at a fraction of it.
+static int stage_file_range(bds_trk* h, long long off, size_t len, int8_t* dst) {
+    constexpr size_t kPiece = (size_t)32 << 20;
+    constexpr int kRing = 4;
+    if (h->stage.empty()) {
+        for (int i = 0; i < kRing; ++i) {
+            int8_t* p = nullptr;
+            cudaEvent_t e;
+            BDS_CUDA(cudaHostAlloc((void**)&p, kPiece, cudaHostAllocDefault));
+            h->stage.push_back(p);
+            BDS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->stageEv.push_back(e);
+        }
+    }
+    const unsigned nThreads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    for (size_t o = 0; o < len; o += kPiece) {
+        const size_t piece = std::min(kPiece, len - o);
+        const size_t slot = h->stageNext++ % h->stage.size();
+        BDS_CUDA(cudaEventSynchronize(h->stageEv[slot]));   // the copy that last used this buffer has drained it
+        int8_t* buf = h->stage[slot];
+        std::atomic<int> bad{0};
+        auto work = [&](unsigned t) {
+            const size_t per = ((piece + nThreads - 1) / nThreads + 4095) & ~(size_t)4095;
+            size_t a = std::min(piece, (size_t)t * per), b = std::min(piece, a + per);
+            while (a < b) {
+                const ssize_t r = pread(h->fd, buf + a, b - a, (off_t)(off + (long long)(o + a)));
+                if (r <= 0) {
+                    bad = 1;
+                    return;
+                }
+                a += (size_t)r;
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nThreads; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& t : th) t.join();
+        if (bad) return set_error(BDS_ERR_IO, "read of the IF file failed at byte %lld", off + (long long)o);
+        BDS_CUDA(cudaMemcpyAsync(dst + o, buf, piece, cudaMemcpyHostToDevice, h->copyStream));
+        BDS_CUDA(cudaEventRecord(h->stageEv[slot], h->copyStream));
+    }
+    return BDS_OK;
+}
+
+// x[n] holds samples [first, first + n) of the record (fileOff >= 0: the same bytes start at this offset of h->fd)
+static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk_bytes, int n_epochs, long long first,
+                             long long fileOff) {
     if (!h || !x || n == 0 || n_epochs <= 0) return set_error(BDS_ERR_ARG, "bds_track_run_streamed: bad arguments");
     int rc = BDS_OK;
     if (h->pending) {
@@ -1251,7 +1310,12 @@ static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk
     const int limit = h->epochsRun + n_epochs;
     auto copy_chunk = [&](size_t i) -> int {
         const size_t o = i ? ends[i - 1] : 0, len = ends[i] - o;
-        BDS_CUDA(cudaMemcpyAsync(h->dX + o, x + o, len, cudaMemcpyHostToDevice, h->copyStream));
+        if (fileOff >= 0 && h->fd >= 0) {
+            int rcf = stage_file_range(h, fileOff + (long long)o, len, h->dX + o);
+            if (rcf) return rcf;
+        } else {
+            BDS_CUDA(cudaMemcpyAsync(h->dX + o, x + o, len, cudaMemcpyHostToDevice, h->copyStream));
+        }
         if (i + 1 == nChunks) BDS_CUDA(cudaMemsetAsync(h->dX + n, 0, 64, h->copyStream));
         BDS_CUDA(cudaEventRecord(h->chunkEv[i], h->copyStream));
         return BDS_OK;
@@ -1261,14 +1325,15 @@ static int run_streamed_from(bds_trk* h, const int8_t* x, size_t n, size_t chunk
     rc = copy_chunk(0);
     if (rc) return rc;
     for (size_t i = 0; i < nChunks; ++i) {
-        if (i + 1 < nChunks) {
-            rc = copy_chunk(i + 1);
-            if (rc) return rc;
-        }
+        // the launch over chunks 0..i is queued before chunk i+1 is brought in: staging a file chunk blocks the host
         BDS_CUDA(cudaStreamWaitEvent(h->stream, h->chunkEv[i], 0));
         h->winLen = (long long)(ends[i] >> h->iq);
         rc = launch_run(h, n_epochs, limit);
         if (rc) return rc;
+        if (i + 1 < nChunks) {
+            rc = copy_chunk(i + 1);
+            if (rc) return rc;
+        }
     }
     BDS_CUDA(cudaEventRecord(h->ev1, h->stream));
     h->pending = true;
@@ -1473,6 +1538,9 @@ void bds_track_close(bds_trk* h) {
     if (h->copyStream) cudaStreamSynchronize(h->copyStream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->map) munmap(h->map, h->mapLen);
+    if (h->fd >= 0) ::close(h->fd);
+    for (auto p : h->stage) cudaFreeHost(p);
+    for (auto e : h->stageEv) cudaEventDestroy(e);
     if (h->ownX && h->dX) cudaFree(h->dX);
     cudaFree(h->dBits);
     cudaFree(h->dCC);
