@@ -657,8 +657,10 @@ def run_b200(args):
                     assert int(pf["epochsDone"].min()) == n_epochs, "file-backed e2e run did not complete every epoch"
                 tfm = sum(tf) / len(tf)
                 e2e_file = {"value": if_samples / tfm / 1e6, "unit": UNIT, "ms_per_step": tfm * 1e3,
-                            "path": "bds_track_open_file (mmap of a page-cache resident file, pageable) + bds_track_run_async + "
-                                    "bds_track_fetch into pageable arrays + bds_track_close, every step"}
+                            "path": "bds_track_open_file (page-cache resident file read by parallel pread()s through pinned staging "
+                                    "buffers) + bds_track_run_async + bds_track_fetch into pageable arrays + bds_track_close, every step"}
+            except (OSError, AssertionError, L.BdsError) as ex:     # e.g. no room for the 3 GB file: the leg is optional
+                e2e_file = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
             finally:
                 try:
                     os.unlink(path)
