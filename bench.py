@@ -60,10 +60,12 @@ def parse():
                     help="length of the synthetic IF record (BASELINE config 4: 30 s)")
     ap.add_argument("--channels", type=int, default=N_CHANNELS)
     ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast"])
-    ap.add_argument("--workload", default="track", choices=["track", "track_b2a", "dual", "acq_b2a", "acq_b1c"],
+    ap.add_argument("--workload", default="track", choices=["track", "track_b2a", "dual", "pipeline", "acq_b2a", "acq_b1c"],
                     help="track = the headline metric (BASELINE config 4; --channels 12 = config 3); track_b2a = 60-channel "
                          "B2a tracking; dual = BASELINE config 5 (--channels B1C + --channels B2a channels co-scheduled on "
-                         "the same GPUs); acq_b2a = BASELINE config 2 (B2a 63-PRN x +-5 kHz acquisition grid); acq_b1c")
+                         "the same GPUs); pipeline = config 5 as a joint run: 63-PRN acquisition of both bands (PRN-sharded), "
+                         "preRun, then tracking of the channels it found; acq_b2a = BASELINE config 2 (B2a 63-PRN x +-5 kHz "
+                         "acquisition grid); acq_b1c")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: --channels in total, sharded over the GPUs (BASELINE config 4); weak: --channels per GPU")
     ap.add_argument("--b2a-cluster", type=int, default=0, choices=[0, 1, 2, 4, 8],
@@ -929,6 +931,165 @@ def run_dual(args):
 
 
 # ----------------------------------------------------------------------------------------------
+# BASELINE config 5 as one joint run: acquisition -> preRun -> tracking of both bands.  Per step and band: the 63-PRN
+# acquisition grid (PRN ranges sharded over the ranks, one all-reduce of the 3 x 63 result doubles), the reference's
+# preRun on every rank (identical results), then the channels it produced are tracked (sharded round robin, sessions
+# opened for them in the step) over the whole record, both bands concurrently.
+# ----------------------------------------------------------------------------------------------
+def run_pipeline(args):
+    import numpy as np
+    import torch
+    import bds3_b200 as B
+    from bds3_b200 import _acq, _lib as L, _shard, _track, synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L.init(local)
+    n_sms = torch.cuda.get_device_properties(local).multi_processor_count
+    n_samples = int(round(args.seconds * FS))
+    total = min(args.channels, 60)
+    bands = []
+    for wl in ("track_b2a", "track"):
+        w = TRACK[wl]
+        st = settings_for(wl, total, args.seconds)
+        st.acqSatelliteList = list(range(1, 64))
+        sats = synth.make_sats(total, st, w["sig"], max_doppler=w["max_doppler"])
+        x_dev = torch.empty(n_samples + 64, dtype=torch.int8, device="cuda")
+        synth.synth_device(w["sig"], st, sats, n_samples, out_ptr=x_dev.data_ptr())
+        spc = w["spc"]
+        # what postProcessing reads for the acquisition: 20 code periods (B1C, postProcessing.m:94) / fineNoncoh + 2 ms (B2a)
+        n_acq = 20 * spc if w["sig"] == "B1C" else spc * (int(st.fineNoncoh) + 2)
+        n_epochs = max(1, int(math.floor((n_samples - 2 * spc) / (spc * (1 + 1e-5)))) - 1)
+        bands.append(dict(w=w, st=st, sats=sats, x_dev=x_dev, n_acq=min(n_acq, n_samples), n_epochs=n_epochs,
+                          sig=L.SIG_B1C if w["sig"] == "B1C" else L.SIG_B2A))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def acquire(b):
+        lo, hi = _shard.prn_range(63, rank, world)
+        acq = _acq.acquire(b["sig"], None, b["st"], prn_range=(lo, hi), device_ptr=b["x_dev"].data_ptr(), n_samples=b["n_acq"])
+        part = torch.tensor(np.stack([acq.carrFreq, acq.codePhase, acq.peakMetric]), device="cuda")
+        if dist is not None:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)      # disjoint PRN shards, zero = not found (acquisition.m:161-165)
+        r = part.cpu().numpy()
+        return B.Settings(carrFreq=r[0], codePhase=r[1], peakMetric=r[2])
+
+    def step(keep=False):
+        t = [time.perf_counter()]
+        chans = []
+        for b in bands:
+            acq = acquire(b)
+            chans.append(_acq.preRun(acq, b["st"], b1c=b["w"]["sig"] == "B1C"))       # preRun.m:44-76, every rank alike
+        t.append(time.perf_counter())
+        sess, b2a_ctas = [], 0
+        for b, ch in zip(bands, chans):
+            ch = [c for c in ch if c.PRN != 0]
+            mine = _shard.shard_list(ch, rank, world)
+            st_local = b["st"].copy()
+            st_local.numberOfChannels = len(mine)
+            st_local.numberOfChannels_total = total
+            if b["w"]["sig"] == "B2a":
+                cs = 8
+                while cs > 1 and len(mine) * cs > n_sms // 2:
+                    cs //= 2
+                tuning = {"b2aClusterSize": cs}
+                b2a_ctas = len(mine) * cs
+            else:
+                tuning = {"fwMaxCtas": max(16, n_sms - b2a_ctas)}
+            s_ = _track.TrackSession(b["w"]["mode"], st_local, mine, device_ptr=b["x_dev"].data_ptr(), n_samples=n_samples,
+                                     tuning=tuning) if mine else None
+            sess.append((s_, mine, st_local))
+        for (s_, _, _), b in zip(sess, bands):
+            if s_ is not None:
+                s_.run_async(b["n_epochs"])
+        for s_, _, _ in sess:
+            if s_ is not None:
+                s_.sync()
+        t.append(time.perf_counter())
+        if keep:
+            return t, chans, sess
+        for s_, _, _ in sess:
+            if s_ is not None:
+                s_.close()
+        return t, chans, None
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    launches0 = B.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    acq_ms, trk_ms = [], []
+    for _ in range(args.steps):
+        t, _, _ = step()
+        acq_ms.append((t[1] - t[0]) * 1e3)
+        trk_ms.append((t[2] - t[1]) * 1e3)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = B.launch_count() - launches0
+    # ---- untimed: what the pipeline found and how the channels it started are doing at the end of the record
+    _, chans, sess = step(keep=True)
+    report = {}
+    for b, ch, (s_, mine, st_local) in zip(bands, chans, sess):
+        want = {st_.PRN: st_ for st_ in b["sats"]}
+        got = [c for c in ch if c.PRN != 0]
+        spc = b["w"]["spc"]
+        ok_code = ok_freq = 0
+        for c in got:
+            if c.PRN in want:
+                d = (c.codePhase - 1 - want[c.PRN].codeDelay) % spc
+                ok_code += min(d, spc - d) <= 1.5
+                ok_freq += abs(c.acquiredFreq - (b["st"].IF + want[c.PRN].doppler)) <= 25.0
+        locked = 0
+        if s_ is not None:
+            planes = s_.fetch(b["n_epochs"])
+            lock = util.lock_report(b["w"]["mode"], B.Settings(dict(st_local)), planes, b["n_epochs"], seconds_tail=10.0)
+            locked = int(((lock["data_pld_min"] > 0.9) & (lock["pilot_pld_min"] > 0.9)).sum())
+            assert int(planes["epochsDone"].min()) == b["n_epochs"]
+            s_.close()
+        agg = torch.tensor([float(locked)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        report[b["w"]["sig"]] = {"satellites_in_record": len(want), "acquired": len(got), "false_alarms": sum(c.PRN not in want for c in got),
+                                 "code_phase_within_1.5_samples": int(ok_code), "carrier_within_25_Hz": int(ok_freq),
+                                 "channels_locked_over_last_10_s": int(agg[0])}
+    tt = torch.tensor([wall * 1e3 / args.steps, sum(acq_ms) / len(acq_ms), sum(trk_ms) / len(trk_ms)], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        step_ms = float(tt[0])
+        if_samples = sum(b["n_epochs"] * float(b["w"]["spc"]) for b in bands)
+        print(json.dumps({
+            "metric": f"IF Msamples/s through the joint {2 * total}-ch B1C + B2a acquisition -> tracking pipeline",
+            "value": if_samples / (step_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (FFT, accumulate) / f64 loop closure (int8 IF)", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 5, joint: 63-PRN x +-5 kHz acquisition of both bands -> preRun -> tracking of the "
+                                   f"{total} + {total} channels found, two int8 IF records at 99.375 MHz, {args.seconds:g} s",
+                       "ms_acquisition_both_bands": float(tt[1]), "ms_sessions_and_tracking": float(tt[2]),
+                       "parallelism": f"PRN ranges (acquisition) and channels (tracking) sharded over {world} GPU(s), records replicated",
+                       "x_realtime": args.seconds * 1e3 / step_ms},
+            "gpu_launches": int(launches), "pipeline": report}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
 # secondary workload: BASELINE config 2 — B2a full 63-PRN x +-5 kHz acquisition grid (one GPU; PRNs shard across
 # ranks through prn_lo/prn_hi when launched under torchrun)
 # ----------------------------------------------------------------------------------------------
@@ -1035,6 +1196,8 @@ def main():
         run_acq_b2a(args, b1c=args.workload == "acq_b1c")
     elif args.workload == "dual":
         run_dual(args)
+    elif args.workload == "pipeline":
+        run_pipeline(args)
     else:
         run_b200(args)
 
