@@ -418,6 +418,240 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_inv_col_kernel(AcqPlan pl,
     }
 }
 
+// =====================================================================================================
+// Inverse passes specialised at compile time for the transform shapes of the shipped configurations.
+// The PRN x Doppler grid spends > 95 % of an acquisition in the two inverse passes (25 326 transforms of 2^22 points
+// for the 63-PRN B1C grid), and ncu (profiles/r02/acq_inv_*_after.csv) showed them bound by instruction issue at
+// 160-180 thread-instructions per point, not by HBM.  Three things remove more than half of those instructions:
+//   * every length, stride and stage count is a template parameter, so the index arithmetic of the padded layout folds
+//     into immediate offsets (16 LDS/STS from one base address per fused step);
+//   * a fused step is a plain radix-2^Q butterfly (constant 16th roots of unity only) applied to inputs that were
+//     multiplied once by their step twiddle exp(+2 pi i j m' / 2^(D+Q)), read from a table laid out [m'][j] so that a
+//     warp's loads are contiguous - instead of one general complex multiply per butterfly and stage; the first step
+//     (D = 0) has no twiddles at all;
+//   * the magnitude / combine / max epilogue works on the rows that can hold a lag < N only (less than half of them:
+//     N < P/2), with MUFU square roots and the (sqrt11, sqrt29) / sqrt40 weights as two constants.
+// Same scrambled spectrum layout, same padded shared-memory layout (pidx) and same results to float rounding as the
+// generic kernels above, which remain the path of every other transform shape.
+template <int Q>
+__host__ __device__ constexpr int brevq(int m) {
+    int r = 0;
+    for (int k = 0; k < Q; ++k) r |= ((m >> k) & 1) << (Q - 1 - k);
+    return r;
+}
+// Steps of a 2^LG-point inverse: D = 0, 4, 8, .. radix-2 stages done before the step, Q = min(4, LG - D) fused.
+// Twiddle table of step D > 0: T[(m' - 1) * 2^D + j], m' = 1 .. 2^Q - 1, j < 2^D; the tables of a transform are
+// concatenated in step order.
+__host__ __device__ constexpr int inv_tw_offset(int LG, int D) {
+    int off = 0;
+    for (int d = 4; d < D; d += 4) off += (((LG - d) < 4 ? (1 << (LG - d)) : 16) - 1) << d;
+    return off;
+}
+__host__ __device__ constexpr int inv_tw_size(int LG) { return inv_tw_offset(LG, ((LG + 3) / 4) * 4); }
+
+// Q fused inverse DIT stages on 2^Q register values (bit-reversed in, natural out), constant twiddles only
+template <int Q>
+__device__ __forceinline__ void ifft_regs_const(float2* r) {
+    constexpr int N = 1 << Q;
+#pragma unroll
+    for (int l = 0; l < Q; ++l) {
+        const int dist = 1 << l;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            if (m & dist) continue;
+            const int k = (m & (dist - 1)) * (8 / dist);
+            const float2 a = r[m], t = mul_w16c(r[m + dist], k);
+            r[m] = make_float2(a.x + t.x, a.y + t.y);
+            r[m + dist] = make_float2(a.x - t.x, a.y - t.y);
+        }
+    }
+}
+
+template <int LG, int LGB, bool kCols, int SEQ, int NT, int D, int Q>
+__device__ __forceinline__ void ifft_step_ct(float2* buf, const float2* __restrict__ T) {
+    constexpr int N = 1 << Q, h = 1 << D, lgItems = LG - Q, items = 1 << (lgItems + LGB);
+    constexpr bool lin = (D >= 4) || (D == 0 && Q == 4);   // the padded offsets of the step's elements do not depend on i
+#pragma unroll 1
+    for (int u = threadIdx.x; u < items; u += NT) {
+        const int b = kCols ? (u & ((1 << LGB) - 1)) : (u >> lgItems);
+        const int v = kCols ? (u >> LGB) : (u & ((1 << lgItems) - 1));
+        const int j = v & (h - 1);
+        const int i = ((v >> D) << (D + Q)) + j;
+        float2* base = kCols ? buf + (pidx(i) << LGB) + b : buf + b * SEQ + pidx(i);
+        float2 r[N];
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            const int off = lin ? ((m << D) + ((m << D) >> 4)) : (pidx(i + (m << D)) - pidx(i));
+            r[m] = base[kCols ? (off << LGB) : off];
+        }
+        if (D > 0) {
+#pragma unroll
+            for (int m = 1; m < N; ++m) r[m] = cmul(r[m], __ldg(T + (brevq<Q>(m) - 1) * h + j));
+        }
+        ifft_regs_const<Q>(r);
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            const int off = lin ? ((m << D) + ((m << D) >> 4)) : (pidx(i + (m << D)) - pidx(i));
+            base[kCols ? (off << LGB) : off] = r[m];
+        }
+    }
+}
+template <int LG, int LGB, bool kCols, int SEQ, int NT, int D = 0>
+__device__ __forceinline__ void ifft_ct(float2* buf, const float2* __restrict__ tws) {
+    if constexpr (D < LG) {
+        constexpr int Q = (LG - D) < 4 ? (LG - D) : 4;
+        ifft_step_ct<LG, LGB, kCols, SEQ, NT, D, Q>(buf, tws + inv_tw_offset(LG, D));
+        __syncthreads();
+        ifft_ct<LG, LGB, kCols, SEQ, NT, D + Q>(buf, tws);
+    }
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+constexpr int inv_row_threads(int LG2, int LGRT) {
+    const int t = (1 << (LG2 - 4)) << LGRT;
+    return t > 512 ? 512 : (t < 128 ? 128 : t);
+}
+constexpr int inv_col_threads(int LG1) {
+    const int t = (1 << (LG1 - 4)) * kColTile;
+    return t > 512 ? 512 : (t < 128 ? 128 : t);
+}
+
+// inverse row pass, see acq_inv_row_kernel.  grid = ((P1 >> LGRT) * ncodes, nbins): the CTAs of the two codes that
+// read the same signal rows are neighbours in launch order (the second read of the rows hits L2).
+template <int LG1, int LG2, int LGRT>
+__global__ void __launch_bounds__(inv_row_threads(LG2, LGRT), 1024 / inv_row_threads(LG2, LGRT))
+acq_inv_row_ct_kernel(AcqPlan pl, const float2* __restrict__ sig, const float2* __restrict__ code, float2* __restrict__ work,
+                      int ncodes, const int* __restrict__ binMap, const float2* __restrict__ twRow) {
+    constexpr int NT = inv_row_threads(LG2, LGRT), P2 = 1 << LG2, rowStride = P2 + (P2 >> 4), total = P2 << LGRT;
+    constexpr int per = total / NT, cpr = P2 / NT;   // elements per thread, chunks of NT elements per row
+    static_assert(total % NT == 0 && P2 % NT == 0 && NT % 16 == 0 && per % 8 == 0, "row tiling");
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float2* buf = reinterpret_cast<float2*>(smraw);
+    const int tid = threadIdx.x;
+    const int dp = blockIdx.x % ncodes, rt = blockIdx.x / ncodes, r0 = rt << LGRT, bi = blockIdx.y;
+    const int bin = binMap ? binMap[bi] : bi;
+    const float2* srow = sig + (size_t)bin * pl.P + (size_t)r0 * P2 + tid;
+    const float2* crow = code + (size_t)dp * pl.P + (size_t)r0 * P2 + tid;
+    float2* bt = buf + tid + (tid >> 4);          // pidx(tid + q * NT) = pidx(tid) + q * (NT + NT / 16)
+#pragma unroll
+    for (int u0 = 0; u0 < per; u0 += 8) {
+        float2 a[8], c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a[u] = srow[(u0 + u) * NT];
+            c[u] = __ldg(crow + (u0 + u) * NT);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) bt[((u0 + u) / cpr) * rowStride + ((u0 + u) % cpr) * (NT + NT / 16)] = cmul(a[u], c[u]);
+    }
+    __syncthreads();
+    ifft_ct<LG2, LGRT, false, rowStride, NT>(buf, twRow);
+    float2* orow = work + ((size_t)bi * ncodes + dp) * pl.P + (size_t)r0 * P2 + tid;
+#pragma unroll
+    for (int row = 0; row < (1 << LGRT); ++row) {
+        // W_P^{k1 n2}, k1 = bitrev(r), n2 = tid + q * NT: m = k1 * n2 mod P advances by k1 * NT per chunk
+        const unsigned k1 = __brev((unsigned)(r0 + row)) >> (32 - LG1);
+        unsigned m = k1 * (unsigned)tid;
+        float2 hi[cpr], lo[cpr];
+#pragma unroll
+        for (int q = 0; q < cpr; ++q) {
+            hi[q] = __ldg(pl.twHi + (m >> 11));
+            lo[q] = __ldg(pl.twLo + (m & 2047));
+            m += k1 * (unsigned)NT;
+        }
+#pragma unroll
+        for (int q = 0; q < cpr; ++q)
+            orow[row * P2 + q * NT] = cmulc(bt[row * rowStride + q * (NT + NT / 16)], cmul(hi[q], lo[q]));
+    }
+}
+
+// inverse column pass + magnitude + combine + max, see acq_inv_col_kernel
+template <int LG1, int LG2>
+__global__ void __launch_bounds__(inv_col_threads(LG1), 1024 / inv_col_threads(LG1))
+acq_inv_col_ct_kernel(AcqPlan pl, const float2* __restrict__ work, int ncodes, int combine, int lo0, int hi0, int lo1, int hi1,
+                      int useRanges, AcqPeak* __restrict__ peaks, const float2* __restrict__ twCol) {
+    constexpr int NT = inv_col_threads(LG1), P1 = 1 << LG1, P2 = 1 << LG2, total = P1 * kColTile, per = total / NT;
+    constexpr int rpc = NT / kColTile;            // rows per chunk of NT elements
+    static_assert(total % NT == 0 && rpc % 16 == 0 && per % 8 == 0, "column tiling");
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float2* buf = reinterpret_cast<float2*>(smraw);
+    float* mag = reinterpret_cast<float*>(buf + (P1 + (P1 >> 4)) * kColTile);
+    const int tid = threadIdx.x, c = tid & (kColTile - 1), rq = tid >> kLgColTile;
+    const int col0 = blockIdx.x * kColTile, bin = blockIdx.y;
+    // chunks of rpc rows that can hold a lag < N (lag = r * P2 + col): uniform over the CTA
+    const int rEnd = min(P1, (pl.N - col0 + P2 - 1) >> LG2);
+    const int uEnd = (rEnd + rpc - 1) / rpc;
+    float2* bt = buf + (rq + (rq >> 4)) * kColTile + c;     // pidx(rq + u * rpc) = pidx(rq) + u * (rpc + rpc / 16)
+    for (int dp = 0; dp < ncodes; ++dp) {
+        const float2* w = work + ((size_t)bin * ncodes + dp) * pl.P + (size_t)rq * P2 + col0 + c;
+#pragma unroll
+        for (int u0 = 0; u0 < per; u0 += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = w[(size_t)(u0 + u) * rpc * P2];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bt[(u0 + u) * (rpc + rpc / 16) * kColTile] = v[u];
+        }
+        __syncthreads();
+        ifft_ct<LG1, kLgColTile, true, 0, NT>(buf, twCol);
+#pragma unroll
+        for (int u = 0; u < per; ++u) {
+            if (u < uEnd) {
+                const float2 v = bt[u * (rpc + rpc / 16) * kColTile];
+                const float m = sqrt_approx(v.x * v.x + v.y * v.y);
+                float* mg = mag + tid + u * NT;
+                if (dp == 0) *mg = m;
+                else if (combine == 1) *mg = *mg * 0.52440442408507577f + m * 0.85146931829632011f;   // sqrt(11/40), sqrt(29/40)
+                else *mg = *mg + m;
+            }
+        }
+        __syncthreads();
+    }
+    float best = -1.f;
+    int bl = 0x7fffffff;
+#pragma unroll
+    for (int u = 0; u < per; ++u) {
+        if (u < uEnd) {
+            const int lag = (rq + u * rpc) * P2 + col0 + c;
+            bool ok = lag < pl.N;
+            if (useRanges) ok = ok && ((lag >= lo0 && lag <= hi0) || (lag >= lo1 && lag <= hi1));
+            const float m = mag[tid + u * NT];
+            if (ok && m > best) {      // lags ascend with u: the first maximum wins
+                best = m;
+                bl = lag;
+            }
+        }
+    }
+    __shared__ float sv[NT / 32];
+    __shared__ int sl[NT / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (ov > best || (ov == best && ol < bl)) {
+            best = ov;
+            bl = ol;
+        }
+    }
+    if ((tid & 31) == 0) {
+        sv[tid >> 5] = best;
+        sl[tid >> 5] = bl;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w)
+            if (sv[w] > best || (sv[w] == best && sl[w] < bl)) {
+                best = sv[w];
+                bl = sl[w];
+            }
+        peaks[(size_t)bin * gridDim.x + blockIdx.x] = AcqPeak{best, bl};
+    }
+}
+
 // Sampled code tables on the device: table[t][k] = code[t][idx[k] - 1]  (makeDataTable.m:49-66; idx is computed once on
 // the host with the reference's own expression, it does not depend on the PRN).  grid = (blocks, tables)
 __global__ void acq_sample_tables_kernel(const int32_t* idx, const int8_t* codes, int codeLen, int spc, int8_t* tables) {
@@ -677,6 +911,50 @@ struct DevBuf {
     }
 };
 
+// ---- compile-time specialised inverse passes: one instantiation per transform shape of the shipped configurations
+typedef void (*InvRowFn)(AcqPlan, const float2*, const float2*, float2*, int, const int*, const float2*);
+typedef void (*InvColFn)(AcqPlan, const float2*, int, int, int, int, int, int, int, AcqPeak*, const float2*);
+struct InvCt {
+    InvRowFn row = nullptr;
+    InvColFn col = nullptr;
+    int thrRow = 0, thrCol = 0;
+};
+template <int LG1, int LG2, int LGRT>
+InvCt make_inv_ct() {
+    InvCt f;
+    f.row = acq_inv_row_ct_kernel<LG1, LG2, LGRT>;
+    f.col = acq_inv_col_ct_kernel<LG1, LG2>;
+    f.thrRow = inv_row_threads(LG2, LGRT);
+    f.thrCol = inv_col_threads(LG1);
+    return f;
+}
+// (log2 P1, log2 P2, log2 rows per CTA) as acquire_core plans them:
+//   (10, 12, 1)  B1C at 99.375 MHz (BASELINE), P = 2^22      (9, 12, 1)  B1C at the reference's shipped 53 MHz, P = 2^21
+//   (9, 10, 2)   B2a at 99.375 MHz, P = 2^19
+// every other shape (e.g. the band-pass rates of the resampling branch) runs on the generic kernels
+InvCt find_inv_ct(const AcqPlan& pl) {
+    if (pl.log2P1 == 10 && pl.log2P2 == 12 && pl.lgRowTile == 1) return make_inv_ct<10, 12, 1>();
+    if (pl.log2P1 == 9 && pl.log2P2 == 12 && pl.lgRowTile == 1) return make_inv_ct<9, 12, 1>();
+    if (pl.log2P1 == 9 && pl.log2P2 == 10 && pl.lgRowTile == 2) return make_inv_ct<9, 10, 2>();
+    return InvCt{};
+}
+// step twiddles of a 2^LG-point inverse, see inv_tw_offset
+std::vector<float2> inv_step_twiddles(int LG) {
+    std::vector<float2> t;
+    const double twoPi = 6.283185307179586476925286766559;
+    for (int D = 4; D < LG; D += 4) {
+        const int Q = std::min(4, LG - D), h = 1 << D;
+        const double L = (double)(1 << (D + Q));
+        for (int mp = 1; mp < (1 << Q); ++mp)
+            for (int j = 0; j < h; ++j) {
+                const double a = twoPi * (double)j * (double)mp / L;
+                t.push_back(make_float2((float)std::cos(a), (float)std::sin(a)));
+            }
+    }
+    if (t.empty()) t.push_back(make_float2(1.f, 0.f));
+    return t;
+}
+
 unsigned long long freq_to_dphi(double f, double fs) {
     double r = f / fs;
     r -= std::floor(r);
@@ -790,6 +1068,34 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     // one thread per 16-element register group (fewer for the short B2a transforms)
     const int thrRow = std::min(kAcqThreads, std::max(128, (pl.P2 >> 4) * rowTile));
     const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
+    const InvCt ct = find_inv_ct(pl);
+    DevBuf dTwRowS, dTwColS;
+    if (ct.row) {
+        const std::vector<float2> tr = inv_step_twiddles(pl.log2P2), tc = inv_step_twiddles(pl.log2P1);
+        TRYA(dTwRowS.alloc(tr.size() * 8));
+        TRYA(dTwColS.alloc(tc.size() * 8));
+        TRYA(cudaMemcpy(dTwRowS.p, tr.data(), tr.size() * 8, cudaMemcpyHostToDevice));
+        TRYA(cudaMemcpy(dTwColS.p, tc.data(), tc.size() * 8, cudaMemcpyHostToDevice));
+        TRYA(cudaFuncSetAttribute((const void*)ct.row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRow));
+        TRYA(cudaFuncSetAttribute((const void*)ct.col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemColInv));
+    }
+    // the inverse passes of nb bins against the ncodes spectra of one PRN; per-bin peaks -> out[nb]
+    auto inverse_passes = [&](const float2* sigBins, int nb, const float2* code, const int* binMap, int lo0, int hi0, int lo1,
+                              int hi1, int useRanges, AcqPeak* out) {
+        if (ct.row) {
+            ct.row<<<dim3((pl.P1 / rowTile) * ncodes, nb), ct.thrRow, smemRow>>>(pl, sigBins, code, dWork.as<float2>(), ncodes, binMap,
+                                                                                 dTwRowS.as<float2>());
+            ct.col<<<dim3(colGroups, nb), ct.thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0, hi0, lo1, hi1,
+                                                                   useRanges, dPeaks.as<AcqPeak>(), dTwColS.as<float2>());
+        } else {
+            acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, nb, ncodes), thrRow, smemRow>>>(pl, sigBins, code, dWork.as<float2>(), ncodes,
+                                                                                       binMap);
+            acq_inv_col_kernel<<<dim3(colGroups, nb), thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0, hi0, lo1,
+                                                                            hi1, useRanges, dPeaks.as<AcqPeak>());
+        }
+        acq_peak_reduce_kernel<<<nb, 256>>>(dPeaks.as<AcqPeak>(), colGroups, out);
+        count_launch(3);
+    };
     acq_fwd_col_kernel<<<dim3(colGroups, nbins), thrCol, smemCol>>>(pl, 0, dx, 0, dDphi.as<unsigned long long>(),
                                                                        dSig.as<float2>(), iq);
     acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, nbins), thrRow, smemRow>>>(pl, dSig.as<float2>(), 0.f);
@@ -883,12 +1189,8 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
             const float2* code = dCode.as<float2>() + (size_t)i * ncodes * pl.P;
             for (int b0 = 0; b0 < nbins; b0 += binsPerBatch) {
                 const int nb = std::min(binsPerBatch, nbins - b0);
-                acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, nb, ncodes), thrRow, smemRow>>>(
-                    pl, dSig.as<float2>() + (size_t)b0 * pl.P, code, dWork.as<float2>(), ncodes, nullptr);
-                acq_inv_col_kernel<<<dim3(colGroups, nb), thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, 0, 0,
-                                                                                   0, 0, 0, dPeaks.as<AcqPeak>());
-                acq_peak_reduce_kernel<<<nb, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dBinPeak.as<AcqPeak>() + (size_t)i * nbins + b0);
-                count_launch(3);
+                inverse_passes(dSig.as<float2>() + (size_t)b0 * pl.P, nb, code, nullptr, 0, 0, 0, 0, 0,
+                               dBinPeak.as<AcqPeak>() + (size_t)i * nbins + b0);
             }
         }
         TRYA(cudaGetLastError());
@@ -937,13 +1239,8 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
                     lo1 = (int)e2 - 1;
                     hi1 = (int)std::min(e4, N) - 1;
                 }
-                acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, 1, ncodes), thrRow, smemRow>>>(
-                    pl, dSig.as<float2>(), dCode.as<float2>() + (size_t)i * ncodes * pl.P, dWork.as<float2>(), ncodes,
-                    dBinMap.as<int>() + i);
-                acq_inv_col_kernel<<<dim3(colGroups, 1), thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0,
-                                                                                  hi0, lo1, hi1, 1, dPeaks.as<AcqPeak>());
-                acq_peak_reduce_kernel<<<1, 256>>>(dPeaks.as<AcqPeak>(), colGroups, dSecond.as<AcqPeak>() + i);
-                count_launch(3);
+                inverse_passes(dSig.as<float2>(), 1, dCode.as<float2>() + (size_t)i * ncodes * pl.P, dBinMap.as<int>() + i, lo0, hi0,
+                               lo1, hi1, 1, dSecond.as<AcqPeak>() + i);
             }
             std::vector<AcqPeak> second(nSel);
             TRYA(cudaMemcpy(second.data(), dSecond.p, sizeof(AcqPeak) * nSel, cudaMemcpyDeviceToHost));
