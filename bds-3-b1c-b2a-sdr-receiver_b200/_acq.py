@@ -22,7 +22,8 @@ def acquire(signal, longSignal, settings, prn_range=None, device_ptr=None, n_sam
                         acqCohT=int(settings.get("acqCohT", 0)), pilotACQflag=int(settings.get("pilotACQflag", 0)),
                         fineNoncoh=int(settings.get("fineNoncoh", 0)),
                         resamplingThreshold=float(settings.get("resamplingThreshold", 0.0)),
-                        resamplingflag=int(settings.get("resamplingflag", 0)))
+                        resamplingflag=int(settings.get("resamplingflag", 0)),
+                        tune=int(settings.get("_tune", 0)))   # test hook, see bdsgpu.h
     # a complex longSignal is the reference's fileType-2 record (postProcessing.m:96-99); a device record says so itself
     if iq is None:
         iq = longSignal is not None and np.iscomplexobj(longSignal)

@@ -21,7 +21,7 @@ class bds_acq_cfg(C.Structure):
                 ("codeLength", C.c_int32), ("acqSearchBand", C.c_double), ("acqStep", C.c_double),
                 ("acqThreshold", C.c_double), ("acqCohT", C.c_int32), ("pilotACQflag", C.c_int32),
                 ("fineNoncoh", C.c_int32), ("fileType", C.c_int32), ("resamplingThreshold", C.c_double),
-                ("resamplingflag", C.c_int32), ("reserved", C.c_int32)]
+                ("resamplingflag", C.c_int32), ("tune", C.c_int32)]
 
 
 class bds_trk_cfg(C.Structure):

@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_col_kernel(AcqPlan pl,
 // ---- forward row pass (in place) -----------------------------------------------------
 // conjScale != 0: store conj(X) * conjScale (code spectra: acquisition.m:180 with the 1/P of
 // the inverse transform folded in).  grid = (P1 >> lgRowTile, batch).
-__global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_row_kernel(AcqPlan pl, float2* spec, float conjScale) {
+// perm = 1: scrambled element 16 v + u of a row is stored at position u * (P2 / 16) + v (the layout the compile-time
+// specialised inverse row pass reads, see acq_inv_row_ct_kernel); stores stay contiguous, the shared-memory reads stride.
+__global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_row_kernel(AcqPlan pl, float2* spec, float conjScale, int perm) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
     float2* rows = spec + (size_t)blockIdx.y * pl.P + ((size_t)blockIdx.x << pl.lgRowTile) * pl.P2;   // 2^lgRowTile contiguous rows
@@ -275,7 +277,9 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_fwd_row_kernel(AcqPlan pl,
     __syncthreads();
     smem_fft<false, false>(buf, pl.log2P2, pl.lgRowTile, rowStride, pl.tw);
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        float2 v = buf[(i >> pl.log2P2) * rowStride + pidx(i & (pl.P2 - 1))];
+        const int d = i & (pl.P2 - 1);
+        const int src = perm ? ((d & ((pl.P2 >> 4) - 1)) << 4) + (d >> (pl.log2P2 - 4)) : d;
+        float2 v = buf[(i >> pl.log2P2) * rowStride + pidx(src)];
         if (conjScale != 0.f) v = make_float2(v.x * conjScale, -v.y * conjScale);
         rows[i] = v;
     }
@@ -512,61 +516,88 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
-constexpr int inv_row_threads(int LG2, int LGRT) {
-    const int t = (1 << (LG2 - 4)) << LGRT;
-    return t > 512 ? 512 : (t < 128 ? 128 : t);
-}
-constexpr int inv_col_threads(int LG1) {
-    const int t = (1 << (LG1 - 4)) * kColTile;
-    return t > 512 ? 512 : (t < 128 ? 128 : t);
-}
+// one thread per 16-element group of the first step
+constexpr int inv_row_threads(int LG2, int LGRT) { return (1 << (LG2 - 4)) << LGRT; }
+constexpr int inv_col_threads(int LG1) { return (1 << (LG1 - 4)) * kColTile; }
+constexpr int inv_last_d(int LG) { return ((LG - 1) / 4) * 4; }   // stages done before the last fused step
 
-// inverse row pass, see acq_inv_row_kernel.  grid = ((P1 >> LGRT) * ncodes, nbins): the CTAs of the two codes that
-// read the same signal rows are neighbours in launch order (the second read of the rows hits L2).
+// The first and the last step of a pass never touch shared memory on their outer side:
+//   * the first step (D = 0: 16 adjacent elements, no twiddles) takes its inputs straight from global memory.  For the
+//     row pass the spectra are stored with the 16 elements of a group 2^(LG2-4) apart (acq_fwd_row_kernel, perm = 1:
+//     scrambled element 16 v + u of a row at position u * 2^(LG2-4) + v), so that the loads of a warp are contiguous;
+//     for the column pass the elements of a group are rows, a warp reads 64-byte row segments as before;
+//   * the last step leaves its outputs (elements j + m * 2^D, contiguous in j across a warp) in registers, where the
+//     row pass multiplies them with the four-step twiddle and writes them to `work`, and the column pass takes the
+//     magnitude, combines data and pilot and keeps the running maximum.
+// Shared-memory traffic per point and pass drops from 64 to 32 bytes, the barriers from four to two.
+
+// inverse row pass, see acq_inv_row_kernel.  grid = ((P1 >> LGRT) * ncodes, nbins): the CTAs of the codes that read the
+// same signal rows are neighbours in launch order (the second read of the rows hits L2).
 template <int LG1, int LG2, int LGRT>
 __global__ void __launch_bounds__(inv_row_threads(LG2, LGRT), 1024 / inv_row_threads(LG2, LGRT))
 acq_inv_row_ct_kernel(AcqPlan pl, const float2* __restrict__ sig, const float2* __restrict__ code, float2* __restrict__ work,
                       int ncodes, const int* __restrict__ binMap, const float2* __restrict__ twRow) {
-    constexpr int NT = inv_row_threads(LG2, LGRT), P2 = 1 << LG2, rowStride = P2 + (P2 >> 4), total = P2 << LGRT;
-    constexpr int per = total / NT, cpr = P2 / NT;   // elements per thread, chunks of NT elements per row
-    static_assert(total % NT == 0 && P2 % NT == 0 && NT % 16 == 0 && per % 8 == 0, "row tiling");
+    constexpr int NT = inv_row_threads(LG2, LGRT), P2 = 1 << LG2, rowStride = P2 + (P2 >> 4), G = P2 >> 4;
+    constexpr int DL = inv_last_d(LG2), QL = LG2 - DL, NL = 1 << QL, HL = 1 << DL;
+    constexpr int itemsL = (P2 >> QL) << LGRT;   // groups of the last step
+    static_assert(NT >= 64 && NT <= 512 && DL >= 4, "row tiling");
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
+    __shared__ float2 sS[1 << LGRT][NL];          // W_P^{k1 m 2^DL}: the four-step twiddle's advance from output m-1 to m
     const int tid = threadIdx.x;
     const int dp = blockIdx.x % ncodes, rt = blockIdx.x / ncodes, r0 = rt << LGRT, bi = blockIdx.y;
     const int bin = binMap ? binMap[bi] : bi;
-    const float2* srow = sig + (size_t)bin * pl.P + (size_t)r0 * P2 + tid;
-    const float2* crow = code + (size_t)dp * pl.P + (size_t)r0 * P2 + tid;
-    float2* bt = buf + tid + (tid >> 4);          // pidx(tid + q * NT) = pidx(tid) + q * (NT + NT / 16)
+    if (tid < (NL << LGRT)) {
+        const int row = tid >> QL, m = tid & (NL - 1);
+        const unsigned k1 = __brev((unsigned)(r0 + row)) >> (32 - LG1);
+        sS[row][m] = twiddleP(pl, (k1 * (unsigned)m) << DL);
+    }
+    {   // ---- first step from global memory
+        const int b = tid >> (LG2 - 4), v = tid & (G - 1);
+        const float2* srow = sig + (size_t)bin * pl.P + (size_t)(r0 + b) * P2 + v;
+        const float2* crow = code + (size_t)dp * pl.P + (size_t)(r0 + b) * P2 + v;
+        float2 r[16];
 #pragma unroll
-    for (int u0 = 0; u0 < per; u0 += 8) {
-        float2 a[8], c[8];
+        for (int u = 0; u < 16; ++u) r[u] = srow[u * G];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a[u] = srow[(u0 + u) * NT];
-            c[u] = __ldg(crow + (u0 + u) * NT);
+        for (int u0 = 0; u0 < 16; u0 += 8) {
+            float2 c[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) c[u] = __ldg(crow + (u0 + u) * G);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u0 + u] = cmul(r[u0 + u], c[u]);
         }
+        ifft_regs_const<4>(r);
+        float2* base = buf + b * rowStride + 17 * v;     // pidx(16 v + m) = 17 v + m
 #pragma unroll
-        for (int u = 0; u < 8; ++u) bt[((u0 + u) / cpr) * rowStride + ((u0 + u) % cpr) * (NT + NT / 16)] = cmul(a[u], c[u]);
+        for (int m = 0; m < 16; ++m) base[m] = r[m];
     }
     __syncthreads();
-    ifft_ct<LG2, LGRT, false, rowStride, NT>(buf, twRow);
-    float2* orow = work + ((size_t)bi * ncodes + dp) * pl.P + (size_t)r0 * P2 + tid;
+    // ---- middle steps in shared memory
+    if constexpr (DL > 4) {
+        ifft_step_ct<LG2, LGRT, false, rowStride, NT, 4, 4>(buf, twRow + inv_tw_offset(LG2, 4));
+        __syncthreads();
+    }
+    static_assert(DL <= 8, "row transforms up to 4096 points");
+    // ---- last step: outputs to global memory
+    const float2* T = twRow + inv_tw_offset(LG2, DL);
+#pragma unroll 1
+    for (int u = tid; u < itemsL; u += NT) {
+        const int b = u >> DL, j = u & (HL - 1);
+        const float2* base = buf + b * rowStride + pidx(j);
+        float2 r[NL];
 #pragma unroll
-    for (int row = 0; row < (1 << LGRT); ++row) {
-        // W_P^{k1 n2}, k1 = bitrev(r), n2 = tid + q * NT: m = k1 * n2 mod P advances by k1 * NT per chunk
-        const unsigned k1 = __brev((unsigned)(r0 + row)) >> (32 - LG1);
-        unsigned m = k1 * (unsigned)tid;
-        float2 hi[cpr], lo[cpr];
+        for (int m = 0; m < NL; ++m) r[m] = base[(m << DL) + ((m << DL) >> 4)];
 #pragma unroll
-        for (int q = 0; q < cpr; ++q) {
-            hi[q] = __ldg(pl.twHi + (m >> 11));
-            lo[q] = __ldg(pl.twLo + (m & 2047));
-            m += k1 * (unsigned)NT;
-        }
+        for (int m = 1; m < NL; ++m) r[m] = cmul(r[m], __ldg(T + (brevq<QL>(m) - 1) * HL + j));
+        ifft_regs_const<QL>(r);
+        // W_P^{k1 n2}, k1 = bitrev(row), n2 = j + m 2^DL
+        const unsigned k1 = __brev((unsigned)(r0 + b)) >> (32 - LG1);
+        const float2 t0 = twiddleP(pl, k1 * (unsigned)j);
+        float2* orow = work + ((size_t)bi * ncodes + dp) * pl.P + (size_t)(r0 + b) * P2 + j;
+        orow[0] = cmulc(r[0], t0);
 #pragma unroll
-        for (int q = 0; q < cpr; ++q)
-            orow[row * P2 + q * NT] = cmulc(bt[row * rowStride + q * (NT + NT / 16)], cmul(hi[q], lo[q]));
+        for (int m = 1; m < NL; ++m) orow[m << DL] = cmulc(r[m], cmul(t0, sS[b][m]));
     }
 }
 
@@ -575,57 +606,73 @@ template <int LG1, int LG2>
 __global__ void __launch_bounds__(inv_col_threads(LG1), 1024 / inv_col_threads(LG1))
 acq_inv_col_ct_kernel(AcqPlan pl, const float2* __restrict__ work, int ncodes, int combine, int lo0, int hi0, int lo1, int hi1,
                       int useRanges, AcqPeak* __restrict__ peaks, const float2* __restrict__ twCol) {
-    constexpr int NT = inv_col_threads(LG1), P1 = 1 << LG1, P2 = 1 << LG2, total = P1 * kColTile, per = total / NT;
-    constexpr int rpc = NT / kColTile;            // rows per chunk of NT elements
-    static_assert(total % NT == 0 && rpc % 16 == 0 && per % 8 == 0, "column tiling");
+    constexpr int NT = inv_col_threads(LG1), P1 = 1 << LG1, P2 = 1 << LG2;
+    constexpr int DL = inv_last_d(LG1), QL = LG1 - DL, NL = 1 << QL, HL = 1 << DL;
+    constexpr int itemsL = (P1 >> QL) * kColTile, itersL = itemsL / NT;
+    static_assert(NT >= 64 && NT <= 512 && DL >= 4 && DL <= 8 && itemsL % NT == 0, "column tiling");
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* buf = reinterpret_cast<float2*>(smraw);
-    float* mag = reinterpret_cast<float*>(buf + (P1 + (P1 >> 4)) * kColTile);
-    const int tid = threadIdx.x, c = tid & (kColTile - 1), rq = tid >> kLgColTile;
+    float* mag = reinterpret_cast<float*>(buf + (P1 + (P1 >> 4)) * kColTile);   // [itersL][NL][NT]
+    const int tid = threadIdx.x, c = tid & (kColTile - 1);
     const int col0 = blockIdx.x * kColTile, bin = blockIdx.y;
-    // chunks of rpc rows that can hold a lag < N (lag = r * P2 + col): uniform over the CTA
+    // rows that can hold a lag < N (lag = r * P2 + col): r < rEnd
     const int rEnd = min(P1, (pl.N - col0 + P2 - 1) >> LG2);
-    const int uEnd = (rEnd + rpc - 1) / rpc;
-    float2* bt = buf + (rq + (rq >> 4)) * kColTile + c;     // pidx(rq + u * rpc) = pidx(rq) + u * (rpc + rpc / 16)
-    for (int dp = 0; dp < ncodes; ++dp) {
-        const float2* w = work + ((size_t)bin * ncodes + dp) * pl.P + (size_t)rq * P2 + col0 + c;
-#pragma unroll
-        for (int u0 = 0; u0 < per; u0 += 8) {
-            float2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = w[(size_t)(u0 + u) * rpc * P2];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) bt[(u0 + u) * (rpc + rpc / 16) * kColTile] = v[u];
-        }
-        __syncthreads();
-        ifft_ct<LG1, kLgColTile, true, 0, NT>(buf, twCol);
-#pragma unroll
-        for (int u = 0; u < per; ++u) {
-            if (u < uEnd) {
-                const float2 v = bt[u * (rpc + rpc / 16) * kColTile];
-                const float m = sqrt_approx(v.x * v.x + v.y * v.y);
-                float* mg = mag + tid + u * NT;
-                if (dp == 0) *mg = m;
-                else if (combine == 1) *mg = *mg * 0.52440442408507577f + m * 0.85146931829632011f;   // sqrt(11/40), sqrt(29/40)
-                else *mg = *mg + m;
-            }
-        }
-        __syncthreads();
-    }
+    const float2* T = twCol + inv_tw_offset(LG1, DL);
     float best = -1.f;
     int bl = 0x7fffffff;
+    for (int dp = 0; dp < ncodes; ++dp) {
+        {   // ---- first step from global memory: rows 16 v .. 16 v + 15 of column c
+            const int v = tid >> kLgColTile;
+            const float2* w = work + ((size_t)bin * ncodes + dp) * pl.P + (size_t)(16 * v) * P2 + col0 + c;
+            float2 r[16];
 #pragma unroll
-    for (int u = 0; u < per; ++u) {
-        if (u < uEnd) {
-            const int lag = (rq + u * rpc) * P2 + col0 + c;
-            bool ok = lag < pl.N;
-            if (useRanges) ok = ok && ((lag >= lo0 && lag <= hi0) || (lag >= lo1 && lag <= hi1));
-            const float m = mag[tid + u * NT];
-            if (ok && m > best) {      // lags ascend with u: the first maximum wins
-                best = m;
-                bl = lag;
+            for (int m = 0; m < 16; ++m) r[m] = w[(size_t)m * P2];
+            ifft_regs_const<4>(r);
+            float2* base = buf + 17 * v * kColTile + c;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) base[m * kColTile] = r[m];
+        }
+        __syncthreads();
+        if constexpr (DL > 4) {
+            ifft_step_ct<LG1, kLgColTile, true, 0, NT, 4, 4>(buf, twCol + inv_tw_offset(LG1, 4));
+            __syncthreads();
+        }
+        // ---- last step: magnitude, combine, running maximum from registers
+        const bool lastCode = dp == ncodes - 1;
+#pragma unroll
+        for (int it = 0; it < itersL; ++it) {
+            const int u = tid + it * NT, j = u >> kLgColTile;      // column c again: NT is a multiple of kColTile
+            if (j < rEnd) {
+                const float2* base = buf + pidx(j) * kColTile + c;
+                float2 r[NL];
+#pragma unroll
+                for (int m = 0; m < NL; ++m) r[m] = base[((m << DL) + ((m << DL) >> 4)) * kColTile];
+#pragma unroll
+                for (int m = 1; m < NL; ++m) r[m] = cmul(r[m], __ldg(T + (brevq<QL>(m) - 1) * HL + j));
+                ifft_regs_const<QL>(r);
+#pragma unroll
+                for (int m = 0; m < NL; ++m) {
+                    const int row = j + (m << DL);
+                    if (row < rEnd) {
+                        float a = sqrt_approx(r[m].x * r[m].x + r[m].y * r[m].y);
+                        float* mg = mag + (it * NL + m) * NT + tid;
+                        if (dp > 0) a = combine == 1 ? *mg * 0.52440442408507577f + a * 0.85146931829632011f   // sqrt(11/40), sqrt(29/40)
+                                                     : *mg + a;
+                        if (!lastCode) *mg = a;
+                        else {
+                            const int lag = row * P2 + col0 + c;
+                            bool ok = lag < pl.N;
+                            if (useRanges) ok = ok && ((lag >= lo0 && lag <= hi0) || (lag >= lo1 && lag <= hi1));
+                            if (ok && (a > best || (a == best && lag < bl))) {
+                                best = a;
+                                bl = lag;
+                            }
+                        }
+                    }
+                }
             }
         }
+        __syncthreads();   // the next code's first step overwrites buf
     }
     __shared__ float sv[NT / 32];
     __shared__ int sl[NT / 32];
@@ -917,7 +964,7 @@ typedef void (*InvColFn)(AcqPlan, const float2*, int, int, int, int, int, int, i
 struct InvCt {
     InvRowFn row = nullptr;
     InvColFn col = nullptr;
-    int thrRow = 0, thrCol = 0;
+    int thrRow = 0, thrCol = 0, lgRT = 0;
 };
 template <int LG1, int LG2, int LGRT>
 InvCt make_inv_ct() {
@@ -926,16 +973,19 @@ InvCt make_inv_ct() {
     f.col = acq_inv_col_ct_kernel<LG1, LG2>;
     f.thrRow = inv_row_threads(LG2, LGRT);
     f.thrCol = inv_col_threads(LG1);
+    f.lgRT = LGRT;
     return f;
 }
-// (log2 P1, log2 P2, log2 rows per CTA) as acquire_core plans them:
-//   (10, 12, 1)  B1C at 99.375 MHz (BASELINE), P = 2^22      (9, 12, 1)  B1C at the reference's shipped 53 MHz, P = 2^21
-//   (9, 10, 2)   B2a at 99.375 MHz, P = 2^19
-// every other shape (e.g. the band-pass rates of the resampling branch) runs on the generic kernels
-InvCt find_inv_ct(const AcqPlan& pl) {
-    if (pl.log2P1 == 10 && pl.log2P2 == 12 && pl.lgRowTile == 1) return make_inv_ct<10, 12, 1>();
-    if (pl.log2P1 == 9 && pl.log2P2 == 12 && pl.lgRowTile == 1) return make_inv_ct<9, 12, 1>();
-    if (pl.log2P1 == 9 && pl.log2P2 == 10 && pl.lgRowTile == 2) return make_inv_ct<9, 10, 2>();
+// (log2 P1, log2 P2) as acquire_core plans them, and the rows per CTA of the specialised row pass:
+//   (10, 12)  B1C at 99.375 MHz (BASELINE), P = 2^22      (9, 12)  B1C at the reference's shipped 53 MHz, P = 2^21
+//   (9, 10)   B2a at 99.375 MHz, P = 2^19
+// every other shape (e.g. the band-pass rates of the resampling branch) runs on the generic kernels, and so does every
+// shape when bit 0 of cfg.tune is set (tests compare the two implementations that way)
+InvCt find_inv_ct(const AcqPlan& pl, int tune) {
+    if (tune & 1) return InvCt{};
+    if (pl.log2P1 == 10 && pl.log2P2 == 12) return (tune & 2) ? make_inv_ct<10, 12, 0>() : make_inv_ct<10, 12, 1>();
+    if (pl.log2P1 == 9 && pl.log2P2 == 12) return (tune & 2) ? make_inv_ct<9, 12, 0>() : make_inv_ct<9, 12, 1>();
+    if (pl.log2P1 == 9 && pl.log2P2 == 10) return (tune & 2) ? make_inv_ct<9, 10, 1>() : make_inv_ct<9, 10, 2>();
     return InvCt{};
 }
 // step twiddles of a 2^LG-point inverse, see inv_tw_offset
@@ -1068,7 +1118,8 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     // one thread per 16-element register group (fewer for the short B2a transforms)
     const int thrRow = std::min(kAcqThreads, std::max(128, (pl.P2 >> 4) * rowTile));
     const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
-    const InvCt ct = find_inv_ct(pl);
+    const InvCt ct = find_inv_ct(pl, cfg->tune);
+    const size_t smemRowCt = sizeof(float2) * ((size_t)(pl.P2 + (pl.P2 >> 4)) << ct.lgRT);
     DevBuf dTwRowS, dTwColS;
     if (ct.row) {
         const std::vector<float2> tr = inv_step_twiddles(pl.log2P2), tc = inv_step_twiddles(pl.log2P1);
@@ -1076,14 +1127,14 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
         TRYA(dTwColS.alloc(tc.size() * 8));
         TRYA(cudaMemcpy(dTwRowS.p, tr.data(), tr.size() * 8, cudaMemcpyHostToDevice));
         TRYA(cudaMemcpy(dTwColS.p, tc.data(), tc.size() * 8, cudaMemcpyHostToDevice));
-        TRYA(cudaFuncSetAttribute((const void*)ct.row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRow));
+        TRYA(cudaFuncSetAttribute((const void*)ct.row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRowCt));
         TRYA(cudaFuncSetAttribute((const void*)ct.col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemColInv));
     }
     // the inverse passes of nb bins against the ncodes spectra of one PRN; per-bin peaks -> out[nb]
     auto inverse_passes = [&](const float2* sigBins, int nb, const float2* code, const int* binMap, int lo0, int hi0, int lo1,
                               int hi1, int useRanges, AcqPeak* out) {
         if (ct.row) {
-            ct.row<<<dim3((pl.P1 / rowTile) * ncodes, nb), ct.thrRow, smemRow>>>(pl, sigBins, code, dWork.as<float2>(), ncodes, binMap,
+            ct.row<<<dim3((pl.P1 >> ct.lgRT) * ncodes, nb), ct.thrRow, smemRowCt>>>(pl, sigBins, code, dWork.as<float2>(), ncodes, binMap,
                                                                                  dTwRowS.as<float2>());
             ct.col<<<dim3(colGroups, nb), ct.thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0, hi0, lo1, hi1,
                                                                    useRanges, dPeaks.as<AcqPeak>(), dTwColS.as<float2>());
@@ -1098,7 +1149,7 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     };
     acq_fwd_col_kernel<<<dim3(colGroups, nbins), thrCol, smemCol>>>(pl, 0, dx, 0, dDphi.as<unsigned long long>(),
                                                                        dSig.as<float2>(), iq);
-    acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, nbins), thrRow, smemRow>>>(pl, dSig.as<float2>(), 0.f);
+    acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, nbins), thrRow, smemRow>>>(pl, dSig.as<float2>(), 0.f, ct.row ? 1 : 0);
     count_launch(2);
     TRYA(cudaGetLastError());
 
@@ -1181,7 +1232,8 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
         TRYA(dCode.alloc(specBytes * ncodes * nSel));
         acq_fwd_col_kernel<<<dim3(colGroups, ncodes * nSel), thrCol, smemCol>>>(pl, 1, dTab.as<int8_t>(), (size_t)spc, nullptr,
                                                                                    dCode.as<float2>(), 0);
-        acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, ncodes * nSel), thrRow, smemRow>>>(pl, dCode.as<float2>(), 1.0f / (float)pl.P);
+        acq_fwd_row_kernel<<<dim3(pl.P1 / rowTile, ncodes * nSel), thrRow, smemRow>>>(pl, dCode.as<float2>(), 1.0f / (float)pl.P,
+                                                                                      ct.row ? 1 : 0);
         count_launch(2);
         // ---- phase 1: coarse PRN x Doppler grid; per (PRN, bin) peak and first lag
         TRYA(dBinPeak.alloc(sizeof(AcqPeak) * (size_t)nbins * nSel));

@@ -1120,6 +1120,8 @@ def run_acq_b2a(args, b1c=False):
         st = B.b2a.initSettings(acqSatelliteList=list(range(1, n_prn + 1)))
         inj = [2, 9, 17, 23, 31, 40, 52, 61]
         n = 17 * 99375                                        # (fineNoncoh + 2) ms, B2a/postProcessing.m:89-90
+    if os.environ.get("BDS_BENCH_ACQ_TUNE"):                   # developer A/B of the inverse passes (bdsgpu.h: cfg.tune)
+        st["_tune"] = int(os.environ["BDS_BENCH_ACQ_TUNE"])
     sats = synth.make_sats(len(inj), st, sig_name, seed=3, prns=inj, cn0=47.0)
     x_dev = torch.empty(n + 64, dtype=torch.int8, device="cuda")
     synth.synth_device(sig_name, st, sats, n, out_ptr=x_dev.data_ptr())

@@ -107,7 +107,8 @@ typedef struct bds_acq_cfg {
      * runs at a band-pass sampling rate on every index-th sample and codePhase / carrFreq are mapped back (:321-338) */
     double resamplingThreshold; /* settings.resamplingThreshold [Hz] */
     int32_t resamplingflag;     /* settings.resamplingflag */
-    int32_t reserved;           /* 0 */
+    int32_t tune;               /* 0.  Test / developer hook, results unchanged: bit 0 = run the inverse passes on the generic
+                                 * kernels for every transform shape, bit 1 = other row tiling of the specialised row pass */
 } bds_acq_cfg;
 
 /* Replaces acquisition(longSignal, settings):

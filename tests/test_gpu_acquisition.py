@@ -174,3 +174,32 @@ def test_b1c_acquisition_full_reference_grid_against_stored_oracle_results():
     np.testing.assert_array_equal(got.codePhase, gold["codePhase"])
     np.testing.assert_array_equal(got.carrFreq, gold["carrFreq"])
     assert got.carrFreq[6] != 0 and got.carrFreq[22] != 0 and got.carrFreq[39] == 0
+
+
+@pytest.mark.parametrize("signal", ["B1C", "B2a"])
+def test_specialised_inverse_passes_equal_the_generic_kernels(signal):
+    """The compile-time specialised inverse passes (AUTO at the shipped transform shapes) against the generic kernels
+    (cfg.tune bit 0) and the other row tiling (bit 1): same Doppler bin and code phase for every PRN, detected or not,
+    peak sizes and normalisers equal to float rounding of two differently ordered transforms."""
+    if signal == "B1C":
+        s, sats, x = _b1c_record(2, 0.0305, 11, acqSearchBand=250, acqSatelliteList=[1, 2, 5, 9])
+        run = B.b1c.acquisition
+    else:
+        s = O.initSettings_B2a(acqSatelliteList=[4, 9, 11])
+        sats = synth.make_sats(2, s, "B2a", seed=12, prns=[4, 11], cn0=47.0)
+        x = synth.synth_numpy("B2a", s, sats, 17 * 99375, seed=12)
+        run = B.b2a.acquisition
+    res = {}
+    for tune in (0, 1, 2):
+        d = dict(s)
+        d["_tune"] = tune
+        res[tune] = run(x, B.Settings(d), return_debug=True)
+    ref, rd = res[1]
+    assert np.count_nonzero(ref.carrFreq) == 2
+    for tune in (0, 2):
+        got, gd = res[tune]
+        np.testing.assert_array_equal(gd[:, :2], rd[:, :2])            # bin, code phase
+        np.testing.assert_allclose(gd[:, 2:], rd[:, 2:], rtol=2e-5)    # peak, normaliser
+        np.testing.assert_array_equal(got.codePhase, ref.codePhase)
+        np.testing.assert_array_equal(got.carrFreq, ref.carrFreq)
+        np.testing.assert_allclose(got.peakMetric, ref.peakMetric, rtol=2e-5)
