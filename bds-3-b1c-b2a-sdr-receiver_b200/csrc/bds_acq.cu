@@ -510,6 +510,26 @@ __device__ __forceinline__ void ifft_ct(float2* buf, const float2* __restrict__ 
     }
 }
 
+// L2 residency hints of the specialised inverse passes: the signal and code spectra stream through once per cell
+// (evict first), the row pass's output is read back by the column pass right after (evict last) and dead after that
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float2 ld_hint(const float2* p, unsigned long long pol) {
+    float2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint(float2* p, float2 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -547,6 +567,7 @@ acq_inv_row_ct_kernel(AcqPlan pl, const float2* __restrict__ sig, const float2* 
     const int tid = threadIdx.x;
     const int dp = blockIdx.x % ncodes, rt = blockIdx.x / ncodes, r0 = rt << LGRT, bi = blockIdx.y;
     const int bin = binMap ? binMap[bi] : bi;
+    const unsigned long long polFirst = l2_policy_evict_first(), polLast = l2_policy_evict_last();
     if (tid < (NL << LGRT)) {
         const int row = tid >> QL, m = tid & (NL - 1);
         const unsigned k1 = __brev((unsigned)(r0 + row)) >> (32 - LG1);
@@ -558,12 +579,12 @@ acq_inv_row_ct_kernel(AcqPlan pl, const float2* __restrict__ sig, const float2* 
         const float2* crow = code + (size_t)dp * pl.P + (size_t)(r0 + b) * P2 + v;
         float2 r[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) r[u] = srow[u * G];
+        for (int u = 0; u < 16; ++u) r[u] = ld_hint(srow + u * G, polFirst);
 #pragma unroll
         for (int u0 = 0; u0 < 16; u0 += 8) {
             float2 c[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) c[u] = __ldg(crow + (u0 + u) * G);
+            for (int u = 0; u < 8; ++u) c[u] = ld_hint(crow + (u0 + u) * G, polFirst);
 #pragma unroll
             for (int u = 0; u < 8; ++u) r[u0 + u] = cmul(r[u0 + u], c[u]);
         }
@@ -595,9 +616,9 @@ acq_inv_row_ct_kernel(AcqPlan pl, const float2* __restrict__ sig, const float2* 
         const unsigned k1 = __brev((unsigned)(r0 + b)) >> (32 - LG1);
         const float2 t0 = twiddleP(pl, k1 * (unsigned)j);
         float2* orow = work + ((size_t)bi * ncodes + dp) * pl.P + (size_t)(r0 + b) * P2 + j;
-        orow[0] = cmulc(r[0], t0);
+        st_hint(orow, cmulc(r[0], t0), polLast);
 #pragma unroll
-        for (int m = 1; m < NL; ++m) orow[m << DL] = cmulc(r[m], cmul(t0, sS[b][m]));
+        for (int m = 1; m < NL; ++m) st_hint(orow + (m << DL), cmulc(r[m], cmul(t0, sS[b][m])), polLast);
     }
 }
 
@@ -618,6 +639,7 @@ acq_inv_col_ct_kernel(AcqPlan pl, const float2* __restrict__ work, int ncodes, i
     // rows that can hold a lag < N (lag = r * P2 + col): r < rEnd
     const int rEnd = min(P1, (pl.N - col0 + P2 - 1) >> LG2);
     const float2* T = twCol + inv_tw_offset(LG1, DL);
+    const unsigned long long polFirst = l2_policy_evict_first();
     float best = -1.f;
     int bl = 0x7fffffff;
     for (int dp = 0; dp < ncodes; ++dp) {
@@ -626,7 +648,7 @@ acq_inv_col_ct_kernel(AcqPlan pl, const float2* __restrict__ work, int ncodes, i
             const float2* w = work + ((size_t)bin * ncodes + dp) * pl.P + (size_t)(16 * v) * P2 + col0 + c;
             float2 r[16];
 #pragma unroll
-            for (int m = 0; m < 16; ++m) r[m] = w[(size_t)m * P2];
+            for (int m = 0; m < 16; ++m) r[m] = ld_hint(w + (size_t)m * P2, polFirst);
             ifft_regs_const<4>(r);
             float2* base = buf + 17 * v * kColTile + c;
 #pragma unroll
@@ -1119,6 +1141,15 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     const int thrRow = std::min(kAcqThreads, std::max(128, (pl.P2 >> 4) * rowTile));
     const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
     const InvCt ct = find_inv_ct(pl, cfg->tune);
+    // two blocking streams (ordered against the legacy default stream the rest of the call uses), made once per process
+    static cudaStream_t streams[2] = {nullptr, nullptr};
+    static std::once_flag streamsOnce;
+    std::call_once(streamsOnce, [] {
+        for (auto& st : streams)
+            if (cudaStreamCreate(&st) != cudaSuccess) st = nullptr;
+    });
+    const int nStreams = (streams[0] && streams[1] && !(cfg->tune & 4)) ? 2 : 1;
+    size_t workElems = 0, peakElems = 0;
     const size_t smemRowCt = sizeof(float2) * ((size_t)(pl.P2 + (pl.P2 >> 4)) << ct.lgRT);
     DevBuf dTwRowS, dTwColS;
     if (ct.row) {
@@ -1130,21 +1161,27 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
         TRYA(cudaFuncSetAttribute((const void*)ct.row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRowCt));
         TRYA(cudaFuncSetAttribute((const void*)ct.col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemColInv));
     }
-    // the inverse passes of nb bins against the ncodes spectra of one PRN; per-bin peaks -> out[nb]
+    // the inverse passes of nb bins against the ncodes spectra of one PRN; per-bin peaks -> out[nb].  Consecutive calls
+    // alternate between two streams with a work buffer each: the row pass of one cell fills the SMs the tail of the
+    // other cell's column pass leaves idle (1024 / 512 CTAs per launch are 3.5 / 1.7 waves of 296 resident CTAs)
+    int slot = 0;
     auto inverse_passes = [&](const float2* sigBins, int nb, const float2* code, const int* binMap, int lo0, int hi0, int lo1,
                               int hi1, int useRanges, AcqPeak* out) {
+        cudaStream_t st = nStreams > 1 ? streams[slot] : (cudaStream_t)0;
+        float2* work = dWork.as<float2>() + (size_t)slot * workElems;
+        AcqPeak* pk = dPeaks.as<AcqPeak>() + (size_t)slot * peakElems;
+        slot = (slot + 1) % nStreams;
         if (ct.row) {
-            ct.row<<<dim3((pl.P1 >> ct.lgRT) * ncodes, nb), ct.thrRow, smemRowCt>>>(pl, sigBins, code, dWork.as<float2>(), ncodes, binMap,
-                                                                                 dTwRowS.as<float2>());
-            ct.col<<<dim3(colGroups, nb), ct.thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0, hi0, lo1, hi1,
-                                                                   useRanges, dPeaks.as<AcqPeak>(), dTwColS.as<float2>());
+            ct.row<<<dim3((pl.P1 >> ct.lgRT) * ncodes, nb), ct.thrRow, smemRowCt, st>>>(pl, sigBins, code, work, ncodes, binMap,
+                                                                                     dTwRowS.as<float2>());
+            ct.col<<<dim3(colGroups, nb), ct.thrCol, smemColInv, st>>>(pl, work, ncodes, combine, lo0, hi0, lo1, hi1, useRanges, pk,
+                                                                       dTwColS.as<float2>());
         } else {
-            acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, nb, ncodes), thrRow, smemRow>>>(pl, sigBins, code, dWork.as<float2>(), ncodes,
-                                                                                       binMap);
-            acq_inv_col_kernel<<<dim3(colGroups, nb), thrCol, smemColInv>>>(pl, dWork.as<float2>(), ncodes, combine, lo0, hi0, lo1,
-                                                                            hi1, useRanges, dPeaks.as<AcqPeak>());
+            acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, nb, ncodes), thrRow, smemRow, st>>>(pl, sigBins, code, work, ncodes, binMap);
+            acq_inv_col_kernel<<<dim3(colGroups, nb), thrCol, smemColInv, st>>>(pl, work, ncodes, combine, lo0, hi0, lo1, hi1,
+                                                                                useRanges, pk);
         }
-        acq_peak_reduce_kernel<<<nb, 256>>>(dPeaks.as<AcqPeak>(), colGroups, out);
+        acq_peak_reduce_kernel<<<nb, 256, 0, st>>>(pk, colGroups, out);
         count_launch(3);
     };
     acq_fwd_col_kernel<<<dim3(colGroups, nbins), thrCol, smemCol>>>(pl, 0, dx, 0, dDphi.as<unsigned long long>(),
@@ -1183,8 +1220,10 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     const int chunkMax = (int)std::max<size_t>(1, std::min<size_t>(64, (freeB / 3) / perPrn));
     // bins per batch: keep the inverse-row output of a batch resident in L2 for the inverse-column pass
     const int binsPerBatch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nbins, (size_t)8, ((size_t)96 << 20) / (specBytes * ncodes)}));
-    TRYA(dWork.alloc(specBytes * ncodes * binsPerBatch));
-    TRYA(dPeaks.alloc(sizeof(AcqPeak) * (size_t)colGroups * binsPerBatch));
+    workElems = (size_t)pl.P * ncodes * binsPerBatch;
+    peakElems = (size_t)colGroups * binsPerBatch;
+    TRYA(dWork.alloc(sizeof(float2) * workElems * nStreams));
+    TRYA(dPeaks.alloc(sizeof(AcqPeak) * peakElems * nStreams));
     DevBuf dBinMap, dSecond, dIdx;
     {   // makeDataTable.m:49-63 / makeB2aDataTable.m:46-62: idx = ceil((ts*k)/tc), k = 1..spc; idx(end) forced to the last
         // element; B1C also forces idx(1) = 1  (same expression as bds_make_code_table)
