@@ -25,6 +25,7 @@
 
 #include "bds_codes.h"
 #include "bds_track.cuh"
+#define FAST_GEOM_MULTI   // the chip-synchronous B1C kernel is instantiated once per geometry (g99, g53) below
 #include "bds_track_fast.cuh"
 
 namespace bds {
@@ -614,8 +615,28 @@ __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
 }
 
 }  // namespace bds
+#include "bds_track_fw.cuh"       // geometry g99: fs = 99.375 MHz (BASELINE)
+#undef FAST_GEOM_NS
+#undef FAST_GEN_INC
+#define FAST_GEOM_NS g53          // geometry g53: fs = 53 MHz, the reference's shipped B1C setting (B1C/initSettings.m:57)
+#define FAST_GEN_INC "bds_track_fast_gen_53.inc"
+#include "bds_track_fast.cuh"
 #include "bds_track_fw.cuh"
 #include "bds_track_b2a.cuh"
+namespace bds {
+// the instantiations of the chip-synchronous B1C kernel
+struct FwGeom {
+    const char* name;
+    bool (*supported)(int mode, int hasPilot, int hasP61, double fs, double fc, int codeLength, double d);
+    void (*kernel)(TrkDev);
+    size_t smemBytes;
+};
+static const FwGeom kFwGeoms[] = {
+    {"fs = 99.375 MHz", g99::fast_wb_supported, g99::trk_fw_kernel, sizeof(g99::FwSmem)},
+    {"fs = 53 MHz", g53::fast_wb_supported, g53::trk_fw_kernel, sizeof(g53::FwSmem)},
+};
+constexpr int kFwGeomCount = (int)(sizeof(kFwGeoms) / sizeof(kFwGeoms[0]));
+}  // namespace bds
 namespace bds {
 
 // ======================================================================================
@@ -686,6 +707,7 @@ struct bds_trk {
     unsigned long long* dTrace = nullptr;
     unsigned traceCap = 0;
     bool fast = false;
+    int geom = 0;           // index into kFwGeoms when fast
     bool b2aUnit = false;   // B2a on the per-channel chip-synchronous kernel
     int b2aCluster = 1;     // ... with this many CTAs (a thread-block cluster) per channel
     int iq = 0;             // 1: the record holds interleaved I/Q int8 pairs (cfg.fileType == 2); window quantities are samples
@@ -797,14 +819,20 @@ void fill_dev(const bds_trk* h, TrkDev& g, int maxEpochs) {
     g.cno = h->dCno;
 }
 
-int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast) {
+int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast, int& geom) {
     int hasPilot, hasP61;
     mode_flags(mode, cfg->pilotTRKflag, hasPilot, hasP61);
     if (cfg->fileType != 0 && cfg->fileType != 1 && cfg->fileType != 2)
         return set_error(BDS_ERR_ARG, "fileType must be 1 (real) or 2 (I/Q), got %d", cfg->fileType);
     const bool iq = cfg->fileType == 2;   // the chip-synchronous bodies pack real samples: I/Q records take the general kernel
-    bool can = !iq && fast_wb_supported(mode, hasPilot, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
-                                        cfg->dllCorrelatorSpacing);
+    bool can = false;
+    geom = 0;
+    for (int k = 0; k < kFwGeomCount && !iq && !can; ++k)
+        if (kFwGeoms[k].supported(mode, hasPilot, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
+                                  cfg->dllCorrelatorSpacing)) {
+            can = true;
+            geom = k;
+        }
     if (cfg->kernel == BDS_KERNEL_FAST && !can &&
         (iq || !fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing)))
         return set_error(BDS_ERR_UNSUPPORTED, "fast tracking kernel does not support this configuration");
@@ -819,8 +847,8 @@ bool b2a_unit_enabled(int mode, const bds_trk_cfg* cfg) {
            fastb_supported(mode, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength, cfg->dllCorrelatorSpacing);
 }
 
-size_t smem_bytes(bool fast) {
-    return fast ? std::max(sizeof(FwSmem), kFwCloseBase + sizeof(FwCloseScratch) * (kFwThreads / 32)) : sizeof(TrkSmem);
+size_t smem_bytes(bool fast, int geom) {
+    return fast ? std::max(kFwGeoms[geom].smemBytes, kFwCloseBase + sizeof(FwCloseScratch) * (kFwThreads / 32)) : sizeof(TrkSmem);
 }
 
 int init_state(bds_trk* h) {
@@ -903,7 +931,7 @@ int ensure_capacity(bds_trk* h, int need) {
 // grid geometry: a cooperative grid of co-resident CTAs; S slices per channel-epoch.
 int plan_grid(bds_trk* h) {
     int occ = 0;
-    h->smemBytes = smem_bytes(h->fast);
+    h->smemBytes = smem_bytes(h->fast, h->geom);
     int nAct = 0;
     for (auto& c : h->ch) nAct += c.PRN != 0;
     h->nAct = std::max(nAct, 1);
@@ -941,8 +969,8 @@ int plan_grid(bds_trk* h) {
         h->gridBlocks = h->nAct * h->b2aCluster;   // one cluster per channel, all resident at once
         h->S = 1;
     } else if (h->fast) {
-        BDS_CUDA(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trk_fw_kernel, kFwThreads, h->smemBytes));
+        BDS_CUDA(cudaFuncSetAttribute(kFwGeoms[h->geom].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+        BDS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kFwGeoms[h->geom].kernel, kFwThreads, h->smemBytes));
         if (occ < 1) return set_error(BDS_ERR_CUDA, "tracking kernel does not fit on an SM");
         h->gridBlocks = g_num_sms;
         if (h->cfg.fwMaxCtas > 0) h->gridBlocks = std::max(2, std::min(g_num_sms, (int)h->cfg.fwMaxCtas));
@@ -985,7 +1013,7 @@ int open_common(int mode, const bds_trk_cfg* cfg, long long skip, const bds_chan
     h->nCh = n_ch;
     h->ch.assign(ch, ch + n_ch);
     h->skip = skip;
-    rc = choose_fast(mode, cfg, h->fast);
+    rc = choose_fast(mode, cfg, h->fast, h->geom);
     if (rc) {
         delete h;
         return rc;
@@ -1167,7 +1195,7 @@ static int launch_run(bds_trk* h, int maxEpochs, int epochLimit) {
     count_launch();
     void* args[] = {&g};
     if (h->fast)
-        BDS_CUDA(cudaLaunchCooperativeKernel((const void*)trk_fw_kernel, dim3(h->gridBlocks), dim3(kFwThreads), args,
+        BDS_CUDA(cudaLaunchCooperativeKernel((const void*)kFwGeoms[h->geom].kernel, dim3(h->gridBlocks), dim3(kFwThreads), args,
                                              h->smemBytes, h->stream));
     else
         BDS_CUDA(cudaLaunchCooperativeKernel((const void*)trk_persistent_kernel, dim3(h->gridBlocks), dim3(kTrkThreads),
@@ -1575,7 +1603,8 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     int rc = require_device();
     if (rc) return rc;
     bool fast = false;
-    rc = choose_fast(mode, cfg, fast);
+    int geom = 0;
+    rc = choose_fast(mode, cfg, fast, geom);
     if (rc) return rc;
     const int nce = n_ch * n_epochs;
     std::vector<EpochParams> hp_(nce);
@@ -1651,14 +1680,14 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
     TRYC(cudaMalloc(&dCnt, 128));
     TRYC(cudaMemset(dCnt, 0, 128));
     g.counters = dCnt;
-    size_t smem = smem_bytes(fast);
+    size_t smem = smem_bytes(fast, geom);
     const bool b2aUnit = !fast && b2a_unit_enabled(mode, cfg);
     if (b2aUnit) {
         smem = sizeof(B2aSmem);
         TRYC(cudaFuncSetAttribute(trk_b2a_unit_open_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         trk_b2a_unit_open_kernel<<<nce, kB2aThreads, smem>>>(g, dP, n_epochs, dSums);
     } else if (fast) {
-        TRYC(cudaFuncSetAttribute(trk_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TRYC(cudaFuncSetAttribute(kFwGeoms[geom].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g.partial = dPart;
         g.olParams = dP;
         g.olEpochs = n_epochs;
@@ -1671,7 +1700,7 @@ int bds_track_correlate_open_loop(int mode, const bds_trk_cfg* cfg, const int8_t
         TRYC(cudaEventCreate(&e0));
         TRYC(cudaEventCreate(&e1));
         TRYC(cudaEventRecord(e0, 0));
-        trk_fw_kernel<<<g_num_sms, kFwThreads, smem>>>(g);
+        kFwGeoms[geom].kernel<<<g_num_sms, kFwThreads, smem>>>(g);
         TRYC(cudaEventRecord(e1, 0));
         TRYC(cudaEventSynchronize(e1));
         float ms = 0.f;

@@ -27,7 +27,9 @@
 // Status: the AUTO choice for B2a (validated on a B200 in round 2).  The generated body and the chip-sign combination are verified on the CPU
 // (tests/test_fast_body_emulation.py), the kernel on hardware (tests/test_gpu_b2a_unit.py).
 #pragma once
+#ifndef BDS_TRACK_FAST_COMMON
 #include "bds_track_fast.cuh"
+#endif
 
 namespace bds {
 

@@ -20,19 +20,33 @@
 //
 // The file also compiles for the host (tests/test_fast_b1c_hostcompile.py includes it after a shim that gives the
 // CUDA intrinsics host definitions), so the arithmetic of a build is checked against the oracle before it gets GPU time.
-#pragma once
+//
+// Geometries: the chip body, its tables and everything sized by them live in namespace bds::FAST_GEOM_NS and come from
+// the generated file FAST_GEN_INC (gen_fast_wb.py).  Included as it is, the header gives the BASELINE geometry
+// (g99: fs = 99.375 MHz) and makes its names visible in namespace bds.  bds_track.cu defines FAST_GEOM_MULTI and includes
+// the header once per geometry (g99, and g53 = the reference's shipped fs = 53 MHz, B1C/initSettings.m:57); the
+// geometry-independent helpers are compiled by the first inclusion only.
 #include "bds_track.cuh"
 
-namespace bds {
-
+#ifndef FAST_GEOM_NS
+#define FAST_GEOM_NS g99
+#define FAST_GEN_INC "bds_track_fast_gen.inc"
+#endif
 #ifndef FAST_CONST
 #define FAST_CONST static __constant__
 #endif
-#include "bds_track_fast_gen.inc"
 
+#ifndef BDS_TRACK_FAST_COMMON
+namespace bds {
 constexpr int kFastBins = 128;        // (B2a body: bins of its rank index)
 constexpr unsigned kFastGuard = 16u;  // fixed-point guard band (2^-32 units of one sample)
-constexpr unsigned kFastNomTol = 1u << 22;   // a threshold may sit this far from its nominal value (half a rank bin)
+}
+#endif
+
+namespace bds {
+namespace FAST_GEOM_NS {
+#include FAST_GEN_INC
+constexpr unsigned kFastNomTol = 1u << (32 - FAST_RANK_BITS - 1);   // a threshold may sit this far from its nominal value (half a rank bin)
 
 // Per-epoch table of one channel, built in shared memory by the table-builder warp of the consuming CTA from the
 // epoch's NCO parameters alone (48 bytes travel from the loop closure to the correlator, nothing else).
@@ -128,6 +142,12 @@ __device__ inline void fast_build_tab_warp(FastTab* tab, const FastStatic& fsx, 
 }
 #endif
 
+}  // namespace FAST_GEOM_NS
+}  // namespace bds
+
+#ifndef BDS_TRACK_FAST_COMMON
+#define BDS_TRACK_FAST_COMMON
+namespace bds {
 // ---- exact per-sample evaluation (shared with the general kernel's arithmetic) --------------
 struct ExactCtx {
     double a[3], stop[3], dd;
@@ -295,6 +315,11 @@ __device__ __forceinline__ float fast_acc_get(const fast_acc_t* a, int i) {
     return (i & 1) ? y : x;
 }
 
+}  // namespace bds
+#endif  // BDS_TRACK_FAST_COMMON
+
+namespace bds {
+namespace FAST_GEOM_NS {
 // ---- one chip (one thread) ---------------------------------------------------------------------
 // Integrates chip c of the epoch described by (tab, p) into acc[9 pairs].  tile/tileBase: staged IF
 // bytes (window byte offset of tile[0]); xblk = g.x + B0 for the exact path.  Returns true if the
@@ -309,11 +334,11 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
     const double psi = (double)nc - q;                       // in (0,1] samples
     const unsigned Psi = (unsigned)fmin(psi * 4294967296.0, 4294967295.0);
     // rank = number of thresholds < Psi.  The thresholds keep their generation-time order and stay within half a
-    // 1/512 bin of nominal (tab.valid), nominal neighbours are > 3 bins apart: the only threshold that can lie within
+    // rank bin (1/512 or 1/1024 sample) of nominal (tab.valid), nominal neighbours are > 3 bins apart: the only threshold that can lie within
     // a bin of Psi - and hence the only one that can decide the rank beyond rankLo, or come within the guard band -
     // is thr[rankLo[bin]].
-    const int jlo = fsx.rankLo[Psi >> (32 - 9)];
-    static_assert(FAST_RANK_BINS == 512, "rank bins");
+    const int jlo = fsx.rankLo[Psi >> (32 - FAST_RANK_BITS)];
+    static_assert(FAST_RANK_BINS == 1 << FAST_RANK_BITS, "rank bins");
     const unsigned tnear = tab.thr[jlo];
     const int j = jlo + (tnear < Psi);
     const uint2 mk = fsx.mask[j];
@@ -405,4 +430,8 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
     return exact;
 }
 
+}  // namespace FAST_GEOM_NS
+#ifndef FAST_GEOM_MULTI
+using namespace FAST_GEOM_NS;
+#endif
 }  // namespace bds

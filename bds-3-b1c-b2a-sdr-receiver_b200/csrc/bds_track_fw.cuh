@@ -18,7 +18,11 @@
 // Closer CTAs (the last few of the grid): one warp per channel polls the arrival counter and, when all S slices of
 // an epoch are in, sums the slice slots in a fixed order, closes the PLL/DLL in fp64 (fw_closure) and queues the
 // next epoch's slices.
-#pragma once
+//
+// Like bds_track_fast.cuh the file is included once per chip-body geometry: the stage layout and the kernel live in
+// namespace bds::FAST_GEOM_NS, everything else (queue, loop closure, the prepare kernel) is compiled once.
+#ifndef BDS_TRACK_FW_COMMON
+#define BDS_TRACK_FW_COMMON
 
 namespace bds {
 
@@ -38,7 +42,6 @@ constexpr int kFwChips = kFwCompute * 32;      // chips per pass
 #define BDS_FW_STAGES 4
 #endif
 constexpr int kFwStages = BDS_FW_STAGES;   // compiled-in maximum; g.stages (2..kFwStages) are used
-constexpr int kFwTile = ((kFwChips * 98 + 256 + 127) / 128) * 128;   // chips * 97.2 samples + margins
 constexpr int kFwBitsBytes = 2 * kPackedWordsDev * 4;
 // qctl words, one 128-byte line each: the head is hit by every producer, the tail by every loop closure
 constexpr int kQHead = 0, kQTail = 32, kQLeft = 64, kQWords = 96;
@@ -51,22 +54,6 @@ struct FwUnit {
     int tileBytes, pad_;   // bytes staged in tile[]
     long long tileBase;    // window byte offset of tile[0]
     long long B0;          // window byte offset of the block start
-};
-
-struct __align__(128) FwStage {
-    FastTab tab;
-    uint32_t bits[2][kPackedWordsDev];
-    EpochParams p;
-    FwUnit u;
-    __align__(128) unsigned char tile[kFwTile + 128];
-};
-
-struct __align__(128) FwSmem {
-    unsigned long long full[kFwStages], empty[kFwStages], pfull[kFwStages], resFull[2], resEmpty[2];
-    int res[2][kFwCompute][kNSum];
-    int resTask[2][4];
-    FastStatic fsx;
-    FwStage st[kFwStages];
 };
 
 // scratch of one loop-closing warp (closer CTAs overlay an array of these on the dynamic smem)
@@ -412,6 +399,77 @@ __device__ bool fw_closure(const TrkDev& g, FwCloseScratch& sm, int c, int e, in
     __syncwarp();
     return more;
 }
+
+// First params of every channel for the current window (run start).  One CTA; warps take the
+// channels in turn, publish their first epoch and queue its slices; if nothing can run the grid is
+// told to terminate right away.
+__global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
+    __shared__ EpochParams nps[32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        g.qctl[kQHead] = 0;
+        g.qctl[kQTail] = 0;
+        g.qctl[kQLeft] = (unsigned)g.nCh + 1u;   // every channel + this kernel hold a reference
+    }
+    __syncthreads();
+    for (int c = w; c < g.nCh; c += nw) {
+        int ok = 0, e = 0;
+        if (lane == 0) {
+            g.count[c] = 0;
+            if (g.cc[c].active) {
+                ChanState st = g.st[c];
+                g.cc[c].pad = st.epoch;
+                e = st.epoch;
+                ok = next_params(g, st, nps[w]) && st.epoch < g.epochLimit && g.maxEpochs > 0;
+                if (!ok && st.epoch < g.epochLimit && st.lockLost == 0)
+                    g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
+                g.ready[c] = ok ? e : e - 1;
+                g.stop[c] = ok ? INT_MAX : e;
+            } else {
+                g.stop[c] = 0;
+                g.ready[c] = -1;
+            }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        __syncwarp();
+        if (ok) {
+            if (lane == 0) store_cg(g.params + c * 2 + (e & 1), nps[w]);
+            __threadfence();
+            __syncwarp();
+            fw_push_slices(g, c, e, nps[w], lane);
+        } else {
+            fw_channel_done(g, lane, nCtas);
+        }
+    }
+    __syncthreads();
+    if (w == 0) fw_channel_done(g, lane, nCtas);   // drop the kernel's own reference
+}
+
+}  // namespace bds
+#endif  // BDS_TRACK_FW_COMMON
+
+namespace bds {
+namespace FAST_GEOM_NS {
+
+// bytes a pass of kFwChips chips can touch: chips * samples per chip + margins (97.2 samples at 99.375 MHz, 51.9 at 53 MHz)
+constexpr int kFwTile = ((kFwChips * ((int)FAST_SAMPLES_PER_CHIP + 1) + 256 + 127) / 128) * 128;
+
+struct __align__(128) FwStage {
+    FastTab tab;
+    uint32_t bits[2][kPackedWordsDev];
+    EpochParams p;
+    FwUnit u;
+    __align__(128) unsigned char tile[kFwTile + 128];
+};
+
+struct __align__(128) FwSmem {
+    unsigned long long full[kFwStages], empty[kFwStages], pfull[kFwStages], resFull[2], resEmpty[2];
+    int res[2][kFwCompute][kNSum];
+    int resTask[2][4];
+    FastStatic fsx;
+    FwStage st[kFwStages];
+};
 
 // ---- the kernel ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
@@ -788,50 +846,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) trk_fw_kernel(TrkDev g) {
     }
 }
 
-// First params of every channel for the current window (run start).  One CTA; warps take the
-// channels in turn, publish their first epoch and queue its slices; if nothing can run the grid is
-// told to terminate right away.
-__global__ void __launch_bounds__(1024) fw_prepare_kernel(TrkDev g, int nCtas) {
-    __shared__ EpochParams nps[32];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    if (threadIdx.x == 0) {
-        g.qctl[kQHead] = 0;
-        g.qctl[kQTail] = 0;
-        g.qctl[kQLeft] = (unsigned)g.nCh + 1u;   // every channel + this kernel hold a reference
-    }
-    __syncthreads();
-    for (int c = w; c < g.nCh; c += nw) {
-        int ok = 0, e = 0;
-        if (lane == 0) {
-            g.count[c] = 0;
-            if (g.cc[c].active) {
-                ChanState st = g.st[c];
-                g.cc[c].pad = st.epoch;
-                e = st.epoch;
-                ok = next_params(g, st, nps[w]) && st.epoch < g.epochLimit && g.maxEpochs > 0;
-                if (!ok && st.epoch < g.epochLimit && st.lockLost == 0)
-                    g.out[((size_t)c * kNFields + F_ABS) * g.capacity + st.epoch] = (double)st.pos;
-                g.ready[c] = ok ? e : e - 1;
-                g.stop[c] = ok ? INT_MAX : e;
-            } else {
-                g.stop[c] = 0;
-                g.ready[c] = -1;
-            }
-        }
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        e = __shfl_sync(0xffffffffu, e, 0);
-        __syncwarp();
-        if (ok) {
-            if (lane == 0) store_cg(g.params + c * 2 + (e & 1), nps[w]);
-            __threadfence();
-            __syncwarp();
-            fw_push_slices(g, c, e, nps[w], lane);
-        } else {
-            fw_channel_done(g, lane, nCtas);
-        }
-    }
-    __syncthreads();
-    if (w == 0) fw_channel_done(g, lane, nCtas);   // drop the kernel's own reference
-}
-
+}  // namespace FAST_GEOM_NS
+#ifndef FAST_GEOM_MULTI
+using namespace FAST_GEOM_NS;
+#endif
 }  // namespace bds

@@ -32,13 +32,14 @@ for the imaginary carrier table, straight into the accumulator of that segment's
 from which X = H2 - H1, SA, SB, SC, W1a, W1b, W2a, W2b follow by additions at the end of the chip.
 
 Usage: python gen_fast_wb.py [fs_hz fc_hz d] > bds_track_fast_gen.inc
+       python gen_fast_wb.py 53000000 1023000 3/50 > bds_track_fast_gen_53.inc   (B1C/initSettings.m:57)
 """
 from __future__ import annotations
 
 import sys
 from fractions import Fraction as F
 
-RANK_BINS = 512
+RANK_BINS = 512     # default; main() doubles it while the nominal thresholds are closer than three bins
 
 
 def geometry(fs, fc, d):
@@ -134,8 +135,16 @@ def main():
     fs = F(sys.argv[1]) if len(sys.argv) > 1 else F(99375000)
     fc = F(sys.argv[2]) if len(sys.argv) > 2 else F(1023000)
     d = F(sys.argv[3]) if len(sys.argv) > 3 else F(6, 100)
+    global RANK_BINS
     S, beta, R, theta = geometry(fs, fc, d)
-    order, pos, thr_nom, masks, rank_lo = rank_tables(R, theta)
+    while True:       # 99.375 MHz: 512 bins; the reference's shipped 53 MHz: 1024 (closest thresholds 0.0046 sample apart)
+        try:
+            order, pos, thr_nom, masks, rank_lo = rank_tables(R, theta)
+            break
+        except AssertionError:
+            if RANK_BINS >= 4096:
+                raise
+            RANK_BINS *= 2
     nsamp = R[36] + 1                  # samples 0..R36 (the last one is the end-boundary jitter sample)
     out = []
     w = out.append
@@ -147,6 +156,7 @@ def main():
     w("#define FAST_NWORDS %d" % ((nsamp + 3) // 4))
     w("#define FAST_RLAST %d" % R[36])
     w("#define FAST_RANK_BINS %d" % RANK_BINS)
+    w("#define FAST_RANK_BITS %d" % (RANK_BINS.bit_length() - 1))
     w("#define FAST_POS_LAST %d   /* sorted position of the chip-end threshold (boundary 36) */" % pos[35])
     w("#define FAST_SAMPLES_PER_CHIP %.17g" % float(12 * S))
     w("FAST_CONST int kFastR[37] = {%s};" % ", ".join(map(str, R)))
@@ -213,6 +223,12 @@ def main():
     for ln in comb:
         w("    " + ln + " \\")
     w("    /* end */")
+    # the file may be included once per geometry in one translation unit: drop the previous geometry's macros first
+    names = []
+    for ln in out:
+        if ln.startswith("#define "):
+            names.append(ln.split()[1].split("(")[0])
+    out[1:1] = ["#undef %s" % n for n in names]
     sys.stdout.write("\n".join(out) + "\n")
 
 

@@ -17,10 +17,12 @@ import pytest
 
 import bds_oracle as O
 from test_fast_b2a_hostcompile import SHIM, EpochParams, _block, _pack_bits
-from test_fast_rank_search import BETA, R
 
 CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bds-3-b1c-b2a-sdr-receiver_b200", "csrc")
-FS, L = 99.375e6, 10230
+L = 10230
+# chip-body geometries of the library (bds_track.cu): namespace, sampling rate, generated file
+GEOMS = {"g99": (99.375e6, "bds_track_fast_gen.inc"),      # BASELINE
+         "g53": (53e6, "bds_track_fast_gen_53.inc")}        # the reference's shipped B1C setting (B1C/initSettings.m:57)
 TWO32, TWO64 = 1 << 32, 1 << 64
 
 F2_SHIM = r"""
@@ -82,7 +84,7 @@ extern "C" int rank_check(const EpochParams* p, unsigned Psi, int* by_definition
     static FastTab tab;
     fast_load_static(&fsx, 0, 1);
     build_tab(&tab, fsx, *p, FAST_FS_HZ);
-    const int jlo = fsx.rankLo[Psi >> (32 - 9)];
+    const int jlo = fsx.rankLo[Psi >> (32 - FAST_RANK_BITS)];
     const int j = jlo + (tab.thr[jlo] < Psi);
     int n = 0;
     for (int k = 1; k <= 36; ++k) {
@@ -95,7 +97,7 @@ extern "C" int rank_check(const EpochParams* p, unsigned Psi, int* by_definition
 """
 
 
-def _build(tmp, flags=()):
+def _build(tmp, flags=(), geom="g99"):
     """bds_track_fast.cuh as it is (its CUDA-only helpers sit behind __CUDACC__), behind a stub of bds_track.cuh"""
     trk = open(os.path.join(CSRC, "bds_track.cuh")).read()
     stub = tmp / "stub"
@@ -105,8 +107,10 @@ def _build(tmp, flags=()):
         "constexpr int kNSum = 18;\nconstexpr int kPackedWordsDev = 320;",
         _block(trk, r"__host__ __device__ constexpr int sum_idx"), "enum { EPL_E = 0, EPL_P = 1, EPL_L = 2 };",
         _block(trk, r"struct EpochParams \{"), "}"]))
-    for f in ("bds_track_fast.cuh", "bds_track_fast_gen.inc"):
+    inc = GEOMS[geom][1]
+    for f in ("bds_track_fast.cuh", inc):
         (stub / f).write_text(open(os.path.join(CSRC, f)).read())
+    flags = tuple(flags) + ("-DFAST_GEOM_NS=" + geom, '-DFAST_GEN_INC="%s"' % inc)
     src = tmp / "b1c_host.cpp"
     src.write_text('#include "bds_track_fast.cuh"\n' + DRIVER)
     so = tmp / "b1c_host.so"
@@ -119,7 +123,7 @@ def _build(tmp, flags=()):
     return lib
 
 
-def make_epoch(rng, prn, rem, codeFreq, carrFreq, remCarr):
+def make_epoch(rng, prn, rem, codeFreq, carrFreq, remCarr, FS=99.375e6):
     """one block of the SURVEY 8(d) B1C signal model + noise, int8"""
     step = codeFreq / FS
     blk = int(math.ceil((L - rem) / step))
@@ -139,19 +143,25 @@ def make_epoch(rng, prn, rem, codeFreq, carrFreq, remCarr):
 NAMES = [f"{fam}_{iq}_{epl}" for fam in ("d", "p", "p61") for epl in ("E", "P", "L") for iq in ("I", "Q")]
 
 
-@pytest.fixture(scope="module")
-def hostlib(tmp_path_factory):
-    return _build(tmp_path_factory.mktemp("b1c_host"))
+@pytest.fixture(scope="module", params=sorted(GEOMS))
+def hostlib(request, tmp_path_factory):
+    lib = _build(tmp_path_factory.mktemp("b1c_host_" + request.param), geom=request.param)
+    lib.FS = GEOMS[request.param][0]
+    text = open(os.path.join(CSRC, GEOMS[request.param][1])).read()
+    lib.R = [int(v) for v in re.search(r"kFastR\[37\] = \{(.*?)\}", text).group(1).split(",")]
+    lib.BETA = [float(v) for v in re.search(r"kFastBeta\[37\] = \{(.*?)\}", text).group(1).split(",")]
+    return lib
 
 
 def test_fast_chip_source_on_host_equals_oracle(hostlib):
     lib = hostlib
+    FS = lib.FS
     rng = np.random.default_rng(33)
     prn = 19
     for rem, cf, fc_, rc, B0, guard in ((0.0, 1.023e6 - 2.7, 14.58e6 + 1830.0, 0.0, 7, 16),
                                         (0.0061, 1.023e6 + 1.9, 14.58e6 - 3920.0, 4.2, 993750 * 2 + 13, 16),
                                         (0.0033, 1.023e6 - 0.4, 14.58e6 + 55.0, 2.2, 48, 1 << 24)):
-        s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc)
+        s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc, FS)
         p = EpochParams(pos=B0, blksize=x.size, pad=0, rem=rem, step=step, carrFreq=fc_, remCarr=rc)
         bits = np.concatenate([_pack_bits(O.b1c_data_primary(prn)), _pack_bits(O.b1c_pilot_primary(prn))])
         tileBase = B0 & ~15
@@ -184,7 +194,7 @@ def test_code_rate_far_from_nominal_invalidates_the_table_and_stays_exact(hostli
     rng = np.random.default_rng(5)
     prn = 7
     rem, cf, fc_, rc, B0 = 0.0042, 1.023e6 * (1 + 60e-6), 14.58e6 + 300.0, 1.0, 32
-    s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc)
+    s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc, lib.FS)
     p = EpochParams(pos=B0, blksize=x.size, pad=0, rem=rem, step=step, carrFreq=fc_, remCarr=rc)
     bits = np.concatenate([_pack_bits(O.b1c_data_primary(prn)), _pack_bits(O.b1c_pilot_primary(prn))])
     tile = np.zeros(B0 + x.size + 256, dtype=np.int8)
@@ -206,6 +216,7 @@ def test_one_compare_rank_search_equals_the_definition(hostlib):
     """rank = number of thresholds below the sub-sample phase: table lookup + one compare (fast_chip) against counting
     all 36, for random phases, phases hugging every threshold from both sides, and code rates across +-12 kHz of Doppler"""
     lib = hostlib
+    FS, BETA, R = lib.FS, lib.BETA, lib.R
     rng = np.random.default_rng(12)
     for dopp in (-12000.0, -4500.0, 0.0, 37.0, 4500.0, 12000.0):
         cf = 1.023e6 * (1 - dopp / 1575.42e6)

@@ -516,3 +516,42 @@ def test_closed_loop_iq_record_array_and_file(mode, seconds, epochs, tmp_path):
         assert np.mean(err <= 1e-4) >= 0.99
         for k in ("carrFreq", "codeFreq"):
             np.testing.assert_allclose(g[k], o[k], rtol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["WB", "NB"])
+def test_chip_synchronous_kernel_at_the_reference_shipped_53_mhz(mode):
+    """The reference ships B1C with samplingFreq = 53 MHz (B1C/initSettings.m:57).  The chip-synchronous kernel has a
+    second instantiation for that geometry (51.8 samples per chip, 1/1024-sample rank bins): AUTO picks it, open-loop
+    sums equal the oracle's at 1e-4, the closed loop is checked one step at a time."""
+    import bds_oracle as O
+    from bds3_b200 import synth
+    s = O.initSettings_B1C(pilotTRKflag=2 if mode == "WB" else 1, numberOfChannels=2)
+    assert s.samplingFreq == 53e6 and s.IF == 1590e6 - 1575.42e6
+    sats = synth.make_sats(2, s, "B1C", seed=21, sigma=25.0, max_doppler=4500.0)
+    x = synth.synth_numpy("B1C", s, sats, int(0.23 * s.samplingFreq), sigma=25.0, seed=21)
+    ch = synth.channels_from_sats(sats, s, "B1C", freq_error=2.0)
+    tr, raw = util.oracle_track(mode, s, x, ch, 3)
+    nco = np.stack([t.nco for t in tr])
+    for wide_guard in (0, 1):
+        cfg = _track.make_cfg(mode, util.product_settings(s), L.KERNEL_FAST)
+        cfg.reserved = wide_guard
+        sums = np.zeros((2, 3, 18))
+        prn = np.asarray([c.PRN for c in ch], dtype=np.int32)
+        L.check(L.lib().bds_track_correlate_open_loop(MODES[mode], C.byref(cfg), L.ptr(x), x.size, L.LOC_HOST, L.ptr(prn),
+                                                      2, 3, L.ptr(np.ascontiguousarray(nco)), L.ptr(sums)))
+        err = np.abs(sums - raw) / util.family_scale(raw)
+        assert np.max(err[np.isfinite(err)]) <= 1e-4, np.max(err[np.isfinite(err)])
+        fast_chips, exact_chips, general_slices, _ = _track.counters(None)
+        assert general_slices == 0 and fast_chips + exact_chips == 2 * 3 * 10230
+        assert (0.1 < exact_chips / (2 * 3 * 10230) < 0.6) if wide_guard else exact_chips <= 2 * 3 + 2
+    ps = util.product_settings(s)
+    res, _ = _track.run_tracking(mode, x, ch, ps, n_epochs=20, raw=True)            # AUTO
+    fast_chips, exact_chips, general_slices, _ = _track.run_tracking.last_counters
+    assert general_slices == 0 and fast_chips + exact_chips == 2 * 20 * 10230 and exact_chips <= 64
+    for c in range(2):
+        assert res[c].status == "T"
+        assert util.one_step_parity(mode, s, x, ch[c], res[c], 20) <= 1e-4
+    gen, _ = _track.run_tracking(mode, x, ch, ps, n_epochs=20, kernel=L.KERNEL_GENERAL, raw=True)
+    for c in range(2):   # the two kernels follow the same trajectory up to chip-edge chaos
+        np.testing.assert_allclose(res[c].carrFreq, gen[c].carrFreq, rtol=0, atol=0.05)
+        np.testing.assert_allclose(res[c].absoluteSample, gen[c].absoluteSample, rtol=0, atol=1)
