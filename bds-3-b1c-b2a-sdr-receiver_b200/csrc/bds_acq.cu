@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) acq_inv_row_kernel(AcqPlan pl,
 }
 
 // ---- inverse column pass + magnitude + combine + max -------------------------------------
-struct AcqPeak {
+struct AcqPeak {   // 8 bytes (the specialised column pass reuses the slot for a packed 64-bit maximum)
     float val;
     int lag;  // 0-based
 };
@@ -626,7 +626,7 @@ acq_inv_row_ct_kernel(AcqPlan pl, const float2* __restrict__ sig, const float2* 
 template <int LG1, int LG2>
 __global__ void __launch_bounds__(inv_col_threads(LG1), 1024 / inv_col_threads(LG1))
 acq_inv_col_ct_kernel(AcqPlan pl, const float2* __restrict__ work, int ncodes, int combine, int lo0, int hi0, int lo1, int hi1,
-                      int useRanges, AcqPeak* __restrict__ peaks, const float2* __restrict__ twCol) {
+                      int useRanges, AcqPeak* __restrict__ peaks /*[bin]: packed, see below*/, const float2* __restrict__ twCol) {
     constexpr int NT = inv_col_threads(LG1), P1 = 1 << LG1, P2 = 1 << LG2;
     constexpr int DL = inv_last_d(LG1), QL = LG1 - DL, NL = 1 << QL, HL = 1 << DL;
     constexpr int itemsL = (P1 >> QL) * kColTile, itersL = itemsL / NT;
@@ -717,7 +717,12 @@ acq_inv_col_ct_kernel(AcqPlan pl, const float2* __restrict__ work, int ncodes, i
                 best = sv[w];
                 bl = sl[w];
             }
-        peaks[(size_t)bin * gridDim.x + blockIdx.x] = AcqPeak{best, bl};
+        // the bin's peak over all column tiles: largest value, then smallest lag, as ONE unsigned maximum of
+        // (value bits << 32 | 0x7fffffff - lag) - magnitudes are non-negative floats, whose bit patterns order like
+        // the values (acq_unpack_peak undoes it on the host); the slot is zeroed before the launch
+        if (best >= 0.f)
+            atomicMax(reinterpret_cast<unsigned long long*>(peaks) + bin,
+                      ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(0x7fffffff - bl));
     }
 }
 
@@ -1027,6 +1032,18 @@ std::vector<float2> inv_step_twiddles(int LG) {
     return t;
 }
 
+// peaks of the specialised column pass arrive packed (value bits << 32 | 0x7fffffff - lag), see acq_inv_col_ct_kernel
+void acq_unpack_peaks(std::vector<AcqPeak>& v) {
+    for (auto& p : v) {
+        unsigned long long u;
+        std::memcpy(&u, &p, 8);
+        const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+        float val;
+        std::memcpy(&val, &hi, 4);
+        p = u == 0 ? AcqPeak{-1.f, 0x7fffffff} : AcqPeak{val, (int)(0x7fffffffu - lo)};
+    }
+}
+
 unsigned long long freq_to_dphi(double f, double fs) {
     double r = f / fs;
     r -= std::floor(r);
@@ -1142,13 +1159,14 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
     const InvCt ct = find_inv_ct(pl, cfg->tune);
     // two blocking streams (ordered against the legacy default stream the rest of the call uses), made once per process
-    static cudaStream_t streams[2] = {nullptr, nullptr};
+    static cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
     static std::once_flag streamsOnce;
     std::call_once(streamsOnce, [] {
         for (auto& st : streams)
             if (cudaStreamCreate(&st) != cudaSuccess) st = nullptr;
     });
-    const int nStreams = (streams[0] && streams[1] && !(cfg->tune & 4)) ? 2 : 1;
+    const bool haveStreams = streams[0] && streams[1] && streams[2] && streams[3];
+    const int nStreams = !haveStreams || (cfg->tune & 4) ? 1 : ((cfg->tune & 8) ? 4 : 2);
     size_t workElems = 0, peakElems = 0;
     const size_t smemRowCt = sizeof(float2) * ((size_t)(pl.P2 + (pl.P2 >> 4)) << ct.lgRT);
     DevBuf dTwRowS, dTwColS;
@@ -1174,8 +1192,10 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
         if (ct.row) {
             ct.row<<<dim3((pl.P1 >> ct.lgRT) * ncodes, nb), ct.thrRow, smemRowCt, st>>>(pl, sigBins, code, work, ncodes, binMap,
                                                                                      dTwRowS.as<float2>());
-            ct.col<<<dim3(colGroups, nb), ct.thrCol, smemColInv, st>>>(pl, work, ncodes, combine, lo0, hi0, lo1, hi1, useRanges, pk,
+            ct.col<<<dim3(colGroups, nb), ct.thrCol, smemColInv, st>>>(pl, work, ncodes, combine, lo0, hi0, lo1, hi1, useRanges, out,
                                                                        dTwColS.as<float2>());
+            count_launch(2);
+            return;
         } else {
             acq_inv_row_kernel<<<dim3(pl.P1 / rowTile, nb, ncodes), thrRow, smemRow, st>>>(pl, sigBins, code, work, ncodes, binMap);
             acq_inv_col_kernel<<<dim3(colGroups, nb), thrCol, smemColInv, st>>>(pl, work, ncodes, combine, lo0, hi0, lo1, hi1,
@@ -1276,6 +1296,7 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
         count_launch(2);
         // ---- phase 1: coarse PRN x Doppler grid; per (PRN, bin) peak and first lag
         TRYA(dBinPeak.alloc(sizeof(AcqPeak) * (size_t)nbins * nSel));
+        if (ct.row) TRYA(cudaMemset(dBinPeak.p, 0, sizeof(AcqPeak) * (size_t)nbins * nSel));
         for (int i = 0; i < nSel; ++i) {
             const float2* code = dCode.as<float2>() + (size_t)i * ncodes * pl.P;
             for (int b0 = 0; b0 < nbins; b0 += binsPerBatch) {
@@ -1287,6 +1308,7 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
         TRYA(cudaGetLastError());
         std::vector<AcqPeak> binPeak((size_t)nbins * nSel);
         TRYA(cudaMemcpy(binPeak.data(), dBinPeak.p, sizeof(AcqPeak) * binPeak.size(), cudaMemcpyDeviceToHost));
+        if (ct.row) acq_unpack_peaks(binPeak);
         std::vector<Cand> cand(nSel);
         for (int i = 0; i < nSel; ++i) {
             // [~, bin] = max(max(results,[],2)); [peak, codePhase] = max(max(results))  (first index wins)
@@ -1313,6 +1335,7 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
             // second peak in the best bin's row, excluding +-samples2CodeChip around the peak and
             // its one-period image   (B2a acquisition.m:224-252)
             TRYA(dSecond.alloc(sizeof(AcqPeak) * nSel));
+            if (ct.row) TRYA(cudaMemset(dSecond.p, 0, sizeof(AcqPeak) * nSel));
             TRYA(dBinMap.alloc(sizeof(int) * nSel));
             std::vector<int> bm(nSel);
             for (int i = 0; i < nSel; ++i) bm[i] = cand[i].bestBin;
@@ -1335,6 +1358,7 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
             }
             std::vector<AcqPeak> second(nSel);
             TRYA(cudaMemcpy(second.data(), dSecond.p, sizeof(AcqPeak) * nSel, cudaMemcpyDeviceToHost));
+            if (ct.row) acq_unpack_peaks(second);
             for (int i = 0; i < nSel; ++i) {
                 cand[i].norm = second[i].val;
                 cand[i].metric = (double)cand[i].peak / (double)second[i].val;

@@ -109,7 +109,7 @@ typedef struct bds_acq_cfg {
     int32_t resamplingflag;     /* settings.resamplingflag */
     int32_t tune;               /* 0.  Test / developer hook, results unchanged: bit 0 = run the inverse passes on the generic
                                  * kernels for every transform shape, bit 1 = other row tiling of the specialised row pass,
-                                 * bit 2 = inverse passes on one stream instead of two */
+                                 * bit 2 = inverse passes on one stream instead of two, bit 3 = on four */
 } bds_acq_cfg;
 
 /* Replaces acquisition(longSignal, settings):
