@@ -1238,8 +1238,10 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     TRYA(cudaMemGetInfo(&freeB, &totalB));
     const size_t perPrn = specBytes * ncodes + (size_t)spc * ncodes;
     const int chunkMax = (int)std::max<size_t>(1, std::min<size_t>(64, (freeB / 3) / perPrn));
-    // bins per batch: keep the inverse-row output of a batch resident in L2 for the inverse-column pass
-    const int binsPerBatch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nbins, (size_t)8, ((size_t)96 << 20) / (specBytes * ncodes)}));
+    // bins per launch: the row pass's output of a launch (two launches are in flight, one per stream) has to stay in L2
+    // until the column pass has read it back.  Measured on the B2a grid (4 MB transforms): 4 bins 16.1 ms, 8 bins 16.6 ms,
+    // 16 bins 18.4 ms, 26 bins 19.2 ms; B1C (32 MB transforms, 64 MB per bin): 1 bin 129 ms, 2 bins 132 ms
+    const int binsPerBatch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nbins, (size_t)8, ((size_t)32 << 20) / (specBytes * ncodes)}));
     workElems = (size_t)pl.P * ncodes * binsPerBatch;
     peakElems = (size_t)colGroups * binsPerBatch;
     TRYA(dWork.alloc(sizeof(float2) * workElems * nStreams));
