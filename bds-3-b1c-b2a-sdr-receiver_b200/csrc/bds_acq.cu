@@ -1158,13 +1158,21 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     const int thrRow = std::min(kAcqThreads, std::max(128, (pl.P2 >> 4) * rowTile));
     const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
     const InvCt ct = find_inv_ct(pl, cfg->tune);
-    // two blocking streams (ordered against the legacy default stream the rest of the call uses), made once per process
+    // blocking streams (ordered against the legacy default stream the rest of the call uses), made once per device
     static cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
-    static std::once_flag streamsOnce;
-    std::call_once(streamsOnce, [] {
-        for (auto& st : streams)
-            if (cudaStreamCreate(&st) != cudaSuccess) st = nullptr;
-    });
+    static int streamsDev = -1;
+    static std::mutex streamsMu;
+    {
+        std::lock_guard<std::mutex> lock(streamsMu);
+        int dev = -1;
+        TRYA(cudaGetDevice(&dev));
+        if (dev != streamsDev) {    // first call, or the caller moved to another device (bds_init)
+            for (auto& st : streams) st = nullptr;   // streams of another device stay with that device's context
+            for (auto& st : streams)
+                if (cudaStreamCreate(&st) != cudaSuccess) st = nullptr;
+            streamsDev = dev;
+        }
+    }
     const bool haveStreams = streams[0] && streams[1] && streams[2] && streams[3];
     const int nStreams = !haveStreams || (cfg->tune & 4) ? 1 : ((cfg->tune & 8) ? 4 : 2);
     size_t workElems = 0, peakElems = 0;
