@@ -63,7 +63,14 @@ extern "C" {
 #define BDS_LOC_DEVICE 1
 
 /* kernel selection for tracking (BDS_KERNEL_AUTO picks the chip-synchronous
- * fast path when the configuration allows it, else the general kernel) */
+ * fast path when the configuration allows it, else the general kernel).
+ * Configurations with a chip-synchronous kernel - real samples (fileType 1), codeLength 10230 and
+ *   B1C WB (pilotTRKflag 2) / NB with pilot: codeFreqBasis 1.023e6, dllCorrelatorSpacing 0.06,
+ *       samplingFreq 99.375e6 or 53e6 (B1C/initSettings.m:57), up to 1023 channels per session;
+ *   B2a: codeFreqBasis 10.23e6, dllCorrelatorSpacing 0.5, samplingFreq 99.375e6 (B2a/initSettings.m:64).
+ * Everything else (other rates / spacings, I/Q records, data-only modes) runs on the general kernel: same
+ * results, roughly 30x slower per sample.  BDS_KERNEL_FAST fails with BDS_ERR_UNSUPPORTED instead of falling
+ * back; bds_track_counters() tells which kernel ran. */
 #define BDS_KERNEL_AUTO 0
 #define BDS_KERNEL_GENERAL 1
 #define BDS_KERNEL_FAST 2
