@@ -333,7 +333,7 @@ def repo_native_libraries():
 
 # ----------------------------------------------------------------------------------------------
 def self_check(sess, st, chans, n_epochs, x_dev, n_samples, mode="WB", injected_cn0=45.0, n_sampled_channels=3,
-               n_sampled_epochs=20, kappa_db=-64.8):
+               n_sampled_epochs=20, kappa_db=-64.8, seconds_tail=10.0):
     """Untimed checks on the result of the timed run (VERDICT r1 'make the headline run prove its own correctness'):
       * every channel completed every epoch;
       * the loop bookkeeping of EVERY epoch of EVERY channel follows from the device's own discriminators through the
@@ -356,7 +356,7 @@ def self_check(sess, st, chans, n_epochs, x_dev, n_samples, mode="WB", injected_
     act = [c for c in chans if c.PRN != 0]
     assert len(act) == len(chans)
     mem = util.replay_loop_chain(mode, so, act, planes, N)                      # [N, 4, nch]
-    lock = util.lock_report(mode, so, planes, N, seconds_tail=10.0)
+    lock = util.lock_report(mode, so, planes, N, seconds_tail=seconds_tail)
     # effective C/N0 with K-1 equal-power interferers: C / (N0 + (K-1) C kappa), kappa = the signal's self spectral
     # separation coefficient (BOC(1,1): -64.8 dB/Hz, BPSK(10): -71.9 dB/Hz); the estimator itself scatters by about
     # +-1 dB over an interval

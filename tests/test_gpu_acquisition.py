@@ -203,3 +203,26 @@ def test_specialised_inverse_passes_equal_the_generic_kernels(signal):
         np.testing.assert_array_equal(got.codePhase, ref.codePhase)
         np.testing.assert_array_equal(got.carrFreq, ref.carrFreq)
         np.testing.assert_allclose(got.peakMetric, ref.peakMetric, rtol=2e-5)
+
+
+def test_b1c_acquisition_at_the_reference_shipped_53_mhz():
+    """B1C/initSettings.m:57 ships samplingFreq = 53 MHz: N = 1 060 000, P = 2^21 = 2^9 x 2^12 - the third shape the inverse
+    passes are specialised for.  Same bin, code phase and fine frequency as the oracle, metric within 1e-4; and equal to the
+    generic kernels (cfg.tune bit 0)."""
+    s = O.initSettings_B1C(acqSearchBand=200, acqSatelliteList=[1, 2, 3])
+    assert s.samplingFreq == 53e6
+    sats = synth.make_sats(2, s, "B1C", seed=7, max_doppler=140.0, cn0=47.0)
+    x = synth.synth_numpy("B1C", s, sats, int(0.0305 * s.samplingFreq), seed=7)
+    want, wd = O.acquisition_B1C(x, s, return_debug=True)
+    got, gd = B.b1c.acquisition(x, B.Settings(dict(s)), return_debug=True)
+    for prn in (1, 2, 3):
+        assert gd[prn - 1, 0] == wd[prn]["bin"]
+        assert gd[prn - 1, 1] == wd[prn]["codePhase"]
+    np.testing.assert_allclose(got.peakMetric, want.peakMetric, rtol=1e-4)
+    np.testing.assert_array_equal(got.codePhase, want.codePhase)
+    np.testing.assert_array_equal(got.carrFreq, want.carrFreq)
+    assert np.count_nonzero(want.carrFreq) == 2
+    gen, dd = B.b1c.acquisition(x, B.Settings(dict(s, _tune=1)), return_debug=True)
+    np.testing.assert_array_equal(dd[:, :2], gd[:, :2])
+    np.testing.assert_allclose(dd[:, 2:], gd[:, 2:], rtol=2e-5)
+    np.testing.assert_array_equal(gen.carrFreq, got.carrFreq)
