@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/r3n
+O=gpurun_out/r3n2
 mkdir -p $O
 # one --set full capture of each inverse kernel, B2a (P = 2^19) and B1C (P = 2^22), taken from the bench command itself
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:acq_inv_ -s 40 -c 2 -f -o $O/acq_inv_b2a \
