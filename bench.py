@@ -112,6 +112,18 @@ def measured_traffic(kernel, channels, seconds, world, key="dram_bytes_per_launc
     return None
 
 
+def acq_traffic(b1c, cells):
+    """DRAM bytes of the inverse passes of one call: the per-cell figure of the committed capture (profiles/traffic.json)
+    x the cells of the grid; else None"""
+    try:
+        for e in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))):
+            if e["kernel"] == ("acq_inv_b1c" if b1c else "acq_inv_b2a"):
+                return int(e["dram_bytes_per_cell"] * cells)
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -1176,8 +1188,8 @@ def run_acq_b2a(args, b1c=False):
                                                                "BASELINE config 2: B2a 63-PRN x +-5 kHz acquisition, 17 ms int8 IF at 99.375 MHz"),
                                                   "prns_found": found, "injected": [s_.PRN for s_ in sats]},
                 "roofline": {"bound": "hbm", "achieved": alg / float(tt[0]) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": alg / float(tt[0]) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "acq_inv_row_kernel + acq_inv_col_kernel (whole bds_acquire call: host code generation, allocation and the three phase synchronisations included)",
+                             "frac": alg / float(tt[0]) / 1e9 / peak, "traffic": acq_traffic(b1c, cells), "peak_source": peak_src,
+                             "kernel": "acq_inv_row_ct_kernel + acq_inv_col_ct_kernel (whole bds_acquire call: host code generation, allocation and the three phase synchronisations included)",
                              "algorithmic_bytes_per_launch": alg},
                 "e2e": {"value": cells / float(tt[1]), "unit": "cells/s", "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": 3 * n_prn * 8},
                 "gpu_launches": int(launches)}
