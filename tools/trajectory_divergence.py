@@ -42,7 +42,8 @@ def main():
     out = {"epochs": n_epochs, "seconds": n_epochs * 0.01, "channel_prn": int(ch[0].PRN),
            "max_abs_carrFreq_Hz": float(np.max(np.abs(g.carrFreq - o.carrFreq))),
            "max_abs_codeFreq_Hz": float(np.max(np.abs(g.codeFreq - o.codeFreq))),
-           "max_abs_remCodePhase_chips": float(np.max(np.abs(g.remCodePhase - o.remCodePhase))),
+           "max_abs_code_phase_chips": float(np.max(np.abs(g.remCodePhase - (g.absoluteSample - o.absoluteSample)
+                                                             * (o.codeFreq / s.samplingFreq) - o.remCodePhase))),
            "max_abs_absoluteSample": float(np.max(np.abs(g.absoluteSample - o.absoluteSample))),
            "max_rel_prompt": float(np.max(np.hypot(g.I_P - o.I_P, g.Q_P - o.Q_P) / np.hypot(o.I_P, o.Q_P))),
            "first_epoch_rel_err_18_sums": float(np.max(np.abs(g.raw[0] - raw[0][0]) / util.family_scale(raw[0][0][None, :])[0])),
