@@ -943,6 +943,10 @@ struct PoolBlock {
 };
 std::mutex g_poolMu;
 std::vector<PoolBlock> g_pool;
+// streams of the inverse passes (acquire_core), made once per device, destroyed by bds_shutdown
+std::mutex g_streamsMu;
+cudaStream_t g_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+int g_streamsDev = -1;
 
 struct DevBuf {
     void* p = nullptr;
@@ -1159,19 +1163,18 @@ int acquire_core(int signal, const int8_t* dx, int fmt, size_t n, const bds_acq_
     const int thrCol = std::min(kAcqThreads, std::max(128, (pl.P1 >> 4) * kColTile));
     const InvCt ct = find_inv_ct(pl, cfg->tune);
     // blocking streams (ordered against the legacy default stream the rest of the call uses), made once per device
-    static cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
-    static int streamsDev = -1;
-    static std::mutex streamsMu;
+    cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
     {
-        std::lock_guard<std::mutex> lock(streamsMu);
+        std::lock_guard<std::mutex> lock(g_streamsMu);
         int dev = -1;
         TRYA(cudaGetDevice(&dev));
-        if (dev != streamsDev) {    // first call, or the caller moved to another device (bds_init)
-            for (auto& st : streams) st = nullptr;   // streams of another device stay with that device's context
-            for (auto& st : streams)
+        if (dev != g_streamsDev) {    // first call, or the caller moved to another device (bds_init)
+            for (auto& st : g_streams) st = nullptr;   // streams of another device stay with that device's context
+            for (auto& st : g_streams)
                 if (cudaStreamCreate(&st) != cudaSuccess) st = nullptr;
-            streamsDev = dev;
+            g_streamsDev = dev;
         }
+        for (int k = 0; k < 4; ++k) streams[k] = g_streams[k];
     }
     const bool haveStreams = streams[0] && streams[1] && streams[2] && streams[3];
     const int nStreams = !haveStreams || (cfg->tune & 4) ? 1 : ((cfg->tune & 8) ? 4 : 2);
@@ -1625,5 +1628,14 @@ void acq_pool_release() {
     std::lock_guard<std::mutex> lock(g_poolMu);
     for (auto& b : g_pool) cudaFree(b.p);
     g_pool.clear();
+}
+void acq_streams_release() {   // bds_shutdown only: no acquisition is in flight
+    std::lock_guard<std::mutex> lk(g_streamsMu);
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev == g_streamsDev)
+        for (auto& st : g_streams)
+            if (st) cudaStreamDestroy(st);
+    for (auto& st : g_streams) st = nullptr;
+    g_streamsDev = -1;
 }
 }  // namespace bds

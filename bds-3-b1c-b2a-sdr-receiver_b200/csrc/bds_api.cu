@@ -64,6 +64,7 @@ void bds_shutdown(void) {
     if (g_device >= 0) {
         cudaDeviceSynchronize();
         acq_pool_release();
+        acq_streams_release();
     }
     g_device = -1;
 }

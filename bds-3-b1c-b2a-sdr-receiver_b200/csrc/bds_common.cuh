@@ -31,6 +31,7 @@ int require_device();
 
 // frees the device work buffers pooled by bds_acquire (bds_acq.cu)
 void acq_pool_release();
+void acq_streams_release();
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# acquisition A/B over cfg.tune values: bash tools/r3_acq_ab.sh 16 32 ...
+# acquisition A/B over cfg.tune values (bdsgpu.h: 1 generic kernels, 2 other row tiling, 4 one stream, 8 four streams): bash tools/r3_acq_ab.sh 0 4 8
 O=gpurun_out/r3ab
 mkdir -p $O
 run() { name=$1; shift; echo "== $name: $*"; timeout 900 "$@" > $O/$name.json 2> $O/$name.err; echo "rc=$?"; tail -c 160 $O/$name.err; python tools/bench_show.py $O/$name.json; echo; }
