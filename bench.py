@@ -60,7 +60,7 @@ def parse():
                     help="length of the synthetic IF record (BASELINE config 4: 30 s)")
     ap.add_argument("--channels", type=int, default=N_CHANNELS)
     ap.add_argument("--fs", type=float, default=FS,
-                    help="--workload track only: sampling rate of the synthetic record [Hz]; 99.375e6 = BASELINE config 4, "
+                    help="--workload track / acq_b1c: sampling rate of the synthetic record [Hz]; 99.375e6 = BASELINE config 4, "
                          "53e6 = the reference's shipped B1C setting (B1C/initSettings.m:57)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast"])
     ap.add_argument("--workload", default="track", choices=["track", "track_b2a", "dual", "pipeline", "acq_b2a", "acq_b1c"],
@@ -1132,7 +1132,7 @@ def run_acq_b2a(args, b1c=False):
     if b1c:
         st = B.b1c.initSettings(samplingFreq=FS, acqSatelliteList=list(range(1, n_prn + 1)))
         inj = [2, 5]
-        n = 4 * 993750                                        # >= len10PlusXms + samplesPerCode (B1C/acquisition.m:135,239-241)
+        n = 4 * int(round(FS * 0.01))                         # >= len10PlusXms + samplesPerCode (B1C/acquisition.m:135,239-241)
     else:
         st = B.b2a.initSettings(acqSatelliteList=list(range(1, n_prn + 1)))
         inj = [2, 9, 17, 23, 31, 40, 52, 61]
@@ -1175,20 +1175,22 @@ def run_acq_b2a(args, b1c=False):
     found = sorted(int(p) + 1 for p in np.nonzero(acq.carrFreq)[0])
     if rank == 0:
         cells = n_prn * nbins
-        P = 1 << (22 if b1c else 19)
+        lgP = (22 if FS == 99.375e6 else max(8, int(math.ceil(math.log2(3 * round(FS * 0.01) - 1))))) if b1c else 19
+        P = 1 << lgP                                          # 2^22 at 99.375 MHz, 2^21 at the shipped 53 MHz (N + M - 1 = 3 code periods - 1)
         # algorithmic bytes: per (PRN, bin) cell 2 inverse P-point complex-fp32 FFTs x 2 passes x (read+write)
         # x 8 B; + per bin one forward FFT (shared by all PRNs) and per PRN two code FFTs, 2 passes each
         alg = (cells * 2 + nbins + n_prn * 2) * 2 * 2 * 8 * P / world
         peak, peak_src = peaks()
-        line = {"metric": f"{sig_name} acquisition grid cells/s ({n_prn} PRN x {nbins} Doppler bins, 2^{22 if b1c else 19}-point FFT, data+pilot)",
+        line = {"metric": f"{sig_name} acquisition grid cells/s ({n_prn} PRN x {nbins} Doppler bins, 2^{lgP}-point FFT, data+pilot)",
                 "value": cells / float(tt[0]),
                 "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(tt[0]) * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (complex FFT), int8 IF",
-                "data": "synthetic", "config": {"workload": (f"B1C {n_prn}-PRN x +-5 kHz acquisition (50 Hz bins, 10 ms coherent), int8 IF at 99.375 MHz" if b1c else
+                "data": "synthetic", "config": {"workload": (f"B1C {n_prn}-PRN x +-5 kHz acquisition (50 Hz bins, 10 ms coherent), int8 IF at {FS / 1e6:g} MHz" if b1c else
                                                                "BASELINE config 2: B2a 63-PRN x +-5 kHz acquisition, 17 ms int8 IF at 99.375 MHz"),
                                                   "prns_found": found, "injected": [s_.PRN for s_ in sats]},
                 "roofline": {"bound": "hbm", "achieved": alg / float(tt[0]) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": alg / float(tt[0]) / 1e9 / peak, "traffic": acq_traffic(b1c, cells), "peak_source": peak_src,
+                             "frac": alg / float(tt[0]) / 1e9 / peak, "traffic": acq_traffic(b1c, cells) if FS == 99.375e6 else None,
+                             "peak_source": peak_src,
                              "kernel": "acq_inv_row_ct_kernel + acq_inv_col_ct_kernel (whole bds_acquire call: host code generation, allocation and the three phase synchronisations included)",
                              "algorithmic_bytes_per_launch": alg},
                 "e2e": {"value": cells / float(tt[1]), "unit": "cells/s", "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": 3 * n_prn * 8},
@@ -1211,8 +1213,8 @@ def main():
     global FS
     args = parse()
     if args.fs != FS:
-        if args.workload != "track":
-            raise SystemExit("--fs applies to --workload track")
+        if args.workload not in ("track", "acq_b1c"):
+            raise SystemExit("--fs applies to --workload track and acq_b1c")
         FS = float(args.fs)
         TRACK["track"]["spc"] = int(round(FS * 0.01))     # samples per 10 ms B1C code period
     if args.impl == "reference":
