@@ -622,6 +622,18 @@ __global__ void __launch_bounds__(kTrkThreads) trk_prepare_kernel(TrkDev g) {
 #define FAST_GEN_INC "bds_track_fast_gen_53.inc"
 #include "bds_track_fast.cuh"
 #include "bds_track_fw.cuh"
+#undef FAST_GEOM_NS
+#undef FAST_GEN_INC
+#define FAST_GEOM_NS g99n         // narrow-band bodies (NB_tracking.m: data + BOC(1,1) pilot, six segments per chip)
+#define FAST_GEN_INC "bds_track_fast_gen_nb.inc"
+#include "bds_track_fast.cuh"
+#include "bds_track_fw.cuh"
+#undef FAST_GEOM_NS
+#undef FAST_GEN_INC
+#define FAST_GEOM_NS g53n
+#define FAST_GEN_INC "bds_track_fast_gen_53_nb.inc"
+#include "bds_track_fast.cuh"
+#include "bds_track_fw.cuh"
 #include "bds_track_b2a.cuh"
 namespace bds {
 // the instantiations of the chip-synchronous B1C kernel
@@ -631,10 +643,13 @@ struct FwGeom {
     void (*kernel)(TrkDev);
     size_t smemBytes;
 };
-static const FwGeom kFwGeoms[] = {
+static const FwGeom kFwGeoms[] = {   // first match wins: the narrow-band bodies come before the wide-band ones, which also serve NB
+    {"fs = 99.375 MHz, narrow band", g99n::fast_wb_supported, g99n::trk_fw_kernel, sizeof(g99n::FwSmem)},
+    {"fs = 53 MHz, narrow band", g53n::fast_wb_supported, g53n::trk_fw_kernel, sizeof(g53n::FwSmem)},
     {"fs = 99.375 MHz", g99::fast_wb_supported, g99::trk_fw_kernel, sizeof(g99::FwSmem)},
     {"fs = 53 MHz", g53::fast_wb_supported, g53::trk_fw_kernel, sizeof(g53::FwSmem)},
 };
+constexpr int kFwGeomFirstWide = 2;   // cfg.reserved bit 1 (test hook): narrow band on the wide-band body, as before the NB bodies existed
 constexpr int kFwGeomCount = (int)(sizeof(kFwGeoms) / sizeof(kFwGeoms[0]));
 }  // namespace bds
 namespace bds {
@@ -827,7 +842,7 @@ int choose_fast(int mode, const bds_trk_cfg* cfg, bool& fast, int& geom) {
     const bool iq = cfg->fileType == 2;   // the chip-synchronous bodies pack real samples: I/Q records take the general kernel
     bool can = false;
     geom = 0;
-    for (int k = 0; k < kFwGeomCount && !iq && !can; ++k)
+    for (int k = (cfg->reserved & 2) ? kFwGeomFirstWide : 0; k < kFwGeomCount && !iq && !can; ++k)
         if (kFwGeoms[k].supported(mode, hasPilot, hasP61, cfg->samplingFreq, cfg->codeFreqBasis, cfg->codeLength,
                                   cfg->dllCorrelatorSpacing)) {
             can = true;

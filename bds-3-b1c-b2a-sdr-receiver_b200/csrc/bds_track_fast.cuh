@@ -52,7 +52,7 @@ constexpr unsigned kFastNomTol = 1u << (32 - FAST_RANK_BITS - 1);   // a thresho
 // epoch's NCO parameters alone (48 bytes travel from the loop closure to the correlator, nothing else).
 struct __align__(16) FastTab {
     int4 w[FAST_NWORDS + 1];            // per 4-sample word: {wr01, wr23, wi01, wi23}, int16 pairs, Q15 exp(-i 2 pi r dphi)
-    unsigned thr[40];                   // thresholds in the (generation-time) sorted order, 2^32 fixed point; [36..] = 0xffffffff
+    unsigned thr[40];                   // thresholds in the (generation-time) sorted order, 2^32 fixed point; [FAST_NSEG..] = 0xffffffff
     double u0, sigma, S;                // 12*rem, 12*step, 1/sigma
     unsigned long long dphi, phi0;      // carrier NCO, 2^-64 turns
     int valid;                          // thresholds within kFastNomTol of nominal (else every chip takes the exact path)
@@ -74,15 +74,20 @@ static_assert(sizeof(FastStatic) % 16 == 0, "FastStatic must be a 16-byte multip
 // B1C with a pilot: wide band (data + BOC(1,1) + BOC(6,1) pilot, 18 sums) or narrow band (the same minus the
 // BOC(6,1) replica, 12 sums — the unused sums are zeroed by the epilogue warp).
 inline bool fast_wb_supported(int mode, int hasPilot, int hasP61, double fs, double fc, int codeLength, double d) {
+#if FAST_NB   // narrow-band body: data + BOC(1,1) pilot only
+    (void)hasP61;
+    const bool modeOk = mode == BDS_TRK_B1C_NB && hasPilot;
+#else
     const bool modeOk = (mode == BDS_TRK_B1C_WB && hasP61) || (mode == BDS_TRK_B1C_NB && hasPilot);
+#endif
     return modeOk && codeLength == 10230 && fs == FAST_FS_HZ && fc == FAST_FC_HZ && d == FAST_D;
 }
 
 // one thread's share of the copy of the static tables (tid = 0 .. nthreads-1; followed by a CTA barrier)
 __device__ inline void fast_load_static(FastStatic* fsx, int tid, int nthreads) {
-    for (int i = tid; i < 37; i += nthreads)
+    for (int i = tid; i < FAST_NSEG + 1; i += nthreads)
         fsx->mask[i] = make_uint2((unsigned)kFastMask[i], (unsigned)(kFastMask[i] >> 32));
-    for (int i = tid; i < 36; i += nthreads) {
+    for (int i = tid; i < FAST_NSEG; i += nthreads) {
         fsx->thrNom[i] = kFastThrNom[i];
         fsx->pos[i] = kFastPos[i];
     }
@@ -108,7 +113,7 @@ __device__ inline int fast_build_tab_lane(FastTab* tab, const FastStatic& fsx, c
     }
     int ok = 1;
     for (int t = lane; t < 40; t += 32) {
-        if (t < 36) {
+        if (t < FAST_NSEG) {
             const int k = t + 1;
             double th = kFastBeta[k] * S - (double)kFastR[k];  // theta_k / sigma
             th = fmin(fmax(th, 0.0), 1.0);
@@ -388,7 +393,10 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
         const float rr = cs * (1.0f / 32767.0f), ri = -sn * (1.0f / 32767.0f);
         const f2_t rotA = f2_pk(rr, ri), rotB = f2_pk(-ri, rr);
 #define ROT(N) const f2_t N##p = f2_sfma((float)N##i, rotB, f2_mul(f2_pk((float)N##r, (float)N##r), rotA));
-        ROT(SA) ROT(SB) ROT(SC) ROT(X) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
+#if !FAST_NB
+        ROT(SA) ROT(SB) ROT(SC)
+#endif
+        ROT(X) ROT(W1a) ROT(W1b) ROT(W2a) ROT(W2b)
 #undef ROT
         const int cp_ = c == 0 ? 10229 : c - 1, cn_ = c == 10229 ? 0 : c + 1;
         const float cd = bit_of(bitsData, c) ? -1.f : 1.f, cdp = bit_of(bitsData, cp_) ? -1.f : 1.f,
@@ -397,8 +405,10 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
                     cpn = bit_of(bitsPilot, cn_) ? -1.f : 1.f;
         const f2_t XEp = f2_sfma(-2.f, W1bp, f2_add(Xp, W1ap));
         const f2_t XLp = f2_sfma(2.f, W2ap, f2_sub(Xp, W2bp));
+#if !FAST_NB
         const f2_t sAB = f2_add(SAp, SBp), sBC = f2_add(SBp, SCp);
         const f2_t SPp = f2_add(sAB, SCp), SEp = f2_sub(SCp, sAB), SLp = f2_sub(SAp, sBC);
+#endif
 #define ACC2(fam, epl, expr)                                       \
     {                                                              \
         const f2_t a0 = acc[sum_idx(fam, epl, 0) >> 1];            \
@@ -410,9 +420,11 @@ __device__ __forceinline__ bool fast_chip(const FastTab& tab, const FastStatic& 
         ACC2(1, EPL_P, f2_sfma(cp, Xp, a0))
         ACC2(1, EPL_E, f2_sfma(cp, XEp, f2_sfma(cpp, W1ap, a0)))
         ACC2(1, EPL_L, f2_sfma(cp, XLp, f2_sfma(-cpn, W2bp, a0)))
+#if !FAST_NB
         ACC2(2, EPL_P, f2_sfma(cp, SPp, a0))
         ACC2(2, EPL_E, f2_sfma(cp, SEp, f2_sfma(cpp - cp, W1ap, a0)))
         ACC2(2, EPL_L, f2_sfma(cp, SLp, f2_sfma(cp - cpn, W2bp, a0)))
+#endif
 #undef ACC2
 #endif  // BDS_ABL & 1
     } else {

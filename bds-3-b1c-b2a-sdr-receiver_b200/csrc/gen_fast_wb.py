@@ -31,8 +31,15 @@ for the imaginary carrier table, straight into the accumulator of that segment's
     A1,B1,A7,B7,B6,C6,B12,C12 - the eight segments that also form the BOC(1,1) early/late windows
 from which X = H2 - H1, SA, SB, SC, W1a, W1b, W2a, W2b follow by additions at the end of the chip.
 
+Narrow band (`nb` as a fourth argument): NB_tracking.m correlates the data and the BOC(1,1) pilot only, whose E/P/L replicas
+change sign at 0, d, 1/2-d, 1/2, 1/2+d, 1-d of a chip: SIX segments instead of 36.  The body then accumulates the six segment
+sums N0..N5 directly (most words are unmasked) and the combination reduces to X = (N3+N4+N5) - (N0+N1+N2), W1a = N0, W2a = N2,
+W1b = N3, W2b = N5 - the five basis sums the data / BOC(1,1) tail of fast_chip uses; SA, SB, SC do not exist.
+
 Usage: python gen_fast_wb.py [fs_hz fc_hz d] > bds_track_fast_gen.inc
        python gen_fast_wb.py 53000000 1023000 3/50 > bds_track_fast_gen_53.inc   (B1C/initSettings.m:57)
+       python gen_fast_wb.py 99375000 1023000 3/50 nb > bds_track_fast_gen_nb.inc
+       python gen_fast_wb.py 53000000 1023000 3/50 nb > bds_track_fast_gen_53_nb.inc
 """
 from __future__ import annotations
 
@@ -42,24 +49,29 @@ from fractions import Fraction as F
 RANK_BINS = 512     # default; main() doubles it while the nominal thresholds are closer than three bins
 
 
-def geometry(fs, fc, d):
+def geometry(fs, fc, d, nb=False):
     S = fs / (12 * fc)                 # samples per sub-chip
     delta = 12 * d
     assert F(1, 2) < delta < 1, "generator assumes 0.5 < 12*d < 1"
     beta = []
-    for j in range(12):
-        beta += [F(j), j + (1 - delta), j + delta]
-    beta.append(F(12))                 # 37 boundaries, beta[0] = chip start, beta[36] = chip end
+    if nb:                             # BOC(1,1) replicas only: 0, d, 1/2-d, 1/2, 1/2+d, 1-d, 1 of a chip, in sub-chips
+        beta = [F(0), delta, 6 - delta, F(6), 6 + delta, 12 - delta]
+    else:
+        for j in range(12):
+            beta += [F(j), j + (1 - delta), j + delta]
+    beta.append(F(12))                 # nseg + 1 boundaries, beta[0] = chip start, beta[nseg] = chip end
+    nseg = len(beta) - 1
     R = [int(b * S // 1) for b in beta]
-    assert all(R[k + 1] - R[k] >= 1 for k in range(36)), "segments shorter than one sample"
+    assert all(R[k + 1] - R[k] >= 1 for k in range(nseg)), "segments shorter than one sample"
     theta = [b * S - r for b, r in zip(beta, R)]        # exact fractions, theta[k] in [0, 1)
     return S, beta, R, theta
 
 
 def rank_tables(R, theta):
     """sorted thresholds, positions, rank -> decision bits, prefix masks, rank lower bounds"""
-    order = sorted(range(1, 37), key=lambda k: (theta[k], k))        # boundary numbers by ascending threshold
-    pos = [0] * 36
+    nseg = len(R) - 1
+    order = sorted(range(1, nseg + 1), key=lambda k: (theta[k], k))   # boundary numbers by ascending threshold
+    pos = [0] * nseg
     for s, k in enumerate(order):
         pos[k - 1] = s
     thr_nom = [int(theta[k] * (1 << 32)) for k in order]
@@ -68,9 +80,9 @@ def rank_tables(R, theta):
     assert min(gaps) > 3 * w, "nominal thresholds too close for the one-compare rank search"
     assert thr_nom[0] > 2 * w and thr_nom[-1] < (1 << 32) - 2 * w, "a threshold too close to the chip edge decision"
     masks = []
-    for j in range(37):                # j = number of thresholds < Psi
+    for j in range(nseg + 1):          # j = number of thresholds < Psi
         # bit k-1: Theta_k >= Psi, i.e. the jitter sample R_k still belongs to segment k-1
-        masks.append(sum(1 << (k - 1) for k in range(1, 37) if pos[k - 1] >= j))
+        masks.append(sum(1 << (k - 1) for k in range(1, nseg + 1) if pos[k - 1] >= j))
     rank_lo = []
     for b in range(RANK_BINS):
         lo = (b - 1) * w
@@ -79,8 +91,8 @@ def rank_tables(R, theta):
 
 
 def emit_body(R, acc_name):
-    """straight-line per-word code with one prefix mask per boundary (FAST_PSEL(k, lo, hi), k = 1..36)"""
-    nseg = 36
+    """straight-line per-word code with one prefix mask per boundary (FAST_PSEL(k, lo, hi), k = 1..nseg)"""
+    nseg = len(R) - 1
     nwords = (R[nseg] + 1 + 3) // 4
     lines = []
     e = lines.append
@@ -135,8 +147,10 @@ def main():
     fs = F(sys.argv[1]) if len(sys.argv) > 1 else F(99375000)
     fc = F(sys.argv[2]) if len(sys.argv) > 2 else F(1023000)
     d = F(sys.argv[3]) if len(sys.argv) > 3 else F(6, 100)
+    nb = len(sys.argv) > 4 and sys.argv[4] == "nb"
     global RANK_BINS
-    S, beta, R, theta = geometry(fs, fc, d)
+    S, beta, R, theta = geometry(fs, fc, d, nb)
+    nseg = len(R) - 1
     while True:       # 99.375 MHz: 512 bins; the reference's shipped 53 MHz: 1024 (closest thresholds 0.0046 sample apart)
         try:
             order, pos, thr_nom, masks, rank_lo = rank_tables(R, theta)
@@ -145,39 +159,43 @@ def main():
             if RANK_BINS >= 4096:
                 raise
             RANK_BINS *= 2
-    nsamp = R[36] + 1                  # samples 0..R36 (the last one is the end-boundary jitter sample)
+    nsamp = R[nseg] + 1                # samples 0..R[nseg] (the last one is the end-boundary jitter sample)
     out = []
     w = out.append
-    w("// GENERATED by gen_fast_wb.py — do not edit.  fs=%s Hz, fc=%s Hz, d=%s" % (fs, fc, float(d)))
+    w("// GENERATED by gen_fast_wb.py — do not edit.  fs=%s Hz, fc=%s Hz, d=%s%s" % (fs, fc, float(d), ", narrow band (BOC(1,1) replicas only)" if nb else ""))
+    w("#define FAST_NSEG %d   /* segments of a chip on which every replica is constant */" % nseg)
+    w("#define FAST_NB %d     /* 1: narrow-band body (data + BOC(1,1) pilot), no BOC(6,1) class sums */" % (1 if nb else 0))
     w("#define FAST_FS_HZ %.1f" % float(fs))
     w("#define FAST_FC_HZ %.1f" % float(fc))
     w("#define FAST_D %.17g" % float(d))
     w("#define FAST_NSAMP %d" % nsamp)
     w("#define FAST_NWORDS %d" % ((nsamp + 3) // 4))
-    w("#define FAST_RLAST %d" % R[36])
+    w("#define FAST_RLAST %d" % R[nseg])
     w("#define FAST_RANK_BINS %d" % RANK_BINS)
     w("#define FAST_RANK_BITS %d" % (RANK_BINS.bit_length() - 1))
-    w("#define FAST_POS_LAST %d   /* sorted position of the chip-end threshold (boundary 36) */" % pos[35])
+    w("#define FAST_POS_LAST %d   /* sorted position of the chip-end threshold (the last boundary) */" % pos[nseg - 1])
     w("#define FAST_SAMPLES_PER_CHIP %.17g" % float(12 * S))
-    w("FAST_CONST int kFastR[37] = {%s};" % ", ".join(map(str, R)))
-    w("FAST_CONST double kFastBeta[37] = {%s};" % ", ".join("%.17g" % float(b) for b in beta))
+    w("FAST_CONST int kFastR[%d] = {%s};" % (nseg + 1, ", ".join(map(str, R))))
+    w("FAST_CONST double kFastBeta[%d] = {%s};" % (nseg + 1, ", ".join("%.17g" % float(b) for b in beta)))
     w("// nominal frac(beta_k * S): %s" % " ".join("%.3f" % float(t) for t in theta[1:]))
-    w("FAST_CONST unsigned kFastThrNom[36] = {%s};" % ", ".join("0x%08xu" % t for t in thr_nom))
-    w("FAST_CONST unsigned char kFastPos[36] = {%s};" % ", ".join(map(str, pos)))
+    w("FAST_CONST unsigned kFastThrNom[%d] = {%s};" % (nseg, ", ".join("0x%08xu" % t for t in thr_nom)))
+    w("FAST_CONST unsigned char kFastPos[%d] = {%s};" % (nseg, ", ".join(map(str, pos))))
     w("FAST_CONST unsigned char kFastRankLo[%d] = {%s};" % (RANK_BINS, ", ".join(map(str, rank_lo))))
-    w("FAST_CONST unsigned long long kFastMask[37] = {%s};" % ", ".join("0x%010xull" % m for m in masks))
+    w("FAST_CONST unsigned long long kFastMask[%d] = {%s};" % (nseg + 1, ", ".join("0x%010xull" % m for m in masks)))
 
     special = {(1, 0): "A1", (1, 1): "B1", (7, 0): "A7", (7, 1): "B7", (6, 1): "B6", (6, 2): "C6", (12, 1): "B12",
                (12, 2): "C12"}
 
     def acc_name(k):
+        if nb:
+            return "N%d" % k
         j, cls = k // 3 + 1, k % 3
         if (j, cls) in special:
             return special[(j, cls)]
         return "%s%d%s" % ("E" if j % 2 == 0 else "O", 1 if j <= 6 else 2, "ABC"[cls])
 
     names = []
-    for k in range(36):
+    for k in range(nseg):
         n = acc_name(k)
         if n not in names:
             names.append(n)
@@ -212,7 +230,11 @@ def main():
             cur, n = dst, n + 1
 
     P, M = "+", "-"
-    for comp in ("r", "i"):
+    if nb:
+        for comp in ("r", "i"):
+            c("const int W1a%s = N0%s, W2a%s = N2%s, W1b%s = N3%s, W2b%s = N5%s;" % ((comp,) * 8))
+            chain("X", comp, [(P, "N3"), (P, "N4"), (P, "N5"), (M, "N0"), (M, "N1"), (M, "N2")])
+    for comp in (() if nb else ("r", "i")):
         c("const int W1a%s = A1%s + B1%s, W1b%s = A7%s + B7%s, W2a%s = B6%s + C6%s, W2b%s = B12%s + C12%s;" % ((comp,) * 12))
         chain("X", comp, [(P, "E2A"), (P, "O2A"), (P, "E2B"), (P, "O2B"), (P, "E2C"), (P, "O2C"), (P, "W1b"), (P, "W2b"),
                           (M, "E1A"), (M, "O1A"), (M, "E1B"), (M, "O1B"), (M, "E1C"), (M, "O1C"), (M, "W1a"), (M, "W2a")])

@@ -39,6 +39,9 @@ TRACK = {
     "track": dict(sig="B1C", mode="WB", spc=993750, max_doppler=4500.0, kappa_db=-64.8, kernel="trk_fw_kernel", cpu_epochs=2,
                   cn0_total=45.0,   # synth: data 11/44 + pilot 33/44 of the 45 dB-Hz carrier
                   what="WB tracking (data + QMBOC pilot)"),
+    "track_nb": dict(sig="B1C", mode="NB", spc=993750, max_doppler=4500.0, kappa_db=-64.8, kernel="trk_fw_kernel", cpu_epochs=2,
+                     cn0_total=44.59,  # data 11/44 + BOC(1,1) pilot 29/44 of the 45 dB-Hz carrier
+                     what="NB tracking (data + BOC(1,1) pilot)"),
     "track_b2a": dict(sig="B2a", mode="B2a", spc=99375, max_doppler=100.0, kappa_db=-71.9, kernel="trk_b2a_unit_kernel",
                       cpu_epochs=20, what="tracking (data + pilot)",
                       cn0_total=48.01),   # synth: data and pilot at 45 dB-Hz EACH (equal amplitudes), B2a_CNo is their sum
@@ -63,8 +66,9 @@ def parse():
                     help="--workload track / acq_b1c: sampling rate of the synthetic record [Hz]; 99.375e6 = BASELINE config 4, "
                          "53e6 = the reference's shipped B1C setting (B1C/initSettings.m:57)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "general", "fast"])
-    ap.add_argument("--workload", default="track", choices=["track", "track_b2a", "dual", "pipeline", "acq_b2a", "acq_b1c"],
-                    help="track = the headline metric (BASELINE config 4; --channels 12 = config 3); track_b2a = 60-channel "
+    ap.add_argument("--workload", default="track", choices=["track", "track_nb", "track_b2a", "dual", "pipeline", "acq_b2a", "acq_b1c"],
+                    help="track = the headline metric (BASELINE config 4; --channels 12 = config 3); track_nb = the same through "
+                         "NB_tracking (data + BOC(1,1) pilot, pilotTRKflag 1); track_b2a = 60-channel "
                          "B2a tracking; dual = BASELINE config 5 (--channels B1C + --channels B2a channels co-scheduled on "
                          "the same GPUs); pipeline = config 5 as a joint run: 63-PRN acquisition of both bands (PRN-sharded), "
                          "preRun, then tracking of the channels it found; acq_b2a = BASELINE config 2 (B2a 63-PRN x +-5 kHz "
@@ -85,16 +89,16 @@ def parse():
     return ap.parse_args()
 
 
-def settings_b1c(n_ch, seconds):
+def settings_b1c(n_ch, seconds, nb=False):
     import bds3_b200 as B
-    return B.b1c.initSettings(samplingFreq=FS, numberOfChannels=n_ch, pilotTRKflag=2,
+    return B.b1c.initSettings(samplingFreq=FS, numberOfChannels=n_ch, pilotTRKflag=1 if nb else 2,
                               msToProcess=int(round(seconds * 1000)))
 
 
 def settings_for(workload, n_ch, seconds):
     import bds3_b200 as B
     if TRACK[workload]["sig"] == "B1C":
-        return settings_b1c(n_ch, seconds)
+        return settings_b1c(n_ch, seconds, nb=TRACK[workload]["mode"] == "NB")
     return B.b2a.initSettings(numberOfChannels=n_ch, msToProcess=int(round(seconds * 1000)))
 
 
@@ -264,7 +268,8 @@ def run_reference(args):
     n_ep, spc, mode = w["cpu_epochs"], w["spc"], w["mode"]
     ms = int(round(args.seconds * 1000))
     if w["sig"] == "B1C":
-        st = Settings(dict(O.initSettings_B1C(samplingFreq=FS, numberOfChannels=args.channels, pilotTRKflag=2, msToProcess=ms)))
+        st = Settings(dict(O.initSettings_B1C(samplingFreq=FS, numberOfChannels=args.channels, pilotTRKflag=1 if mode == "NB" else 2,
+                                              msToProcess=ms)))
     else:
         st = Settings(dict(O.initSettings_B2a(numberOfChannels=args.channels, msToProcess=ms)))
     sats = synth.make_sats(args.channels, st, w["sig"], max_doppler=w["max_doppler"])
@@ -1213,10 +1218,10 @@ def main():
     global FS
     args = parse()
     if args.fs != FS:
-        if args.workload not in ("track", "acq_b1c"):
-            raise SystemExit("--fs applies to --workload track and acq_b1c")
+        if args.workload not in ("track", "track_nb", "acq_b1c"):
+            raise SystemExit("--fs applies to --workload track, track_nb and acq_b1c")
         FS = float(args.fs)
-        TRACK["track"]["spc"] = int(round(FS * 0.01))     # samples per 10 ms B1C code period
+        TRACK["track"]["spc"] = TRACK["track_nb"]["spc"] = int(round(FS * 0.01))     # samples per 10 ms B1C code period
     if args.impl == "reference":
         run_reference(args)
     elif args.workload in ("acq_b2a", "acq_b1c"):

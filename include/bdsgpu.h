@@ -149,7 +149,8 @@ typedef struct bds_trk_cfg {
     double pf3, pf2, pf1;
     double wbFactor;             /* WB only */
     int32_t kernel;              /* BDS_KERNEL_* */
-    int32_t reserved;            /* 0; bit 0 = test hook: widen the fast kernel's exact-path guard band */
+    int32_t reserved;            /* 0; test hooks: bit 0 = widen the fast kernel's exact-path guard band, bit 1 = narrow band on the
+                                  * wide-band chip body instead of the narrow-band one */
     /* Tuning and diagnostics of the chip-synchronous kernel.  All 0 = library defaults.  The library never reads the
      * caller's environment: everything that changes its behaviour is in this struct. */
     int32_t fwPassesPerTask;     /* passes of 512 chips per queued (channel, epoch, slice) task, 1..8 */

@@ -22,7 +22,9 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 L = 10230
 # chip-body geometries of the library (bds_track.cu): namespace, sampling rate, generated file
 GEOMS = {"g99": (99.375e6, "bds_track_fast_gen.inc"),      # BASELINE
-         "g53": (53e6, "bds_track_fast_gen_53.inc")}        # the reference's shipped B1C setting (B1C/initSettings.m:57)
+         "g53": (53e6, "bds_track_fast_gen_53.inc"),        # the reference's shipped B1C setting (B1C/initSettings.m:57)
+         "g99n": (99.375e6, "bds_track_fast_gen_nb.inc"),   # narrow-band bodies (NB_tracking.m): six segments per chip
+         "g53n": (53e6, "bds_track_fast_gen_53_nb.inc")}
 TWO32, TWO64 = 1 << 32, 1 << 64
 
 F2_SHIM = r"""
@@ -87,7 +89,7 @@ extern "C" int rank_check(const EpochParams* p, unsigned Psi, int* by_definition
     const int jlo = fsx.rankLo[Psi >> (32 - FAST_RANK_BITS)];
     const int j = jlo + (tab.thr[jlo] < Psi);
     int n = 0;
-    for (int k = 1; k <= 36; ++k) {
+    for (int k = 1; k <= FAST_NSEG; ++k) {
         double th = kFastBeta[k] * tab.S - (double)kFastR[k];
         n += (unsigned)std::fmin(th * 4294967296.0, 4294967295.0) < Psi;
     }
@@ -123,12 +125,16 @@ def _build(tmp, flags=(), geom="g99"):
     return lib
 
 
-def make_epoch(rng, prn, rem, codeFreq, carrFreq, remCarr, FS=99.375e6):
-    """one block of the SURVEY 8(d) B1C signal model + noise, int8"""
+def make_epoch(rng, prn, rem, codeFreq, carrFreq, remCarr, FS=99.375e6, mode="WB"):
+    """one block of the SURVEY 8(d) B1C signal model + noise, int8 (the signal always carries all three components;
+    settings and replica codes are those of the tracking mode)"""
     step = codeFreq / FS
     blk = int(math.ceil((L - rem) / step))
     s = O.initSettings_B1C(samplingFreq=FS, pilotTRKflag=2)
     codes = O.make_track_codes("WB", s, prn)
+    if mode == "NB":
+        s_nb = O.initSettings_B1C(samplingFreq=FS, pilotTRKflag=1)
+        codes_nb = O.make_track_codes("NB", s_nb, prn)
     k = np.arange(blk)
     t = rem + k * step
     i2 = np.ceil(t * 2).astype(np.int64)
@@ -137,6 +143,8 @@ def make_epoch(rng, prn, rem, codeFreq, carrFreq, remCarr, FS=99.375e6):
     sig = math.sqrt(11 / 44) * codes["data"][i2] * np.cos(th) - (math.sqrt(29 / 44) * codes["pilot"][i2] * np.sin(th)
                                                                     + math.sqrt(4 / 44) * codes["pilot61"][i12] * np.cos(th))
     x = np.clip(np.rint(24.0 * rng.standard_normal(blk) + 30.0 * sig), -127, 127).astype(np.int8)
+    if mode == "NB":
+        return s_nb, codes_nb, x, step
     return s, codes, x, step
 
 
@@ -147,9 +155,10 @@ NAMES = [f"{fam}_{iq}_{epl}" for fam in ("d", "p", "p61") for epl in ("E", "P", 
 def hostlib(request, tmp_path_factory):
     lib = _build(tmp_path_factory.mktemp("b1c_host_" + request.param), geom=request.param)
     lib.FS = GEOMS[request.param][0]
+    lib.MODE = "NB" if request.param.endswith("n") else "WB"
     text = open(os.path.join(CSRC, GEOMS[request.param][1])).read()
-    lib.R = [int(v) for v in re.search(r"kFastR\[37\] = \{(.*?)\}", text).group(1).split(",")]
-    lib.BETA = [float(v) for v in re.search(r"kFastBeta\[37\] = \{(.*?)\}", text).group(1).split(",")]
+    lib.R = [int(v) for v in re.search(r"kFastR\[\d+\] = \{(.*?)\}", text).group(1).split(",")]
+    lib.BETA = [float(v) for v in re.search(r"kFastBeta\[\d+\] = \{(.*?)\}", text).group(1).split(",")]
     return lib
 
 
@@ -161,7 +170,7 @@ def test_fast_chip_source_on_host_equals_oracle(hostlib):
     for rem, cf, fc_, rc, B0, guard in ((0.0, 1.023e6 - 2.7, 14.58e6 + 1830.0, 0.0, 7, 16),
                                         (0.0061, 1.023e6 + 1.9, 14.58e6 - 3920.0, 4.2, 993750 * 2 + 13, 16),
                                         (0.0033, 1.023e6 - 0.4, 14.58e6 + 55.0, 2.2, 48, 1 << 24)):
-        s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc, FS)
+        s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc, FS, lib.MODE)
         p = EpochParams(pos=B0, blksize=x.size, pad=0, rem=rem, step=step, carrFreq=fc_, remCarr=rc)
         bits = np.concatenate([_pack_bits(O.b1c_data_primary(prn)), _pack_bits(O.b1c_pilot_primary(prn))])
         tileBase = B0 & ~15
@@ -175,11 +184,13 @@ def test_fast_chip_source_on_host_equals_oracle(hostlib):
         assert valid.value == 1
         if guard == 16:
             assert n_exact <= 4, n_exact
-        else:
-            assert 0.1 < n_exact / L < 0.6, n_exact
-        ref, _, _ = O.correlate_epoch("WB", s, x.astype(np.float64), codes, rem, step, fc_, rc)
+        else:   # guard 2^24 / 2^32 of a sample on either side of every threshold and of the chip edges
+            nthr = len(lib.R) - 1
+            assert 0.5 * 2 * (nthr + 2) / 256 < n_exact / L < 2.5 * 2 * (nthr + 2) / 256, n_exact
+        ref, _, _ = O.correlate_epoch(lib.MODE, s, x.astype(np.float64), codes, rem, step, fc_, rc)
         got = dict(zip(NAMES, sums))
-        for fam in ("d", "p", "p61"):
+        # (narrow band: the BOC(6,1) sums only receive what the exact per-sample path adds; the kernel's epilogue zeroes them)
+        for fam in (("d", "p") if lib.MODE == "NB" else ("d", "p", "p61")):
             scale = max(abs(ref[f"{fam}_I_P"]), abs(ref[f"{fam}_Q_P"]))
             for nm in "EPL":
                 for iq in "IQ":
@@ -194,7 +205,7 @@ def test_code_rate_far_from_nominal_invalidates_the_table_and_stays_exact(hostli
     rng = np.random.default_rng(5)
     prn = 7
     rem, cf, fc_, rc, B0 = 0.0042, 1.023e6 * (1 + 60e-6), 14.58e6 + 300.0, 1.0, 32
-    s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc, lib.FS)
+    s, codes, x, step = make_epoch(rng, prn, rem, cf, fc_, rc, lib.FS, lib.MODE)
     p = EpochParams(pos=B0, blksize=x.size, pad=0, rem=rem, step=step, carrFreq=fc_, remCarr=rc)
     bits = np.concatenate([_pack_bits(O.b1c_data_primary(prn)), _pack_bits(O.b1c_pilot_primary(prn))])
     tile = np.zeros(B0 + x.size + 256, dtype=np.int8)
@@ -205,9 +216,11 @@ def test_code_rate_far_from_nominal_invalidates_the_table_and_stays_exact(hostli
                             C.c_int(tile.size), C.c_longlong(B0), x.ctypes.data_as(C.c_void_p), C.c_uint(16),
                             sums.ctypes.data_as(C.c_void_p), C.byref(valid))
     assert valid.value == 0 and n_exact == L
-    ref, _, _ = O.correlate_epoch("WB", s, x.astype(np.float64), codes, rem, step, fc_, rc)
+    ref, _, _ = O.correlate_epoch(lib.MODE, s, x.astype(np.float64), codes, rem, step, fc_, rc)
     for k, v in zip(NAMES, sums):
         fam = k.split("_")[0]
+        if k not in ref:
+            continue   # narrow band: no BOC(6,1) family
         scale = max(abs(ref[f"{fam}_I_P"]), abs(ref[f"{fam}_Q_P"]))
         assert abs(v - ref[k]) <= 1e-4 * scale, (k, v, ref[k])
 
@@ -223,7 +236,7 @@ def test_one_compare_rank_search_equals_the_definition(hostlib):
         step = cf / FS
         p = EpochParams(pos=0, blksize=993750, pad=0, rem=float(rng.uniform(0, step)), step=step, carrFreq=14.58e6 + dopp, remCarr=0.3)
         S = 1.0 / (12.0 * step)
-        thr = [int(min((BETA[k] * S - R[k]) * 4294967296.0, 4294967295.0)) for k in range(1, 37)]
+        thr = [int(min((BETA[k] * S - R[k]) * 4294967296.0, 4294967295.0)) for k in range(1, len(R))]
         probes = list(rng.integers(0, 1 << 32, size=3000)) + [t + d for t in thr for d in (-2, -1, 0, 1, 2)] + [0, 1, (1 << 32) - 1]
         for Psi in probes:
             Psi = int(Psi) & 0xFFFFFFFF

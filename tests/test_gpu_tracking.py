@@ -543,7 +543,9 @@ def test_chip_synchronous_kernel_at_the_reference_shipped_53_mhz(mode):
         assert np.max(err[np.isfinite(err)]) <= 1e-4, np.max(err[np.isfinite(err)])
         fast_chips, exact_chips, general_slices, _ = _track.counters(None)
         assert general_slices == 0 and fast_chips + exact_chips == 2 * 3 * 10230
-        assert (0.1 < exact_chips / (2 * 3 * 10230) < 0.6) if wide_guard else exact_chips <= 2 * 3 + 2
+        # wide guard: 2^-8 sample on either side of every threshold (36 wide band, 6 narrow band) and of the chip edges
+        lo, hi = (0.1, 0.6) if mode == "WB" else (0.03, 0.16)
+        assert (lo < exact_chips / (2 * 3 * 10230) < hi) if wide_guard else exact_chips <= 2 * 3 + 2
     ps = util.product_settings(s)
     res, _ = _track.run_tracking(mode, x, ch, ps, n_epochs=20, raw=True)            # AUTO
     fast_chips, exact_chips, general_slices, _ = _track.run_tracking.last_counters
@@ -630,3 +632,29 @@ def test_one_second_trajectory_against_the_stored_oracle_trajectory():
     # one codePhaseStep more remCodePhase: compare the code phase referred to the oracle's block start
     rem = r.remCodePhase - (r.absoluteSample - g["absoluteSample"]) * (g["codeFreq"] / s.samplingFreq)
     np.testing.assert_allclose(rem, g["remCodePhase"], rtol=0, atol=1e-3)             # chips
+
+
+def test_narrow_band_body_against_oracle_and_wide_band_body():
+    """NB_tracking on its own chip body (six segments per chip, the AUTO / FAST choice) and on the wide-band body
+    (cfg.reserved bit 1, the path before the narrow-band bodies existed): both within the north-star tolerance of the
+    oracle, the BOC(6,1) family exactly zero, and equal to each other to float rounding."""
+    s, sats, x, ch = util.record("NB", 2, 0.06)
+    tr, raw = util.oracle_track("NB", s, x, ch, 3)
+    nco = np.ascontiguousarray(np.stack([t.nco for t in tr]))
+    prn = np.asarray([c.PRN for c in ch], dtype=np.int32)
+    got = {}
+    for hook in (0, 2, 1, 3):       # bit 0: wide guard band (a quarter of the chips through the exact path)
+        cfg = _track.make_cfg("NB", util.product_settings(s), L.KERNEL_FAST)
+        cfg.reserved = hook
+        sums = np.zeros((2, 3, 18))
+        L.check(L.lib().bds_track_correlate_open_loop(L.TRK_B1C_NB, C.byref(cfg), L.ptr(x), x.size, L.LOC_HOST, L.ptr(prn),
+                                                      2, 3, L.ptr(nco), L.ptr(sums)))
+        err = np.abs(sums - raw) / util.family_scale(raw)
+        assert np.max(err[np.isfinite(err)]) <= 1e-4, (hook, np.max(err[np.isfinite(err)]))
+        assert np.all(sums[..., 12:] == 0.0)
+        fast_chips, exact_chips, general_slices, _ = _track.counters(None)
+        assert general_slices == 0 and fast_chips + exact_chips == 2 * 3 * 10230
+        got[hook] = sums
+    sc = util.family_scale(raw)
+    d = np.abs(got[0] - got[2]) / sc
+    assert np.max(d[np.isfinite(d)]) <= 2e-5
