@@ -448,6 +448,8 @@ def run_b200(args):
     st_local.numberOfChannels = len(mine)
     st_local.numberOfChannels_total = total_channels   # satellites in the record (self_check: multiple-access noise)
     tuning = {"b2aClusterSize": args.b2a_cluster} if (sig == "B2a" and args.b2a_cluster) else None
+    if os.environ.get("BDS_BENCH_TRK_TUNING"):        # developer A/B of bds_trk_cfg tuning fields: "fwPassesPerTask=3,fwPrefetch=2"
+        tuning = dict(tuning or {}, **{k: int(v) for k, v in (kv.split("=") for kv in os.environ["BDS_BENCH_TRK_TUNING"].split(","))})
     sess = _track.TrackSession(mode, st_local, mine, kernel=kern, device_ptr=x_dev.data_ptr(), n_samples=n_samples, tuning=tuning)
 
     def barrier():
